@@ -1,0 +1,266 @@
+/*
+ * nutpie_b200.h — C-ABI of the B200-native NUTS sampler core.
+ *
+ * This header is the drop-in boundary for the path BASELINE.json's north_star
+ * names: everything nutpie (pymc-devs/nutpie @ d3ffb850) delegates to the
+ * external crate nuts-rs 0.18.3 — chain scheduling, the NUTS transition,
+ * the leapfrog integrator with a diagonal mass matrix, dual-averaging
+ * step-size adaptation and the Welford draw/gradient variance estimators —
+ * re-expressed as hand-written sm_100a CUDA kernels behind plain C entry
+ * points.  Each entry point cites the reference interface it replaces
+ * (paths relative to /root/reference).
+ *
+ *   - plain pointers and sizes only, no C++/torch types;
+ *   - every function returns 0 on success, a negative NB200_E* code on
+ *     failure, and leaves a message retrievable with nb200_last_error();
+ *   - the library owns its device memory (cudaMalloc) and its stream; host
+ *     buffers handed in are copied before the call returns unless stated.
+ *
+ * The reference-side binding (the `extern "C"` block a maintainer would add
+ * to src/wrapper.rs in place of `use nuts_rs::{Sampler, ...}`) is shown in
+ * INTEGRATION.md.
+ */
+#ifndef NUTPIE_B200_H
+#define NUTPIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define NB200_OK 0
+#define NB200_EINVAL (-1)   /* bad argument / unsupported option            */
+#define NB200_ECUDA (-2)    /* CUDA runtime error (see nb200_last_error)    */
+#define NB200_ESTATE (-3)   /* call not valid in the sampler's state        */
+#define NB200_ELOGP (-4)    /* fatal (non-recoverable) logp error, cf.      */
+                            /* src/pymc.rs:166-181 (rc < 0 is fatal)        */
+#define NB200_EINIT (-5)    /* no finite initial point found for a chain    */
+#define NB200_ETIMEOUT 1    /* nb200_sampler_wait: still running            */
+
+/* ---- settings ----------------------------------------------------------
+ * Field-for-field the subset of nuts_rs::DiagNutsSettings that nutpie's
+ * PyNutsSettings::apply_update can reach for adaptation="diag"/"draw_diag"
+ * (src/wrapper.rs:210-451, 563-620).  Defaults: nb200_settings_default().
+ */
+typedef struct nb200_settings {
+    uint64_t seed;             /* wrapper.rs:453-458 (random if None)          */
+    uint64_t num_tune;         /* wrapper.rs:398-402; default 400              */
+    uint64_t num_draws;        /* wrapper.rs:408-412; default 1000             */
+    uint32_t maxdepth;         /* wrapper.rs:565-568; default 10               */
+    uint32_t mindepth;         /* wrapper.rs:569-572; default 0                */
+    int32_t check_turning;     /* wrapper.rs:573-576; default 1                */
+    int32_t store_gradient;    /* wrapper.rs:393-397                           */
+    int32_t store_mass_matrix; /* wrapper.rs:271-282                           */
+    int32_t use_grad_based_estimate; /* wrapper.rs:283-294; 1 = "diag"         */
+    double max_energy_error;   /* wrapper.rs:443-447; default 1000             */
+    /* step size (nuts_rs step-size settings; wrapper.rs:240-270, 347-392) */
+    double initial_step;       /* default 0.1                                  */
+    double target_accept;      /* default 0.8                                  */
+    double max_step_size;      /* dual_average.max_step_size; default +inf     */
+    double da_k;               /* 0.75                                         */
+    double da_t0;              /* 10                                           */
+    double da_gamma;           /* 0.05                                         */
+    int32_t step_size_method;  /* 0 dual_average | 2 fixed (wrapper.rs:347)    */
+    int32_t _pad0;
+    double fixed_step_size;    /* used when step_size_method == 2              */
+    /* mass-matrix schedule (nuts_rs EuclideanAdaptOptions) */
+    double early_window;       /* 0.3 of num_tune                              */
+    double step_size_window;   /* 0.15 of num_tune: final step-size-only part  */
+    uint64_t mass_matrix_switch_freq;        /* 80 (wrapper.rs:295-306)        */
+    uint64_t early_mass_matrix_switch_freq;  /* 10 (wrapper.rs:225-239)        */
+    uint64_t mass_matrix_update_freq;        /* 1                              */
+    /* initial positions (nuts_rs::Model::init_position; src/pymc.rs:505-534,
+     * src/stan.rs:798-808, src/pyfunc.rs:535-569) when no explicit q0 given */
+    int32_t init_kind;         /* 0 uniform(-r,r)+mean | 1 normal(0,1)+mean    */
+    int32_t num_try_init;      /* sample.py:860-863; default 10                */
+    double init_radius;        /* 2.0 (pyfunc) / 1.0 (PyMC jitter)             */
+    /* trace thinning (ours; config 4 cannot store 82 GB of raw draws) */
+    uint64_t store_dims;       /* store only the first store_dims coordinates  */
+                               /* of each draw; 0 = all                        */
+    int32_t save_warmup;       /* sample.py:831; 1 = keep tuning draws         */
+    int32_t _pad1;
+} nb200_settings;
+
+/* ---- model density plug-in ---------------------------------------------
+ * The reference's own plug-in ABI (src/pymc.rs:23-29, produced by
+ * python/nutpie/compile_pymc.py:970-1006) is a HOST function pointer.  The
+ * device engine cannot call it per leapfrog, so a model is either one of the
+ * built-in device densities below (hand-written CUDA, host twin in oracle/)
+ * or — next row, SURVEY §8f-3 — a host callback.
+ */
+typedef int (*nb200_logp_fn)(size_t dim, const double *x, double *grad_out,
+                             double *logp_out, const void *user_data);
+typedef int (*nb200_expand_fn)(size_t dim, size_t expanded_dim, const double *x,
+                               double *out, const void *user_data);
+
+#define NB200_MODEL_NORMAL 1 /* logp = -1/2 sum ((x-mu)/sigma)^2 ; configs 1,4 */
+#define NB200_MODEL_FUNNEL 2 /* Neal's funnel: x0~N(0,1), x[1:]~N(0,exp(x0))   */
+#define NB200_MODEL_RADON 3  /* README.md:53-88 / notebooks/pytensor_logp.md    */
+                             /* :57-88 hierarchical radon, plain-Normal raws,   */
+                             /* dim = 2*n_county + 5                            */
+
+typedef struct nb200_model_desc {
+    int32_t kind;
+    int32_t _pad;
+    uint64_t dim;
+    double mu, sigma;        /* NB200_MODEL_NORMAL                             */
+    int32_t n_obs, n_county; /* NB200_MODEL_RADON                              */
+    const double *y;         /* [n_obs] log_radon                              */
+    const int32_t *county;   /* [n_obs] county index, any order                */
+    const uint8_t *floor;    /* [n_obs] 0/1                                    */
+} nb200_model_desc;
+
+/* ---- per-draw sampler statistics ---------------------------------------
+ * One row of NB200_NSTAT doubles per (chain, draw); integers are stored
+ * exactly as doubles.  Names follow nutpie's sample_stats
+ * (docs/sample-stats.qmd:47-57, python/nutpie/sample.py:83).
+ */
+enum {
+    NB200_STAT_DEPTH = 0,
+    NB200_STAT_MAXDEPTH_REACHED = 1,
+    NB200_STAT_INDEX_IN_TRAJECTORY = 2,
+    NB200_STAT_LOGP = 3,
+    NB200_STAT_ENERGY = 4,
+    NB200_STAT_ENERGY_ERROR = 5,
+    NB200_STAT_DIVERGING = 6,
+    NB200_STAT_STEP_SIZE = 7,
+    NB200_STAT_STEP_SIZE_BAR = 8,
+    NB200_STAT_N_STEPS = 9,
+    NB200_STAT_MEAN_TREE_ACCEPT = 10,
+    NB200_STAT_MEAN_TREE_ACCEPT_SYM = 11,
+    NB200_STAT_TUNING = 12,
+    NB200_STAT_DRAW = 13,
+    NB200_STAT_CHAIN = 14,
+    NB200_STAT_RESERVED = 15,
+    NB200_NSTAT = 16
+};
+
+/* src/wrapper.rs:38-104 (PyChainProgress) */
+typedef struct nb200_progress {
+    uint64_t finished_draws;
+    uint64_t total_draws;
+    uint64_t divergences;
+    uint64_t latest_num_steps;
+    uint64_t total_num_steps;
+    double step_size;
+    int32_t tuning;
+    int32_t started;
+} nb200_progress;
+
+/* View into the library's pinned host copy of the trace.  Valid until the
+ * next nb200_sampler_trace() call or nb200_sampler_destroy().
+ * Replaces PySampler::{inspect,take_results,abort} → Vec<ArrowTrace>
+ * (src/wrapper.rs:1332-1456): chain c's rows are contiguous, so each chain
+ * maps 1:1 onto the (posterior, sample_stats) RecordBatch pair of
+ * src/wrapper.rs:1477-1494. */
+typedef struct nb200_trace_view {
+    uint64_t n_chains;
+    uint64_t n_rows;         /* rows allocated per chain (tune+draws, or draws) */
+    uint64_t dim;            /* model dimension                                 */
+    uint64_t store_dims;     /* coordinates stored per draw                     */
+    const double *draws;     /* [n_chains][n_rows][store_dims] unconstrained    */
+    const double *stats;     /* [n_chains][n_rows][NB200_NSTAT]                 */
+    const double *gradients; /* [n_chains][n_rows][store_dims] or NULL          */
+    const double *mass_matrix_inv; /* [n_chains][n_rows][store_dims] or NULL    */
+    const uint64_t *rows_filled;   /* [n_chains] rows valid so far              */
+} nb200_trace_view;
+
+typedef struct nb200_sampler nb200_sampler;
+
+/* ---- library ------------------------------------------------------------ */
+int nb200_abi_version(void);
+const char *nb200_last_error(void);
+int nb200_device_count(void);
+/* nuts_rs::DiagNutsSettings::default() as surfaced by
+ * PyNutsSettings::new_diag (src/wrapper.rs:525-533). */
+void nb200_settings_default(nb200_settings *out);
+
+/* ---- sampler life cycle -------------------------------------------------
+ * nb200_sampler_create  ⇔ nuts_rs::Sampler::new(model, settings, storage,
+ *                          cores, callback)        src/wrapper.rs:977-1085
+ *   n_chains chains are created on `device`; chain c uses the random stream
+ *   of GLOBAL chain id chain_id_offset + c, so a run sharded over several
+ *   GPUs/processes reproduces the single-GPU run chain for chain.
+ *   q0: optional host array [n_chains][dim] of initial positions
+ *   (Model::init_position, src/pymc.rs:505-534); NULL → drawn on device per
+ *   settings.init_kind around init_mean (NULL → zeros).
+ * The call allocates and initialises device state and returns; sampling
+ * starts with nb200_sampler_start (non-blocking, like Sampler::new). */
+nb200_sampler *nb200_sampler_create(const nb200_settings *settings,
+                                    const nb200_model_desc *model,
+                                    uint64_t n_chains, uint64_t chain_id_offset,
+                                    int device, const double *q0,
+                                    const double *init_mean);
+int nb200_sampler_start(nb200_sampler *s);
+/* SamplerWaitResult / wait_timeout (src/wrapper.rs:1099-1185): returns
+ * NB200_OK when finished, NB200_ETIMEOUT when still running after
+ * timeout_seconds (<0 = forever), <0 on sampler error. */
+int nb200_sampler_wait(nb200_sampler *s, double timeout_seconds);
+/* progress callback payload (src/wrapper.rs:38-104); out has n_chains rows */
+int nb200_sampler_progress(nb200_sampler *s, nb200_progress *out);
+int nb200_sampler_is_finished(nb200_sampler *s); /* wrapper.rs:1252-1261 */
+int nb200_sampler_pause(nb200_sampler *s);       /* wrapper.rs:1263-1282 */
+int nb200_sampler_resume(nb200_sampler *s);      /* wrapper.rs:1284-1303 */
+int nb200_sampler_abort(nb200_sampler *s);       /* wrapper.rs:1332-1365 */
+/* inspect()/take_results(): copy the trace so far to pinned host memory
+ * (src/wrapper.rs:1401-1456).  Allowed while running (snapshot). */
+int nb200_sampler_trace(nb200_sampler *s, nb200_trace_view *out);
+/* Copy the trace to caller-provided host buffers instead (may be NULL to
+ * skip one); used by the end-to-end path to land draws directly in numpy /
+ * Arrow buffers. */
+int nb200_sampler_trace_into(nb200_sampler *s, double *draws, double *stats,
+                             double *gradients, double *mass_matrix_inv,
+                             uint64_t *rows_filled);
+int nb200_sampler_destroy(nb200_sampler *s);
+
+/* ---- measurement hooks --------------------------------------------------
+ * Device time (CUDA events recorded on the sampler's own stream around the
+ * sampling kernel launches) and launch count, for bench.py. */
+double nb200_sampler_kernel_ms(nb200_sampler *s);
+uint64_t nb200_sampler_launch_count(nb200_sampler *s);
+/* raw device pointers (for torch.distributed gathers without a host hop) */
+int nb200_sampler_device_buffers(nb200_sampler *s, void **draws, void **stats);
+/* launch geometry chosen for this sampler (threads per chain, block, grid) */
+int nb200_sampler_geometry(nb200_sampler *s, int32_t *threads_per_chain,
+                           int32_t *block, int32_t *grid);
+/* override threads per chain (0 = auto; 32..1024, power of two) and chains
+ * per CTA (0 = auto; only used when threads per chain == 32) for samplers
+ * created afterwards; testing/tuning */
+void nb200_set_threads_per_chain(int32_t t);
+void nb200_set_chains_per_block(int32_t c);
+/* limit the draws one kernel launch may advance each chain by (0 = run to the
+ * end in one persistent launch); the host relaunches until done */
+int nb200_sampler_set_draws_per_launch(nb200_sampler *s, uint64_t n);
+/* tests: replace the momentum stream by a host tape [n_chains][tune+draws][dim]
+ * of standard normals; must precede start() */
+int nb200_sampler_set_z_tape(nb200_sampler *s, const double *z_tape);
+/* pinned host memory for trace buffers handed to nb200_sampler_trace_into */
+void *nb200_host_alloc(size_t bytes);
+void nb200_host_free(void *p);
+
+/* ---- component entry points (parity tests at the nuts-rs Math seam) -----
+ * nb200_logp_grad  ⇔ CpuLogpFunc::logp (src/pymc.rs:197-215): evaluate the
+ *   device density for n points; rc[i] follows the reference convention
+ *   (0 ok, 3 non-finite grad, 4 non-finite logp; compile_pymc.py:996-999).
+ * nb200_leapfrog   ⇔ one nuts-rs leapfrog with a diagonal mass matrix for n
+ *   independent states; all arrays host [n][dim]
+ *   except eps [n], dir [n], and outputs logp/kinetic [n].
+ */
+int nb200_logp_grad(const nb200_model_desc *model, int device, uint64_t n,
+                    const double *q, double *logp, double *grad, int32_t *rc);
+int nb200_leapfrog(const nb200_model_desc *model, int device, uint64_t n,
+                   const double *q, const double *p, const double *g,
+                   const double *var, const double *p_sum, const double *eps,
+                   const int32_t *dir, const int64_t *idx, double *q_out,
+                   double *p_out, double *g_out, double *p_sum_out,
+                   double *logp_out, double *kinetic_out, int32_t *rc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUTPIE_B200_H */

@@ -1,0 +1,672 @@
+"""Host-side mirror of `nutpie._lib` over the C-ABI of libnutpie_b200.so.
+
+The reference's `_lib` is a PyO3 module (src/wrapper.rs:1738-1758) that owns a
+`nuts_rs::Sampler`.  There is no Rust toolchain in this image, so the same
+Python-visible surface — PyNutsSettings, PySampler, PyChainProgress, PyTrace,
+ProgressType, PyStorage — is written in Python on top of `ctypes` bindings of
+include/nutpie_b200.h; every class cites the PyO3 item it mirrors.  All
+sampling work happens in the CUDA library: if it cannot be loaded this module
+raises, there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+__version__ = "0.1.0"
+
+_PKG = Path(__file__).resolve().parent
+_SO = _PKG / "libnutpie_b200.so"
+_lib = None
+_lib_lock = threading.Lock()
+
+NSTAT = 16
+STAT_NAMES = [
+    "depth", "maxdepth_reached", "index_in_trajectory", "logp", "energy", "energy_error",
+    "diverging", "step_size", "step_size_bar", "n_steps", "mean_tree_accept",
+    "mean_tree_accept_sym", "tuning", "draw", "chain", "reserved",
+]
+_STAT_DTYPES = {
+    "depth": np.uint64, "maxdepth_reached": np.bool_, "index_in_trajectory": np.int64,
+    "diverging": np.bool_, "n_steps": np.uint64, "tuning": np.bool_, "draw": np.uint64,
+    "chain": np.uint64,
+}
+
+NB200_ETIMEOUT = 1
+_ERRORS = {-1: ValueError, -2: RuntimeError, -3: ValueError, -4: RuntimeError, -5: RuntimeError}
+
+
+class Settings(C.Structure):
+    """nb200_settings (include/nutpie_b200.h)."""
+
+    _fields_ = [
+        ("seed", C.c_uint64), ("num_tune", C.c_uint64), ("num_draws", C.c_uint64),
+        ("maxdepth", C.c_uint32), ("mindepth", C.c_uint32),
+        ("check_turning", C.c_int32), ("store_gradient", C.c_int32),
+        ("store_mass_matrix", C.c_int32), ("use_grad_based_estimate", C.c_int32),
+        ("max_energy_error", C.c_double),
+        ("initial_step", C.c_double), ("target_accept", C.c_double),
+        ("max_step_size", C.c_double), ("da_k", C.c_double), ("da_t0", C.c_double),
+        ("da_gamma", C.c_double),
+        ("step_size_method", C.c_int32), ("_pad0", C.c_int32),
+        ("fixed_step_size", C.c_double),
+        ("early_window", C.c_double), ("step_size_window", C.c_double),
+        ("mass_matrix_switch_freq", C.c_uint64),
+        ("early_mass_matrix_switch_freq", C.c_uint64),
+        ("mass_matrix_update_freq", C.c_uint64),
+        ("init_kind", C.c_int32), ("num_try_init", C.c_int32),
+        ("init_radius", C.c_double),
+        ("store_dims", C.c_uint64),
+        ("save_warmup", C.c_int32), ("_pad1", C.c_int32),
+    ]
+
+
+class ModelDesc(C.Structure):
+    """nb200_model_desc."""
+
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("dim", C.c_uint64),
+                ("mu", C.c_double), ("sigma", C.c_double),
+                ("n_obs", C.c_int32), ("n_county", C.c_int32),
+                ("y", C.c_void_p), ("county", C.c_void_p), ("floor", C.c_void_p)]
+
+
+class Progress(C.Structure):
+    """nb200_progress."""
+
+    _fields_ = [("finished_draws", C.c_uint64), ("total_draws", C.c_uint64),
+                ("divergences", C.c_uint64), ("latest_num_steps", C.c_uint64),
+                ("total_num_steps", C.c_uint64), ("step_size", C.c_double),
+                ("tuning", C.c_int32), ("started", C.c_int32)]
+
+
+MODEL_KINDS = {"normal": 1, "funnel": 2, "radon": 3}
+
+
+def library_path() -> Path:
+    return _SO
+
+
+def load_library() -> C.CDLL:
+    """Load libnutpie_b200.so, building it with nvcc when sources are newer.
+    Raises RuntimeError when the CUDA library is unavailable — never falls back."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if os.environ.get("NUTPIE_B200_NO_BUILD") != "1":
+            try:
+                from . import build as _build
+
+                if _build.needs_build():
+                    _build.build()
+            except Exception as exc:  # no nvcc on this host: use the shipped .so if any
+                if not _SO.exists():
+                    raise RuntimeError(
+                        f"libnutpie_b200.so is missing and could not be built ({exc}); "
+                        "the B200 engine has no CPU fallback") from exc
+        if not _SO.exists():
+            raise RuntimeError("libnutpie_b200.so is missing; run `python -m nutpie_b200.build`")
+        L = C.CDLL(str(_SO))
+        L.nb200_abi_version.restype = C.c_int
+        L.nb200_last_error.restype = C.c_char_p
+        L.nb200_device_count.restype = C.c_int
+        L.nb200_sampler_create.restype = C.c_void_p
+        L.nb200_sampler_create.argtypes = [C.POINTER(Settings), C.POINTER(ModelDesc), C.c_uint64,
+                                           C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        for name in ("start", "is_finished", "pause", "resume", "abort", "destroy"):
+            f = getattr(L, f"nb200_sampler_{name}")
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p]
+        L.nb200_sampler_wait.restype = C.c_int
+        L.nb200_sampler_wait.argtypes = [C.c_void_p, C.c_double]
+        L.nb200_sampler_progress.restype = C.c_int
+        L.nb200_sampler_progress.argtypes = [C.c_void_p, C.POINTER(Progress)]
+        L.nb200_sampler_trace_into.restype = C.c_int
+        L.nb200_sampler_trace_into.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.nb200_sampler_kernel_ms.restype = C.c_double
+        L.nb200_sampler_kernel_ms.argtypes = [C.c_void_p]
+        L.nb200_sampler_launch_count.restype = C.c_uint64
+        L.nb200_sampler_launch_count.argtypes = [C.c_void_p]
+        L.nb200_sampler_geometry.restype = C.c_int
+        L.nb200_sampler_geometry.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3
+        L.nb200_sampler_device_buffers.restype = C.c_int
+        L.nb200_sampler_device_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p),
+                                                   C.POINTER(C.c_void_p)]
+        L.nb200_sampler_set_draws_per_launch.restype = C.c_int
+        L.nb200_sampler_set_draws_per_launch.argtypes = [C.c_void_p, C.c_uint64]
+        L.nb200_sampler_set_z_tape.restype = C.c_int
+        L.nb200_sampler_set_z_tape.argtypes = [C.c_void_p, C.c_void_p]
+        L.nb200_settings_default.restype = None
+        L.nb200_settings_default.argtypes = [C.POINTER(Settings)]
+        L.nb200_set_threads_per_chain.restype = None
+        L.nb200_set_threads_per_chain.argtypes = [C.c_int32]
+        L.nb200_set_chains_per_block.restype = None
+        L.nb200_set_chains_per_block.argtypes = [C.c_int32]
+        L.nb200_host_alloc.restype = C.c_void_p
+        L.nb200_host_alloc.argtypes = [C.c_size_t]
+        L.nb200_host_free.restype = None
+        L.nb200_host_free.argtypes = [C.c_void_p]
+        L.nb200_logp_grad.restype = C.c_int
+        L.nb200_logp_grad.argtypes = [C.POINTER(ModelDesc), C.c_int, C.c_uint64] + [C.c_void_p] * 4
+        L.nb200_leapfrog.restype = C.c_int
+        L.nb200_leapfrog.argtypes = [C.POINTER(ModelDesc), C.c_int, C.c_uint64] + [C.c_void_p] * 15
+        if L.nb200_abi_version() != 1:
+            raise RuntimeError("libnutpie_b200.so ABI version mismatch")
+        _lib = L
+        return L
+
+
+def _check(rc: int):
+    if rc >= 0:
+        return rc
+    msg = load_library().nb200_last_error().decode("utf-8", "replace")
+    raise _ERRORS.get(rc, RuntimeError)(msg or f"nb200 error {rc}")
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class PinnedArray:
+    """numpy array backed by pinned host memory from nb200_host_alloc."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self._L = load_library()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = self._L.nb200_host_alloc(max(n, 8))
+        if not self._p:
+            raise MemoryError("nb200_host_alloc failed")
+        buf = (C.c_char * max(n, 8)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._p:
+                self.array = None
+                self._L.nb200_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------
+# settings façade — PyNutsSettings (src/wrapper.rs:106-826)
+# --------------------------------------------------------------------------
+_FLAT_DIRECT = {
+    "maxdepth": ("maxdepth", int), "mindepth": ("mindepth", int),
+    "check_turning": ("check_turning", bool),
+    "initial_step": ("initial_step", float), "target_accept": ("target_accept", float),
+    "max_step_size": ("max_step_size", float),
+    "store_mass_matrix": ("store_mass_matrix", bool),
+    "use_grad_based_mass_matrix": ("use_grad_based_estimate", bool),
+    "mass_matrix_switch_freq": ("mass_matrix_switch_freq", int),
+    "window_switch_freq": ("mass_matrix_switch_freq", int),
+    "early_window_switch_freq": ("early_mass_matrix_switch_freq", int),
+    "store_gradient": ("store_gradient", bool),
+    "num_tune": ("num_tune", int), "num_draws": ("num_draws", int),
+    "max_energy_error": ("max_energy_error", float),
+    # ours (not in the reference): initial-point and trace controls
+    "init_radius": ("init_radius", float), "num_try_init": ("num_try_init", int),
+    "store_dims": ("store_dims", int),
+}
+# options that exist in the reference but belong to samplers / adaptations that
+# are out of scope for the B200 engine
+_UNSUPPORTED = {
+    "target_integration_time": None, "extra_doublings": 0,
+    "mass_matrix_eigval_cutoff": None, "mass_matrix_gamma": None, "train_on_orbit": None,
+    "step_size_adam_learning_rate": None, "step_size_jitter": None,
+    "store_transformed": False, "store_divergences": False,
+    "microcanonical_trajectory": False, "exact_normal_trajectory": False,
+}
+
+
+class PyNutsSettings:
+    """Mirror of PyNutsSettings (src/wrapper.rs:106-110, 525-620, 716-770)."""
+
+    def __init__(self, kind: str, seed=None):
+        object.__setattr__(self, "_kind", kind)
+        s = Settings()
+        load_library().nb200_settings_default(C.byref(s))
+        if seed is None:  # random_seed(), src/wrapper.rs:453-458
+            seed = int.from_bytes(os.urandom(8), "little")
+        s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        object.__setattr__(self, "_c", s)
+        object.__setattr__(self, "_num_chains", 6)
+        object.__setattr__(self, "_store_unconstrained", False)
+
+    # static constructors: src/wrapper.rs:718-737
+    @staticmethod
+    def Diag(seed=None):
+        return PyNutsSettings("diag", seed)
+
+    @staticmethod
+    def LowRank(seed=None):
+        raise NotImplementedError(
+            "adaptation='low_rank' is not supported by the B200 engine (diag / draw_diag only)")
+
+    @staticmethod
+    def Flow(seed=None):
+        raise NotImplementedError(
+            "adaptation='flow' is not supported by the B200 engine (diag / draw_diag only)")
+
+    def update(self, updates: dict):  # src/wrapper.rs:739-745
+        for k, v in updates.items():
+            setattr(self, k, v)
+
+    def __setattr__(self, name, value):  # apply_update, src/wrapper.rs:563-620
+        c = self._c
+        if name == "num_chains":
+            object.__setattr__(self, "_num_chains", int(value))
+        elif name == "store_unconstrained":
+            object.__setattr__(self, "_store_unconstrained", bool(value))
+        elif name == "step_size_adapt_method":
+            if not isinstance(value, str):
+                raise ValueError("step_size_adapt_method must be a string")
+            if value == "dual_average":
+                c.step_size_method = 0
+            elif value == "adam":
+                raise ValueError("step_size_adapt_method='adam' is not supported by the B200 engine")
+            else:
+                try:
+                    c.fixed_step_size = float(value)
+                except ValueError:
+                    raise ValueError("step_size_adapt_method must be a positive float when "
+                                     "using fixed step size") from None
+                c.step_size_method = 2
+        elif name in _FLAT_DIRECT:
+            field, typ = _FLAT_DIRECT[name]
+            setattr(c, field, typ(value))
+        elif name in _UNSUPPORTED:
+            if value not in (None, False, 0, _UNSUPPORTED[name]):
+                raise ValueError(f"Option {name} not available for the B200 diag engine")
+        else:
+            raise AttributeError(f"Unknown settings attribute: {name}")
+
+    @property
+    def num_chains(self):
+        return self._num_chains
+
+    @property
+    def num_tune(self):
+        return int(self._c.num_tune)
+
+    @property
+    def num_draws(self):
+        return int(self._c.num_draws)
+
+    @property
+    def seed(self):
+        return int(self._c.seed)
+
+    def as_dict(self):  # src/wrapper.rs:751-769
+        c = self._c
+        flat = {name: getattr(c, name) for name, _ in Settings._fields_ if not name.startswith("_")}
+        flat["num_chains"] = self._num_chains
+        return {"sampler": "nuts", "adaptation": self._kind, "settings": flat}
+
+    def update_settings(self, nested: dict):  # src/wrapper.rs:747-749
+        for k, v in nested.get("settings", nested).items():
+            if k == "num_chains":
+                self.num_chains = v
+            elif hasattr(self._c, k):
+                setattr(self._c, k, v)
+            else:
+                raise AttributeError(f"Unknown settings attribute: {k}")
+
+    def _copy_c(self) -> Settings:
+        s = Settings()
+        C.memmove(C.byref(s), C.byref(self._c), C.sizeof(Settings))
+        return s
+
+
+class PyMclmcSettings:
+    """src/wrapper.rs:772-826 — the MCLMC sampler is out of scope for the B200 engine."""
+
+    @staticmethod
+    def _no(*a, **k):
+        raise NotImplementedError("sampler='mclmc' is not supported by the B200 engine")
+
+    Diag = LowRank = Flow = _no
+
+
+class PyChainProgress:
+    """Mirror of PyChainProgress (src/wrapper.rs:38-104)."""
+
+    def __init__(self, p: Progress, runtime_ms: float, divergent_draws):
+        self.finished_draws = int(p.finished_draws)
+        self.total_draws = int(p.total_draws)
+        self.divergences = int(p.divergences)
+        self.started = bool(p.started)
+        self.tuning = bool(p.tuning)
+        self.latest_num_steps = int(p.latest_num_steps)
+        self.num_steps = int(p.latest_num_steps)
+        self.total_num_steps = int(p.total_num_steps)
+        self.step_size = float(p.step_size)
+        self.runtime_ms = float(runtime_ms)
+        self.divergent_draws = list(divergent_draws)
+
+
+class ProgressType:
+    """Mirror of ProgressType (src/wrapper.rs:907-930).  Terminal/HTML rendering
+    (src/progress.rs) is out of scope; callbacks receive PyChainProgress lists."""
+
+    def __init__(self, kind, rate_ms=500, callback=None):
+        self.kind, self.rate_ms, self.callback = kind, rate_ms, callback
+
+    @staticmethod
+    def none():
+        return ProgressType("none")
+
+    @staticmethod
+    def indicatif(rate_ms):
+        return ProgressType("indicatif", rate_ms)
+
+    @staticmethod
+    def template_callback(rate_ms, template, n_cores, callback):
+        return ProgressType("template_callback", rate_ms, callback)
+
+
+class PyStorage:
+    """Mirror of PyStorage (src/wrapper.rs:940-951).  Zarr stores are out of scope."""
+
+    def __init__(self, kind):
+        self.kind = kind
+
+    @staticmethod
+    def arrow():
+        return PyStorage("arrow")
+
+    @staticmethod
+    def zarr(store):
+        raise NotImplementedError("zarr storage is not supported by the B200 engine")
+
+
+class PyTrace:
+    """Mirror of PyTrace (src/wrapper.rs:1467-1494): the trace of all chains.
+
+    Besides the reference's `get_arrow_trace()` (one (posterior, sample_stats)
+    RecordBatch pair per chain) it exposes the raw arrays (`draws`, `stats`),
+    which is what the end-to-end path uses to avoid a per-chain Arrow hop."""
+
+    def __init__(self, draws, stats, rows_filled, gradients=None, mass_matrix_inv=None,
+                 variables=None, expand=None, keep=None):
+        self.draws, self.stats, self.rows_filled = draws, stats, rows_filled
+        self.gradients, self.mass_matrix_inv = gradients, mass_matrix_inv
+        self.variables, self._expand, self._keep = variables, expand, keep
+        self._taken = False
+
+    def is_zarr(self):
+        return False
+
+    def is_arrow(self):
+        return True
+
+    def stat(self, name):
+        a = self.stats[..., STAT_NAMES.index(name)]
+        dt = _STAT_DTYPES.get(name)
+        return a.astype(dt) if dt is not None else a
+
+    def get_arrow_trace(self):
+        """list[(posterior RecordBatch, sample_stats RecordBatch)] per chain
+        (src/wrapper.rs:1477-1494); single-take like the reference."""
+        import pyarrow as pa
+
+        if self._taken:
+            raise ValueError("Trace was already taken")
+        self._taken = True
+        out = []
+        n_chains = self.draws.shape[0]
+        for c in range(n_chains):
+            n = int(self.rows_filled[c])
+            q = self.draws[c, :n]
+            cols, fields = [], []
+            values = self._expand(q) if self._expand is not None else {"unconstrained_draw": q}
+            for name, arr in values.items():
+                arr = np.ascontiguousarray(arr)
+                shape = arr.shape[1:]
+                size = int(np.prod(shape)) if shape else 1
+                meta = {"dims": "", "shape": ",".join(map(str, shape))}
+                if self.variables and name in self.variables:
+                    meta["dims"] = ",".join(self.variables[name])
+                if shape:
+                    col = pa.FixedSizeListArray.from_arrays(pa.array(arr.reshape(-1)), size)
+                else:
+                    col = pa.array(arr)
+                cols.append(col)
+                fields.append(pa.field(name, col.type, metadata=meta))
+            posterior = pa.RecordBatch.from_arrays(cols, schema=pa.schema(fields))
+            scols, sfields = [], []
+            for name in STAT_NAMES[:-1]:
+                a = self.stats[c, :n, STAT_NAMES.index(name)]
+                dt = _STAT_DTYPES.get(name)
+                col = pa.array(a.astype(dt) if dt is not None else a)
+                scols.append(col)
+                sfields.append(pa.field(name, col.type, metadata={"dims": "", "shape": ""}))
+            for name, arr in (("gradient", self.gradients), ("mass_matrix_inv", self.mass_matrix_inv)):
+                if arr is not None:
+                    a = np.ascontiguousarray(arr[c, :n])
+                    col = pa.FixedSizeListArray.from_arrays(pa.array(a.reshape(-1)), a.shape[1])
+                    scols.append(col)
+                    sfields.append(pa.field(name, col.type, metadata={
+                        "dims": "unconstrained_parameter", "shape": str(a.shape[1])}))
+            stats = pa.RecordBatch.from_arrays(scols, schema=pa.schema(sfields))
+            out.append((posterior, stats))
+        return out
+
+
+class PySampler:
+    """Mirror of PySampler (src/wrapper.rs:953-1457) driving one nb200_sampler.
+
+    `from_device_model` takes the place of from_pymc / from_stan / from_pyfunc
+    (src/wrapper.rs:1187-1250): the model is a device density descriptor."""
+
+    def __init__(self, settings: PyNutsSettings, model, *, n_chains=None, chain_id_offset=0,
+                 device=0, progress_type=None, init_mean=None, q0=None, z_tape=None,
+                 draws_per_launch=0):
+        L = load_library()
+        self._L = L
+        self._settings = settings
+        self._model = model
+        self._c = settings._copy_c()
+        self.n_chains = int(n_chains if n_chains is not None else settings.num_chains)
+        self._desc, self._keep = model._descriptor()
+        self.dim = int(self._desc.dim)
+        if init_mean is not None:
+            init_mean = np.ascontiguousarray(init_mean, dtype=np.float64).reshape(self.dim)
+        if q0 is not None:
+            q0 = np.ascontiguousarray(q0, dtype=np.float64).reshape(self.n_chains, self.dim)
+        h = L.nb200_sampler_create(C.byref(self._c), C.byref(self._desc), self.n_chains,
+                                   int(chain_id_offset), int(device), _ptr(q0), _ptr(init_mean))
+        if not h:
+            msg = L.nb200_last_error().decode("utf-8", "replace")
+            raise (ValueError if "must" in msg or "unknown" in msg else RuntimeError)(msg)
+        self._h = C.c_void_p(h)
+        if z_tape is not None:
+            z_tape = np.ascontiguousarray(z_tape, dtype=np.float64)
+            _check(L.nb200_sampler_set_z_tape(self._h, _ptr(z_tape)))
+        if draws_per_launch:
+            _check(L.nb200_sampler_set_draws_per_launch(self._h, int(draws_per_launch)))
+        self.n_total = int(self._c.num_tune + self._c.num_draws)
+        self.n_rows = self.n_total if self._c.save_warmup else int(self._c.num_draws)
+        sd = int(self._c.store_dims)
+        self.sdim = sd if 0 < sd < self.dim else self.dim
+        self._lock = threading.Lock()
+        self._taken = False
+        self._t_start = None
+        self._progress_type = progress_type or ProgressType.none()
+        self._progress_thread = None
+        self._stop_progress = threading.Event()
+        _check(L.nb200_sampler_start(self._h))
+        self._t_start = time.perf_counter()
+        if self._progress_type.callback is not None:
+            self._progress_thread = threading.Thread(target=self._progress_loop, daemon=True)
+            self._progress_thread.start()
+
+    @staticmethod
+    def from_device_model(settings, cores, model, progress_type=None, extra_callback=None,
+                          extra_callback_rate=None, store=None, **kw):
+        pt = progress_type
+        if extra_callback is not None and (pt is None or pt.callback is None):
+            pt = ProgressType("callback", extra_callback_rate or 500, extra_callback)
+        return PySampler(settings, model, progress_type=pt, **kw)
+
+    # -- progress ---------------------------------------------------------
+    def progress(self):
+        arr = (Progress * self.n_chains)()
+        _check(self._L.nb200_sampler_progress(self._h, arr))
+        rt = (time.perf_counter() - self._t_start) * 1e3 if self._t_start else 0.0
+        return [PyChainProgress(arr[i], rt, ()) for i in range(self.n_chains)]
+
+    def _progress_loop(self):
+        rate = max(self._progress_type.rate_ms, 10) / 1e3
+        while not self._stop_progress.wait(rate):
+            try:
+                self._progress_type.callback(self.progress())
+            except Exception as exc:  # src/progress.rs:426-431: printed, not raised
+                import sys
+
+                print(f"progress callback failed: {exc}", file=sys.stderr)
+            if self._h is None or self._L.nb200_sampler_is_finished(self._h):
+                break
+
+    # -- control (src/wrapper.rs:1252-1365) -------------------------------
+    def wait(self, timeout_seconds=None):
+        """Block until finished.  Raises TimeoutError like wrapper.rs:1113 and
+        polls in 100 ms slices so KeyboardInterrupt is honoured (wrapper.rs:1099-1143)."""
+        deadline = None if timeout_seconds is None else time.perf_counter() + timeout_seconds
+        while True:
+            slice_s = 0.1
+            if deadline is not None:
+                slice_s = min(slice_s, max(deadline - time.perf_counter(), 0.0))
+            rc = _check(self._L.nb200_sampler_wait(self._h, slice_s))
+            if rc == 0:
+                return
+            if deadline is not None and time.perf_counter() >= deadline:
+                raise TimeoutError("Timeout while waiting for sampler to finish")
+
+    def pause(self):
+        _check(self._L.nb200_sampler_pause(self._h))
+
+    def resume(self):
+        _check(self._L.nb200_sampler_resume(self._h))
+
+    def abort(self):
+        _check(self._L.nb200_sampler_abort(self._h))
+
+    def is_finished(self):
+        return bool(self._L.nb200_sampler_is_finished(self._h))
+
+    def is_empty(self, ignore_error=False):
+        return self._taken
+
+    def flush(self):
+        return None
+
+    # -- results (src/wrapper.rs:1401-1456) --------------------------------
+    def _trace(self, out=None) -> PyTrace:
+        shape_d = (self.n_chains, self.n_rows, self.sdim)
+        shape_s = (self.n_chains, self.n_rows, NSTAT)
+        keep = []
+        if out is not None:
+            draws, stats = out["draws"], out["stats"]
+        else:
+            draws, stats = np.empty(shape_d), np.empty(shape_s)
+        grads = np.empty(shape_d) if self._c.store_gradient else None
+        mm = np.empty(shape_d) if self._c.store_mass_matrix else None
+        rows = np.zeros(self.n_chains, dtype=np.uint64)
+        _check(self._L.nb200_sampler_trace_into(self._h, _ptr(draws), _ptr(stats), _ptr(grads),
+                                                _ptr(mm), _ptr(rows)))
+        return PyTrace(draws, stats, rows, grads, mm, variables=self._model._variable_dims(),
+                       expand=self._model._expand if self.sdim == self.dim else None, keep=keep)
+
+    def inspect(self, out=None):
+        return self._trace(out)
+
+    def take_results(self, out=None):
+        if not self.is_finished():
+            raise ValueError("Sampler is still running")
+        if self._taken:
+            raise ValueError("Sampler is empty")
+        tr = self._trace(out)
+        self._taken = True
+        return tr
+
+    # -- measurement hooks --------------------------------------------------
+    def kernel_ms(self):
+        return float(self._L.nb200_sampler_kernel_ms(self._h))
+
+    def launch_count(self):
+        return int(self._L.nb200_sampler_launch_count(self._h))
+
+    def geometry(self):
+        a, b, g = C.c_int32(), C.c_int32(), C.c_int32()
+        _check(self._L.nb200_sampler_geometry(self._h, C.byref(a), C.byref(b), C.byref(g)))
+        return dict(threads_per_chain=a.value, block=b.value, grid=g.value)
+
+    def device_buffers(self):
+        d, s = C.c_void_p(), C.c_void_p()
+        _check(self._L.nb200_sampler_device_buffers(self._h, C.byref(d), C.byref(s)))
+        return d.value, s.value
+
+    def close(self):
+        self._stop_progress.set()
+        if self._progress_thread is not None and self._progress_thread is not threading.current_thread():
+            self._progress_thread.join(timeout=2.0)
+        if self._h is not None:
+            self._L.nb200_sampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------
+# component entry points (parity tests)
+# --------------------------------------------------------------------------
+def logp_grad(model, q, device=0):
+    L = load_library()
+    desc, keep = model._descriptor()
+    q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, int(desc.dim))
+    n = len(q)
+    lp, g, rc = np.empty(n), np.empty_like(q), np.empty(n, dtype=np.int32)
+    _check(L.nb200_logp_grad(C.byref(desc), device, n, _ptr(q), _ptr(lp), _ptr(g), _ptr(rc)))
+    return lp, g, rc
+
+
+def leapfrog(model, q, p, g, var, p_sum, eps, direction, idx, device=0):
+    L = load_library()
+    desc, keep = model._descriptor()
+    D = int(desc.dim)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64).reshape(-1, D)
+    q, p, g, var, p_sum = map(f, (q, p, g, var, p_sum))
+    n = len(q)
+    eps = np.ascontiguousarray(np.broadcast_to(eps, (n,)), dtype=np.float64)
+    direction = np.ascontiguousarray(np.broadcast_to(direction, (n,)), dtype=np.int32)
+    idx = np.ascontiguousarray(np.broadcast_to(idx, (n,)), dtype=np.int64)
+    qo, po, go, so = (np.empty_like(q) for _ in range(4))
+    lp, kin, rc = np.empty(n), np.empty(n), np.empty(n, dtype=np.int32)
+    _check(L.nb200_leapfrog(C.byref(desc), device, n, _ptr(q), _ptr(p), _ptr(g), _ptr(var),
+                            _ptr(p_sum), _ptr(eps), _ptr(direction), _ptr(idx), _ptr(qo),
+                            _ptr(po), _ptr(go), _ptr(so), _ptr(lp), _ptr(kin), _ptr(rc)))
+    return dict(q=qo, p=po, g=go, p_sum=so, logp=lp, kinetic=kin, rc=rc)
+
+
+def set_threads_per_chain(t: int):
+    load_library().nb200_set_threads_per_chain(int(t))
+
+
+def set_chains_per_block(c: int):
+    load_library().nb200_set_chains_per_block(int(c))
+
+
+def device_count() -> int:
+    return int(load_library().nb200_device_count())

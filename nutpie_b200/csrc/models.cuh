@@ -1,0 +1,187 @@
+// models.cuh — device log-densities (logp + gradient on the unconstrained space).
+//
+// These replace `CpuLogpFunc::logp` (src/pymc.rs:197-215, src/stan.rs:454-463)
+// for the BASELINE.json configs.  The reference obtains the density as a HOST
+// function pointer compiled by numba (python/nutpie/compile_pymc.py:970-1006);
+// a device engine needs device code, so each density is hand-written here and
+// has a host twin in the reference plug-in ABI under oracle/models.c.
+//
+// Interface (all members static, `G` = thread group owning the chain):
+//   kElementwise = true : logp = finish(sum_i term(i, q_i)), g_i local.  The
+//       leapfrog fuses these into its single streaming pass (72 B per
+//       dimension per gradient evaluation).
+//   kElementwise = false: logp_grad(grp, data, D, q, g, sm) is called by all
+//       threads of the group after q is visible; it writes g and returns the
+//       (group-uniform) logp.
+#pragma once
+#include "group.cuh"
+#include "portable.cuh"
+
+namespace nb200 {
+
+#define NB_LOG_2PI 1.8378770664093454835606594728112
+#define NB_HALF_LOG_2_OVER_PI (-0.22579135264472743236309761494744)
+
+// logp = -1/2 sum ((x - mu)/sigma)^2 : Stan `x ~ normal(mu, 1)` (README.md:148-163,
+// tests/test_stan.py:16-24) and the D = 10 000 bandwidth-bound config 4.
+struct NormalModel {
+    static constexpr bool kElementwise = true;
+    struct Data {
+        double mu, inv_var;
+    };
+    NB_HD static int smem_doubles(const Data&, int) { return 0; }
+    NB_HD static double term(const Data& d, int, double q, double& g) {
+        double r = q - d.mu;
+        g = -r * d.inv_var;
+        return r * r;
+    }
+    NB_HD static double finish(const Data& d, double acc, int) { return -0.5 * acc * d.inv_var; }
+};
+
+// Neal's funnel (docs/sample-stats.qmd:19-21; 9 parameters in BASELINE.json)
+struct FunnelModel {
+    static constexpr bool kElementwise = false;
+    struct Data {
+        int unused;
+    };
+    NB_HD static int smem_doubles(const Data&, int) { return 0; }
+    template <class G>
+    NB_HD static double logp_grad(const G& grp, const Data&, int D, const double* q, double* g,
+                                  double*) {
+        const double v = q[0];
+        const double e = exp(-2.0 * v);
+        double acc[1] = {0.0};
+        for (int i = grp.tid; i < D; i += grp.size()) {
+            if (i >= 1) {
+                double x = q[i];
+                acc[0] += x * x;
+                g[i] = -x * e;
+            }
+        }
+        grp.reduce(acc);
+        const double n = (double)(D - 1);
+        if (grp.tid == 0) g[0] = -v + acc[0] * e - n;
+        return -0.5 * v * v - 0.5 * acc[0] * e - n * v;
+    }
+};
+
+// Hierarchical radon model (README.md:53-88, plain-Normal raw effects as in
+// notebooks/pytensor_logp.md:57-88), D = 2J + 5, parameter order = PyMC value
+// variable order: intercept, county_raw[J], log county_sd, floor_effect,
+// county_floor_raw[J], log county_floor_sd, log sigma.
+//
+// Data layout (built on the host for the group size T, nb200_api.cu): the
+// observations are sorted by county and cut into T contiguous ranges, one per
+// thread, stored transposed ([step][thread]) so a warp's loads coalesce.  A
+// thread walks its range keeping run sums per county; every run of equal
+// county inside a range gets a private slot in shared memory, and because
+// ranges are contiguous the runs of one county are contiguous in that list:
+// the per-county gradient is a short fixed-order sum — no atomics, bitwise
+// reproducible (determinism contract, tests/test_stan.py:67-101).
+struct RadonModel {
+    static constexpr bool kElementwise = false;
+    struct Data {
+        int J, N, n_steps, R;       // counties, observations, steps per thread, total runs
+        const int32_t* packed;      // [n_steps][T]  (county << 1 | floor), -1 = padding
+        const double* y;            // [n_steps][T]
+        const int32_t* run_base;    // [T]   first run slot of each thread
+        const int32_t* run_start;   // [J+1] first run slot of each county
+    };
+    NB_HD static int smem_doubles(const Data& d, int) { return 2 * d.J + 2 * d.R; }
+
+    template <class G>
+    NB_HD static double logp_grad(const G& grp, const Data& d, int, const double* q, double* g,
+                                  double* sm) {
+        const int J = d.J, T = grp.size();
+        const double intercept = q[0];
+        const double log_sd_a = q[J + 1];
+        const double floor_eff = q[J + 2];
+        const double log_sd_b = q[2 * J + 3];
+        const double log_sigma = q[2 * J + 4];
+        const double sd_a = exp(log_sd_a), sd_b = exp(log_sd_b), sigma = exp(log_sigma);
+        const double inv_sigma = 1.0 / sigma;
+        const double inv_s2 = inv_sigma * inv_sigma;
+        double* effA = sm;               // intercept + county_effect[c]
+        double* effB = sm + J;           // floor_effect + county_floor_effect[c]
+        double* runE = sm + 2 * J;       // per-run sum of residuals
+        double* runF = sm + 2 * J + d.R; // per-run sum of floor * residual
+        for (int c = grp.tid; c < J; c += T) {
+            effA[c] = intercept + q[1 + c] * sd_a;
+            effB[c] = floor_eff + q[J + 3 + c] * sd_b;
+        }
+        grp.sync();
+        double ss = 0.0;
+        {
+            int cur = -1, k = nb_ldg(d.run_base + grp.tid);
+            double sE = 0.0, sF = 0.0, a = 0.0, ab = 0.0;
+            for (int j = 0; j < d.n_steps; ++j) {
+                const int pk = nb_ldg(d.packed + (size_t)j * T + grp.tid);
+                if (pk < 0) break;
+                const double yv = nb_ldg(d.y + (size_t)j * T + grp.tid);
+                const int c = pk >> 1;
+                if (c != cur) {
+                    if (cur >= 0) {
+                        runE[k] = sE;
+                        runF[k] = sF;
+                        ++k;
+                        sE = 0.0;
+                        sF = 0.0;
+                    }
+                    cur = c;
+                    a = effA[c];
+                    ab = a + effB[c];
+                }
+                const bool f = pk & 1;
+                const double r = yv - (f ? ab : a);
+                ss += r * r;
+                sE += r;
+                if (f) sF += r;
+            }
+            if (cur >= 0) {
+                runE[k] = sE;
+                runF[k] = sF;
+            }
+        }
+        grp.sync();
+        double acc[7] = {ss, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int c = grp.tid; c < J; c += T) {
+            double E = 0.0, F = 0.0;
+            const int r0 = nb_ldg(d.run_start + c), r1 = nb_ldg(d.run_start + c + 1);
+            for (int r = r0; r < r1; ++r) {
+                E += runE[r];
+                F += runF[r];
+            }
+            E *= inv_s2;
+            F *= inv_s2;
+            const double ra = q[1 + c], rb = q[J + 3 + c];
+            acc[1] += ra * sd_a * E;
+            acc[2] += rb * sd_b * F;
+            acc[3] += ra * ra;
+            acc[4] += rb * rb;
+            acc[5] += E;
+            acc[6] += F;
+            g[1 + c] = sd_a * E - ra;
+            g[J + 3 + c] = sd_b * F - rb;
+        }
+        grp.reduce(acc);
+        const double ssn = acc[0] * inv_s2;
+        double logp = -0.5 * ssn - d.N * log_sigma - 0.5 * d.N * NB_LOG_2PI;
+        logp += -0.5 * acc[3] - 0.5 * J * NB_LOG_2PI;
+        logp += -0.5 * acc[4] - 0.5 * J * NB_LOG_2PI;
+        logp += -0.5 * intercept * intercept / 100.0 - log(10.0) - 0.5 * NB_LOG_2PI;
+        logp += -0.5 * floor_eff * floor_eff / 4.0 - log(2.0) - 0.5 * NB_LOG_2PI;
+        logp += NB_HALF_LOG_2_OVER_PI - 0.5 * sd_a * sd_a + log_sd_a;
+        logp += NB_HALF_LOG_2_OVER_PI - 0.5 * sd_b * sd_b + log_sd_b;
+        logp += NB_HALF_LOG_2_OVER_PI - log(1.5) - 0.5 * sigma * sigma / 2.25 + log_sigma;
+        if (grp.tid == 0) {
+            g[0] = acc[5] - intercept / 100.0;
+            g[J + 1] = acc[1] - sd_a * sd_a + 1.0;
+            g[J + 2] = acc[6] - floor_eff / 4.0;
+            g[2 * J + 3] = acc[2] - sd_b * sd_b + 1.0;
+            g[2 * J + 4] = ssn - d.N - sigma * sigma / 2.25 + 1.0;
+        }
+        return logp;
+    }
+};
+
+}  // namespace nb200

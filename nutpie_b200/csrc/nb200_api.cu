@@ -1,0 +1,926 @@
+// nb200_api.cu — sm_100a kernels + the C-ABI of include/nutpie_b200.h.
+//
+// One persistent kernel launch advances every chain of a sampler through all
+// of its tuning and sampling draws (nuts_kernel); chains never synchronise with
+// each other.  The host side of this file is the replacement for what
+// nuts_rs::Sampler does around its rayon pool (src/wrapper.rs:977-1456):
+// start, poll progress, pause/resume/abort, hand out the trace.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "nuts_core.cuh"
+#include "radon_layout.hpp"
+
+using namespace nb200;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess)                                                          \
+            return fail(NB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define CUP(call)                                                                       \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            fail(NB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+            return nullptr;                                                             \
+        }                                                                               \
+    } while (0)
+
+static std::atomic<int> g_threads_per_chain{0};
+static std::atomic<int> g_chains_per_block{0};
+
+// ------------------------------------------------------------------ kernels
+static inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+template <class M, int W>
+static size_t chain_smem_bytes(const typename M::Data& md) {
+    size_t b = align16(sizeof(ChainShared));
+    b += align16(sizeof(double) * (size_t)M::smem_doubles(md, 32 * W));
+    if (W > 1) b += align16(sizeof(double) * W * GroupCuda<W>::kMaxRed);
+    return b;
+}
+
+template <class M, int W>
+__device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>>& ctx, const KParams<M>& P,
+                                          unsigned long long chain, unsigned char* smem_chain) {
+    ctx.g.tid = (W == 1) ? (threadIdx.x & 31) : threadIdx.x;
+    ctx.P = &P;
+    ctx.sh = reinterpret_cast<ChainShared*>(smem_chain);
+    size_t off = (sizeof(ChainShared) + 15) & ~size_t(15);
+    ctx.msm = reinterpret_cast<double*>(smem_chain + off);
+    off += (sizeof(double) * (size_t)M::smem_doubles(P.mdata, 32 * W) + 15) & ~size_t(15);
+    ctx.g.red = reinterpret_cast<double*>(smem_chain + off);
+    ctx.D = P.D;
+    ctx.Dp = P.Dp;
+    ctx.NS = P.NS;
+    ctx.chain_local = chain;
+    ctx.chain_gid = (uint32_t)(P.chain_id_offset + chain);
+    ctx.pool = P.pool + (size_t)chain * P.NS * 4 * (size_t)P.Dp;
+    ctx.var = P.var + (size_t)chain * P.Dp;
+    ctx.wf = P.welford + (size_t)chain * 8 * (size_t)P.Dp;
+    ctx.mL = ctx.mR = ctx.mD = ctx.tL = ctx.tR = ctx.tD = -1;
+    ctx.lv_valid = 0;
+}
+
+// The sampler: W warps per chain, CPB chains per CTA (CPB > 1 only for W == 1).
+template <class M, int W>
+__global__ void __launch_bounds__(W == 1 ? 256 : 32 * W)
+    nuts_kernel(const __grid_constant__ KParams<M> P, size_t smem_per_chain) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int local = (W == 1) ? (threadIdx.x >> 5) : 0;
+    const int cpb = (W == 1) ? (blockDim.x >> 5) : 1;
+    const unsigned long long chain = (unsigned long long)blockIdx.x * cpb + local;
+    if (chain >= P.n_chains) return;
+    ChainCtx<M, GroupCuda<W>> ctx;
+    setup_ctx<M, W>(ctx, P, chain, smem + (size_t)local * smem_per_chain);
+    ctx.run();
+}
+
+// Component kernel: mode 0 = density at q (slot 0); mode 1 = one leapfrog
+// slot 0 -> slot 1 with per-state eps/dir/idx.  scal: [n][4] = eps, dir, idx, unused;
+// out_scal: [n][4] = logp, kinetic, rc, unused.
+template <class M, int W>
+__global__ void __launch_bounds__(32 * W)
+    component_kernel(const __grid_constant__ KParams<M> P, int mode, const double* scal,
+                     double* out_scal) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const unsigned long long chain = blockIdx.x;
+    if (chain >= P.n_chains) return;
+    ChainCtx<M, GroupCuda<W>> ctx;
+    setup_ctx<M, W>(ctx, P, chain, smem);
+    ctx.acc_sum = ctx.acc_sym = 0.0;
+    ctx.acc_count = 0;
+    if (mode == 0) {
+        bool bad;
+        const double lp = ctx.eval_logp(0, bad);
+        if (ctx.g.tid == 0) {
+            out_scal[chain * 4 + 0] = lp;
+            out_scal[chain * 4 + 1] = 0.0;
+            out_scal[chain * 4 + 2] = bad ? (isfinite(lp) ? 3.0 : 4.0) : 0.0;
+        }
+    } else {
+        const double eps = scal[chain * 4 + 0];
+        const int dir = scal[chain * 4 + 1] > 0 ? 1 : -1;
+        if (ctx.g.tid == 0) {
+            ctx.sh->idx[0] = (int)scal[chain * 4 + 2];
+            ctx.sh->U[0] = 0.0;
+            ctx.sh->K[0] = 0.0;
+        }
+        ctx.g.sync();
+        ctx.step_size = eps;
+        ctx.E0 = 0.0;
+        const int rc = ctx.leapfrog(0, 1, dir);
+        if (ctx.g.tid == 0) {
+            out_scal[chain * 4 + 0] = -ctx.sh->U[1];
+            out_scal[chain * 4 + 1] = ctx.sh->K[1];
+            out_scal[chain * 4 + 2] = (double)rc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ sampler
+enum class RunState { Created, Running, Paused, Finished, Aborted, Error };
+
+struct nb200_sampler {
+    virtual ~nb200_sampler() {}
+    int device = 0;
+    nb200_settings st{};
+    nb200_model_desc model{};
+    uint64_t n_chains = 0, chain_id_offset = 0;
+    int W = 1, cpb = 1, grid = 0, block = 0;
+    size_t smem_per_chain = 0;
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    RunState state = RunState::Created;
+    std::mutex mu;
+    double kernel_ms = 0.0;
+    uint64_t launches = 0;
+    uint64_t draws_per_launch = 0;
+    int* d_stop = nullptr;
+    ChainScalars* d_sc = nullptr;
+    ChainScalars* h_sc = nullptr;  // pinned
+    double *d_pool = nullptr, *d_var = nullptr, *d_wf = nullptr;
+    double *d_draws = nullptr, *d_stats = nullptr, *d_grads = nullptr, *d_mm = nullptr;
+    double *d_q0 = nullptr, *d_init_mean = nullptr, *d_tape = nullptr;
+    // pinned host trace (lazy)
+    double *h_draws = nullptr, *h_stats = nullptr, *h_grads = nullptr, *h_mm = nullptr;
+    std::vector<uint64_t> rows_filled;
+    uint64_t n_rows = 0, sdim = 0, n_total = 0;
+    int Dp = 0, NS = 0;
+    std::vector<void*> model_allocs;
+    virtual int launch() = 0;
+    int sampler_error = 0;
+};
+
+template <class M>
+struct SamplerImpl : nb200_sampler {
+    KParams<M> P;
+    template <int W_>
+    int launch_w() {
+        const size_t smem = smem_per_chain * cpb;
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<M, W_>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(NB200_ECUDA, cudaGetErrorString(e));
+        nuts_kernel<M, W_><<<grid, block, smem, stream>>>(P, smem_per_chain);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(NB200_ECUDA, cudaGetErrorString(e));
+        return 0;
+    }
+    int launch() override {
+        P.max_draws_per_launch = draws_per_launch;
+        switch (W) {
+        case 1: return launch_w<1>();
+        case 2: return launch_w<2>();
+        case 4: return launch_w<4>();
+        case 8: return launch_w<8>();
+        case 16: return launch_w<16>();
+        case 32: return launch_w<32>();
+        }
+        return fail(NB200_EINVAL, "threads per chain must be 32..1024, power of two");
+    }
+};
+
+template <class M>
+static size_t smem_for(int W, const typename M::Data& md) {
+    switch (W) {
+    case 1: return chain_smem_bytes<M, 1>(md);
+    case 2: return chain_smem_bytes<M, 2>(md);
+    case 4: return chain_smem_bytes<M, 4>(md);
+    case 8: return chain_smem_bytes<M, 8>(md);
+    case 16: return chain_smem_bytes<M, 16>(md);
+    default: return chain_smem_bytes<M, 32>(md);
+    }
+}
+
+static int pick_W(const nb200_model_desc& m, uint64_t n_chains) {
+    int t = g_threads_per_chain.load();
+    if (t > 0) return t / 32;
+    const uint64_t work = m.kind == NB200_MODEL_RADON ? (uint64_t)m.n_obs : m.dim;
+    // enough warps per chain that each thread still has >= 4 work items, and
+    // enough warps in total to fill 148 SMs x 16 warps
+    int w = 1;
+    while (w < 32 && (uint64_t)(32 * w * 2) * 4 <= work && n_chains * (uint64_t)w < 148ull * 24) w *= 2;
+    return w;
+}
+
+static int validate(const nb200_settings* st, const nb200_model_desc* m) {
+    if (!st || !m) return fail(NB200_EINVAL, "null settings/model");
+    if (st->maxdepth < 1 || 3 * ((int)st->maxdepth + 1) + 3 > kMaxSlots)
+        return fail(NB200_EINVAL, "maxdepth must be in 1..19");
+    if (m->dim < 1) return fail(NB200_EINVAL, "model dimension must be >= 1");
+    if (st->step_size_method != 0 && st->step_size_method != 2)
+        return fail(NB200_EINVAL, "step_size_adapt_method: only dual_average and fixed are supported");
+    if (m->kind == NB200_MODEL_RADON) {
+        if (m->dim != (uint64_t)(2 * m->n_county + 5))
+            return fail(NB200_EINVAL, "radon: dim must equal 2*n_county+5");
+        if (!m->y || !m->county || !m->floor || m->n_obs < 1)
+            return fail(NB200_EINVAL, "radon: missing data arrays");
+        for (int i = 0; i < m->n_obs; ++i)
+            if (m->county[i] < 0 || m->county[i] >= m->n_county)
+                return fail(NB200_EINVAL, "radon: county index out of range");
+    } else if (m->kind == NB200_MODEL_NORMAL) {
+        if (!(m->sigma > 0)) return fail(NB200_EINVAL, "normal: sigma must be > 0");
+    } else if (m->kind == NB200_MODEL_FUNNEL) {
+        if (m->dim < 2) return fail(NB200_EINVAL, "funnel: dim must be >= 2");
+    } else {
+        return fail(NB200_EINVAL, "unknown model kind");
+    }
+    return 0;
+}
+
+template <class T>
+static int to_device(const std::vector<T>& v, T** out, std::vector<void*>& keep) {
+    CU(cudaMalloc((void**)out, sizeof(T) * (v.size() ? v.size() : 1)));
+    keep.push_back(*out);
+    if (!v.empty()) CU(cudaMemcpy(*out, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int build_model_data(const nb200_model_desc& m, int T, NormalModel::Data& d,
+                            std::vector<void*>&) {
+    d.mu = m.mu;
+    d.inv_var = 1.0 / (m.sigma * m.sigma);
+    (void)T;
+    return 0;
+}
+static int build_model_data(const nb200_model_desc&, int, FunnelModel::Data& d,
+                            std::vector<void*>&) {
+    d.unused = 0;
+    return 0;
+}
+static int build_model_data(const nb200_model_desc& m, int T, RadonModel::Data& d,
+                            std::vector<void*>& keep) {
+    RadonLayout L = build_radon_layout(m.n_obs, m.n_county, m.y, m.county, m.floor, T);
+    d.J = L.J; d.N = L.N; d.n_steps = L.n_steps; d.R = L.R;
+    int32_t *packed, *run_base, *run_start;
+    double* y;
+    int rc;
+    if ((rc = to_device(L.packed, &packed, keep))) return rc;
+    if ((rc = to_device(L.y, &y, keep))) return rc;
+    if ((rc = to_device(L.run_base, &run_base, keep))) return rc;
+    if ((rc = to_device(L.run_start, &run_start, keep))) return rc;
+    d.packed = packed; d.y = y; d.run_base = run_base; d.run_start = run_start;
+    return 0;
+}
+
+template <class M>
+static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_desc* m,
+                                  uint64_t n_chains, uint64_t chain_id_offset, int device,
+                                  const double* q0, const double* init_mean) {
+    auto* s = new SamplerImpl<M>();
+    auto bail = [&](void) -> nb200_sampler* {
+        nb200_sampler_destroy(s);
+        return nullptr;
+    };
+    s->device = device;
+    s->st = *st;
+    s->model = *m;
+    s->n_chains = n_chains;
+    s->chain_id_offset = chain_id_offset;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(NB200_ECUDA, "cudaSetDevice failed");
+        return bail();
+    }
+    s->W = pick_W(*m, n_chains);
+    if (s->W < 1 || s->W > 32 || (s->W & (s->W - 1))) {
+        fail(NB200_EINVAL, "threads per chain must be 32..1024, power of two");
+        return bail();
+    }
+    const int D = (int)m->dim;
+    s->Dp = (D + 3) / 4 * 4;
+    s->NS = 3 * ((int)st->maxdepth + 1) + 3;
+    s->n_total = st->num_tune + st->num_draws;
+    s->n_rows = st->save_warmup ? s->n_total : st->num_draws;
+    s->sdim = (st->store_dims && st->store_dims < m->dim) ? st->store_dims : m->dim;
+    KParams<M>& P = s->P;
+    std::memset(&P, 0, sizeof(P));
+    P.st = *st;
+    if (build_model_data(*m, 32 * s->W, P.mdata, s->model_allocs) != 0) return bail();
+    s->smem_per_chain = smem_for<M>(s->W, P.mdata);
+    if (s->W == 1) {
+        int c = g_chains_per_block.load();
+        if (c <= 0) {
+            c = 1;
+            while (c < 8 && (n_chains + c - 1) / c > 148ull * 24) c *= 2;
+        }
+        while (c > 1 && s->smem_per_chain * c > 200 * 1024) c /= 2;
+        s->cpb = c;
+    } else {
+        s->cpb = 1;
+    }
+    if (s->smem_per_chain * s->cpb > 227 * 1024) {
+        fail(NB200_EINVAL, "model needs more shared memory per chain than an SM has");
+        return bail();
+    }
+    s->block = 32 * s->W * s->cpb;
+    s->grid = (int)((n_chains + s->cpb - 1) / s->cpb);
+    P.D = D; P.Dp = s->Dp; P.NS = s->NS;
+    P.n_chains = n_chains; P.chain_id_offset = chain_id_offset;
+    P.n_rows = s->n_rows; P.sdim = s->sdim; P.n_total = s->n_total;
+#define ALLOC(ptr, bytes)                                                               \
+    do {                                                                                \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes) ? (bytes) : 8);             \
+        if (e_ != cudaSuccess) {                                                        \
+            fail(NB200_ECUDA, std::string("cudaMalloc ") + #ptr + ": " + cudaGetErrorString(e_)); \
+            return bail();                                                              \
+        }                                                                               \
+    } while (0)
+#define CHK(call)                                                                       \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            fail(NB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+            return bail();                                                              \
+        }                                                                               \
+    } while (0)
+    const size_t vecb = sizeof(double) * (size_t)s->Dp;
+    ALLOC(s->d_pool, n_chains * (size_t)s->NS * 4 * vecb);
+    ALLOC(s->d_var, n_chains * vecb);
+    ALLOC(s->d_wf, n_chains * 8 * vecb);
+    ALLOC(s->d_sc, n_chains * sizeof(ChainScalars));
+    ALLOC(s->d_draws, n_chains * s->n_rows * s->sdim * sizeof(double));
+    ALLOC(s->d_stats, n_chains * s->n_rows * NB200_NSTAT * sizeof(double));
+    if (st->store_gradient) ALLOC(s->d_grads, n_chains * s->n_rows * s->sdim * sizeof(double));
+    if (st->store_mass_matrix) ALLOC(s->d_mm, n_chains * s->n_rows * s->sdim * sizeof(double));
+    ALLOC(s->d_stop, sizeof(int));
+    CHK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CHK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+    CHK(cudaEventCreate(&s->ev0));
+    CHK(cudaEventCreate(&s->ev1));
+    CHK(cudaMemsetAsync(s->d_sc, 0, n_chains * sizeof(ChainScalars), s->stream));
+    CHK(cudaMemsetAsync(s->d_stop, 0, sizeof(int), s->stream));
+    CHK(cudaMemsetAsync(s->d_pool, 0, n_chains * (size_t)s->NS * 4 * vecb, s->stream));
+    CHK(cudaMemsetAsync(s->d_var, 0, n_chains * vecb, s->stream));
+    CHK(cudaMemsetAsync(s->d_wf, 0, n_chains * 8 * vecb, s->stream));
+    CHK(cudaMemsetAsync(s->d_stats, 0, n_chains * s->n_rows * NB200_NSTAT * sizeof(double), s->stream));
+    CHK(cudaHostAlloc((void**)&s->h_sc, n_chains * sizeof(ChainScalars), cudaHostAllocDefault));
+    std::memset(s->h_sc, 0, n_chains * sizeof(ChainScalars));
+    if (q0) {
+        ALLOC(s->d_q0, n_chains * D * sizeof(double));
+        CHK(cudaMemcpyAsync(s->d_q0, q0, n_chains * D * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    }
+    if (init_mean) {
+        ALLOC(s->d_init_mean, D * sizeof(double));
+        CHK(cudaMemcpyAsync(s->d_init_mean, init_mean, D * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    }
+    CHK(cudaStreamSynchronize(s->stream));
+#undef ALLOC
+#undef CHK
+    P.pool = s->d_pool; P.var = s->d_var; P.welford = s->d_wf; P.sc = s->d_sc;
+    P.draws = s->d_draws; P.stats = s->d_stats; P.grads = s->d_grads; P.mminv = s->d_mm;
+    P.q0 = s->d_q0; P.init_mean = s->d_init_mean; P.z_tape = nullptr;
+    P.stop_flag = s->d_stop;
+    s->rows_filled.assign(n_chains, 0);
+    return s;
+}
+
+// ------------------------------------------------------------------ C-ABI
+extern "C" {
+
+int nb200_abi_version(void) { return NB200_ABI_VERSION; }
+const char* nb200_last_error(void) { return g_err.c_str(); }
+int nb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+void nb200_set_threads_per_chain(int32_t t) { g_threads_per_chain.store(t); }
+void nb200_set_chains_per_block(int32_t c) { g_chains_per_block.store(c); }
+
+void nb200_settings_default(nb200_settings* s) {
+    std::memset(s, 0, sizeof(*s));
+    s->seed = 0;
+    s->num_tune = 400;
+    s->num_draws = 1000;
+    s->maxdepth = 10;
+    s->mindepth = 0;
+    s->check_turning = 1;
+    s->store_gradient = 0;
+    s->store_mass_matrix = 0;
+    s->use_grad_based_estimate = 1;
+    s->max_energy_error = 1000.0;
+    s->initial_step = 0.1;
+    s->target_accept = 0.8;
+    s->max_step_size = INFINITY;
+    s->da_k = 0.75;
+    s->da_t0 = 10.0;
+    s->da_gamma = 0.05;
+    s->step_size_method = 0;
+    s->fixed_step_size = 0.1;
+    s->early_window = 0.3;
+    s->step_size_window = 0.15;
+    s->mass_matrix_switch_freq = 80;
+    s->early_mass_matrix_switch_freq = 10;
+    s->mass_matrix_update_freq = 1;
+    s->init_kind = 0;
+    s->num_try_init = 10;
+    s->init_radius = 2.0;
+    s->store_dims = 0;
+    s->save_warmup = 1;
+}
+
+void* nb200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocDefault) != cudaSuccess) {
+        fail(NB200_ECUDA, "cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+void nb200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+nb200_sampler* nb200_sampler_create(const nb200_settings* settings, const nb200_model_desc* model,
+                                    uint64_t n_chains, uint64_t chain_id_offset, int device,
+                                    const double* q0, const double* init_mean) {
+    if (validate(settings, model) != 0) return nullptr;
+    if (n_chains < 1) {
+        fail(NB200_EINVAL, "n_chains must be >= 1");
+        return nullptr;
+    }
+    if (chain_id_offset + n_chains > 0xFFFFFFFFull) {
+        fail(NB200_EINVAL, "global chain id must fit 32 bits");
+        return nullptr;
+    }
+    if (settings->num_tune + settings->num_draws >= 0xFFFFFFFFull) {
+        fail(NB200_EINVAL, "num_tune + num_draws must fit 32 bits");
+        return nullptr;
+    }
+    int ndev = nb200_device_count();
+    if (ndev < 1) {
+        fail(NB200_ECUDA, "no CUDA device available: the B200 engine has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        fail(NB200_EINVAL, "device index out of range");
+        return nullptr;
+    }
+    switch (model->kind) {
+    case NB200_MODEL_NORMAL:
+        return create_impl<NormalModel>(settings, model, n_chains, chain_id_offset, device, q0, init_mean);
+    case NB200_MODEL_FUNNEL:
+        return create_impl<FunnelModel>(settings, model, n_chains, chain_id_offset, device, q0, init_mean);
+    case NB200_MODEL_RADON:
+        return create_impl<RadonModel>(settings, model, n_chains, chain_id_offset, device, q0, init_mean);
+    }
+    fail(NB200_EINVAL, "unknown model kind");
+    return nullptr;
+}
+
+int nb200_sampler_set_draws_per_launch(nb200_sampler* s, uint64_t n) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->draws_per_launch = n;
+    return 0;
+}
+
+}  // extern "C"
+// set the tape pointer inside the model-typed KParams
+template <class M>
+static void set_tape(nb200_sampler* s) {
+    static_cast<SamplerImpl<M>*>(s)->P.z_tape = s->d_tape;
+}
+extern "C" {
+
+int nb200_sampler_set_z_tape(nb200_sampler* s, const double* z_tape) {
+    if (!s || !z_tape) return fail(NB200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state != RunState::Created) return fail(NB200_ESTATE, "tape must be set before start");
+    CU(cudaSetDevice(s->device));
+    const size_t n = s->n_chains * s->n_total * s->model.dim;
+    CU(cudaMalloc((void**)&s->d_tape, n * sizeof(double)));
+    CU(cudaMemcpy(s->d_tape, z_tape, n * sizeof(double), cudaMemcpyHostToDevice));
+    switch (s->model.kind) {
+    case NB200_MODEL_NORMAL: set_tape<NormalModel>(s); break;
+    case NB200_MODEL_FUNNEL: set_tape<FunnelModel>(s); break;
+    case NB200_MODEL_RADON: set_tape<RadonModel>(s); break;
+    }
+    return 0;
+}
+
+static int launch_locked(nb200_sampler* s) {
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventRecord(s->ev0, s->stream));
+    int rc = s->launch();
+    if (rc != 0) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    s->launches += 1;
+    return 0;
+}
+
+int nb200_sampler_start(nb200_sampler* s) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state != RunState::Created) return fail(NB200_ESTATE, "sampler already started");
+    int rc = launch_locked(s);
+    if (rc != 0) {
+        s->state = RunState::Error;
+        s->sampler_error = rc;
+        return rc;
+    }
+    s->state = RunState::Running;
+    return 0;
+}
+
+// refresh h_sc from the device on the side stream (safe while the kernel runs)
+static int fetch_scalars(nb200_sampler* s) {
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(s->h_sc, s->d_sc, s->n_chains * sizeof(ChainScalars), cudaMemcpyDeviceToHost,
+                       s->side));
+    CU(cudaStreamSynchronize(s->side));
+    return 0;
+}
+
+// called with the lock held when the current launch has completed
+static int on_launch_done(nb200_sampler* s) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->kernel_ms += ms;
+    int rc = fetch_scalars(s);
+    if (rc != 0) return rc;
+    bool all_done = true;
+    for (uint64_t c = 0; c < s->n_chains; ++c) {
+        if (s->h_sc[c].status < 0) {
+            s->state = RunState::Error;
+            s->sampler_error = s->h_sc[c].status;
+            return fail(s->h_sc[c].status,
+                        s->h_sc[c].status == NB200_EINIT
+                            ? "chain " + std::to_string(c) + ": no finite initial point found"
+                            : "chain " + std::to_string(c) + ": fatal logp error");
+        }
+        if (s->h_sc[c].status != 2) all_done = false;
+    }
+    if (all_done) {
+        s->state = RunState::Finished;
+        return 0;
+    }
+    return 1;  // more draws to do
+}
+
+int nb200_sampler_wait(nb200_sampler* s, double timeout_seconds) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            switch (s->state) {
+            case RunState::Created: return fail(NB200_ESTATE, "sampler not started");
+            case RunState::Finished:
+            case RunState::Aborted: return NB200_OK;
+            case RunState::Error: return fail(s->sampler_error, g_err.empty() ? "sampler error" : g_err);
+            case RunState::Paused: break;
+            case RunState::Running: {
+                CU(cudaSetDevice(s->device));
+                cudaError_t q = cudaEventQuery(s->ev1);
+                if (q == cudaSuccess) {
+                    int rc = on_launch_done(s);
+                    if (rc < 0) return rc;
+                    if (rc == 0) return NB200_OK;
+                    rc = launch_locked(s);  // chunked mode: next launch
+                    if (rc != 0) {
+                        s->state = RunState::Error;
+                        s->sampler_error = rc;
+                        return rc;
+                    }
+                } else if (q != cudaErrorNotReady) {
+                    s->state = RunState::Error;
+                    s->sampler_error = NB200_ECUDA;
+                    return fail(NB200_ECUDA, std::string("kernel failed: ") + cudaGetErrorString(q));
+                }
+                break;
+            }
+            }
+        }
+        if (timeout_seconds >= 0) {
+            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (el >= timeout_seconds) return NB200_ETIMEOUT;
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+}
+
+int nb200_sampler_is_finished(nb200_sampler* s) {
+    if (!s) return 0;
+    int rc = nb200_sampler_wait(s, 0.0);
+    std::lock_guard<std::mutex> lk(s->mu);
+    (void)rc;
+    return s->state == RunState::Finished || s->state == RunState::Aborted ||
+           s->state == RunState::Error;
+}
+
+int nb200_sampler_progress(nb200_sampler* s, nb200_progress* out) {
+    if (!s || !out) return fail(NB200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = fetch_scalars(s);
+    if (rc != 0) return rc;
+    for (uint64_t c = 0; c < s->n_chains; ++c) {
+        const ChainScalars& sc = s->h_sc[c];
+        out[c].finished_draws = sc.draw;
+        out[c].total_draws = s->n_total;
+        out[c].divergences = sc.divergences;
+        out[c].latest_num_steps = sc.latest_n_steps;
+        out[c].total_num_steps = sc.total_steps;
+        out[c].step_size = sc.step_size;
+        out[c].tuning = sc.draw < s->st.num_tune;
+        out[c].started = sc.status != 0;
+    }
+    return 0;
+}
+
+static int stop_and_drain(nb200_sampler* s) {
+    CU(cudaSetDevice(s->device));
+    int one = 1;
+    CU(cudaMemcpyAsync(s->d_stop, &one, sizeof(int), cudaMemcpyHostToDevice, s->side));
+    CU(cudaStreamSynchronize(s->side));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->kernel_ms += ms;
+    int zero = 0;
+    CU(cudaMemcpy(s->d_stop, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    return fetch_scalars(s);
+}
+
+int nb200_sampler_pause(nb200_sampler* s) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state != RunState::Running) return 0;
+    int rc = stop_and_drain(s);
+    if (rc != 0) return rc;
+    bool all_done = true;
+    for (uint64_t c = 0; c < s->n_chains; ++c)
+        if (s->h_sc[c].status != 2) all_done = false;
+    s->state = all_done ? RunState::Finished : RunState::Paused;
+    return 0;
+}
+
+int nb200_sampler_resume(nb200_sampler* s) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state != RunState::Paused) return 0;
+    int rc = launch_locked(s);
+    if (rc != 0) return rc;
+    s->state = RunState::Running;
+    return 0;
+}
+
+int nb200_sampler_abort(nb200_sampler* s) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state == RunState::Running) {
+        int rc = stop_and_drain(s);
+        if (rc != 0) return rc;
+    }
+    if (s->state == RunState::Running || s->state == RunState::Paused) s->state = RunState::Aborted;
+    return 0;
+}
+
+static int copy_trace(nb200_sampler* s, double* draws, double* stats, double* grads, double* mm,
+                      uint64_t* rows) {
+    CU(cudaSetDevice(s->device));
+    int rc = fetch_scalars(s);
+    if (rc != 0) return rc;
+    const bool live = s->state == RunState::Running;
+    for (uint64_t c = 0; c < s->n_chains; ++c) {
+        uint64_t d = s->h_sc[c].draw;
+        if (live && d > 0) d -= 1;  // the row being written may be incomplete
+        uint64_t r = s->st.save_warmup ? d : (d > s->st.num_tune ? d - s->st.num_tune : 0);
+        s->rows_filled[c] = r < s->n_rows ? r : s->n_rows;
+        if (rows) rows[c] = s->rows_filled[c];
+    }
+    const size_t nd = s->n_chains * s->n_rows * s->sdim * sizeof(double);
+    const size_t ns = s->n_chains * s->n_rows * NB200_NSTAT * sizeof(double);
+    if (draws) CU(cudaMemcpyAsync(draws, s->d_draws, nd, cudaMemcpyDeviceToHost, s->side));
+    if (stats) CU(cudaMemcpyAsync(stats, s->d_stats, ns, cudaMemcpyDeviceToHost, s->side));
+    if (grads && s->d_grads) CU(cudaMemcpyAsync(grads, s->d_grads, nd, cudaMemcpyDeviceToHost, s->side));
+    if (mm && s->d_mm) CU(cudaMemcpyAsync(mm, s->d_mm, nd, cudaMemcpyDeviceToHost, s->side));
+    CU(cudaStreamSynchronize(s->side));
+    return 0;
+}
+
+int nb200_sampler_trace_into(nb200_sampler* s, double* draws, double* stats, double* gradients,
+                             double* mass_matrix_inv, uint64_t* rows_filled) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state == RunState::Created) return fail(NB200_ESTATE, "sampler not started");
+    return copy_trace(s, draws, stats, gradients, mass_matrix_inv, rows_filled);
+}
+
+int nb200_sampler_trace(nb200_sampler* s, nb200_trace_view* out) {
+    if (!s || !out) return fail(NB200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state == RunState::Created) return fail(NB200_ESTATE, "sampler not started");
+    CU(cudaSetDevice(s->device));
+    const size_t nd = s->n_chains * s->n_rows * s->sdim * sizeof(double);
+    const size_t ns = s->n_chains * s->n_rows * NB200_NSTAT * sizeof(double);
+    if (!s->h_draws) CU(cudaHostAlloc((void**)&s->h_draws, nd ? nd : 8, cudaHostAllocDefault));
+    if (!s->h_stats) CU(cudaHostAlloc((void**)&s->h_stats, ns ? ns : 8, cudaHostAllocDefault));
+    if (s->d_grads && !s->h_grads) CU(cudaHostAlloc((void**)&s->h_grads, nd ? nd : 8, cudaHostAllocDefault));
+    if (s->d_mm && !s->h_mm) CU(cudaHostAlloc((void**)&s->h_mm, nd ? nd : 8, cudaHostAllocDefault));
+    int rc = copy_trace(s, s->h_draws, s->h_stats, s->h_grads, s->h_mm, nullptr);
+    if (rc != 0) return rc;
+    out->n_chains = s->n_chains;
+    out->n_rows = s->n_rows;
+    out->dim = s->model.dim;
+    out->store_dims = s->sdim;
+    out->draws = s->h_draws;
+    out->stats = s->h_stats;
+    out->gradients = s->h_grads;
+    out->mass_matrix_inv = s->h_mm;
+    out->rows_filled = s->rows_filled.data();
+    return 0;
+}
+
+double nb200_sampler_kernel_ms(nb200_sampler* s) {
+    if (!s) return 0.0;
+    std::lock_guard<std::mutex> lk(s->mu);
+    return s->kernel_ms;
+}
+uint64_t nb200_sampler_launch_count(nb200_sampler* s) {
+    if (!s) return 0;
+    std::lock_guard<std::mutex> lk(s->mu);
+    return s->launches;
+}
+int nb200_sampler_device_buffers(nb200_sampler* s, void** draws, void** stats) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    if (draws) *draws = s->d_draws;
+    if (stats) *stats = s->d_stats;
+    return 0;
+}
+int nb200_sampler_geometry(nb200_sampler* s, int32_t* tpc, int32_t* block, int32_t* grid) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    if (tpc) *tpc = 32 * s->W;
+    if (block) *block = s->block;
+    if (grid) *grid = s->grid;
+    return 0;
+}
+
+int nb200_sampler_destroy(nb200_sampler* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    if (s->state == RunState::Running) {
+        int one = 1;
+        if (s->d_stop && s->side) {
+            cudaMemcpyAsync(s->d_stop, &one, sizeof(int), cudaMemcpyHostToDevice, s->side);
+            cudaStreamSynchronize(s->side);
+        }
+        if (s->stream) cudaStreamSynchronize(s->stream);
+    }
+    void* dev[] = {s->d_pool, s->d_var, s->d_wf, s->d_sc, s->d_draws, s->d_stats, s->d_grads,
+                   s->d_mm, s->d_q0, s->d_init_mean, s->d_tape, s->d_stop};
+    for (void* p : dev)
+        if (p) cudaFree(p);
+    for (void* p : s->model_allocs) cudaFree(p);
+    void* host[] = {s->h_sc, s->h_draws, s->h_stats, s->h_grads, s->h_mm};
+    for (void* p : host)
+        if (p) cudaFreeHost(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->side) cudaStreamDestroy(s->side);
+    delete s;
+    return 0;
+}
+
+}  // extern "C"
+// ------------------------------------------------------ component entry points
+template <class M>
+static int component_run(const nb200_model_desc* model, int device, uint64_t n, int mode,
+                         const double* q, const double* p, const double* g, const double* var,
+                         const double* p_sum, const double* eps, const int32_t* dir,
+                         const int64_t* idx, double* q_out, double* p_out, double* g_out,
+                         double* p_sum_out, double* logp_out, double* kin_out, int32_t* rc_out) {
+    CU(cudaSetDevice(device));
+    int W = g_threads_per_chain.load() > 0 ? g_threads_per_chain.load() / 32 : 1;
+    if (W < 1 || W > 32 || (W & (W - 1))) return fail(NB200_EINVAL, "bad threads per chain");
+    const int D = (int)model->dim, Dp = (D + 3) / 4 * 4, NS = 2;
+    KParams<M> P;
+    std::memset(&P, 0, sizeof(P));
+    nb200_settings_default(&P.st);
+    P.st.max_energy_error = INFINITY;
+    std::vector<void*> keep;
+    int rc = build_model_data(*model, 32 * W, P.mdata, keep);
+    if (rc != 0) return rc;
+    P.D = D; P.Dp = Dp; P.NS = NS; P.n_chains = n;
+    const size_t vecb = sizeof(double) * (size_t)Dp;
+    double *d_pool, *d_var, *d_scal, *d_out;
+    CU(cudaMalloc((void**)&d_pool, n * NS * 4 * vecb)); keep.push_back(d_pool);
+    CU(cudaMalloc((void**)&d_var, n * vecb)); keep.push_back(d_var);
+    CU(cudaMalloc((void**)&d_scal, n * 4 * sizeof(double))); keep.push_back(d_scal);
+    CU(cudaMalloc((void**)&d_out, n * 4 * sizeof(double))); keep.push_back(d_out);
+    CU(cudaMemset(d_pool, 0, n * NS * 4 * vecb));
+    std::vector<double> hv(n * Dp, 1.0), hs(n * 4, 0.0);
+    auto upload = [&](const double* src, int comp) -> int {
+        if (!src) return 0;
+        for (uint64_t c = 0; c < n; ++c)
+            CU(cudaMemcpy(d_pool + ((c * NS + 0) * 4 + comp) * (size_t)Dp, src + c * D,
+                          sizeof(double) * D, cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if ((rc = upload(q, VQ)) || (rc = upload(p, VP)) || (rc = upload(g, VG)) || (rc = upload(p_sum, VS)))
+        return rc;
+    if (var)
+        for (uint64_t c = 0; c < n; ++c)
+            for (int i = 0; i < D; ++i) hv[c * Dp + i] = var[c * D + i];
+    CU(cudaMemcpy(d_var, hv.data(), n * vecb, cudaMemcpyHostToDevice));
+    for (uint64_t c = 0; c < n; ++c) {
+        hs[c * 4 + 0] = eps ? eps[c] : 0.0;
+        hs[c * 4 + 1] = dir ? (double)dir[c] : 1.0;
+        hs[c * 4 + 2] = idx ? (double)idx[c] : 0.0;
+    }
+    CU(cudaMemcpy(d_scal, hs.data(), n * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    P.pool = d_pool; P.var = d_var;
+    const size_t smem = smem_for<M>(W, P.mdata);
+#define LAUNCH(WW)                                                                          \
+    case WW:                                                                                \
+        CU(cudaFuncSetAttribute(component_kernel<M, WW>,                                    \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        component_kernel<M, WW><<<(unsigned)n, 32 * WW, smem>>>(P, mode, d_scal, d_out);    \
+        break;
+    switch (W) {
+        LAUNCH(1) LAUNCH(2) LAUNCH(4) LAUNCH(8) LAUNCH(16) LAUNCH(32)
+    }
+#undef LAUNCH
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    std::vector<double> ho(n * 4);
+    CU(cudaMemcpy(ho.data(), d_out, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    auto download = [&](double* dst, int slot, int comp) -> int {
+        if (!dst) return 0;
+        for (uint64_t c = 0; c < n; ++c)
+            CU(cudaMemcpy(dst + c * D, d_pool + ((c * NS + slot) * 4 + comp) * (size_t)Dp,
+                          sizeof(double) * D, cudaMemcpyDeviceToHost));
+        return 0;
+    };
+    const int oslot = mode == 0 ? 0 : 1;
+    if ((rc = download(q_out, oslot, VQ)) || (rc = download(p_out, oslot, VP)) ||
+        (rc = download(g_out, oslot, VG)) || (rc = download(p_sum_out, oslot, VS)))
+        return rc;
+    for (uint64_t c = 0; c < n; ++c) {
+        if (logp_out) logp_out[c] = ho[c * 4 + 0];
+        if (kin_out) kin_out[c] = ho[c * 4 + 1];
+        if (rc_out) rc_out[c] = (int32_t)ho[c * 4 + 2];
+    }
+    for (void* ptr : keep) cudaFree(ptr);
+    return 0;
+}
+
+extern "C" {
+#define DISPATCH_MODEL(CALL)                                                   \
+    switch (model->kind) {                                                     \
+    case NB200_MODEL_NORMAL: return CALL(NormalModel);                         \
+    case NB200_MODEL_FUNNEL: return CALL(FunnelModel);                         \
+    case NB200_MODEL_RADON: return CALL(RadonModel);                           \
+    }                                                                          \
+    return fail(NB200_EINVAL, "unknown model kind");
+
+int nb200_logp_grad(const nb200_model_desc* model, int device, uint64_t n, const double* q,
+                    double* logp, double* grad, int32_t* rc) {
+    nb200_settings st;
+    nb200_settings_default(&st);
+    if (validate(&st, model) != 0) return NB200_EINVAL;
+    if (nb200_device_count() < 1) return fail(NB200_ECUDA, "no CUDA device available");
+    if (!q || n < 1) return fail(NB200_EINVAL, "null/empty input");
+#define CALL(M)                                                                               \
+    component_run<M>(model, device, n, 0, q, nullptr, nullptr, nullptr, nullptr, nullptr,     \
+                     nullptr, nullptr, nullptr, nullptr, grad, nullptr, logp, nullptr, rc)
+    DISPATCH_MODEL(CALL)
+#undef CALL
+}
+
+int nb200_leapfrog(const nb200_model_desc* model, int device, uint64_t n, const double* q,
+                   const double* p, const double* g, const double* var, const double* p_sum,
+                   const double* eps, const int32_t* dir, const int64_t* idx, double* q_out,
+                   double* p_out, double* g_out, double* p_sum_out, double* logp_out,
+                   double* kinetic_out, int32_t* rc) {
+    nb200_settings st;
+    nb200_settings_default(&st);
+    if (validate(&st, model) != 0) return NB200_EINVAL;
+    if (nb200_device_count() < 1) return fail(NB200_ECUDA, "no CUDA device available");
+    if (!q || !p || !g || !var || !p_sum || !eps || n < 1) return fail(NB200_EINVAL, "null/empty input");
+#define CALL(M)                                                                                \
+    component_run<M>(model, device, n, 1, q, p, g, var, p_sum, eps, dir, idx, q_out, p_out,    \
+                     g_out, p_sum_out, logp_out, kinetic_out, rc)
+    DISPATCH_MODEL(CALL)
+#undef CALL
+}
+
+}  // extern "C"

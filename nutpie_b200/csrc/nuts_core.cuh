@@ -1,0 +1,831 @@
+// nuts_core.cuh — the per-chain NUTS engine (transition + adaptation), written
+// once against a thread-group policy `G` and a density `M`.
+//
+// What it replaces (nuts-rs 0.18.3 behind nuts_rs::Sampler::new,
+// src/wrapper.rs:977-1085; semantics per SURVEY.md Appendix A):
+//   leapfrog()            — Euclidean Hamiltonian with diagonal mass matrix (A.2)
+//   is_turning()          — U-turn criterion on momentum prefix sums (A.3)
+//   transition()          — tree doubling, multinomial + biased-progressive
+//                           selection, divergence rule (A.4); ITERATIVE: the
+//                           crate's recursion is unrolled onto a binary-counter
+//                           stack of sub-trees, one entry per level
+//   adapt()               — dual averaging, Welford draw+gradient estimators
+//                           with foreground/background windows, mass-matrix
+//                           refresh, initial step-size search (A.5)
+//
+// Memory plan (B200): every trajectory state is a SLOT of four vectors
+// (q, p, grad, p_sum) in a per-chain pool in HBM; a leapfrog reads one slot and
+// writes a fresh one exactly once (72 B per dimension per gradient evaluation,
+// the algorithmic figure of SURVEY.md §8d) and all tree bookkeeping is done on
+// slot indices, so merging sub-trees never copies a vector.  Per-slot scalars
+// (index in trajectory, potential, kinetic energy) and the level stack live in
+// shared memory.
+#pragma once
+#include "../../include/nutpie_b200.h"
+#include "group.cuh"
+#include "models.cuh"
+#include "philox.cuh"
+#include "portable.cuh"
+
+namespace nb200 {
+
+constexpr int kMaxSlots = 64;
+constexpr int kMaxLevels = 20;
+constexpr double kVarLower = 1e-20, kVarUpper = 1e20;
+
+enum { VQ = 0, VP = 1, VG = 2, VS = 3 };  // q, p, grad, p_sum inside a slot
+
+// persistent per-chain scalar state (global memory; also the progress record)
+struct ChainScalars {
+    double step_size;
+    double da_log_step, da_log_step_adapted, da_hbar, da_mu;
+    unsigned long long da_count;
+    unsigned long long cnt[2];   // sample counts of the two Welford sets
+    unsigned long long last_update;
+    unsigned long long draw;     // next draw index == finished draws
+    unsigned long long total_steps;
+    unsigned long long divergences;
+    unsigned long long latest_n_steps;
+    double cur_U;                // potential energy (-logp) of the current point
+    int fg_sel;                  // which Welford set is the foreground
+    int has_initial_mm;
+    int cur_slot;
+    int status;                  // 0 not started, 1 running, 2 finished, <0 NB200_E*
+};
+
+// per-chain shared-memory scalars
+struct ChainShared {
+    double U[kMaxSlots];
+    double K[kMaxSlots];
+    double lvLS[kMaxLevels];
+    int idx[kMaxSlots];
+    int lvL[kMaxLevels], lvR[kMaxLevels], lvD[kMaxLevels];
+};
+
+template <class M>
+struct KParams {
+    nb200_settings st;
+    typename M::Data mdata;
+    int D, Dp, NS;
+    unsigned long long n_chains, chain_id_offset;
+    unsigned long long n_rows, sdim, n_total;
+    unsigned long long max_draws_per_launch;  // 0 = run to the end
+    double* pool;      // [n_chains][NS][4][Dp]
+    double* var;       // [n_chains][Dp]        diagonal of M^-1
+    double* welford;   // [n_chains][2][4][Dp]  (mean_q, m2_q, mean_g, m2_g) x 2 sets
+    ChainScalars* sc;  // [n_chains]
+    double* draws;     // [n_chains][n_rows][sdim]
+    double* stats;     // [n_chains][n_rows][NB200_NSTAT]
+    double* grads;     // optional, like draws
+    double* mminv;     // optional, like draws
+    const double* q0;        // optional [n_chains][D]
+    const double* init_mean; // optional [D]
+    const double* z_tape;    // optional [n_chains][n_total][D] (tests)
+    const volatile int* stop_flag;
+};
+
+struct SampleInfo {
+    int depth, diverging, maxdepth_reached;
+};
+
+NB_HD double nb_logaddexp(double a, double b) {
+    if (a == b) return a + 0.69314718055994530941723212145818;
+    double diff = a - b;
+    if (diff > 0) return a + log1p(exp(-diff));
+    if (diff < 0) return b + log1p(exp(diff));
+    return diff;
+}
+
+template <class M, class G>
+struct ChainCtx {
+    G g;
+    const KParams<M>* P;
+    ChainShared* sh;
+    double* msm;  // model scratch (shared)
+    int D, Dp, NS;
+    unsigned long long chain_local;
+    uint32_t chain_gid;
+    double *pool, *var, *wf;
+    // hamiltonian
+    double step_size, E0;
+    // collectors of the running transition (AcceptanceRateCollector)
+    double acc_sum, acc_sym;
+    uint32_t acc_count, n_merge, draw;
+    double last_de;
+    // tree bookkeeping (slot ids; -1 = none)
+    int mL, mR, mD, tL, tR, tD;
+    unsigned lv_valid;
+    // strategy state
+    double da_log_step, da_log_step_adapted, da_hbar, da_mu;
+    unsigned long long da_count;
+    unsigned long long cnt[2], last_update, total_steps, divergences;
+    int fg_sel, has_initial_mm;
+    double last_mean, last_sym;
+    uint32_t last_n_steps;
+
+    NB_HD double* vec(int slot, int comp) const {
+        return pool + ((size_t)slot * 4 + comp) * (size_t)Dp;
+    }
+    NB_HD const nb200_settings& st() const { return P->st; }
+
+    // ------------------------------------------------------------ slot pool
+    NB_HD int alloc() const {
+        unsigned long long live = 0;
+        if (mL >= 0) live |= 1ull << mL;
+        if (mR >= 0) live |= 1ull << mR;
+        if (mD >= 0) live |= 1ull << mD;
+        if (tL >= 0) live |= 1ull << tL;
+        if (tR >= 0) live |= 1ull << tR;
+        if (tD >= 0) live |= 1ull << tD;
+        unsigned v = lv_valid;
+        while (v) {
+            int k = nb_ffsll(v) - 1;
+            v &= v - 1;
+            live |= (1ull << sh->lvL[k]) | (1ull << sh->lvR[k]) | (1ull << sh->lvD[k]);
+        }
+        const unsigned long long all = NS >= 64 ? ~0ull : ((1ull << NS) - 1ull);
+        return nb_ffsll(~live & all) - 1;  // lowest free slot: keeps the hot set small
+    }
+
+    // ---------------------------------------------------------- density at a slot
+    NB_HD double eval_logp(int slot, bool& bad) {
+        const double* q = vec(slot, VQ);
+        double* gr = vec(slot, VG);
+        double lp;
+        double flag[1] = {0.0};
+        if constexpr (M::kElementwise) {
+            double acc[2] = {0.0, 0.0};
+            for (int i = g.tid; i < D; i += g.size()) {
+                double gn;
+                acc[0] += M::term(P->mdata, i, q[i], gn);
+                gr[i] = gn;
+                if (!nb_isfinite(gn)) acc[1] += 1.0;
+            }
+            g.reduce(acc);
+            lp = M::finish(P->mdata, acc[0], D);
+            flag[0] = acc[1];
+        } else {
+            g.sync();
+            lp = M::logp_grad(g, P->mdata, D, q, gr, msm);
+            g.sync();
+            for (int i = g.tid; i < D; i += g.size())
+                if (!nb_isfinite(gr[i])) flag[0] += 1.0;
+            g.reduce(flag);
+        }
+        bad = flag[0] > 0.0 || !nb_isfinite(lp);
+        return lp;
+    }
+
+    // ---------------------------------------------------------------- leapfrog
+    // src -> dst (dst is a fresh slot).  Returns 0 ok, 1 divergence.
+    NB_HD int leapfrog(int src, int dst, int dir) {
+        const double eps = (double)dir * step_size;
+        const double heps = 0.5 * eps;
+        const double* qs = vec(src, VQ);
+        const double* ps = vec(src, VP);
+        const double* gs = vec(src, VG);
+        const double* ss = vec(src, VS);
+        double* qd = vec(dst, VQ);
+        double* pd = vec(dst, VP);
+        double* gd = vec(dst, VG);
+        double* sd = vec(dst, VS);
+        const int new_idx = sh->idx[src] + dir;
+        const bool restart_sum = new_idx == -1;
+        double lp, kin;
+        bool bad;
+        if constexpr (M::kElementwise) {
+            // one streaming pass: 5 loads + 4 stores per dimension
+            double acc[3] = {0.0, 0.0, 0.0};
+            for (int i = g.tid; i < D; i += g.size()) {
+                const double vr = var[i];
+                const double ph = ps[i] + heps * gs[i];
+                const double qn = qs[i] + eps * (vr * ph);
+                double gn;
+                acc[0] += M::term(P->mdata, i, qn, gn);
+                const double pn = ph + heps * gn;
+                acc[1] += pn * (vr * pn);
+                const double sn = restart_sum ? pn : ss[i] + pn;
+                qd[i] = qn;
+                pd[i] = pn;
+                gd[i] = gn;
+                sd[i] = sn;
+                if (!nb_isfinite(gn)) acc[2] += 1.0;
+            }
+            g.reduce(acc);
+            lp = M::finish(P->mdata, acc[0], D);
+            kin = 0.5 * acc[1];
+            bad = acc[2] > 0.0;
+        } else {
+            for (int i = g.tid; i < D; i += g.size()) {
+                const double ph = ps[i] + heps * gs[i];
+                pd[i] = ph;
+                qd[i] = qs[i] + eps * (var[i] * ph);
+            }
+            g.sync();
+            lp = M::logp_grad(g, P->mdata, D, qd, gd, msm);
+            g.sync();
+            double acc[2] = {0.0, 0.0};
+            for (int i = g.tid; i < D; i += g.size()) {
+                const double gn = gd[i];
+                const double pn = pd[i] + heps * gn;
+                acc[0] += pn * (var[i] * pn);
+                pd[i] = pn;
+                sd[i] = restart_sum ? pn : ss[i] + pn;
+                if (!nb_isfinite(gn)) acc[1] += 1.0;
+            }
+            g.reduce(acc);
+            kin = 0.5 * acc[0];
+            bad = acc[1] > 0.0;
+        }
+        int rc = (bad || !nb_isfinite(lp)) ? 1 : 0;  // recoverable logp error (rc 3/4)
+        const double U = -lp;
+        const double de = (kin + U) - E0;
+        if (rc == 0 && (de > st().max_energy_error || !nb_isfinite(de))) rc = 1;
+        if (g.tid == 0) {
+            sh->idx[dst] = new_idx;
+            sh->U[dst] = U;
+            sh->K[dst] = kin;
+        }
+        g.sync();
+        acc_count += 1;
+        if (rc == 0) {
+            const double w = exp(-de);
+            const double a = w < 1.0 ? w : 1.0;
+            acc_sum += a;
+            acc_sym += 2.0 * a / (1.0 + w);
+        }
+        last_de = de;
+        return rc;
+    }
+
+    // ------------------------------------------------------------------ U-turn
+    NB_HD bool is_turning(int s1, int s2) const {
+        int a = sh->idx[s1], b = sh->idx[s2];
+        int ss_ = s1, se_ = s2;
+        if (!(a < b)) {
+            int t = a; a = b; b = t;
+            ss_ = s2; se_ = s1;
+        }
+        const double* p_s = vec(ss_, VP);
+        const double* sum_s = vec(ss_, VS);
+        const double* p_e = vec(se_, VP);
+        const double* sum_e = vec(se_, VS);
+        const int mode = (a >= 0 && b >= 0) ? 0 : ((b >= 0 && a < 0) ? 1 : 2);
+        double acc[2] = {0.0, 0.0};
+        for (int i = g.tid; i < D; i += g.size()) {
+            const double pse = sum_e[i], pss = sum_s[i], pe = p_e[i], ps = p_s[i];
+            double rho;
+            if (mode == 0) rho = pse - pss + ps;
+            else if (mode == 1) rho = pse + pss;
+            else rho = pss - pse + pe;
+            const double vr = var[i];
+            acc[0] += rho * (vr * pe);
+            acc[1] += rho * (vr * ps);
+        }
+        g.reduce(acc);
+        return (acc[0] < 0.0) | (acc[1] < 0.0);
+    }
+
+    // ------------------------------------------------------- fresh momentum
+    // p = z / sqrt(var), p_sum = p, K, idx = 0, E0 = K + U   (initialize_trajectory)
+    NB_HD void init_momentum(int slot, uint32_t purpose, uint32_t rng_draw) {
+        double* pd = vec(slot, VP);
+        double* sd = vec(slot, VS);
+        const double* tape = nullptr;
+        if (purpose == RNG_MOMENTUM && P->z_tape)
+            tape = P->z_tape + ((size_t)chain_local * P->n_total + rng_draw) * (size_t)D;
+        double acc[1] = {0.0};
+        for (int j = g.tid; 2 * j < D; j += g.size()) {
+            double z0, z1;
+            const int i0 = 2 * j, i1 = 2 * j + 1;
+            if (tape) {
+                z0 = tape[i0];
+                z1 = i1 < D ? tape[i1] : 0.0;
+            } else {
+                uint64_t a, b;
+                rng_u64x2(st().seed, chain_gid, rng_draw, purpose, (uint32_t)j, a, b);
+                rng_normal_pair(a, b, z0, z1);
+            }
+            {
+                const double vr = var[i0];
+                const double p = sqrt(1.0 / vr) * z0;
+                pd[i0] = p;
+                sd[i0] = p;
+                acc[0] += p * (vr * p);
+            }
+            if (i1 < D) {
+                const double vr = var[i1];
+                const double p = sqrt(1.0 / vr) * z1;
+                pd[i1] = p;
+                sd[i1] = p;
+                acc[0] += p * (vr * p);
+            }
+        }
+        g.reduce(acc);
+        const double kin = 0.5 * acc[0];
+        if (g.tid == 0) {
+            sh->idx[slot] = 0;
+            sh->K[slot] = kin;
+        }
+        E0 = kin + sh->U[slot];  // U[slot] was written before the previous sync
+        g.sync();
+    }
+
+    // ------------------------------------------------------------- transition
+    NB_HD int transition(int cur, uint32_t t, SampleInfo& info) {
+        draw = t;
+        n_merge = 0;
+        acc_sum = acc_sym = 0.0;
+        acc_count = 0;
+        init_momentum(cur, RNG_MOMENTUM, t);
+        mL = mR = mD = cur;
+        tL = tR = tD = -1;
+        lv_valid = 0;
+        double m_ls = 0.0;
+        int depth = 0;
+        info.diverging = 0;
+        info.maxdepth_reached = 0;
+        bool done = false;
+        const int maxdepth = (int)st().maxdepth;
+        while (depth < maxdepth && !done) {
+            uint64_t ra, rb;
+            rng_u64x2(st().seed, chain_gid, t, RNG_DIRECTION, (uint32_t)depth, ra, rb);
+            const int dir = (ra & 1) ? 1 : -1;
+            const bool check = st().check_turning && depth >= (int)st().mindepth;
+            const unsigned n_leaf = 1u << depth;
+            int prev = dir > 0 ? mR : mL;
+            double t_ls = 0.0;
+            bool sub_ok = true;
+            lv_valid = 0;
+            tL = tR = tD = -1;
+            for (unsigned j = 0; j < n_leaf && sub_ok; ++j) {
+                const int dst = alloc();
+                const int rc = leapfrog(prev, dst, dir);
+                if (rc != 0) {
+                    info.diverging = 1;
+                    sub_ok = false;
+                    break;
+                }
+                tL = tR = tD = dst;
+                t_ls = -last_de;
+                int k = 0;
+                while ((j >> k) & 1u) {  // level k holds the earlier sibling: merge
+                    const int sL = sh->lvL[k], sR = sh->lvR[k], sD = sh->lvD[k];
+                    const double s_ls = sh->lvLS[k];
+                    bool turn = false;
+                    if (check) {
+                        const int first = dir > 0 ? sL : tL;
+                        const int last = dir > 0 ? tR : sR;
+                        turn = is_turning(first, last);
+                        if (k > 0) {
+                            if (!turn) turn = is_turning(sR, tR);
+                            if (!turn) turn = is_turning(sL, tL);
+                        }
+                    }
+                    const double new_ls = nb_logaddexp(s_ls, t_ls);
+                    rng_u64x2(st().seed, chain_gid, t, RNG_MERGE, n_merge, ra, rb);
+                    n_merge += 1;
+                    const double u = rng_u01(ra);
+                    // multinomial pick inside a sub-tree
+                    if (!(t_ls >= new_ls || u < exp(t_ls - new_ls))) tD = sD;
+                    if (dir > 0) tL = sL;
+                    else tR = sR;
+                    t_ls = new_ls;
+                    lv_valid &= ~(1u << k);
+                    ++k;
+                    if (turn) {
+                        sub_ok = false;
+                        break;
+                    }
+                }
+                if (!sub_ok) break;
+                if (j + 1 < n_leaf) {  // park the finished sub-tree at its level
+                    g.sync();          // earlier readers of the level arrays are done
+                    if (g.tid == 0) {
+                        sh->lvL[k] = tL;
+                        sh->lvR[k] = tR;
+                        sh->lvD[k] = tD;
+                        sh->lvLS[k] = t_ls;
+                    }
+                    g.sync();
+                    lv_valid |= 1u << k;
+                    tL = tR = tD = -1;
+                }
+                prev = dst;
+            }
+            if (!sub_ok) {  // turning inside the new sub-tree or divergence: discard it
+                done = true;
+                break;
+            }
+            bool turn = false;
+            if (check) {
+                const int first = dir > 0 ? mL : tL;
+                const int last = dir > 0 ? tR : mR;
+                turn = is_turning(first, last);
+                if (depth > 0) {
+                    if (!turn) turn = is_turning(mR, tR);
+                    if (!turn) turn = is_turning(mL, tL);
+                }
+            }
+            const double new_ls = nb_logaddexp(m_ls, t_ls);
+            rng_u64x2(st().seed, chain_gid, t, RNG_MERGE, n_merge, ra, rb);
+            n_merge += 1;
+            const double u = rng_u01(ra);
+            // biased progressive pick for the main tree
+            if (t_ls >= m_ls || u < exp(t_ls - m_ls)) mD = tD;
+            if (dir > 0) mR = tR;
+            else mL = tL;
+            m_ls = new_ls;
+            depth += 1;
+            tL = tR = tD = -1;
+            if (turn) done = true;
+        }
+        if (!done) info.maxdepth_reached = 1;
+        info.depth = depth;
+        lv_valid = 0;
+        tL = tR = tD = -1;
+        return mD;
+    }
+
+    // -------------------------------------------------------- dual averaging
+    NB_HD void da_new(double initial_step) {
+        da_log_step = log(initial_step);
+        da_log_step_adapted = da_log_step;
+        da_hbar = 0.0;
+        da_mu = log(10.0 * initial_step);
+        da_count = 1;
+    }
+    NB_HD void da_advance(double accept_stat) {
+        const double count = (double)da_count;
+        const double w = 1.0 / (count + st().da_t0);
+        da_hbar = (1.0 - w) * da_hbar + w * (st().target_accept - accept_stat);
+        da_log_step = da_mu - da_hbar * sqrt(count) / st().da_gamma;
+        const double mk = pow(count, -st().da_k);
+        da_log_step_adapted = mk * da_log_step + (1.0 - mk) * da_log_step_adapted;
+        da_count += 1;
+    }
+    NB_HD double clamp_step(double s) const {
+        const double m = st().max_step_size;
+        return (m > 0 && s > m) ? m : s;
+    }
+
+    // ------------------------------------------------- initial step-size search
+    // point: slot holding (q, grad, U).  Its momentum is overwritten.
+    NB_HD void step_size_search(int point, uint32_t rng_draw) {
+        if (st().step_size_method == 2) {
+            step_size = st().fixed_step_size;
+            return;
+        }
+        const double keep_sum = acc_sum, keep_sym = acc_sym;
+        const uint32_t keep_count = acc_count;
+        mL = mR = mD = point;
+        tL = tR = tD = -1;
+        lv_valid = 0;
+        init_momentum(point, RNG_STEP_INIT, rng_draw);
+        const int nxt = alloc();
+        step_size = st().initial_step;
+        acc_sum = 0.0;
+        acc_count = 0;
+        int found = 0;
+        int rc = leapfrog(point, nxt, 1);
+        if (rc == 0) {
+            double accept = acc_sum;
+            const int dir = accept > st().target_accept ? 1 : -1;
+            for (int it = 0; it < 100; ++it) {
+                acc_sum = 0.0;
+                acc_count = 0;
+                rc = leapfrog(point, nxt, dir);
+                if (rc != 0) {
+                    step_size = st().initial_step;
+                    found = -1;
+                    break;
+                }
+                accept = acc_sum;
+                if (dir > 0) {
+                    if (accept <= st().target_accept || step_size > 1e5) { found = 1; break; }
+                    step_size *= 2.0;
+                } else {
+                    if (accept >= st().target_accept || step_size < 1e-10) { found = 1; break; }
+                    step_size /= 2.0;
+                }
+            }
+            if (found == 0) {
+                step_size = st().initial_step;
+                found = 1;
+            }
+            if (found == 1) da_new(step_size);
+        }
+        acc_sum = keep_sum;
+        acc_sym = keep_sym;
+        acc_count = keep_count;
+    }
+
+    // --------------------------------------------------- estimator / mass matrix
+    // One fused pass over the dimensions: Welford update of both estimator sets
+    // with (q, grad) of `slot` (if add), then the diagonal refresh from the
+    // (post-switch) foreground set (if update).  fg_after = set that is the
+    // foreground after the optional switch.
+    NB_HD void estimator_pass(int slot, bool add, unsigned long long n0, unsigned long long n1,
+                              bool update, int fg_after, unsigned long long fg_count) {
+        const double* q = vec(slot, VQ);
+        const double* gr = vec(slot, VG);
+        double* w0 = wf;                       // set 0: mean_q, m2_q, mean_g, m2_g
+        double* w1 = wf + 4 * (size_t)Dp;      // set 1
+        const bool use_grad = st().use_grad_based_estimate != 0;
+        for (int i = g.tid; i < D; i += g.size()) {
+            double m2q[2], m2g[2];
+            if (add) {
+                const double x = q[i], y = gr[i];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    double* w = s ? w1 : w0;
+                    const unsigned long long n = s ? n1 : n0;
+                    if (n == 1) {
+                        w[i] = x;
+                        w[Dp + i] = 0.0;
+                        w[2 * Dp + i] = y;
+                        w[3 * Dp + i] = 0.0;
+                        m2q[s] = 0.0;
+                        m2g[s] = 0.0;
+                    } else {
+                        const double inv = 1.0 / (double)n;
+                        double mean = w[i];
+                        double diff = x - mean;
+                        mean += diff * inv;
+                        m2q[s] = w[Dp + i] + diff * (x - mean);
+                        w[i] = mean;
+                        w[Dp + i] = m2q[s];
+                        mean = w[2 * Dp + i];
+                        diff = y - mean;
+                        mean += diff * inv;
+                        m2g[s] = w[3 * Dp + i] + diff * (y - mean);
+                        w[2 * Dp + i] = mean;
+                        w[3 * Dp + i] = m2g[s];
+                    }
+                }
+            } else if (update) {
+                const double* w = fg_after ? w1 : w0;
+                m2q[fg_after] = w[Dp + i];
+                m2g[fg_after] = w[3 * Dp + i];
+            }
+            if (update) {
+                const double a = m2q[fg_after], b = m2g[fg_after];
+                double val = use_grad ? sqrt(a / b) : a / (double)fg_count;
+                if (nb_isfinite(val) && val != 0.0) {
+                    if (val < kVarLower) val = kVarLower;
+                    if (val > kVarUpper) val = kVarUpper;
+                    var[i] = val;
+                }
+            }
+        }
+        g.sync();
+    }
+
+    // GlobalStrategy::adapt, after every draw
+    NB_HD void adapt(unsigned long long t, int dslot, const SampleInfo& info) {
+        last_mean = acc_count ? acc_sum / (double)acc_count : 0.0;
+        last_sym = acc_count ? acc_sym / (double)acc_count : 0.0;
+        last_n_steps = acc_count;
+        const unsigned long long num_tune = st().num_tune;
+        if (t >= num_tune) return;
+        const bool fixed = st().step_size_method == 2;
+        const unsigned long long early_end =
+            (unsigned long long)ceil(st().early_window * (double)num_tune);
+        const unsigned long long sw =
+            (unsigned long long)ceil(st().step_size_window * (double)num_tune);
+        const unsigned long long final_window = sw > num_tune ? 0 : num_tune - sw;
+        if (t < final_window) {
+            const bool is_early = t < early_end;
+            const unsigned long long switch_freq =
+                is_early ? st().early_mass_matrix_switch_freq : st().mass_matrix_switch_freq;
+            const int didx = sh->idx[dslot];
+            const bool is_good = info.diverging ? ((didx < 0 ? -didx : didx) > 4) : (didx != 0);
+            if (is_good) {
+                cnt[0] += 1;
+                cnt[1] += 1;
+            }
+            const unsigned long long n0 = cnt[0], n1 = cnt[1];
+            const int bg = 1 - fg_sel;
+            const bool could_switch = cnt[bg] >= switch_freq;
+            const bool is_late = switch_freq + t > final_window;
+            bool force_update = false;
+            if (could_switch && !is_late) {
+                cnt[fg_sel] = 0;  // the old foreground becomes the empty background
+                fg_sel = bg;
+                force_update = true;
+            }
+            bool did_change = false;
+            bool update = false;
+            if (force_update || (t - last_update >= st().mass_matrix_update_freq))
+                update = cnt[fg_sel] >= 3;
+            if (is_good || update)
+                estimator_pass(dslot, is_good, n0, n1, update, fg_sel, cnt[fg_sel]);
+            did_change = update;
+            if (did_change) last_update = t;
+            if (!fixed) da_advance(is_late ? last_sym : last_mean);
+            if (did_change && has_initial_mm) {
+                has_initial_mm = 0;
+                step_size_search(dslot, (uint32_t)t);
+            } else if (!fixed) {
+                step_size = clamp_step(exp(da_log_step));
+            }
+            return;
+        }
+        if (fixed) return;
+        da_advance(last_sym);
+        if (t == num_tune - 1) step_size = clamp_step(exp(da_log_step_adapted));
+        else step_size = clamp_step(exp(da_log_step));
+    }
+
+    // -------------------------------------------------------------- chain init
+    // Model::init_position + GlobalStrategy::init.  Returns 0 or NB200_E*.
+    NB_HD int init_chain() {
+        const int slot = 0;
+        double* q = vec(slot, VQ);
+        const int tries = P->q0 ? 1 : (st().num_try_init > 0 ? st().num_try_init : 1);
+        bool ok = false;
+        double lp = 0.0;
+        for (int attempt = 0; attempt < tries && !ok; ++attempt) {
+            g.sync();
+            if (P->q0) {
+                const double* src = P->q0 + (size_t)chain_local * D;
+                for (int i = g.tid; i < D; i += g.size()) q[i] = src[i];
+            } else {
+                for (int j = g.tid; 2 * j < D; j += g.size()) {
+                    uint64_t a, b;
+                    rng_u64x2(st().seed, chain_gid, (uint32_t)attempt, RNG_INIT_POS, (uint32_t)j, a, b);
+                    double e0, e1;
+                    if (st().init_kind == 1) {
+                        rng_normal_pair(a, b, e0, e1);
+                    } else {
+                        e0 = st().init_radius * (2.0 * rng_u01(a) - 1.0);
+                        e1 = st().init_radius * (2.0 * rng_u01(b) - 1.0);
+                    }
+                    const int i0 = 2 * j, i1 = 2 * j + 1;
+                    q[i0] = (P->init_mean ? P->init_mean[i0] : 0.0) + e0;
+                    if (i1 < D) q[i1] = (P->init_mean ? P->init_mean[i1] : 0.0) + e1;
+                }
+            }
+            g.sync();
+            bool bad;
+            lp = eval_logp(slot, bad);
+            ok = !bad;
+        }
+        if (!ok) return NB200_EINIT;
+        if (g.tid == 0) {
+            sh->U[slot] = -lp;
+            sh->idx[slot] = 0;
+            sh->K[slot] = 0.0;
+        }
+        g.sync();
+        // mass matrix from |grad| (normalizing_flow.py:1905-1909) and estimator seeds
+        const double* gr = vec(slot, VG);
+        double* w0 = wf;
+        double* w1 = wf + 4 * (size_t)Dp;
+        for (int i = g.tid; i < D; i += g.size()) {
+            double a = fabs(gr[i]);
+            if (a < kVarLower) a = kVarLower;
+            if (a > kVarUpper) a = kVarUpper;
+            double val = 1.0 / a;
+            if (!nb_isfinite(val)) val = 1.0;
+            var[i] = val;
+            const double x = q[i], y = gr[i];
+            w0[i] = x; w0[Dp + i] = 0.0; w0[2 * Dp + i] = y; w0[3 * Dp + i] = 0.0;
+            w1[i] = x; w1[Dp + i] = 0.0; w1[2 * Dp + i] = y; w1[3 * Dp + i] = 0.0;
+        }
+        g.sync();
+        cnt[0] = cnt[1] = 1;
+        fg_sel = 0;
+        has_initial_mm = 1;
+        last_update = 0;
+        total_steps = 0;
+        divergences = 0;
+        da_new(st().initial_step);
+        step_size = st().initial_step;
+        acc_sum = acc_sym = 0.0;
+        acc_count = 0;
+        step_size_search(slot, 0xFFFFFFFFu);
+        return 0;
+    }
+
+    // ---------------------------------------------------------------- run
+    NB_HD void load(const ChainScalars& s) {
+        step_size = s.step_size;
+        da_log_step = s.da_log_step; da_log_step_adapted = s.da_log_step_adapted;
+        da_hbar = s.da_hbar; da_mu = s.da_mu; da_count = s.da_count;
+        cnt[0] = s.cnt[0]; cnt[1] = s.cnt[1]; last_update = s.last_update;
+        total_steps = s.total_steps; divergences = s.divergences;
+        fg_sel = s.fg_sel; has_initial_mm = s.has_initial_mm;
+    }
+    NB_HD void store(ChainScalars& s, unsigned long long next_draw, int cur, int status) const {
+        s.step_size = step_size;
+        s.cur_U = sh->U[cur];
+        s.da_log_step = da_log_step; s.da_log_step_adapted = da_log_step_adapted;
+        s.da_hbar = da_hbar; s.da_mu = da_mu; s.da_count = da_count;
+        s.cnt[0] = cnt[0]; s.cnt[1] = cnt[1]; s.last_update = last_update;
+        s.total_steps = total_steps; s.divergences = divergences;
+        s.latest_n_steps = last_n_steps;
+        s.fg_sel = fg_sel; s.has_initial_mm = has_initial_mm;
+        s.cur_slot = cur;
+        s.draw = next_draw;
+        s.status = status;
+    }
+
+    // Runs the chain from its persisted state until finished, stopped or the
+    // per-launch draw budget is used up.
+    NB_HD void run() {
+        ChainScalars& sc = P->sc[chain_local];
+        int status = sc.status;
+        if (status == 2 || status < 0) return;
+        int cur;
+        unsigned long long t = sc.draw;
+        last_n_steps = 0;
+        if (status == 0) {
+            const int rc = init_chain();
+            g.sync();
+            if (rc != 0) {
+                if (g.tid == 0) store(sc, 0, 0, rc);
+                return;
+            }
+            cur = 0;
+            t = 0;
+        } else {
+            load(sc);
+            cur = sc.cur_slot;
+            if (g.tid == 0) {
+                sh->U[cur] = sc.cur_U;
+                sh->idx[cur] = 0;
+                sh->K[cur] = 0.0;
+            }
+            g.sync();
+        }
+        const unsigned long long n_total = P->n_total, num_tune = st().num_tune;
+        unsigned long long done_here = 0;
+        while (t < n_total) {
+            if (P->stop_flag && *P->stop_flag) break;
+            if (P->max_draws_per_launch && done_here >= P->max_draws_per_launch) break;
+            const double step_used = step_size;
+            const bool keep = st().save_warmup || t >= num_tune;
+            const unsigned long long row = st().save_warmup ? t : t - num_tune;
+            const size_t row_off = ((size_t)chain_local * P->n_rows + row);
+            if (keep && P->mminv) {
+                double* o = P->mminv + row_off * P->sdim;
+                for (int i = g.tid; i < (int)P->sdim; i += g.size()) o[i] = var[i];
+            }
+            SampleInfo info;
+            const int sel = transition(cur, (uint32_t)t, info);
+            total_steps += acc_count;
+            divergences += info.diverging;
+            // scalars of the selected state, captured before adapt() may reuse the slot
+            const double selU = sh->U[sel], selK = sh->K[sel], E0t = E0;
+            const int selIdx = sh->idx[sel];
+            g.sync();
+            adapt(t, sel, info);
+            if (keep) {
+                const double* q = vec(sel, VQ);
+                double* o = P->draws + row_off * P->sdim;
+                for (int i = g.tid; i < (int)P->sdim; i += g.size()) o[i] = q[i];
+                if (P->grads) {
+                    const double* gr = vec(sel, VG);
+                    double* og = P->grads + row_off * P->sdim;
+                    for (int i = g.tid; i < (int)P->sdim; i += g.size()) og[i] = gr[i];
+                }
+                if (g.tid == 0) {
+                    double* s = P->stats + row_off * NB200_NSTAT;
+                    const double U = selU, K = selK;
+                    s[NB200_STAT_DEPTH] = info.depth;
+                    s[NB200_STAT_MAXDEPTH_REACHED] = info.maxdepth_reached;
+                    s[NB200_STAT_INDEX_IN_TRAJECTORY] = (double)selIdx;
+                    s[NB200_STAT_LOGP] = -U;
+                    s[NB200_STAT_ENERGY] = K + U;
+                    s[NB200_STAT_ENERGY_ERROR] = (K + U) - E0t;
+                    s[NB200_STAT_DIVERGING] = info.diverging;
+                    s[NB200_STAT_STEP_SIZE] = step_used;
+                    s[NB200_STAT_STEP_SIZE_BAR] = exp(da_log_step_adapted);
+                    s[NB200_STAT_N_STEPS] = (double)last_n_steps;
+                    s[NB200_STAT_MEAN_TREE_ACCEPT] = last_mean;
+                    s[NB200_STAT_MEAN_TREE_ACCEPT_SYM] = last_sym;
+                    s[NB200_STAT_TUNING] = t < num_tune ? 1.0 : 0.0;
+                    s[NB200_STAT_DRAW] = (double)t;
+                    s[NB200_STAT_CHAIN] = (double)chain_gid;
+                    s[NB200_STAT_RESERVED] = 0.0;
+                }
+            }
+            cur = sel;
+            t += 1;
+            done_here += 1;
+            if (g.tid == 0) {  // progress record, polled by the host on a side stream
+                sc.draw = t;
+                sc.total_steps = total_steps;
+                sc.divergences = divergences;
+                sc.latest_n_steps = last_n_steps;
+                sc.step_size = step_size;
+                sc.status = 1;
+            }
+        }
+        g.sync();
+        if (g.tid == 0) store(sc, t, cur, t >= n_total ? 2 : 1);
+    }
+};
+
+}  // namespace nb200

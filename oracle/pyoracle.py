@@ -1,0 +1,199 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE — see oracle/oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product package nutpie_b200 never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+NSTAT = 16
+STAT_NAMES = [
+    "depth", "maxdepth_reached", "index_in_trajectory", "logp", "energy", "energy_error",
+    "diverging", "step_size", "step_size_bar", "n_steps", "mean_tree_accept",
+    "mean_tree_accept_sym", "tuning", "draw", "chain", "reserved",
+]
+
+
+class Settings(C.Structure):
+    """Mirror of nb200_settings (include/nutpie_b200.h)."""
+
+    _fields_ = [
+        ("seed", C.c_uint64), ("num_tune", C.c_uint64), ("num_draws", C.c_uint64),
+        ("maxdepth", C.c_uint32), ("mindepth", C.c_uint32),
+        ("check_turning", C.c_int32), ("store_gradient", C.c_int32),
+        ("store_mass_matrix", C.c_int32), ("use_grad_based_estimate", C.c_int32),
+        ("max_energy_error", C.c_double),
+        ("initial_step", C.c_double), ("target_accept", C.c_double),
+        ("max_step_size", C.c_double), ("da_k", C.c_double), ("da_t0", C.c_double),
+        ("da_gamma", C.c_double),
+        ("step_size_method", C.c_int32), ("_pad0", C.c_int32),
+        ("fixed_step_size", C.c_double),
+        ("early_window", C.c_double), ("step_size_window", C.c_double),
+        ("mass_matrix_switch_freq", C.c_uint64),
+        ("early_mass_matrix_switch_freq", C.c_uint64),
+        ("mass_matrix_update_freq", C.c_uint64),
+        ("init_kind", C.c_int32), ("num_try_init", C.c_int32),
+        ("init_radius", C.c_double),
+        ("store_dims", C.c_uint64),
+        ("save_warmup", C.c_int32), ("_pad1", C.c_int32),
+    ]
+
+
+def default_settings(**kw) -> Settings:
+    """nuts_rs DiagNutsSettings::default() as recalled in SURVEY.md Appendix A.1."""
+    s = Settings()
+    s.seed = 0
+    s.num_tune, s.num_draws = 400, 1000
+    s.maxdepth, s.mindepth = 10, 0
+    s.check_turning = 1
+    s.store_gradient = 0
+    s.store_mass_matrix = 0
+    s.use_grad_based_estimate = 1
+    s.max_energy_error = 1000.0
+    s.initial_step, s.target_accept = 0.1, 0.8
+    s.max_step_size = float("inf")
+    s.da_k, s.da_t0, s.da_gamma = 0.75, 10.0, 0.05
+    s.step_size_method = 0
+    s.fixed_step_size = 0.1
+    s.early_window, s.step_size_window = 0.3, 0.15
+    s.mass_matrix_switch_freq, s.early_mass_matrix_switch_freq = 80, 10
+    s.mass_matrix_update_freq = 1
+    s.init_kind, s.num_try_init, s.init_radius = 0, 10, 2.0
+    s.store_dims = 0
+    s.save_warmup = 1
+    for k, v in kw.items():
+        if not hasattr(s, k):
+            raise AttributeError(k)
+        setattr(s, k, v)
+    return s
+
+
+class NormalData(C.Structure):
+    _fields_ = [("mu", C.c_double), ("sigma", C.c_double)]
+
+
+class RadonData(C.Structure):
+    _fields_ = [("n_obs", C.c_int32), ("n_county", C.c_int32), ("y", C.c_void_p),
+                ("county", C.c_void_p), ("floor", C.c_void_p)]
+
+
+LOGP_FN = C.CFUNCTYPE(C.c_int, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                      C.POINTER(C.c_double), C.c_void_p)
+
+
+def build(force: bool = False) -> Path:
+    so = _HERE / "liboracle.so"
+    srcs = [_HERE / n for n in ("nuts_oracle.c", "models.c", "oracle.h", "philox.h")]
+    srcs.append(_HERE.parent / "include" / "nutpie_b200.h")
+    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        subprocess.run(["make", "-C", str(_HERE), "liboracle.so"], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return so
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        so = _HERE / "liboracle.so"
+        if not so.exists():
+            build()
+        else:
+            try:
+                build()
+            except Exception:
+                pass  # GPU box without sources newer than the .so: use as is
+        _LIB = C.CDLL(str(so))
+        _LIB.oracle_sample.restype = C.c_int
+        _LIB.oracle_leapfrog.restype = C.c_int
+        _LIB.oracle_is_turning.restype = C.c_int
+    return _LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Model:
+    """A host density in the reference plug-in ABI plus its user_data."""
+
+    def __init__(self, kind: str, dim: int, **kw):
+        L = lib()
+        self.kind, self.dim = kind, int(dim)
+        self._keep = []
+        if kind == "normal":
+            self.fn = L.oracle_logp_normal
+            self.ud = NormalData(float(kw.get("mu", 0.0)), float(kw.get("sigma", 1.0)))
+        elif kind == "funnel":
+            self.fn = L.oracle_logp_funnel
+            self.ud = NormalData(0.0, 1.0)
+        elif kind == "radon":
+            y = np.ascontiguousarray(kw["y"], dtype=np.float64)
+            county = np.ascontiguousarray(kw["county"], dtype=np.int32)
+            floor = np.ascontiguousarray(kw["floor"], dtype=np.uint8)
+            self._keep += [y, county, floor]
+            self.fn = L.oracle_logp_radon
+            self.ud = RadonData(len(y), int(kw["n_county"]), _ptr(y), _ptr(county), _ptr(floor))
+            assert self.dim == 2 * int(kw["n_county"]) + 5
+        else:
+            raise ValueError(kind)
+        self.fn_ptr = C.cast(self.fn, C.c_void_p)
+        self.ud_ptr = C.cast(C.pointer(self.ud), C.c_void_p)
+
+    def logp_grad(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        single = q.ndim == 1
+        q2 = q.reshape(-1, self.dim)
+        g = np.empty_like(q2)
+        lp = np.empty(len(q2))
+        rc = np.empty(len(q2), dtype=np.int32)
+        fn = C.cast(self.fn_ptr, LOGP_FN)
+        for i in range(len(q2)):
+            out = C.c_double()
+            rc[i] = fn(self.dim, q2[i].ctypes.data_as(C.POINTER(C.c_double)),
+                       g[i].ctypes.data_as(C.POINTER(C.c_double)), C.byref(out), self.ud_ptr)
+            lp[i] = out.value
+        if single:
+            return lp[0], g[0], rc[0]
+        return lp, g, rc
+
+
+def sample(model: Model, settings: Settings, n_chains: int, chain_id_offset: int = 0,
+           n_threads: int = 0, q0=None, init_mean=None, z_tape=None):
+    """Run the oracle sampler.  Returns dict(draws, stats, gradients, mass_matrix_inv,
+    total_steps) with the nb200_trace_view layout."""
+    L = lib()
+    n_total = settings.num_tune + settings.num_draws
+    n_rows = n_total if settings.save_warmup else settings.num_draws
+    sdim = settings.store_dims if 0 < settings.store_dims < model.dim else model.dim
+    draws = np.zeros((n_chains, n_rows, sdim))
+    stats = np.zeros((n_chains, n_rows, NSTAT))
+    grads = np.zeros((n_chains, n_rows, sdim)) if settings.store_gradient else None
+    mm = np.zeros((n_chains, n_rows, sdim)) if settings.store_mass_matrix else None
+    if q0 is not None:
+        q0 = np.ascontiguousarray(q0, dtype=np.float64).reshape(n_chains, model.dim)
+    if init_mean is not None:
+        init_mean = np.ascontiguousarray(init_mean, dtype=np.float64).reshape(model.dim)
+    if z_tape is not None:
+        z_tape = np.ascontiguousarray(z_tape, dtype=np.float64).reshape(n_chains, n_total, model.dim)
+    steps = C.c_uint64(0)
+    rc = L.oracle_sample(C.byref(settings), model.fn_ptr, model.ud_ptr, C.c_uint64(model.dim),
+                         C.c_uint64(n_chains), C.c_uint64(chain_id_offset), C.c_int(n_threads),
+                         _ptr(q0), _ptr(init_mean), _ptr(z_tape), _ptr(draws), _ptr(stats),
+                         _ptr(grads), _ptr(mm), C.byref(steps))
+    if rc != 0:
+        raise RuntimeError(f"oracle_sample failed with code {rc}")
+    return dict(draws=draws, stats=stats, gradients=grads, mass_matrix_inv=mm,
+                total_steps=int(steps.value))
+
+
+def stat(stats: np.ndarray, name: str) -> np.ndarray:
+    return stats[..., STAT_NAMES.index(name)]

@@ -1,0 +1,95 @@
+// tests/emul/emul.cpp — TEST INFRASTRUCTURE, never shipped or loaded by the product.
+//
+// Compiles the sampler core (nutpie_b200/csrc/nuts_core.cuh) as plain host C++
+// with a one-thread group, so the iterative tree / slot bookkeeping / adaptation
+// logic of the CUDA engine can be checked against the recursive oracle on a
+// machine without a GPU.  The CUDA build uses the very same header with
+// GroupCuda<W>; only the thread-group policy differs.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../nutpie_b200/csrc/nuts_core.cuh"
+#include "../../nutpie_b200/csrc/radon_layout.hpp"
+
+using namespace nb200;
+
+template <class M>
+static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_t dim,
+                   uint64_t n_chains, uint64_t chain_id_offset, const double* q0,
+                   const double* init_mean, const double* z_tape, double* draws, double* stats,
+                   double* grads, double* mminv, uint64_t* total_steps, int max_per_launch) {
+    KParams<M> P;
+    std::memset(&P, 0, sizeof(P));
+    P.st = *st;
+    P.mdata = md;
+    P.D = (int)dim;
+    P.Dp = (int)((dim + 3) / 4 * 4);
+    P.NS = 3 * ((int)st->maxdepth + 1) + 3;
+    if (P.NS > kMaxSlots) return NB200_EINVAL;
+    P.n_chains = n_chains;
+    P.chain_id_offset = chain_id_offset;
+    P.n_total = st->num_tune + st->num_draws;
+    P.n_rows = st->save_warmup ? P.n_total : st->num_draws;
+    P.sdim = (st->store_dims && st->store_dims < dim) ? st->store_dims : dim;
+    P.max_draws_per_launch = max_per_launch;
+    std::vector<double> pool((size_t)P.NS * 4 * P.Dp), var(P.Dp), wf(8 * (size_t)P.Dp);
+    std::vector<ChainScalars> sc(n_chains);
+    std::memset(sc.data(), 0, sizeof(ChainScalars) * n_chains);
+    P.sc = sc.data();
+    P.draws = draws; P.stats = stats; P.grads = grads; P.mminv = mminv;
+    P.q0 = q0; P.init_mean = init_mean; P.z_tape = z_tape;
+    P.stop_flag = nullptr;
+    std::vector<double> msm(M::smem_doubles(md, 1) + 1);
+    ChainShared sh;
+    uint64_t steps = 0;
+    int err = 0;
+    for (uint64_t c = 0; c < n_chains; ++c) {
+        // the pool is per chain; chains run one after another here, but a chain may
+        // be resumed over several "launches" (max_per_launch) to exercise pause/resume
+        std::fill(pool.begin(), pool.end(), 0.0);
+        for (;;) {
+            ChainCtx<M, GroupSerial> ctx;
+            std::memset((void*)&ctx, 0, sizeof(ctx));
+            ctx.P = &P; ctx.sh = &sh; ctx.msm = msm.data();
+            ctx.D = P.D; ctx.Dp = P.Dp; ctx.NS = P.NS;
+            ctx.chain_local = c;
+            ctx.chain_gid = (uint32_t)(chain_id_offset + c);
+            ctx.pool = pool.data(); ctx.var = var.data(); ctx.wf = wf.data();
+            ctx.run();
+            if (sc[c].status == 2 || sc[c].status < 0) break;
+        }
+        if (sc[c].status < 0) err = sc[c].status;
+        steps += sc[c].total_steps;
+    }
+    if (total_steps) *total_steps = steps;
+    return err;
+}
+
+extern "C" int emul_sample(const nb200_settings* st, const nb200_model_desc* model,
+                           uint64_t n_chains, uint64_t chain_id_offset, const double* q0,
+                           const double* init_mean, const double* z_tape, double* draws,
+                           double* stats, double* grads, double* mminv, uint64_t* total_steps,
+                           int max_per_launch) {
+    switch (model->kind) {
+    case NB200_MODEL_NORMAL: {
+        NormalModel::Data d{model->mu, 1.0 / (model->sigma * model->sigma)};
+        return run_all<NormalModel>(st, d, model->dim, n_chains, chain_id_offset, q0, init_mean,
+                                    z_tape, draws, stats, grads, mminv, total_steps, max_per_launch);
+    }
+    case NB200_MODEL_FUNNEL: {
+        FunnelModel::Data d{0};
+        return run_all<FunnelModel>(st, d, model->dim, n_chains, chain_id_offset, q0, init_mean,
+                                    z_tape, draws, stats, grads, mminv, total_steps, max_per_launch);
+    }
+    case NB200_MODEL_RADON: {
+        RadonLayout L = build_radon_layout(model->n_obs, model->n_county, model->y, model->county,
+                                           model->floor, 1);
+        RadonModel::Data d{L.J, L.N, L.n_steps, L.R, L.packed.data(), L.y.data(),
+                           L.run_base.data(), L.run_start.data()};
+        return run_all<RadonModel>(st, d, model->dim, n_chains, chain_id_offset, q0, init_mean,
+                                   z_tape, draws, stats, grads, mminv, total_steps, max_per_launch);
+    }
+    }
+    return NB200_EINVAL;
+}
