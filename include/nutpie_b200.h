@@ -233,6 +233,9 @@ int nb200_sampler_geometry(nb200_sampler *s, int32_t *threads_per_chain,
  * created afterwards; testing/tuning */
 void nb200_set_threads_per_chain(int32_t t);
 void nb200_set_chains_per_block(int32_t c);
+/* force the number of pool slots kept in shared memory (-1 = auto) */
+void nb200_set_smem_slots(int32_t n);
+int nb200_sampler_smem(nb200_sampler *s, int32_t *smem_slots, int32_t *bytes_per_chain);
 /* limit the draws one kernel launch may advance each chain by (0 = run to the
  * end in one persistent launch); the host relaunches until done */
 int nb200_sampler_set_draws_per_launch(nb200_sampler *s, uint64_t n);

@@ -148,6 +148,10 @@ def load_library() -> C.CDLL:
         L.nb200_set_threads_per_chain.argtypes = [C.c_int32]
         L.nb200_set_chains_per_block.restype = None
         L.nb200_set_chains_per_block.argtypes = [C.c_int32]
+        L.nb200_set_smem_slots.restype = None
+        L.nb200_set_smem_slots.argtypes = [C.c_int32]
+        L.nb200_sampler_smem.restype = C.c_int
+        L.nb200_sampler_smem.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.nb200_host_alloc.restype = C.c_void_p
         L.nb200_host_alloc.argtypes = [C.c_size_t]
         L.nb200_host_free.restype = None
@@ -468,7 +472,7 @@ class PySampler:
 
     def __init__(self, settings: PyNutsSettings, model, *, n_chains=None, chain_id_offset=0,
                  device=0, progress_type=None, init_mean=None, q0=None, z_tape=None,
-                 draws_per_launch=0):
+                 draws_per_launch=0, autostart=True):
         L = load_library()
         self._L = L
         self._settings = settings
@@ -502,7 +506,17 @@ class PySampler:
         self._progress_type = progress_type or ProgressType.none()
         self._progress_thread = None
         self._stop_progress = threading.Event()
-        _check(L.nb200_sampler_start(self._h))
+        self._started = False
+        if autostart:
+            self.start()
+
+    def start(self):
+        """Launch the sampling kernel (non-blocking), like nuts_rs::Sampler::new returning
+        while its workers run (src/wrapper.rs:983-990)."""
+        if self._started:
+            raise ValueError("sampler already started")
+        _check(self._L.nb200_sampler_start(self._h))
+        self._started = True
         self._t_start = time.perf_counter()
         if self._progress_type.callback is not None:
             self._progress_thread = threading.Thread(target=self._progress_loop, daemon=True)
@@ -607,7 +621,10 @@ class PySampler:
     def geometry(self):
         a, b, g = C.c_int32(), C.c_int32(), C.c_int32()
         _check(self._L.nb200_sampler_geometry(self._h, C.byref(a), C.byref(b), C.byref(g)))
-        return dict(threads_per_chain=a.value, block=b.value, grid=g.value)
+        sl, by = C.c_int32(), C.c_int32()
+        _check(self._L.nb200_sampler_smem(self._h, C.byref(sl), C.byref(by)))
+        return dict(threads_per_chain=a.value, block=b.value, grid=g.value,
+                    smem_slots=sl.value, smem_bytes_per_chain=by.value)
 
     def device_buffers(self):
         d, s = C.c_void_p(), C.c_void_p()
@@ -627,6 +644,12 @@ class PySampler:
             self.close()
         except Exception:
             pass
+
+
+def PySamplerDeferred(*args, **kwargs):
+    """A PySampler whose device state is allocated and initialised but whose kernel is
+    only launched by .start() — lets a benchmark time the resident-input path."""
+    return PySampler(*args, autostart=False, **kwargs)
 
 
 # --------------------------------------------------------------------------
@@ -666,6 +689,10 @@ def set_threads_per_chain(t: int):
 
 def set_chains_per_block(c: int):
     load_library().nb200_set_chains_per_block(int(c))
+
+
+def set_smem_slots(n: int):
+    load_library().nb200_set_smem_slots(int(n))
 
 
 def device_count() -> int:

@@ -114,28 +114,38 @@ struct RadonModel {
         {
             int cur = -1, k = nb_ldg(d.run_base + grp.tid);
             double sE = 0.0, sF = 0.0, a = 0.0, ab = 0.0;
-            for (int j = 0; j < d.n_steps; ++j) {
-                const int pk = nb_ldg(d.packed + (size_t)j * T + grp.tid);
-                if (pk < 0) break;
-                const double yv = nb_ldg(d.y + (size_t)j * T + grp.tid);
-                const int c = pk >> 1;
-                if (c != cur) {
-                    if (cur >= 0) {
-                        runE[k] = sE;
-                        runF[k] = sF;
-                        ++k;
-                        sE = 0.0;
-                        sF = 0.0;
-                    }
-                    cur = c;
-                    a = effA[c];
-                    ab = a + effB[c];
+            // n_steps is padded to a multiple of 4 with packed = -1: four independent
+            // loads are issued before the dependent run-length arithmetic
+            for (int j0 = 0; j0 < d.n_steps; j0 += 4) {
+                int pk[4];
+                double yv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    pk[u] = nb_ldg(d.packed + (size_t)(j0 + u) * T + grp.tid);
+                    yv[u] = nb_ldg(d.y + (size_t)(j0 + u) * T + grp.tid);
                 }
-                const bool f = pk & 1;
-                const double r = yv - (f ? ab : a);
-                ss += r * r;
-                sE += r;
-                if (f) sF += r;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (pk[u] < 0) continue;
+                    const int c = pk[u] >> 1;
+                    if (c != cur) {
+                        if (cur >= 0) {
+                            runE[k] = sE;
+                            runF[k] = sF;
+                            ++k;
+                            sE = 0.0;
+                            sF = 0.0;
+                        }
+                        cur = c;
+                        a = effA[c];
+                        ab = a + effB[c];
+                    }
+                    const bool f = pk[u] & 1;
+                    const double r = yv[u] - (f ? ab : a);
+                    ss += r * r;
+                    sE += r;
+                    if (f) sF += r;
+                }
             }
             if (cur >= 0) {
                 runE[k] = sE;

@@ -22,6 +22,11 @@
 
 using namespace nb200;
 
+// the Python/Rust bindings mirror these layouts field by field
+static_assert(sizeof(nb200_settings) == 192, "nb200_settings ABI layout changed");
+static_assert(sizeof(nb200_model_desc) == 64, "nb200_model_desc ABI layout changed");
+static_assert(sizeof(nb200_progress) == 56, "nb200_progress ABI layout changed");
+
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -45,16 +50,23 @@ static int fail(int code, const std::string& msg) {
 
 static std::atomic<int> g_threads_per_chain{0};
 static std::atomic<int> g_chains_per_block{0};
+static std::atomic<int> g_smem_slots{-1};
 
 // ------------------------------------------------------------------ kernels
 static inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
+// fixed part of a chain's shared memory (scalars, model scratch, reduction scratch)
 template <class M, int W>
-static size_t chain_smem_bytes(const typename M::Data& md) {
+static size_t chain_smem_fixed(const typename M::Data& md) {
     size_t b = align16(sizeof(ChainShared));
     b += align16(sizeof(double) * (size_t)M::smem_doubles(md, 32 * W));
     if (W > 1) b += align16(sizeof(double) * W * GroupCuda<W>::kMaxRed);
     return b;
+}
+// + working mass matrix + hot tier of the pool
+static size_t chain_smem_total(size_t fixed, int Dp, int var_in_smem, int smem_slots) {
+    return fixed + (var_in_smem ? align16(sizeof(double) * Dp) : 0) +
+           align16(sizeof(double) * 4 * (size_t)Dp * smem_slots);
 }
 
 template <class M, int W>
@@ -67,13 +79,19 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>>& ctx, const 
     ctx.msm = reinterpret_cast<double*>(smem_chain + off);
     off += (sizeof(double) * (size_t)M::smem_doubles(P.mdata, 32 * W) + 15) & ~size_t(15);
     ctx.g.red = reinterpret_cast<double*>(smem_chain + off);
+    if (W > 1) off += (sizeof(double) * W * GroupCuda<W>::kMaxRed + 15) & ~size_t(15);
+    double* svar = reinterpret_cast<double*>(smem_chain + off);
+    if (P.var_in_smem) off += (sizeof(double) * P.Dp + 15) & ~size_t(15);
+    ctx.spool = reinterpret_cast<double*>(smem_chain + off);
+    ctx.smem_slots = P.smem_slots;
     ctx.D = P.D;
     ctx.Dp = P.Dp;
     ctx.NS = P.NS;
     ctx.chain_local = chain;
     ctx.chain_gid = (uint32_t)(P.chain_id_offset + chain);
     ctx.pool = P.pool + (size_t)chain * P.NS * 4 * (size_t)P.Dp;
-    ctx.var = P.var + (size_t)chain * P.Dp;
+    ctx.varg = P.var + (size_t)chain * P.Dp;
+    ctx.var = P.var_in_smem ? svar : ctx.varg;
     ctx.wf = P.welford + (size_t)chain * 8 * (size_t)P.Dp;
     ctx.mL = ctx.mR = ctx.mD = ctx.tL = ctx.tR = ctx.tD = -1;
     ctx.lv_valid = 0;
@@ -163,7 +181,7 @@ struct nb200_sampler {
     double *h_draws = nullptr, *h_stats = nullptr, *h_grads = nullptr, *h_mm = nullptr;
     std::vector<uint64_t> rows_filled;
     uint64_t n_rows = 0, sdim = 0, n_total = 0;
-    int Dp = 0, NS = 0;
+    int Dp = 0, NS = 0, smem_slots = 0;
     std::vector<void*> model_allocs;
     virtual int launch() = 0;
     int sampler_error = 0;
@@ -178,6 +196,8 @@ struct SamplerImpl : nb200_sampler {
         cudaError_t e = cudaFuncSetAttribute(nuts_kernel<M, W_>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(NB200_ECUDA, cudaGetErrorString(e));
+        cudaFuncSetAttribute(nuts_kernel<M, W_>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
         nuts_kernel<M, W_><<<grid, block, smem, stream>>>(P, smem_per_chain);
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(NB200_ECUDA, cudaGetErrorString(e));
@@ -200,12 +220,12 @@ struct SamplerImpl : nb200_sampler {
 template <class M>
 static size_t smem_for(int W, const typename M::Data& md) {
     switch (W) {
-    case 1: return chain_smem_bytes<M, 1>(md);
-    case 2: return chain_smem_bytes<M, 2>(md);
-    case 4: return chain_smem_bytes<M, 4>(md);
-    case 8: return chain_smem_bytes<M, 8>(md);
-    case 16: return chain_smem_bytes<M, 16>(md);
-    default: return chain_smem_bytes<M, 32>(md);
+    case 1: return chain_smem_fixed<M, 1>(md);
+    case 2: return chain_smem_fixed<M, 2>(md);
+    case 4: return chain_smem_fixed<M, 4>(md);
+    case 8: return chain_smem_fixed<M, 8>(md);
+    case 16: return chain_smem_fixed<M, 16>(md);
+    default: return chain_smem_fixed<M, 32>(md);
     }
 }
 
@@ -313,21 +333,45 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     std::memset(&P, 0, sizeof(P));
     P.st = *st;
     if (build_model_data(*m, 32 * s->W, P.mdata, s->model_allocs) != 0) return bail();
-    s->smem_per_chain = smem_for<M>(s->W, P.mdata);
+    const size_t fixed = smem_for<M>(s->W, P.mdata);
     if (s->W == 1) {
         int c = g_chains_per_block.load();
         if (c <= 0) {
             c = 1;
             while (c < 8 && (n_chains + c - 1) / c > 148ull * 24) c *= 2;
         }
-        while (c > 1 && s->smem_per_chain * c > 200 * 1024) c /= 2;
         s->cpb = c;
     } else {
         s->cpb = 1;
     }
-    if (s->smem_per_chain * s->cpb > 227 * 1024) {
-        fail(NB200_EINVAL, "model needs more shared memory per chain than an SM has");
-        return bail();
+    // Shared-memory budget per chain: the SM's 227 KB divided by the chains that
+    // will be co-resident on it (chains spread evenly over the 148 SMs).
+    {
+        const size_t kSmemSM = 227 * 1024, kSlack = 1024;  // 1 KB/CTA reserved by the driver
+        uint64_t per_sm = (n_chains + 147) / 148;
+        const uint64_t max_res = (uint64_t)(2048 / (32 * s->W));  // thread limit per SM
+        if (per_sm > max_res) per_sm = max_res;
+        if (per_sm > 32ull * s->cpb) per_sm = 32ull * s->cpb;     // CTA limit per SM
+        if (per_sm < 1) per_sm = 1;
+        const uint64_t ctas = (per_sm + s->cpb - 1) / s->cpb;
+        size_t budget = (kSmemSM - ctas * kSlack) / (ctas * s->cpb);
+        const size_t slot_b = align16(sizeof(double) * 4 * (size_t)s->Dp);
+        const size_t var_b = align16(sizeof(double) * (size_t)s->Dp);
+        int slots = 0, var_in = 0;
+        if (budget > fixed + var_b) {
+            var_in = 1;
+            slots = (int)((budget - fixed - var_b) / slot_b);
+            if (slots > s->NS) slots = s->NS;
+        }
+        const int forced = g_smem_slots.load();
+        if (forced >= 0) {
+            slots = forced > s->NS ? s->NS : forced;
+            var_in = (fixed + var_b + slots * slot_b) <= kSmemSM - kSlack;
+        }
+        P.smem_slots = slots;
+        s->smem_slots = slots;
+        P.var_in_smem = var_in;
+        s->smem_per_chain = chain_smem_total(fixed, s->Dp, var_in, slots);
     }
     s->block = 32 * s->W * s->cpb;
     s->grid = (int)((n_chains + s->cpb - 1) / s->cpb);
@@ -403,6 +447,7 @@ int nb200_device_count(void) {
 }
 void nb200_set_threads_per_chain(int32_t t) { g_threads_per_chain.store(t); }
 void nb200_set_chains_per_block(int32_t c) { g_chains_per_block.store(c); }
+void nb200_set_smem_slots(int32_t n) { g_smem_slots.store(n); }
 
 void nb200_settings_default(nb200_settings* s) {
     std::memset(s, 0, sizeof(*s));
@@ -770,6 +815,13 @@ int nb200_sampler_geometry(nb200_sampler* s, int32_t* tpc, int32_t* block, int32
     if (tpc) *tpc = 32 * s->W;
     if (block) *block = s->block;
     if (grid) *grid = s->grid;
+    return 0;
+}
+
+int nb200_sampler_smem(nb200_sampler* s, int32_t* smem_slots, int32_t* bytes_per_chain) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    if (smem_slots) *smem_slots = s->smem_slots;
+    if (bytes_per_chain) *bytes_per_chain = (int32_t)s->smem_per_chain;
     return 0;
 }
 

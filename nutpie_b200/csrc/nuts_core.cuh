@@ -67,6 +67,8 @@ struct KParams {
     nb200_settings st;
     typename M::Data mdata;
     int D, Dp, NS;
+    int smem_slots;    // pool slots 0..smem_slots-1 live in shared memory (hot tier)
+    int var_in_smem;   // working copy of the mass matrix in shared memory
     unsigned long long n_chains, chain_id_offset;
     unsigned long long n_rows, sdim, n_total;
     unsigned long long max_draws_per_launch;  // 0 = run to the end
@@ -106,6 +108,9 @@ struct ChainCtx {
     unsigned long long chain_local;
     uint32_t chain_gid;
     double *pool, *var, *wf;
+    double* spool;     // shared-memory tier of the pool (slots < smem_slots)
+    double* varg;      // persistent (global) copy of the mass matrix; var may alias it
+    int smem_slots;
     // hamiltonian
     double step_size, E0;
     // collectors of the running transition (AcceptanceRateCollector)
@@ -118,12 +123,19 @@ struct ChainCtx {
     // strategy state
     double da_log_step, da_log_step_adapted, da_hbar, da_mu;
     unsigned long long da_count;
-    unsigned long long cnt[2], last_update, total_steps, divergences;
+    unsigned long long cnt0, cnt1, last_update, total_steps, divergences;
     int fg_sel, has_initial_mm;
     double last_mean, last_sym;
     uint32_t last_n_steps;
 
+    // Slots below smem_slots are the hot tier in shared memory: alloc() hands out
+    // the lowest free slot, so leaves and low tree levels stay on chip; deeper
+    // levels (touched every 2^k leapfrogs) spill to the HBM/L2 tier.
     NB_HD double* vec(int slot, int comp) const {
+        if (slot < smem_slots) return spool + ((size_t)slot * 4 + comp) * (size_t)Dp;
+        return pool + ((size_t)slot * 4 + comp) * (size_t)Dp;
+    }
+    NB_HD double* gvec(int slot, int comp) const {
         return pool + ((size_t)slot * 4 + comp) * (size_t)Dp;
     }
     NB_HD const nb200_settings& st() const { return P->st; }
@@ -533,48 +545,53 @@ struct ChainCtx {
         double* w1 = wf + 4 * (size_t)Dp;      // set 1
         const bool use_grad = st().use_grad_based_estimate != 0;
         for (int i = g.tid; i < D; i += g.size()) {
-            double m2q[2], m2g[2];
+            double fq = 0.0, fg = 0.0;  // m2 of draws / grads in the (post-switch) foreground set
             if (add) {
                 const double x = q[i], y = gr[i];
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     double* w = s ? w1 : w0;
                     const unsigned long long n = s ? n1 : n0;
+                    double a, b;
                     if (n == 1) {
                         w[i] = x;
                         w[Dp + i] = 0.0;
                         w[2 * Dp + i] = y;
                         w[3 * Dp + i] = 0.0;
-                        m2q[s] = 0.0;
-                        m2g[s] = 0.0;
+                        a = 0.0;
+                        b = 0.0;
                     } else {
                         const double inv = 1.0 / (double)n;
                         double mean = w[i];
                         double diff = x - mean;
                         mean += diff * inv;
-                        m2q[s] = w[Dp + i] + diff * (x - mean);
+                        a = w[Dp + i] + diff * (x - mean);
                         w[i] = mean;
-                        w[Dp + i] = m2q[s];
+                        w[Dp + i] = a;
                         mean = w[2 * Dp + i];
                         diff = y - mean;
                         mean += diff * inv;
-                        m2g[s] = w[3 * Dp + i] + diff * (y - mean);
+                        b = w[3 * Dp + i] + diff * (y - mean);
                         w[2 * Dp + i] = mean;
-                        w[3 * Dp + i] = m2g[s];
+                        w[3 * Dp + i] = b;
+                    }
+                    if (s == fg_after) {
+                        fq = a;
+                        fg = b;
                     }
                 }
             } else if (update) {
                 const double* w = fg_after ? w1 : w0;
-                m2q[fg_after] = w[Dp + i];
-                m2g[fg_after] = w[3 * Dp + i];
+                fq = w[Dp + i];
+                fg = w[3 * Dp + i];
             }
             if (update) {
-                const double a = m2q[fg_after], b = m2g[fg_after];
-                double val = use_grad ? sqrt(a / b) : a / (double)fg_count;
+                double val = use_grad ? sqrt(fq / fg) : fq / (double)fg_count;
                 if (nb_isfinite(val) && val != 0.0) {
                     if (val < kVarLower) val = kVarLower;
                     if (val > kVarUpper) val = kVarUpper;
                     var[i] = val;
+                    if (varg != var) varg[i] = val;
                 }
             }
         }
@@ -601,25 +618,26 @@ struct ChainCtx {
             const int didx = sh->idx[dslot];
             const bool is_good = info.diverging ? ((didx < 0 ? -didx : didx) > 4) : (didx != 0);
             if (is_good) {
-                cnt[0] += 1;
-                cnt[1] += 1;
+                cnt0 += 1;
+                cnt1 += 1;
             }
-            const unsigned long long n0 = cnt[0], n1 = cnt[1];
+            const unsigned long long n0 = cnt0, n1 = cnt1;
             const int bg = 1 - fg_sel;
-            const bool could_switch = cnt[bg] >= switch_freq;
+            const bool could_switch = (bg ? cnt1 : cnt0) >= switch_freq;
             const bool is_late = switch_freq + t > final_window;
             bool force_update = false;
             if (could_switch && !is_late) {
-                cnt[fg_sel] = 0;  // the old foreground becomes the empty background
+                if (fg_sel) cnt1 = 0;  // the old foreground becomes the empty background
+                else cnt0 = 0;
                 fg_sel = bg;
                 force_update = true;
             }
             bool did_change = false;
             bool update = false;
             if (force_update || (t - last_update >= st().mass_matrix_update_freq))
-                update = cnt[fg_sel] >= 3;
+                update = (fg_sel ? cnt1 : cnt0) >= 3;
             if (is_good || update)
-                estimator_pass(dslot, is_good, n0, n1, update, fg_sel, cnt[fg_sel]);
+                estimator_pass(dslot, is_good, n0, n1, update, fg_sel, fg_sel ? cnt1 : cnt0);
             did_change = update;
             if (did_change) last_update = t;
             if (!fixed) da_advance(is_late ? last_sym : last_mean);
@@ -689,12 +707,13 @@ struct ChainCtx {
             double val = 1.0 / a;
             if (!nb_isfinite(val)) val = 1.0;
             var[i] = val;
+            if (varg != var) varg[i] = val;
             const double x = q[i], y = gr[i];
             w0[i] = x; w0[Dp + i] = 0.0; w0[2 * Dp + i] = y; w0[3 * Dp + i] = 0.0;
             w1[i] = x; w1[Dp + i] = 0.0; w1[2 * Dp + i] = y; w1[3 * Dp + i] = 0.0;
         }
         g.sync();
-        cnt[0] = cnt[1] = 1;
+        cnt0 = cnt1 = 1;
         fg_sel = 0;
         has_initial_mm = 1;
         last_update = 0;
@@ -713,7 +732,7 @@ struct ChainCtx {
         step_size = s.step_size;
         da_log_step = s.da_log_step; da_log_step_adapted = s.da_log_step_adapted;
         da_hbar = s.da_hbar; da_mu = s.da_mu; da_count = s.da_count;
-        cnt[0] = s.cnt[0]; cnt[1] = s.cnt[1]; last_update = s.last_update;
+        cnt0 = s.cnt[0]; cnt1 = s.cnt[1]; last_update = s.last_update;
         total_steps = s.total_steps; divergences = s.divergences;
         fg_sel = s.fg_sel; has_initial_mm = s.has_initial_mm;
     }
@@ -722,7 +741,7 @@ struct ChainCtx {
         s.cur_U = sh->U[cur];
         s.da_log_step = da_log_step; s.da_log_step_adapted = da_log_step_adapted;
         s.da_hbar = da_hbar; s.da_mu = da_mu; s.da_count = da_count;
-        s.cnt[0] = cnt[0]; s.cnt[1] = cnt[1]; s.last_update = last_update;
+        s.cnt[0] = cnt0; s.cnt[1] = cnt1; s.last_update = last_update;
         s.total_steps = total_steps; s.divergences = divergences;
         s.latest_n_steps = last_n_steps;
         s.fg_sel = fg_sel; s.has_initial_mm = has_initial_mm;
@@ -752,6 +771,16 @@ struct ChainCtx {
         } else {
             load(sc);
             cur = sc.cur_slot;
+            if (varg != var)
+                for (int i = g.tid; i < D; i += g.size()) var[i] = varg[i];
+            if (cur < smem_slots) {  // the current point was parked in the HBM tier
+                const double *gq = gvec(cur, VQ), *gg = gvec(cur, VG);
+                double *q = vec(cur, VQ), *gr = vec(cur, VG);
+                for (int i = g.tid; i < D; i += g.size()) {
+                    q[i] = gq[i];
+                    gr[i] = gg[i];
+                }
+            }
             if (g.tid == 0) {
                 sh->U[cur] = sc.cur_U;
                 sh->idx[cur] = 0;
@@ -824,6 +853,14 @@ struct ChainCtx {
             }
         }
         g.sync();
+        if (cur < smem_slots && t < n_total) {  // park the current point for a later resume
+            double *gq = gvec(cur, VQ), *gg = gvec(cur, VG);
+            const double *q = vec(cur, VQ), *gr = vec(cur, VG);
+            for (int i = g.tid; i < D; i += g.size()) {
+                gq[i] = q[i];
+                gg[i] = gr[i];
+            }
+        }
         if (g.tid == 0) store(sc, t, cur, t >= n_total ? 2 : 1);
     }
 };

@@ -32,7 +32,7 @@ inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
     std::stable_sort(order.begin(), order.end(),
                      [&](int a, int b) { return county[a] < county[b]; });
     const int per = (n_obs + T - 1) / T;  // observations per thread
-    L.n_steps = per > 0 ? per : 1;
+    L.n_steps = ((per > 0 ? per : 1) + 3) / 4 * 4;  // padded: the device loop is unrolled by 4
     L.packed.assign((size_t)L.n_steps * T, -1);
     L.y.assign((size_t)L.n_steps * T, 0.0);
     L.run_base.assign(T, 0);

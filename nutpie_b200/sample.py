@@ -1,0 +1,284 @@
+"""`nutpie.sample` for the B200 engine.
+
+Mirrors python/nutpie/sample.py (reference): `sample()` (:823-1102) with the
+same keyword surface, `_BackgroundSampler` (:481-725) with wait / pause /
+resume / abort / cancel / inspect, and the trace assembly of `_arrow_to_arviz`
+(:62-164) — except that the trace arrives as two dense arrays for ALL chains
+([chain, draw, dim] draws and [chain, draw, stat] statistics, one D2H copy each)
+instead of one Arrow RecordBatch pair per chain, so posterior / sample_stats
+groups are built by slicing, not by per-chain padding loops.  `arviz` is not
+installed in the build image; when it is importable the result is converted
+with `arviz.from_dict`, otherwise a light `Trace` container with the same
+groups is returned.
+"""
+from __future__ import annotations
+
+import json
+import os
+import warnings
+from dataclasses import dataclass, field
+from typing import Any, Literal
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass
+class Trace:
+    """Plain stand-in for arviz.InferenceData: groups of {name: array[chain, draw, ...]}."""
+
+    posterior: dict = field(default_factory=dict)
+    sample_stats: dict = field(default_factory=dict)
+    warmup_posterior: dict = field(default_factory=dict)
+    warmup_sample_stats: dict = field(default_factory=dict)
+    unconstrained_posterior: dict = field(default_factory=dict)
+    dims: dict = field(default_factory=dict)
+    coords: dict = field(default_factory=dict)
+    attrs: dict = field(default_factory=dict)
+
+    def groups(self):
+        return [g for g in ("posterior", "sample_stats", "warmup_posterior", "warmup_sample_stats",
+                            "unconstrained_posterior") if getattr(self, g)]
+
+
+_STAT_EXPORT = ["depth", "maxdepth_reached", "index_in_trajectory", "logp", "energy",
+                "energy_error", "diverging", "step_size", "step_size_bar", "n_steps",
+                "mean_tree_accept", "mean_tree_accept_sym"]
+
+
+def _trace_to_groups(trace: _lib.PyTrace, compiled_model, settings, save_warmup, var_names=None,
+                     store_unconstrained=False):
+    """The job of _arrow_to_arviz (sample.py:62-164) on dense arrays."""
+    num_tune = settings.num_tune if save_warmup else 0
+    rows = trace.rows_filled.astype(np.int64)
+    n_rows = int(rows.min()) if len(rows) else 0  # equal for finished runs
+    draws = trace.draws[:, :n_rows]
+    n_tune_rows = min(num_tune, n_rows)
+    full = draws.shape[-1] == compiled_model.n_dim
+    values = compiled_model._expand(draws) if full else {"unconstrained_draw": draws}
+    if var_names is not None:
+        values = {k: v for k, v in values.items() if k in var_names}
+    out = Trace(dims={k: list(v) for k, v in compiled_model.dims.items()},
+                coords=dict(compiled_model.coords))
+    for name, arr in values.items():
+        out.warmup_posterior[name] = arr[:, :n_tune_rows]
+        out.posterior[name] = arr[:, n_tune_rows:]
+    for name in _STAT_EXPORT:
+        a = trace.stat(name)[:, :n_rows]
+        out.warmup_sample_stats[name] = a[:, :n_tune_rows]
+        out.sample_stats[name] = a[:, n_tune_rows:]
+    for name, arr in (("gradient", trace.gradients), ("mass_matrix_inv", trace.mass_matrix_inv)):
+        if arr is not None:
+            out.warmup_sample_stats[name] = arr[:, :n_tune_rows]
+            out.sample_stats[name] = arr[:, n_tune_rows:n_rows]
+            out.dims[name] = ["unconstrained_parameter"]
+    if store_unconstrained and full:
+        out.sample_stats["unconstrained_draw"] = draws[:, n_tune_rows:]
+        out.warmup_sample_stats["unconstrained_draw"] = draws[:, :n_tune_rows]
+        out.dims["unconstrained_draw"] = ["unconstrained_parameter"]
+    if not save_warmup:
+        out.warmup_posterior, out.warmup_sample_stats = {}, {}
+    out.attrs = {"inference_library": "nutpie_b200", "_version": _lib.__version__,
+                 "_settings": json.dumps(settings.as_dict())}  # sample.py:666-672
+    return out
+
+
+def _maybe_arviz(tr: Trace):
+    try:
+        import arviz  # noqa: F401
+    except Exception:
+        return tr
+    import arviz
+
+    kwargs = dict(dims=tr.dims, coords=tr.coords)
+    groups = {"posterior": tr.posterior, "sample_stats": tr.sample_stats}
+    if tr.warmup_posterior:
+        groups["warmup_posterior"] = tr.warmup_posterior
+        groups["warmup_sample_stats"] = tr.warmup_sample_stats
+    try:
+        return arviz.from_dict(groups, **kwargs)  # arviz >= 1.0
+    except TypeError:
+        return arviz.from_dict(**groups, **kwargs)
+
+
+class _BackgroundSampler:
+    """sample.py:481-725 — owns the running PySampler and turns its trace into a result."""
+
+    def __init__(self, compiled_model, settings, init_mean, cores, *, progress_bar=True,
+                 progress_callback=None, save_warmup=True, return_raw_trace=False,
+                 progress_rate=100, var_names=None, store_unconstrained=False, device=0,
+                 chain_id_offset=0, trace_buffers=None, **sampler_kw):
+        self._settings = settings
+        self._compiled_model = compiled_model
+        self._save_warmup = save_warmup
+        self._return_raw_trace = return_raw_trace
+        self._var_names = var_names
+        self._store_unconstrained = store_unconstrained
+        self._trace_buffers = trace_buffers
+        settings._c.save_warmup = 1 if save_warmup else 0
+        if progress_callback is not None:
+            progress_type = _lib.ProgressType("callback", progress_rate, progress_callback)
+        else:
+            progress_type = _lib.ProgressType.none()
+        self._sampler = compiled_model._make_sampler(
+            settings, init_mean, cores, progress_type, device=device,
+            chain_id_offset=chain_id_offset, **sampler_kw)
+        self._html = None
+
+    def wait(self, *, timeout=None):
+        """Wait until sampling is finished and return the trace (sample.py:596-608).
+        Raises TimeoutError if `timeout` seconds pass first."""
+        self._sampler.wait(timeout)
+        results = self._sampler.take_results(self._trace_buffers)
+        return self._extract(results)
+
+    def inspect(self):
+        """Snapshot of the draws so far, sampling continues (sample.py:688-691)."""
+        results = self._sampler.inspect()
+        return self._extract(results)
+
+    def _extract(self, results: _lib.PyTrace):
+        if self._return_raw_trace:
+            return results
+        tr = _trace_to_groups(results, self._compiled_model, self._settings, self._save_warmup,
+                              self._var_names, self._store_unconstrained)
+        return _maybe_arviz(tr)
+
+    def pause(self):
+        self._sampler.pause()
+
+    def resume(self):
+        self._sampler.resume()
+
+    @property
+    def is_finished(self):
+        return self._sampler.is_finished()
+
+    def abort(self):
+        """Stop sampling and return the partial trace (sample.py:699-707)."""
+        self._sampler.abort()
+        return self._extract(self._sampler.inspect())
+
+    def cancel(self):
+        """Stop sampling and discard progress (sample.py:709-715)."""
+        self._sampler.abort()
+        self._sampler.close()
+
+    def kernel_ms(self):
+        return self._sampler.kernel_ms()
+
+    def close(self):
+        self._sampler.close()
+
+    def __del__(self):  # sample.py:717-721
+        try:
+            self._sampler.close()
+        except Exception:
+            pass
+
+
+def sample(
+    compiled_model,
+    *,
+    draws: int | None = None,
+    tune: int | None = None,
+    chains: int | None = None,
+    cores: int | None = None,
+    seed: int | None = None,
+    save_warmup: bool = True,
+    progress_bar: bool = True,
+    sampler: Literal["nuts", "mclmc"] = "nuts",
+    adaptation: Literal["diag", "draw_diag", "low_rank", "flow"] = "diag",
+    init_mean: np.ndarray | None = None,
+    return_raw_trace: bool = False,
+    blocking: bool = True,
+    progress_callback: Any | None = None,
+    progress_template: str | None = None,
+    progress_style: str | None = None,
+    progress_rate: int = 100,
+    zarr_store=None,
+    store_unconstrained: bool = False,
+    var_names=None,
+    device: int = 0,
+    chain_id_offset: int = 0,
+    trace_buffers=None,
+    **kwargs,
+):
+    """Sample the posterior of a compiled device model on a B200.
+
+    Same keyword surface as `nutpie.sample` (python/nutpie/sample.py:823-1102);
+    `cores` is accepted and ignored (chains map to warps/CTAs, not host threads).
+    Extra keywords: `device` (CUDA device index), `chain_id_offset` (global id
+    of this process's first chain when a run is sharded over GPUs),
+    `trace_buffers` (dict(draws=, stats=) of preallocated — ideally pinned —
+    host arrays to receive the trace)."""
+    if zarr_store is not None:
+        raise NotImplementedError("zarr_store is not supported by the B200 engine")
+    _use_grad_based = None
+    for _old, _new in (("low_rank_modified_mass_matrix", "low_rank"), ("transform_adapt", "flow")):
+        if _old in kwargs:
+            if kwargs.pop(_old):
+                warnings.warn(f"`{_old}` is deprecated. Use `adaptation='{_new}'` instead.",
+                              FutureWarning, stacklevel=2)
+                if adaptation == "diag":
+                    adaptation = _new
+                else:
+                    raise ValueError(f"`{_old}` is deprecated and cannot be combined with the "
+                                     "`adaptation` argument.")
+    if "use_grad_based_mass_matrix" in kwargs:
+        _use_grad_based = kwargs.pop("use_grad_based_mass_matrix")
+        warnings.warn("`use_grad_based_mass_matrix` is deprecated. Use `adaptation='draw_diag'` "
+                      "instead of `use_grad_based_mass_matrix=False`.", FutureWarning, stacklevel=2)
+
+    if sampler == "nuts":
+        if adaptation == "low_rank":
+            settings = _lib.PyNutsSettings.LowRank(seed)
+        elif adaptation == "flow":
+            settings = _lib.PyNutsSettings.Flow(seed)
+        elif adaptation in ("diag", "draw_diag"):
+            settings = _lib.PyNutsSettings.Diag(seed)
+            if adaptation == "draw_diag" or _use_grad_based is False:
+                settings.use_grad_based_mass_matrix = False
+        else:
+            raise ValueError(f"Unknown adaptation strategy '{adaptation}'. "
+                             "Expected one of: 'diag', 'draw_diag', 'low_rank', 'flow'.")
+    elif sampler == "mclmc":
+        settings = _lib.PyMclmcSettings.Diag(seed)
+    else:
+        raise ValueError(f"Unknown sampler '{sampler}'. Expected one of: 'nuts', 'mclmc'.")
+
+    sampler_kw = {}
+    for k in ("q0", "z_tape", "draws_per_launch"):
+        if k in kwargs:
+            sampler_kw[k] = kwargs.pop(k)
+    updates = dict(kwargs)
+    if tune is not None:
+        updates["num_tune"] = tune
+    if draws is not None:
+        updates["num_draws"] = draws
+    if chains is not None:
+        updates["num_chains"] = chains
+    settings.update(updates)
+    if store_unconstrained:
+        settings.store_unconstrained = True
+    if init_mean is None:
+        init_mean = np.zeros(compiled_model.n_dim)
+
+    bg = _BackgroundSampler(
+        compiled_model, settings, init_mean, cores, progress_bar=progress_bar,
+        progress_callback=progress_callback, save_warmup=save_warmup,
+        return_raw_trace=return_raw_trace, progress_rate=progress_rate, var_names=var_names,
+        store_unconstrained=store_unconstrained, device=device, chain_id_offset=chain_id_offset,
+        trace_buffers=trace_buffers, **sampler_kw)
+    if not blocking:
+        return bg
+    try:
+        result = bg.wait()
+    except KeyboardInterrupt:
+        result = bg.abort()
+    except BaseException:
+        bg.cancel()
+        raise
+    bg.close()
+    return result

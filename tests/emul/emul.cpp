@@ -18,7 +18,7 @@ template <class M>
 static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_t dim,
                    uint64_t n_chains, uint64_t chain_id_offset, const double* q0,
                    const double* init_mean, const double* z_tape, double* draws, double* stats,
-                   double* grads, double* mminv, uint64_t* total_steps, int max_per_launch) {
+                   double* grads, double* mminv, uint64_t* total_steps, int max_per_launch, int smem_slots) {
     KParams<M> P;
     std::memset(&P, 0, sizeof(P));
     P.st = *st;
@@ -33,6 +33,8 @@ static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_
     P.n_rows = st->save_warmup ? P.n_total : st->num_draws;
     P.sdim = (st->store_dims && st->store_dims < dim) ? st->store_dims : dim;
     P.max_draws_per_launch = max_per_launch;
+    P.smem_slots = smem_slots < P.NS ? smem_slots : P.NS;
+    P.var_in_smem = smem_slots > 0;
     std::vector<double> pool((size_t)P.NS * 4 * P.Dp), var(P.Dp), wf(8 * (size_t)P.Dp);
     std::vector<ChainScalars> sc(n_chains);
     std::memset(sc.data(), 0, sizeof(ChainScalars) * n_chains);
@@ -41,6 +43,7 @@ static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_
     P.q0 = q0; P.init_mean = init_mean; P.z_tape = z_tape;
     P.stop_flag = nullptr;
     std::vector<double> msm(M::smem_doubles(md, 1) + 1);
+    std::vector<double> spool((size_t)P.smem_slots * 4 * P.Dp + 1), svar(P.Dp);
     ChainShared sh;
     uint64_t steps = 0;
     int err = 0;
@@ -49,13 +52,18 @@ static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_
         // be resumed over several "launches" (max_per_launch) to exercise pause/resume
         std::fill(pool.begin(), pool.end(), 0.0);
         for (;;) {
+            // the shared-memory tier does not survive a launch: scramble it
+            std::fill(spool.begin(), spool.end(), -777.0);
+            std::fill(svar.begin(), svar.end(), -777.0);
             ChainCtx<M, GroupSerial> ctx;
             std::memset((void*)&ctx, 0, sizeof(ctx));
             ctx.P = &P; ctx.sh = &sh; ctx.msm = msm.data();
             ctx.D = P.D; ctx.Dp = P.Dp; ctx.NS = P.NS;
             ctx.chain_local = c;
             ctx.chain_gid = (uint32_t)(chain_id_offset + c);
-            ctx.pool = pool.data(); ctx.var = var.data(); ctx.wf = wf.data();
+            ctx.pool = pool.data(); ctx.varg = var.data(); ctx.wf = wf.data();
+            ctx.var = P.var_in_smem ? svar.data() : var.data();
+            ctx.spool = spool.data(); ctx.smem_slots = P.smem_slots;
             ctx.run();
             if (sc[c].status == 2 || sc[c].status < 0) break;
         }
@@ -70,17 +78,17 @@ extern "C" int emul_sample(const nb200_settings* st, const nb200_model_desc* mod
                            uint64_t n_chains, uint64_t chain_id_offset, const double* q0,
                            const double* init_mean, const double* z_tape, double* draws,
                            double* stats, double* grads, double* mminv, uint64_t* total_steps,
-                           int max_per_launch) {
+                           int max_per_launch, int smem_slots) {
     switch (model->kind) {
     case NB200_MODEL_NORMAL: {
         NormalModel::Data d{model->mu, 1.0 / (model->sigma * model->sigma)};
         return run_all<NormalModel>(st, d, model->dim, n_chains, chain_id_offset, q0, init_mean,
-                                    z_tape, draws, stats, grads, mminv, total_steps, max_per_launch);
+                                    z_tape, draws, stats, grads, mminv, total_steps, max_per_launch, smem_slots);
     }
     case NB200_MODEL_FUNNEL: {
         FunnelModel::Data d{0};
         return run_all<FunnelModel>(st, d, model->dim, n_chains, chain_id_offset, q0, init_mean,
-                                    z_tape, draws, stats, grads, mminv, total_steps, max_per_launch);
+                                    z_tape, draws, stats, grads, mminv, total_steps, max_per_launch, smem_slots);
     }
     case NB200_MODEL_RADON: {
         RadonLayout L = build_radon_layout(model->n_obs, model->n_county, model->y, model->county,
@@ -88,7 +96,7 @@ extern "C" int emul_sample(const nb200_settings* st, const nb200_model_desc* mod
         RadonModel::Data d{L.J, L.N, L.n_steps, L.R, L.packed.data(), L.y.data(),
                            L.run_base.data(), L.run_start.data()};
         return run_all<RadonModel>(st, d, model->dim, n_chains, chain_id_offset, q0, init_mean,
-                                   z_tape, draws, stats, grads, mminv, total_steps, max_per_launch);
+                                   z_tape, draws, stats, grads, mminv, total_steps, max_per_launch, smem_slots);
     }
     }
     return NB200_EINVAL;

@@ -54,7 +54,7 @@ def _ptr(a):
 
 
 def sample(kind, dim, settings, n_chains, chain_id_offset=0, q0=None, init_mean=None,
-           z_tape=None, max_per_launch=0, **model_kw):
+           z_tape=None, max_per_launch=0, smem_slots=0, **model_kw):
     L = lib()
     desc, keep = make_desc(kind, dim, **model_kw)
     n_total = settings.num_tune + settings.num_draws
@@ -74,7 +74,7 @@ def sample(kind, dim, settings, n_chains, chain_id_offset=0, q0=None, init_mean=
     rc = L.emul_sample(C.byref(settings), C.byref(desc), C.c_uint64(n_chains),
                        C.c_uint64(chain_id_offset), _ptr(q0), _ptr(init_mean), _ptr(z_tape),
                        _ptr(draws), _ptr(stats), _ptr(grads), _ptr(mm), C.byref(steps),
-                       C.c_int(max_per_launch))
+                       C.c_int(max_per_launch), C.c_int(smem_slots))
     if rc != 0:
         raise RuntimeError(f"emul_sample failed: {rc}")
     return dict(draws=draws, stats=stats, gradients=grads, mass_matrix_inv=mm,

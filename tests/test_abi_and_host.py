@@ -1,0 +1,144 @@
+"""CPU tests: the C-ABI library loads and exports every symbol the header declares;
+host-side mirror of nutpie's settings/sampler surface behaves like the reference."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    txt = (ROOT / "include" / "nutpie_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(nb200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nutpie_b200 import _lib
+
+    L = _lib.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"missing export {n}"
+    assert L.nb200_abi_version() == 1
+
+
+def test_settings_struct_layout_matches_header():
+    from nutpie_b200 import _lib
+    from oracle import pyoracle as O
+
+    assert C.sizeof(_lib.Settings) == C.sizeof(O.Settings) == 192
+    s = _lib.Settings()
+    _lib.load_library().nb200_settings_default(C.byref(s))
+    d = O.default_settings()
+    for name, _ in _lib.Settings._fields_:
+        if name.startswith("_"):
+            continue
+        assert getattr(s, name) == getattr(d, name), name
+    # SURVEY.md Appendix A.1 pins
+    assert (s.num_tune, s.num_draws, s.maxdepth, s.target_accept) == (400, 1000, 10, 0.8)
+    assert s.max_energy_error == 1000.0 and s.use_grad_based_estimate == 1
+
+
+def test_settings_facade_follows_wrapper_rs():
+    from nutpie_b200 import _lib
+
+    s = _lib.PyNutsSettings.Diag(7)
+    assert s.seed == 7
+    s.update({"num_tune": 50, "num_draws": 20, "num_chains": 3, "maxdepth": 6, "target_accept": 0.9})
+    assert (s.num_tune, s.num_draws, s.num_chains) == (50, 20, 3)
+    s.use_grad_based_mass_matrix = False
+    assert s._c.use_grad_based_estimate == 0
+    s.step_size_adapt_method = "0.25"
+    assert s._c.step_size_method == 2 and s._c.fixed_step_size == 0.25
+    with pytest.raises(AttributeError):  # src/wrapper.rs:611-613
+        s.no_such_option = 1
+    with pytest.raises(ValueError):      # src/wrapper.rs:138-145
+        s.mass_matrix_gamma = 1e-3
+    with pytest.raises(ValueError):
+        s.step_size_adapt_method = "bogus"
+    d = s.as_dict()
+    assert d["sampler"] == "nuts" and d["adaptation"] == "diag" and d["settings"]["maxdepth"] == 6
+    assert _lib.PyNutsSettings.Diag(None).seed != _lib.PyNutsSettings.Diag(None).seed
+    with pytest.raises(NotImplementedError):
+        _lib.PyNutsSettings.LowRank(1)
+
+
+def test_sampler_fails_loudly_without_gpu():
+    """No CPU fallback: on a box without a CUDA device creating a sampler raises."""
+    import nutpie_b200
+    from nutpie_b200 import _lib
+
+    if _lib.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nutpie_b200.sample(nutpie_b200.normal_model(1), chains=2, draws=5, tune=5, seed=1)
+
+
+def test_invalid_arguments_rejected():
+    from nutpie_b200 import _lib
+
+    L = _lib.load_library()
+    s = _lib.Settings()
+    L.nb200_settings_default(C.byref(s))
+    d = _lib.ModelDesc()
+    d.kind, d.dim = 99, 3
+    assert not L.nb200_sampler_create(C.byref(s), C.byref(d), 1, 0, 0, None, None)
+    assert b"unknown model" in L.nb200_last_error()
+    d.kind, d.dim = 2, 1  # funnel needs dim >= 2
+    assert not L.nb200_sampler_create(C.byref(s), C.byref(d), 1, 0, 0, None, None)
+    d.kind, d.dim, d.sigma = 1, 1, 1.0
+    s.maxdepth = 40
+    assert not L.nb200_sampler_create(C.byref(s), C.byref(d), 1, 0, 0, None, None)
+    assert b"maxdepth" in L.nb200_last_error()
+
+
+def test_radon_layout_invariants(radon_data):
+    """The host 'compile' step of the radon density: every observation lands in exactly
+    one thread range, runs of a county are contiguous (models.cuh relies on it)."""
+    d = radon_data
+    order = np.argsort(d["county"], kind="stable")
+    for T in (1, 32, 128):
+        per = -(-len(order) // T)
+        runs = []
+        for t in range(T):
+            seg = d["county"][order[t * per:(t + 1) * per]]
+            if len(seg):
+                runs += list(seg[np.r_[True, seg[1:] != seg[:-1]]])
+        runs = np.array(runs)
+        assert (np.diff(runs) >= 0).all()
+        assert len(runs) <= d["n_county"] + T
+
+
+def test_expand_matches_oracle_expand(radon_data):
+    """CompiledDeviceModel._expand == oracle_expand_radon (src/pymc.rs:217-286)."""
+    import nutpie_b200
+    from oracle import pyoracle as O
+
+    d = radon_data
+    J = d["n_county"]; D = 2 * J + 5
+    cm = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], J)
+    om = O.Model("radon", D, y=d["y"], county=d["county"], floor=d["floor"], n_county=J)
+    q = np.random.default_rng(0).normal(size=D) * 0.3
+    out = np.zeros(4 * J + 5)
+    rc = O.lib().oracle_expand_radon(C.c_size_t(D), C.c_size_t(4 * J + 5), q.ctypes.data_as(C.c_void_p),
+                                     out.ctypes.data_as(C.c_void_p), om.ud_ptr)
+    assert rc == 0
+    ex = cm._expand(q)
+    flat = np.concatenate([np.atleast_1d(ex[k]) for k in
+                           ("intercept", "county_raw", "county_sd", "floor_effect", "county_floor_raw",
+                            "county_floor_sd", "sigma", "county_effect", "county_floor_effect")])
+    np.testing.assert_allclose(flat, out, rtol=1e-15)
+
+
+def test_ess_estimator():
+    from nutpie_b200.diagnostics import ess
+
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(8, 1000, 2))
+    e = ess(x, None, device="cpu")
+    assert (e > 6000).all() and (e < 10500).all()

@@ -1,0 +1,347 @@
+"""GPU parity tests (-m gpu): the CUDA engine, called through the C-ABI, against the CPU
+oracle on identical seeds/inputs.
+
+Tolerances (fp64, BASELINE.json north_star "stated fp64 tolerance"):
+  * single density / leapfrog evaluations: 1e-12 relative (reduction order + FMA only);
+  * whole runs on order-independent densities (normal): identical tree shapes
+    (depth, n_steps, index_in_trajectory, diverging) and positions within 1e-8;
+  * radon / funnel (chaotic amplification of rounding differences): identical for the
+    first draws, then statistical parity — means within 4 MCSE, sds within 5 %,
+    step size within 10 % (SURVEY.md §8d "Parity report").
+"""
+import numpy as np
+import pytest
+
+import nutpie_b200
+from nutpie_b200 import _lib
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+
+STAT = {n: i for i, n in enumerate(_lib.STAT_NAMES)}
+
+
+def settings_pair(seed=1, **kw):
+    s = _lib.PyNutsSettings.Diag(seed)
+    so = O.default_settings(seed=seed)
+    for k, v in kw.items():
+        setattr(s._c, k, v)
+        setattr(so, k, v)
+    return s, so
+
+
+def run_gpu(s, model, n_chains, **kw):
+    smp = _lib.PySampler(s, model, n_chains=n_chains, **kw)
+    try:
+        smp.wait()
+        return smp.take_results()
+    finally:
+        smp.close()
+
+
+@pytest.fixture(autouse=True)
+def _reset_geometry():
+    yield
+    _lib.set_threads_per_chain(0)
+    _lib.set_chains_per_block(0)
+    _lib.set_smem_slots(-1)
+
+
+def models(radon_data):
+    d = radon_data
+    J = d["n_county"]
+    return {
+        "normal1": (nutpie_b200.normal_model(1), O.Model("normal", 1)),
+        "normal37": (nutpie_b200.normal_model(37, 2.0, 0.5), O.Model("normal", 37, mu=2.0, sigma=0.5)),
+        "funnel": (nutpie_b200.funnel_model(9), O.Model("funnel", 9)),
+        "radon": (nutpie_b200.radon_model(d["y"], d["county"], d["floor"], J),
+                  O.Model("radon", 2 * J + 5, y=d["y"], county=d["county"], floor=d["floor"], n_county=J)),
+    }
+
+
+@pytest.mark.parametrize("tpc", [32, 128, 1024])
+@pytest.mark.parametrize("name", ["normal1", "normal37", "funnel", "radon"])
+def test_logp_grad_matches_oracle(radon_data, name, tpc):
+    gm, om = models(radon_data)[name]
+    _lib.set_threads_per_chain(tpc)
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=(24, gm.n_dim)) * 0.6
+    lp, g, rc = _lib.logp_grad(gm, q)
+    lpo, go, rco = om.logp_grad(q)
+    np.testing.assert_allclose(lp, lpo, rtol=1e-12)
+    np.testing.assert_allclose(g, go, rtol=1e-11, atol=1e-11 * np.abs(go).max())
+    assert (rc == 0).all() and (rco == 0).all()
+
+
+def test_logp_nonfinite_codes():
+    gm = nutpie_b200.funnel_model(3)
+    lp, g, rc = _lib.logp_grad(gm, np.array([[-800.0, 1.0, 1.0], [0.1, 1.0, 1.0]]))
+    assert rc[0] in (3, 4) and rc[1] == 0
+
+
+@pytest.mark.parametrize("tpc", [32, 256])
+@pytest.mark.parametrize("name", ["normal37", "funnel", "radon"])
+def test_leapfrog_matches_oracle(radon_data, name, tpc):
+    import ctypes as C
+
+    gm, om = models(radon_data)[name]
+    _lib.set_threads_per_chain(tpc)
+    D = gm.n_dim
+    rng = np.random.default_rng(1)
+    n = 12
+    q = rng.normal(size=(n, D)) * 0.4
+    p = rng.normal(size=(n, D))
+    var = np.exp(rng.normal(size=(n, D)) * 0.5)
+    psum = rng.normal(size=(n, D))
+    _, g, _ = om.logp_grad(q)
+    eps = rng.uniform(0.01, 0.1, size=n)
+    direction = np.where(rng.random(n) < 0.5, 1, -1).astype(np.int32)
+    idx = np.where(direction > 0, rng.integers(0, 5, n), -rng.integers(0, 5, n)).astype(np.int64)
+    out = _lib.leapfrog(gm, q, p, g, var, psum, eps, direction, idx)
+    L = O.lib()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    for i in range(n):
+        o = [np.zeros(D) for _ in range(4)]
+        lp, kin = C.c_double(), C.c_double()
+        L.oracle_leapfrog(om.fn_ptr, om.ud_ptr, C.c_size_t(D), ptr(q[i]), ptr(p[i]), ptr(g[i]), ptr(var[i]),
+                          ptr(psum[i]), C.c_double(eps[i]), C.c_int(int(direction[i])), C.c_int64(int(idx[i])),
+                          ptr(o[0]), ptr(o[1]), ptr(o[2]), ptr(o[3]), C.byref(lp), C.byref(kin))
+        for key, ref in zip(("q", "p", "g", "p_sum"), o):
+            np.testing.assert_allclose(out[key][i], ref, rtol=1e-11, atol=1e-11 * max(1.0, np.abs(ref).max()), err_msg=key)
+        np.testing.assert_allclose(out["logp"][i], lp.value, rtol=1e-12)
+        np.testing.assert_allclose(out["kinetic"][i], kin.value, rtol=1e-12)
+
+
+@pytest.mark.parametrize("tpc,slots", [(32, -1), (32, 0), (64, -1), (256, 2)])
+@pytest.mark.parametrize("name", ["normal1", "normal37"])
+def test_sampler_matches_oracle_draw_for_draw(radon_data, name, tpc, slots):
+    """Identical seeds -> identical tree shapes and positions to rounding, including
+    warm-up adaptation (step size, mass matrix)."""
+    gm, om = models(radon_data)[name]
+    _lib.set_threads_per_chain(tpc)
+    _lib.set_smem_slots(slots)
+    s, so = settings_pair(seed=5, num_tune=300, num_draws=200, store_mass_matrix=1, store_gradient=1)
+    tr = run_gpu(s, gm, 16)
+    ref = O.sample(om, so, 16)
+    for k in ("depth", "n_steps", "index_in_trajectory", "diverging", "maxdepth_reached", "tuning"):
+        assert np.array_equal(tr.stats[..., STAT[k]], ref["stats"][..., STAT[k]]), k
+    np.testing.assert_allclose(tr.draws, ref["draws"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(tr.stats[..., STAT["step_size"]], ref["stats"][..., STAT["step_size"]], rtol=1e-8)
+    np.testing.assert_allclose(tr.stats[..., STAT["step_size_bar"]], ref["stats"][..., STAT["step_size_bar"]], rtol=1e-8)
+    np.testing.assert_allclose(tr.mass_matrix_inv, ref["mass_matrix_inv"], rtol=1e-7)
+    np.testing.assert_allclose(tr.stats[..., STAT["energy"]], ref["stats"][..., STAT["energy"]], rtol=1e-7, atol=1e-7)
+
+
+def test_sampler_tape_driven_fixed_step(radon_data):
+    """same z tape, fixed step size, no adaptation."""
+    gm, om = models(radon_data)["normal37"]
+    rng = np.random.default_rng(3)
+    z = rng.normal(size=(4, 120, 37))
+    q0 = rng.normal(size=(4, 37)) * 0.5 + 2.0
+    s, so = settings_pair(seed=2, num_tune=0, num_draws=120, step_size_method=2, fixed_step_size=0.2)
+    tr = run_gpu(s, gm, 4, q0=q0, z_tape=z)
+    ref = O.sample(om, so, 4, q0=q0, z_tape=z)
+    for k in ("depth", "n_steps", "index_in_trajectory"):
+        assert np.array_equal(tr.stats[..., STAT[k]], ref["stats"][..., STAT[k]]), k
+    np.testing.assert_allclose(tr.draws, ref["draws"], atol=1e-10)
+    np.testing.assert_allclose(tr.stats[..., STAT["logp"]], ref["stats"][..., STAT["logp"]], rtol=1e-10)
+
+
+def _mcse_compare(a, b):
+    """a, b: [chain, draw, dim]; compare means in units of combined MCSE (chains as
+    independent replicates) and sds relatively."""
+    ma, mb = a.mean(1), b.mean(1)  # per-chain means
+    se = np.sqrt(ma.var(0, ddof=1) / len(ma) + mb.var(0, ddof=1) / len(mb))
+    zscore = np.abs(ma.mean(0) - mb.mean(0)) / se
+    sd_ratio = a.std((0, 1)) / b.std((0, 1))
+    return zscore, sd_ratio
+
+
+def test_radon_parity(radon_data):
+    gm, om = models(radon_data)["radon"]
+    s, so = settings_pair(seed=7, num_tune=400, num_draws=400, init_radius=1.0)
+    n = 96
+    tr = run_gpu(s, gm, n)
+    ref = O.sample(om, so, n)
+    # identical start: first draws agree to rounding before chaos separates the runs
+    dd = np.abs(tr.draws - ref["draws"]).max(axis=(0, 2))
+    assert dd[0] < 1e-11 and dd[:4].max() < 1e-7
+    z, r = _mcse_compare(tr.draws[:, 400:], ref["draws"][:, 400:])
+    assert z.max() < 4.5, z.max()
+    assert np.abs(r - 1).max() < 0.05, r
+    g_step = tr.stats[:, -1, STAT["step_size"]].mean()
+    o_step = ref["stats"][:, -1, STAT["step_size"]].mean()
+    assert abs(g_step / o_step - 1) < 0.10
+    g_n = tr.stats[:, 400:, STAT["n_steps"]].mean()
+    o_n = ref["stats"][:, 400:, STAT["n_steps"]].mean()
+    assert abs(g_n / o_n - 1) < 0.10
+    assert abs(tr.stats[:, 400:, STAT["mean_tree_accept"]].mean() - 0.8) < 0.06
+    assert tr.stats[:, 400:, STAT["diverging"]].mean() < 0.01
+
+
+def test_funnel_divergence_and_depth_parity(radon_data):
+    """BASELINE config 5 (reduced chains): divergence rate and depth histogram vs oracle."""
+    gm, om = models(radon_data)["funnel"]
+    s, so = settings_pair(seed=11, num_tune=300, num_draws=300, maxdepth=12)
+    n = 256
+    tr = run_gpu(s, gm, n)
+    ref = O.sample(om, so, n)
+    gd = tr.stats[:, 300:, STAT["diverging"]].mean()
+    od = ref["stats"][:, 300:, STAT["diverging"]].mean()
+    assert abs(gd - od) < 0.01 + 0.25 * od, (gd, od)
+    hg = np.bincount(tr.stats[:, 300:, STAT["depth"]].astype(int).ravel(), minlength=13) / (n * 300)
+    ho = np.bincount(ref["stats"][:, 300:, STAT["depth"]].astype(int).ravel(), minlength=13) / (n * 300)
+    assert np.abs(hg - ho).max() < 0.03, (hg, ho)
+    # log_sigma marginal ~ N(0,1) up to funnel bias, same in both
+    assert abs(tr.draws[:, 300:, 0].mean() - ref["draws"][:, 300:, 0].mean()) < 0.1
+
+
+def test_determinism_and_seed_contract():
+    """tests/test_stan.py:67-101, 282-302: same seed -> bit-identical (also on the GPU,
+    no atomics in the data path); different seed / different chain -> different."""
+    m = nutpie_b200.funnel_model(9)
+    a = run_gpu(settings_pair(seed=42, num_tune=100, num_draws=50)[0], m, 32)
+    b = run_gpu(settings_pair(seed=42, num_tune=100, num_draws=50)[0], m, 32)
+    c = run_gpu(settings_pair(seed=43, num_tune=100, num_draws=50)[0], m, 32)
+    assert np.array_equal(a.draws, b.draws) and np.array_equal(a.stats, b.stats)
+    assert not np.array_equal(a.draws, c.draws)
+    for i in range(1, 32):
+        assert not np.allclose(a.draws[0], a.draws[i])
+
+
+def test_radon_bitwise_reproducible(radon_data):
+    gm, _ = models(radon_data)["radon"]
+    for tpc in (32, 128):
+        _lib.set_threads_per_chain(tpc)
+        a = run_gpu(settings_pair(seed=1, num_tune=60, num_draws=40, init_radius=1.0)[0], gm, 24)
+        b = run_gpu(settings_pair(seed=1, num_tune=60, num_draws=40, init_radius=1.0)[0], gm, 24)
+        assert np.array_equal(a.draws, b.draws)
+
+
+def test_chain_sharding_reproduces_single_run(radon_data):
+    """RNG keyed by global chain id -> a run split over several samplers
+    (GPUs) equals the unsplit run chain for chain."""
+    gm, _ = models(radon_data)["radon"]
+    s = lambda: settings_pair(seed=9, num_tune=80, num_draws=40, init_radius=1.0)[0]
+    full = run_gpu(s(), gm, 16)
+    lo = run_gpu(s(), gm, 8)
+    hi = run_gpu(s(), gm, 8, chain_id_offset=8)
+    assert np.array_equal(full.draws[:8], lo.draws) and np.array_equal(full.draws[8:], hi.draws)
+    assert np.array_equal(full.stats[8:, :, STAT["chain"]], hi.stats[:, :, STAT["chain"]])
+
+
+def test_pause_resume_and_chunked_launch_are_bit_identical(radon_data):
+    gm, _ = models(radon_data)["radon"]
+    mk = lambda: settings_pair(seed=4, num_tune=150, num_draws=100, init_radius=1.0)[0]
+    ref = run_gpu(mk(), gm, 16)
+    chunked = run_gpu(mk(), gm, 16, draws_per_launch=37)
+    assert np.array_equal(ref.draws, chunked.draws) and np.array_equal(ref.stats, chunked.stats)
+    smp = _lib.PySampler(mk(), gm, n_chains=16)
+    try:
+        smp.pause()
+        part = smp.inspect()
+        assert part.rows_filled.max() <= 250
+        smp.resume()
+        smp.wait()
+        tr = smp.take_results()
+    finally:
+        smp.close()
+    assert np.array_equal(ref.draws, tr.draws)
+
+
+def test_config4_leapfrog_properties():
+    """BASELINE config 4 at full dimension (D = 10 000, fewer chains): size-independent
+    properties — posterior sd ~ 1 per coordinate, energy error small, acceptance near
+    the target, and the first draws equal to the oracle's."""
+    D = 10000
+    gm, om = nutpie_b200.normal_model(D), O.Model("normal", D)
+    s, so = settings_pair(seed=3, num_tune=120, num_draws=60, store_dims=16)
+    tr = run_gpu(s, gm, 12)
+    ref = O.sample(om, so, 12)
+    for k in ("depth", "n_steps", "index_in_trajectory"):
+        assert np.array_equal(tr.stats[..., STAT[k]], ref["stats"][..., STAT[k]]), k
+    np.testing.assert_allclose(tr.draws, ref["draws"], atol=1e-7)
+    post = tr.draws[:, 120:]
+    assert abs(post.std() - 1.0) < 0.08
+    assert np.abs(tr.stats[:, 120:, STAT["energy_error"]]).max() < 5.0
+    assert abs(tr.stats[:, 120:, STAT["mean_tree_accept"]].mean() - 0.8) < 0.1
+    # logp of a D-dim standard normal draw: -chi2_D/2 ~ -D/2 +- sqrt(D/2)
+    assert abs(tr.stats[:, 120:, STAT["logp"]].mean() + D / 2) < 5 * np.sqrt(D / 2)
+
+
+def test_config1_through_public_api():
+    """BASELINE config 1 through nutpie_b200.sample (the reference's public call)."""
+    tr = nutpie_b200.sample(nutpie_b200.normal_model(1), chains=4, draws=1000, tune=400, seed=0,
+                            progress_bar=False)
+    assert set(tr.groups()) >= {"posterior", "sample_stats", "warmup_posterior", "warmup_sample_stats"}
+    x = tr.posterior["x"]
+    assert x.shape == (4, 1000) and tr.warmup_posterior["x"].shape == (4, 400)
+    assert abs(x.mean()) < 0.1 and abs(x.std() - 1) < 0.06
+    assert tr.sample_stats["diverging"].dtype == np.bool_
+    assert tr.sample_stats["depth"].shape == (4, 1000)
+
+
+def test_public_api_radon_shapes_and_save_warmup(radon_data):
+    d = radon_data
+    J = d["n_county"]
+    cm = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], J)
+    tr = nutpie_b200.sample(cm, chains=8, draws=50, tune=100, seed=1, save_warmup=False,
+                            init_radius=1.0, store_gradient=True)
+    assert tr.posterior["county_effect"].shape == (8, 50, J)
+    assert tr.posterior["sigma"].shape == (8, 50) and (tr.posterior["sigma"] > 0).all()
+    assert not tr.warmup_posterior
+    assert tr.sample_stats["gradient"].shape == (8, 50, 2 * J + 5)
+    np.testing.assert_allclose(tr.posterior["county_effect"],
+                               tr.posterior["county_raw"] * tr.posterior["county_sd"][..., None])
+    raw = nutpie_b200.sample(cm, chains=2, draws=10, tune=10, seed=1, return_raw_trace=True,
+                             init_radius=1.0)
+    batches = raw.get_arrow_trace()
+    assert len(batches) == 2 and batches[0][0].num_rows == 20
+    assert batches[0][1].column("tuning").to_numpy(zero_copy_only=False).sum() == 10
+    with pytest.raises(ValueError):
+        raw.get_arrow_trace()  # single-take, src/wrapper.rs:1477-1494
+
+
+def test_nonblocking_control_surface(radon_data):
+    """tests/test_pymc.py:224-286: non-blocking sampling, wait(timeout) raising
+    TimeoutError, pause/resume, abort returning a partial trace."""
+    big = nutpie_b200.normal_model(100_000)  # the reference uses a 100 000-dim model too
+    bg = nutpie_b200.sample(big, chains=64, draws=2000, tune=2000, seed=1, blocking=False,
+                            store_dims=4, progress_bar=False)
+    with pytest.raises(TimeoutError):
+        bg.wait(timeout=0.1)
+    assert not bg.is_finished
+    bg.pause()
+    bg.resume()
+    part = bg.abort()
+    n = part.posterior["unconstrained_draw"].shape[1] + part.warmup_posterior["unconstrained_draw"].shape[1]
+    assert 0 <= n < 4000
+    bg.close()
+
+
+def test_progress_callback_contents():
+    """tests/test_pymc.py:37-66"""
+    seen = []
+    tr = nutpie_b200.sample(nutpie_b200.normal_model(50_000), chains=32, draws=300, tune=300, seed=2,
+                            progress_callback=lambda p: seen.append(p), progress_rate=20,
+                            store_dims=2)
+    assert seen, "callback never fired"
+    last = seen[-1]
+    assert len(last) == 32
+    p = last[0]
+    assert p.total_draws == 600 and 0 <= p.finished_draws <= 600
+    assert p.step_size > 0 and p.total_num_steps >= p.latest_num_steps
+    assert isinstance(p.divergent_draws, list) and p.runtime_ms >= 0
+
+
+def test_init_failure_is_reported():
+    """A chain that finds no finite initial point surfaces as RuntimeError from wait
+    (src/wrapper.rs:1131-1136), not as silent garbage."""
+    m = nutpie_b200.funnel_model(3)
+    s = _lib.PyNutsSettings.Diag(1)
+    s.update({"num_tune": 10, "num_draws": 10})
+    q0 = np.array([[-800.0, 1.0, 1.0]])
+    smp = _lib.PySampler(s, m, n_chains=1, q0=q0)
+    with pytest.raises(RuntimeError, match="initial point"):
+        smp.wait()
+    smp.close()
