@@ -150,6 +150,8 @@ def load_library() -> C.CDLL:
         L.nb200_set_chains_per_block.argtypes = [C.c_int32]
         L.nb200_set_smem_slots.restype = None
         L.nb200_set_smem_slots.argtypes = [C.c_int32]
+        L.nb200_set_unroll.restype = None
+        L.nb200_set_unroll.argtypes = [C.c_int32]
         L.nb200_sampler_smem.restype = C.c_int
         L.nb200_sampler_smem.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.nb200_host_alloc.restype = C.c_void_p
@@ -693,6 +695,10 @@ def set_chains_per_block(c: int):
 
 def set_smem_slots(n: int):
     load_library().nb200_set_smem_slots(int(n))
+
+
+def set_unroll(on: bool):
+    load_library().nb200_set_unroll(1 if on else 0)
 
 
 def device_count() -> int:

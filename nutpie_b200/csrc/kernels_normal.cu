@@ -1,0 +1,6 @@
+// kernels_normal.cu — sm_100a kernels of the NUTS engine for NormalModel (see launch_impl.cuh)
+#include "launch_impl.cuh"
+
+namespace nb200 {
+NB200_INSTANTIATE_MODEL(NormalModel)
+}

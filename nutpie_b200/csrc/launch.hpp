@@ -1,0 +1,21 @@
+// launch.hpp — declarations of the per-density kernel launchers (defined in
+// launch_impl.cuh, instantiated in kernels_<model>.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "nuts_core.cuh"
+
+namespace nb200 {
+
+template <class M>
+int supported_nit(int W, int nit);
+template <class M>
+cudaError_t launch_nuts(int W, int NIT, const KParams<M>& P, size_t smem_per_chain, int cpb,
+                        int grid, int block, cudaStream_t stream);
+template <class M>
+cudaError_t launch_component(int W, const KParams<M>& P, int mode, const double* scal, double* out,
+                             size_t smem, unsigned n);
+template <class M>
+size_t smem_fixed(int W, const typename M::Data& md);
+
+}  // namespace nb200

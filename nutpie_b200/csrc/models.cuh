@@ -70,24 +70,28 @@ struct FunnelModel {
 // variable order: intercept, county_raw[J], log county_sd, floor_effect,
 // county_floor_raw[J], log county_floor_sd, log sigma.
 //
-// Data layout (built on the host for the group size T, nb200_api.cu): the
-// observations are sorted by county and cut into T contiguous ranges, one per
-// thread, stored transposed ([step][thread]) so a warp's loads coalesce.  A
-// thread walks its range keeping run sums per county; every run of equal
-// county inside a range gets a private slot in shared memory, and because
-// ranges are contiguous the runs of one county are contiguous in that list:
-// the per-county gradient is a short fixed-order sum — no atomics, bitwise
+// Data layout (built on the host for the group size T, radon_layout.hpp): the
+// observations are sorted by (county, floor) and cut into T contiguous ranges,
+// one per thread, stored transposed ([step][thread]) so a warp's loads
+// coalesce.  Inside a range, a GROUP is a maximal run of equal (county, floor):
+// all its observations share the linear predictor mu[2*county + floor], which
+// every thread reads from a shared table.  A thread keeps one running sum of
+// residuals and stores it into the group's private slot when the group ends
+// (flag bit in the per-observation word).  Because ranges are contiguous the
+// groups of one (county, floor) pair are contiguous in slot order: the
+// per-county gradient is a short fixed-order sum — no atomics, bitwise
 // reproducible (determinism contract, tests/test_stan.py:67-101).
 struct RadonModel {
     static constexpr bool kElementwise = false;
+    static constexpr int kEndFlag = 1 << 30;
     struct Data {
-        int J, N, n_steps, R;       // counties, observations, steps per thread, total runs
-        const int32_t* packed;      // [n_steps][T]  (county << 1 | floor), -1 = padding
+        int J, N, n_steps, G;       // counties, observations, steps per thread, total groups
+        const int32_t* meta;        // [n_steps][T]  (2*county + floor) | kEndFlag; -1 = padding
         const double* y;            // [n_steps][T]
-        const int32_t* run_base;    // [T]   first run slot of each thread
-        const int32_t* run_start;   // [J+1] first run slot of each county
+        const int32_t* group_base;  // [T]     first group slot of each thread
+        const int32_t* group_start; // [2J+1]  first group slot of each (county, floor) pair
     };
-    NB_HD static int smem_doubles(const Data& d, int) { return 2 * d.J + 2 * d.R; }
+    NB_HD static int smem_doubles(const Data& d, int) { return 2 * d.J + d.G; }
 
     template <class G>
     NB_HD static double logp_grad(const G& grp, const Data& d, int, const double* q, double* g,
@@ -101,68 +105,53 @@ struct RadonModel {
         const double sd_a = exp(log_sd_a), sd_b = exp(log_sd_b), sigma = exp(log_sigma);
         const double inv_sigma = 1.0 / sigma;
         const double inv_s2 = inv_sigma * inv_sigma;
-        double* effA = sm;               // intercept + county_effect[c]
-        double* effB = sm + J;           // floor_effect + county_floor_effect[c]
-        double* runE = sm + 2 * J;       // per-run sum of residuals
-        double* runF = sm + 2 * J + d.R; // per-run sum of floor * residual
+        double* mu = sm;            // [2J] linear predictor per (county, floor)
+        double* gsum = sm + 2 * J;  // [G]  per-group sum of residuals
         for (int c = grp.tid; c < J; c += T) {
-            effA[c] = intercept + q[1 + c] * sd_a;
-            effB[c] = floor_eff + q[J + 3 + c] * sd_b;
+            const double a = intercept + q[1 + c] * sd_a;
+            mu[2 * c] = a;
+            mu[2 * c + 1] = a + (floor_eff + q[J + 3 + c] * sd_b);
         }
         grp.sync();
         double ss = 0.0;
         {
-            int cur = -1, k = nb_ldg(d.run_base + grp.tid);
-            double sE = 0.0, sF = 0.0, a = 0.0, ab = 0.0;
-            // n_steps is padded to a multiple of 4 with packed = -1: four independent
-            // loads are issued before the dependent run-length arithmetic
+            int k = nb_ldg(d.group_base + grp.tid);
+            double s1 = 0.0;
+            // n_steps is padded to a multiple of 4 with meta = -1: the loads of four
+            // steps and their mu lookups are independent of the running sums
             for (int j0 = 0; j0 < d.n_steps; j0 += 4) {
-                int pk[4];
+                int mt[4];
                 double yv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    pk[u] = nb_ldg(d.packed + (size_t)(j0 + u) * T + grp.tid);
+                    mt[u] = nb_ldg(d.meta + (size_t)(j0 + u) * T + grp.tid);
                     yv[u] = nb_ldg(d.y + (size_t)(j0 + u) * T + grp.tid);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (pk[u] < 0) continue;
-                    const int c = pk[u] >> 1;
-                    if (c != cur) {
-                        if (cur >= 0) {
-                            runE[k] = sE;
-                            runF[k] = sF;
+                    if (mt[u] >= 0) {
+                        const double r = yv[u] - mu[mt[u] & 0xFFFF];
+                        ss += r * r;
+                        s1 += r;
+                        if (mt[u] & kEndFlag) {
+                            gsum[k] = s1;
                             ++k;
-                            sE = 0.0;
-                            sF = 0.0;
+                            s1 = 0.0;
                         }
-                        cur = c;
-                        a = effA[c];
-                        ab = a + effB[c];
                     }
-                    const bool f = pk[u] & 1;
-                    const double r = yv[u] - (f ? ab : a);
-                    ss += r * r;
-                    sE += r;
-                    if (f) sF += r;
                 }
-            }
-            if (cur >= 0) {
-                runE[k] = sE;
-                runF[k] = sF;
             }
         }
         grp.sync();
         double acc[7] = {ss, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         for (int c = grp.tid; c < J; c += T) {
-            double E = 0.0, F = 0.0;
-            const int r0 = nb_ldg(d.run_start + c), r1 = nb_ldg(d.run_start + c + 1);
-            for (int r = r0; r < r1; ++r) {
-                E += runE[r];
-                F += runF[r];
-            }
-            E *= inv_s2;
-            F *= inv_s2;
+            const int g0 = nb_ldg(d.group_start + 2 * c), g1 = nb_ldg(d.group_start + 2 * c + 1),
+                      g2 = nb_ldg(d.group_start + 2 * c + 2);
+            double S0 = 0.0, S1 = 0.0;
+            for (int r = g0; r < g1; ++r) S0 += gsum[r];
+            for (int r = g1; r < g2; ++r) S1 += gsum[r];
+            const double E = (S0 + S1) * inv_s2;  // sum over the county of d logp / d mu_i
+            const double F = S1 * inv_s2;         // same, floor = 1 observations only
             const double ra = q[1 + c], rb = q[J + 3 + c];
             acc[1] += ra * sd_a * E;
             acc[2] += rb * sd_b * F;
@@ -175,20 +164,22 @@ struct RadonModel {
         }
         grp.reduce(acc);
         const double ssn = acc[0] * inv_s2;
-        double logp = -0.5 * ssn - d.N * log_sigma - 0.5 * d.N * NB_LOG_2PI;
-        logp += -0.5 * acc[3] - 0.5 * J * NB_LOG_2PI;
-        logp += -0.5 * acc[4] - 0.5 * J * NB_LOG_2PI;
-        logp += -0.5 * intercept * intercept / 100.0 - log(10.0) - 0.5 * NB_LOG_2PI;
-        logp += -0.5 * floor_eff * floor_eff / 4.0 - log(2.0) - 0.5 * NB_LOG_2PI;
-        logp += NB_HALF_LOG_2_OVER_PI - 0.5 * sd_a * sd_a + log_sd_a;
-        logp += NB_HALF_LOG_2_OVER_PI - 0.5 * sd_b * sd_b + log_sd_b;
-        logp += NB_HALF_LOG_2_OVER_PI - log(1.5) - 0.5 * sigma * sigma / 2.25 + log_sigma;
+        // constants: -1/2 (N + 2J + 2) log 2pi - log 10 - log 2 + 3/2 log(2/pi) - log 1.5
+        const double kConst = -0.5 * NB_LOG_2PI * (double)(d.N + 2 * J + 2) - 2.3025850929940456840 -
+                              0.69314718055994530942 + 3.0 * NB_HALF_LOG_2_OVER_PI -
+                              0.40546510810816438198;
+        double logp = kConst - 0.5 * ssn - d.N * log_sigma;
+        logp += -0.5 * (acc[3] + acc[4]);
+        logp += -0.005 * intercept * intercept - 0.125 * floor_eff * floor_eff;
+        logp += -0.5 * sd_a * sd_a + log_sd_a;
+        logp += -0.5 * sd_b * sd_b + log_sd_b;
+        logp += -0.5 * sigma * sigma * (1.0 / 2.25) + log_sigma;
         if (grp.tid == 0) {
-            g[0] = acc[5] - intercept / 100.0;
+            g[0] = acc[5] - 0.01 * intercept;
             g[J + 1] = acc[1] - sd_a * sd_a + 1.0;
-            g[J + 2] = acc[6] - floor_eff / 4.0;
+            g[J + 2] = acc[6] - 0.25 * floor_eff;
             g[2 * J + 3] = acc[2] - sd_b * sd_b + 1.0;
-            g[2 * J + 4] = ssn - d.N - sigma * sigma / 2.25 + 1.0;
+            g[2 * J + 4] = ssn - d.N - sigma * sigma * (1.0 / 2.25) + 1.0;
         }
         return logp;
     }

@@ -17,6 +17,7 @@
 #include <thread>
 #include <vector>
 
+#include "launch.hpp"
 #include "nuts_core.cuh"
 #include "radon_layout.hpp"
 
@@ -51,106 +52,12 @@ static int fail(int code, const std::string& msg) {
 static std::atomic<int> g_threads_per_chain{0};
 static std::atomic<int> g_chains_per_block{0};
 static std::atomic<int> g_smem_slots{-1};
-
-// ------------------------------------------------------------------ kernels
+static std::atomic<int> g_force_nit{-1};
 static inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-
-// fixed part of a chain's shared memory (scalars, model scratch, reduction scratch)
-template <class M, int W>
-static size_t chain_smem_fixed(const typename M::Data& md) {
-    size_t b = align16(sizeof(ChainShared));
-    b += align16(sizeof(double) * (size_t)M::smem_doubles(md, 32 * W));
-    if (W > 1) b += align16(sizeof(double) * W * GroupCuda<W>::kMaxRed);
-    return b;
-}
 // + working mass matrix + hot tier of the pool
 static size_t chain_smem_total(size_t fixed, int Dp, int var_in_smem, int smem_slots) {
     return fixed + (var_in_smem ? align16(sizeof(double) * Dp) : 0) +
            align16(sizeof(double) * 4 * (size_t)Dp * smem_slots);
-}
-
-template <class M, int W>
-__device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>>& ctx, const KParams<M>& P,
-                                          unsigned long long chain, unsigned char* smem_chain) {
-    ctx.g.tid = (W == 1) ? (threadIdx.x & 31) : threadIdx.x;
-    ctx.P = &P;
-    ctx.sh = reinterpret_cast<ChainShared*>(smem_chain);
-    size_t off = (sizeof(ChainShared) + 15) & ~size_t(15);
-    ctx.msm = reinterpret_cast<double*>(smem_chain + off);
-    off += (sizeof(double) * (size_t)M::smem_doubles(P.mdata, 32 * W) + 15) & ~size_t(15);
-    ctx.g.red = reinterpret_cast<double*>(smem_chain + off);
-    if (W > 1) off += (sizeof(double) * W * GroupCuda<W>::kMaxRed + 15) & ~size_t(15);
-    double* svar = reinterpret_cast<double*>(smem_chain + off);
-    if (P.var_in_smem) off += (sizeof(double) * P.Dp + 15) & ~size_t(15);
-    ctx.spool = reinterpret_cast<double*>(smem_chain + off);
-    ctx.smem_slots = P.smem_slots;
-    ctx.D = P.D;
-    ctx.Dp = P.Dp;
-    ctx.NS = P.NS;
-    ctx.chain_local = chain;
-    ctx.chain_gid = (uint32_t)(P.chain_id_offset + chain);
-    ctx.pool = P.pool + (size_t)chain * P.NS * 4 * (size_t)P.Dp;
-    ctx.varg = P.var + (size_t)chain * P.Dp;
-    ctx.var = P.var_in_smem ? svar : ctx.varg;
-    ctx.wf = P.welford + (size_t)chain * 8 * (size_t)P.Dp;
-    ctx.mL = ctx.mR = ctx.mD = ctx.tL = ctx.tR = ctx.tD = -1;
-    ctx.lv_valid = 0;
-}
-
-// The sampler: W warps per chain, CPB chains per CTA (CPB > 1 only for W == 1).
-template <class M, int W>
-__global__ void __launch_bounds__(W == 1 ? 256 : 32 * W)
-    nuts_kernel(const __grid_constant__ KParams<M> P, size_t smem_per_chain) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int local = (W == 1) ? (threadIdx.x >> 5) : 0;
-    const int cpb = (W == 1) ? (blockDim.x >> 5) : 1;
-    const unsigned long long chain = (unsigned long long)blockIdx.x * cpb + local;
-    if (chain >= P.n_chains) return;
-    ChainCtx<M, GroupCuda<W>> ctx;
-    setup_ctx<M, W>(ctx, P, chain, smem + (size_t)local * smem_per_chain);
-    ctx.run();
-}
-
-// Component kernel: mode 0 = density at q (slot 0); mode 1 = one leapfrog
-// slot 0 -> slot 1 with per-state eps/dir/idx.  scal: [n][4] = eps, dir, idx, unused;
-// out_scal: [n][4] = logp, kinetic, rc, unused.
-template <class M, int W>
-__global__ void __launch_bounds__(32 * W)
-    component_kernel(const __grid_constant__ KParams<M> P, int mode, const double* scal,
-                     double* out_scal) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const unsigned long long chain = blockIdx.x;
-    if (chain >= P.n_chains) return;
-    ChainCtx<M, GroupCuda<W>> ctx;
-    setup_ctx<M, W>(ctx, P, chain, smem);
-    ctx.acc_sum = ctx.acc_sym = 0.0;
-    ctx.acc_count = 0;
-    if (mode == 0) {
-        bool bad;
-        const double lp = ctx.eval_logp(0, bad);
-        if (ctx.g.tid == 0) {
-            out_scal[chain * 4 + 0] = lp;
-            out_scal[chain * 4 + 1] = 0.0;
-            out_scal[chain * 4 + 2] = bad ? (isfinite(lp) ? 3.0 : 4.0) : 0.0;
-        }
-    } else {
-        const double eps = scal[chain * 4 + 0];
-        const int dir = scal[chain * 4 + 1] > 0 ? 1 : -1;
-        if (ctx.g.tid == 0) {
-            ctx.sh->idx[0] = (int)scal[chain * 4 + 2];
-            ctx.sh->U[0] = 0.0;
-            ctx.sh->K[0] = 0.0;
-        }
-        ctx.g.sync();
-        ctx.step_size = eps;
-        ctx.E0 = 0.0;
-        const int rc = ctx.leapfrog(0, 1, dir);
-        if (ctx.g.tid == 0) {
-            out_scal[chain * 4 + 0] = -ctx.sh->U[1];
-            out_scal[chain * 4 + 1] = ctx.sh->K[1];
-            out_scal[chain * 4 + 2] = (double)rc;
-        }
-    }
 }
 
 // ------------------------------------------------------------------ sampler
@@ -162,7 +69,7 @@ struct nb200_sampler {
     nb200_settings st{};
     nb200_model_desc model{};
     uint64_t n_chains = 0, chain_id_offset = 0;
-    int W = 1, cpb = 1, grid = 0, block = 0;
+    int W = 1, NIT = 0, cpb = 1, grid = 0, block = 0;
     size_t smem_per_chain = 0;
     cudaStream_t stream = nullptr, side = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -190,48 +97,23 @@ struct nb200_sampler {
 template <class M>
 struct SamplerImpl : nb200_sampler {
     KParams<M> P;
-    template <int W_>
-    int launch_w() {
-        const size_t smem = smem_per_chain * cpb;
-        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<M, W_>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(NB200_ECUDA, cudaGetErrorString(e));
-        cudaFuncSetAttribute(nuts_kernel<M, W_>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-        nuts_kernel<M, W_><<<grid, block, smem, stream>>>(P, smem_per_chain);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return fail(NB200_ECUDA, cudaGetErrorString(e));
-        return 0;
-    }
     int launch() override {
         P.max_draws_per_launch = draws_per_launch;
-        switch (W) {
-        case 1: return launch_w<1>();
-        case 2: return launch_w<2>();
-        case 4: return launch_w<4>();
-        case 8: return launch_w<8>();
-        case 16: return launch_w<16>();
-        case 32: return launch_w<32>();
-        }
-        return fail(NB200_EINVAL, "threads per chain must be 32..1024, power of two");
+        cudaError_t e = launch_nuts<M>(W, NIT, P, smem_per_chain, cpb, grid, block, stream);
+        if (e != cudaSuccess) return fail(NB200_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+        return 0;
     }
 };
 
 template <class M>
 static size_t smem_for(int W, const typename M::Data& md) {
-    switch (W) {
-    case 1: return chain_smem_fixed<M, 1>(md);
-    case 2: return chain_smem_fixed<M, 2>(md);
-    case 4: return chain_smem_fixed<M, 4>(md);
-    case 8: return chain_smem_fixed<M, 8>(md);
-    case 16: return chain_smem_fixed<M, 16>(md);
-    default: return chain_smem_fixed<M, 32>(md);
-    }
+    return smem_fixed<M>(W, md);
 }
 
 static int pick_W(const nb200_model_desc& m, uint64_t n_chains) {
     int t = g_threads_per_chain.load();
     if (t > 0) return t / 32;
+    if (m.dim >= 2048) return 32;  // streaming regime (config 4): a full CTA per chain
     const uint64_t work = m.kind == NB200_MODEL_RADON ? (uint64_t)m.n_obs : m.dim;
     // enough warps per chain that each thread still has >= 4 work items, and
     // enough warps in total to fill 148 SMs x 16 warps
@@ -248,6 +130,8 @@ static int validate(const nb200_settings* st, const nb200_model_desc* m) {
     if (st->step_size_method != 0 && st->step_size_method != 2)
         return fail(NB200_EINVAL, "step_size_adapt_method: only dual_average and fixed are supported");
     if (m->kind == NB200_MODEL_RADON) {
+        if (m->n_county < 1 || m->n_county > 32767)
+            return fail(NB200_EINVAL, "radon: n_county must be in 1..32767");
         if (m->dim != (uint64_t)(2 * m->n_county + 5))
             return fail(NB200_EINVAL, "radon: dim must equal 2*n_county+5");
         if (!m->y || !m->county || !m->floor || m->n_obs < 1)
@@ -288,15 +172,15 @@ static int build_model_data(const nb200_model_desc&, int, FunnelModel::Data& d,
 static int build_model_data(const nb200_model_desc& m, int T, RadonModel::Data& d,
                             std::vector<void*>& keep) {
     RadonLayout L = build_radon_layout(m.n_obs, m.n_county, m.y, m.county, m.floor, T);
-    d.J = L.J; d.N = L.N; d.n_steps = L.n_steps; d.R = L.R;
-    int32_t *packed, *run_base, *run_start;
+    d.J = L.J; d.N = L.N; d.n_steps = L.n_steps; d.G = L.G;
+    int32_t *meta, *group_base, *group_start;
     double* y;
     int rc;
-    if ((rc = to_device(L.packed, &packed, keep))) return rc;
+    if ((rc = to_device(L.meta, &meta, keep))) return rc;
     if ((rc = to_device(L.y, &y, keep))) return rc;
-    if ((rc = to_device(L.run_base, &run_base, keep))) return rc;
-    if ((rc = to_device(L.run_start, &run_start, keep))) return rc;
-    d.packed = packed; d.y = y; d.run_base = run_base; d.run_start = run_start;
+    if ((rc = to_device(L.group_base, &group_base, keep))) return rc;
+    if ((rc = to_device(L.group_start, &group_start, keep))) return rc;
+    d.meta = meta; d.y = y; d.group_base = group_base; d.group_start = group_start;
     return 0;
 }
 
@@ -373,6 +257,13 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         P.var_in_smem = var_in;
         s->smem_per_chain = chain_smem_total(fixed, s->Dp, var_in, slots);
     }
+    {
+        const int T = 32 * s->W;
+        int nit = (D + T - 1) / T;
+        s->NIT = supported_nit<M>(s->W, nit);
+        const int f = g_force_nit.load();
+        if (f == 0) s->NIT = 0;
+    }
     s->block = 32 * s->W * s->cpb;
     s->grid = (int)((n_chains + s->cpb - 1) / s->cpb);
     P.D = D; P.Dp = s->Dp; P.NS = s->NS;
@@ -448,6 +339,7 @@ int nb200_device_count(void) {
 void nb200_set_threads_per_chain(int32_t t) { g_threads_per_chain.store(t); }
 void nb200_set_chains_per_block(int32_t c) { g_chains_per_block.store(c); }
 void nb200_set_smem_slots(int32_t n) { g_smem_slots.store(n); }
+void nb200_set_unroll(int32_t on) { g_force_nit.store(on ? -1 : 0); }
 
 void nb200_settings_default(nb200_settings* s) {
     std::memset(s, 0, sizeof(*s));
@@ -901,16 +793,7 @@ static int component_run(const nb200_model_desc* model, int device, uint64_t n, 
     CU(cudaMemcpy(d_scal, hs.data(), n * 4 * sizeof(double), cudaMemcpyHostToDevice));
     P.pool = d_pool; P.var = d_var;
     const size_t smem = smem_for<M>(W, P.mdata);
-#define LAUNCH(WW)                                                                          \
-    case WW:                                                                                \
-        CU(cudaFuncSetAttribute(component_kernel<M, WW>,                                    \
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        component_kernel<M, WW><<<(unsigned)n, 32 * WW, smem>>>(P, mode, d_scal, d_out);    \
-        break;
-    switch (W) {
-        LAUNCH(1) LAUNCH(2) LAUNCH(4) LAUNCH(8) LAUNCH(16) LAUNCH(32)
-    }
-#undef LAUNCH
+    CU(launch_component<M>(W, P, mode, d_scal, d_out, smem, (unsigned)n));
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     std::vector<double> ho(n * 4);

@@ -1,5 +1,6 @@
 // nuts_core.cuh — the per-chain NUTS engine (transition + adaptation), written
-// once against a thread-group policy `G` and a density `M`.
+// once against a thread-group policy `G`, a density `M` and a compile-time trip
+// count `NIT` of the per-dimension loops.
 //
 // What it replaces (nuts-rs 0.18.3 behind nuts_rs::Sampler::new,
 // src/wrapper.rs:977-1085; semantics per SURVEY.md Appendix A):
@@ -20,6 +21,10 @@
 // slot indices, so merging sub-trees never copies a vector.  Per-slot scalars
 // (index in trajectory, potential, kinetic energy) and the level stack live in
 // shared memory.
+//
+// Code-size discipline: leapfrog() is inlined at two call sites and
+// is_turning() at one (with every site inlined the kernel was 335 KB of SASS and
+// the profile showed instruction-fetch stalls).
 #pragma once
 #include "../../include/nutpie_b200.h"
 #include "group.cuh"
@@ -98,7 +103,10 @@ NB_HD double nb_logaddexp(double a, double b) {
     return diff;
 }
 
-template <class M, class G>
+// NIT > 0: every per-dimension loop runs exactly NIT predicated iterations
+// (NIT * group size >= D), fully unrolled so independent loads overlap;
+// NIT == 0: run-time trip count (any D).
+template <class M, class G, int NIT = 0>
 struct ChainCtx {
     G g;
     const KParams<M>* P;
@@ -127,6 +135,20 @@ struct ChainCtx {
     int fg_sel, has_initial_mm;
     double last_mean, last_sym;
     uint32_t last_n_steps;
+
+    // f(i) for every dimension index owned by this thread
+    template <class F>
+    NB_HD void for_dims(F&& f) const {
+        if constexpr (NIT > 0) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = g.tid + it * G::kThreads;
+                if (i < D) f(i);
+            }
+        } else {
+            for (int i = g.tid; i < D; i += g.size()) f(i);
+        }
+    }
 
     // Slots below smem_slots are the hot tier in shared memory: alloc() hands out
     // the lowest free slot, so leaves and low tree levels stay on chip; deeper
@@ -167,12 +189,12 @@ struct ChainCtx {
         double flag[1] = {0.0};
         if constexpr (M::kElementwise) {
             double acc[2] = {0.0, 0.0};
-            for (int i = g.tid; i < D; i += g.size()) {
+            for_dims([&](int i) {
                 double gn;
                 acc[0] += M::term(P->mdata, i, q[i], gn);
                 gr[i] = gn;
                 if (!nb_isfinite(gn)) acc[1] += 1.0;
-            }
+            });
             g.reduce(acc);
             lp = M::finish(P->mdata, acc[0], D);
             flag[0] = acc[1];
@@ -180,8 +202,9 @@ struct ChainCtx {
             g.sync();
             lp = M::logp_grad(g, P->mdata, D, q, gr, msm);
             g.sync();
-            for (int i = g.tid; i < D; i += g.size())
+            for_dims([&](int i) {
                 if (!nb_isfinite(gr[i])) flag[0] += 1.0;
+            });
             g.reduce(flag);
         }
         bad = flag[0] > 0.0 || !nb_isfinite(lp);
@@ -208,7 +231,7 @@ struct ChainCtx {
         if constexpr (M::kElementwise) {
             // one streaming pass: 5 loads + 4 stores per dimension
             double acc[3] = {0.0, 0.0, 0.0};
-            for (int i = g.tid; i < D; i += g.size()) {
+            for_dims([&](int i) {
                 const double vr = var[i];
                 const double ph = ps[i] + heps * gs[i];
                 const double qn = qs[i] + eps * (vr * ph);
@@ -222,11 +245,43 @@ struct ChainCtx {
                 gd[i] = gn;
                 sd[i] = sn;
                 if (!nb_isfinite(gn)) acc[2] += 1.0;
-            }
+            });
             g.reduce(acc);
             lp = M::finish(P->mdata, acc[0], D);
             kin = 0.5 * acc[1];
             bad = acc[2] > 0.0;
+        } else if constexpr (NIT > 0) {
+            // half-step momenta and the mass matrix stay in registers across the
+            // density evaluation
+            double ph[NIT], vr[NIT];
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = g.tid + it * G::kThreads;
+                if (i < D) {
+                    vr[it] = var[i];
+                    ph[it] = ps[i] + heps * gs[i];
+                    qd[i] = qs[i] + eps * (vr[it] * ph[it]);
+                }
+            }
+            g.sync();
+            lp = M::logp_grad(g, P->mdata, D, qd, gd, msm);
+            g.sync();
+            double acc[2] = {0.0, 0.0};
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = g.tid + it * G::kThreads;
+                if (i < D) {
+                    const double gn = gd[i];
+                    const double pn = ph[it] + heps * gn;
+                    acc[0] += pn * (vr[it] * pn);
+                    pd[i] = pn;
+                    sd[i] = restart_sum ? pn : ss[i] + pn;
+                    if (!nb_isfinite(gn)) acc[1] += 1.0;
+                }
+            }
+            g.reduce(acc);
+            kin = 0.5 * acc[0];
+            bad = acc[1] > 0.0;
         } else {
             for (int i = g.tid; i < D; i += g.size()) {
                 const double ph = ps[i] + heps * gs[i];
@@ -284,7 +339,7 @@ struct ChainCtx {
         const double* sum_e = vec(se_, VS);
         const int mode = (a >= 0 && b >= 0) ? 0 : ((b >= 0 && a < 0) ? 1 : 2);
         double acc[2] = {0.0, 0.0};
-        for (int i = g.tid; i < D; i += g.size()) {
+        for_dims([&](int i) {
             const double pse = sum_e[i], pss = sum_s[i], pe = p_e[i], ps = p_s[i];
             double rho;
             if (mode == 0) rho = pse - pss + ps;
@@ -293,7 +348,7 @@ struct ChainCtx {
             const double vr = var[i];
             acc[0] += rho * (vr * pe);
             acc[1] += rho * (vr * ps);
-        }
+        });
         g.reduce(acc);
         return (acc[0] < 0.0) | (acc[1] < 0.0);
     }
@@ -366,91 +421,85 @@ struct ChainCtx {
             const bool check = st().check_turning && depth >= (int)st().mindepth;
             const unsigned n_leaf = 1u << depth;
             int prev = dir > 0 ? mR : mL;
-            double t_ls = 0.0;
-            bool sub_ok = true;
             lv_valid = 0;
             tL = tR = tD = -1;
-            for (unsigned j = 0; j < n_leaf && sub_ok; ++j) {
+            bool stop = false;  // the new sub-tree is discarded and the transition ends
+            for (unsigned j = 0; j < n_leaf && !stop && !done; ++j) {
                 const int dst = alloc();
                 const int rc = leapfrog(prev, dst, dir);
                 if (rc != 0) {
                     info.diverging = 1;
-                    sub_ok = false;
+                    stop = true;
                     break;
                 }
                 tL = tR = tD = dst;
-                t_ls = -last_de;
+                double t_ls = -last_de;
                 int k = 0;
-                while ((j >> k) & 1u) {  // level k holds the earlier sibling: merge
-                    const int sL = sh->lvL[k], sR = sh->lvR[k], sD = sh->lvD[k];
-                    const double s_ls = sh->lvLS[k];
+                // Merge the new leaf with the parked siblings of equal depth (binary
+                // counter) and — once the sub-tree is complete — with the main tree.
+                for (;;) {
+                    bool with_main;
+                    if ((j >> k) & 1u) with_main = false;
+                    else if (j + 1 == n_leaf && k == depth) with_main = true;
+                    else break;
+                    const int sL = with_main ? mL : sh->lvL[k];
+                    const int sR = with_main ? mR : sh->lvR[k];
+                    const int sD = with_main ? mD : sh->lvD[k];
+                    const double s_ls = with_main ? m_ls : sh->lvLS[k];
                     bool turn = false;
                     if (check) {
-                        const int first = dir > 0 ? sL : tL;
-                        const int last = dir > 0 ? tR : sR;
-                        turn = is_turning(first, last);
-                        if (k > 0) {
-                            if (!turn) turn = is_turning(sR, tR);
-                            if (!turn) turn = is_turning(sL, tL);
+                        // full span, then the two cross-junction checks (depth > 0 only)
+                        const int pa0 = dir > 0 ? sL : tL, pb0 = dir > 0 ? tR : sR;
+                        const int n_checks = k > 0 ? 3 : 1;
+                        for (int c = 0; c < n_checks && !turn; ++c) {
+                            const int pa = c == 0 ? pa0 : (c == 1 ? sR : sL);
+                            const int pb = c == 0 ? pb0 : (c == 1 ? tR : tL);
+                            turn = is_turning(pa, pb);
                         }
                     }
                     const double new_ls = nb_logaddexp(s_ls, t_ls);
                     rng_u64x2(st().seed, chain_gid, t, RNG_MERGE, n_merge, ra, rb);
                     n_merge += 1;
                     const double u = rng_u01(ra);
-                    // multinomial pick inside a sub-tree
-                    if (!(t_ls >= new_ls || u < exp(t_ls - new_ls))) tD = sD;
+                    // multinomial pick inside a sub-tree, biased progressive for the main tree
+                    const double ref_ls = with_main ? s_ls : new_ls;
+                    const bool take_new = t_ls >= ref_ls || u < exp(t_ls - ref_ls);
+                    if (with_main) {
+                        if (take_new) mD = tD;
+                        if (dir > 0) mR = tR;
+                        else mL = tL;
+                        m_ls = new_ls;
+                        depth += 1;
+                        tL = tR = tD = -1;
+                        if (turn) done = true;
+                        break;
+                    }
+                    if (!take_new) tD = sD;
                     if (dir > 0) tL = sL;
                     else tR = sR;
                     t_ls = new_ls;
                     lv_valid &= ~(1u << k);
                     ++k;
                     if (turn) {
-                        sub_ok = false;
+                        stop = true;
                         break;
                     }
                 }
-                if (!sub_ok) break;
-                if (j + 1 < n_leaf) {  // park the finished sub-tree at its level
-                    g.sync();          // earlier readers of the level arrays are done
-                    if (g.tid == 0) {
-                        sh->lvL[k] = tL;
-                        sh->lvR[k] = tR;
-                        sh->lvD[k] = tD;
-                        sh->lvLS[k] = t_ls;
-                    }
-                    g.sync();
-                    lv_valid |= 1u << k;
-                    tL = tR = tD = -1;
+                if (stop || tL < 0) break;  // discarded, or merged into the main tree
+                // park the finished sub-tree at its level
+                g.sync();  // earlier readers of the level arrays are done
+                if (g.tid == 0) {
+                    sh->lvL[k] = tL;
+                    sh->lvR[k] = tR;
+                    sh->lvD[k] = tD;
+                    sh->lvLS[k] = t_ls;
                 }
+                g.sync();
+                lv_valid |= 1u << k;
+                tL = tR = tD = -1;
                 prev = dst;
             }
-            if (!sub_ok) {  // turning inside the new sub-tree or divergence: discard it
-                done = true;
-                break;
-            }
-            bool turn = false;
-            if (check) {
-                const int first = dir > 0 ? mL : tL;
-                const int last = dir > 0 ? tR : mR;
-                turn = is_turning(first, last);
-                if (depth > 0) {
-                    if (!turn) turn = is_turning(mR, tR);
-                    if (!turn) turn = is_turning(mL, tL);
-                }
-            }
-            const double new_ls = nb_logaddexp(m_ls, t_ls);
-            rng_u64x2(st().seed, chain_gid, t, RNG_MERGE, n_merge, ra, rb);
-            n_merge += 1;
-            const double u = rng_u01(ra);
-            // biased progressive pick for the main tree
-            if (t_ls >= m_ls || u < exp(t_ls - m_ls)) mD = tD;
-            if (dir > 0) mR = tR;
-            else mL = tL;
-            m_ls = new_ls;
-            depth += 1;
-            tL = tR = tD = -1;
-            if (turn) done = true;
+            if (stop) done = true;
         }
         if (!done) info.maxdepth_reached = 1;
         info.depth = depth;
@@ -496,37 +545,36 @@ struct ChainCtx {
         init_momentum(point, RNG_STEP_INIT, rng_draw);
         const int nxt = alloc();
         step_size = st().initial_step;
-        acc_sum = 0.0;
-        acc_count = 0;
-        int found = 0;
-        int rc = leapfrog(point, nxt, 1);
-        if (rc == 0) {
-            double accept = acc_sum;
-            const int dir = accept > st().target_accept ? 1 : -1;
-            for (int it = 0; it < 100; ++it) {
-                acc_sum = 0.0;
-                acc_count = 0;
-                rc = leapfrog(point, nxt, dir);
-                if (rc != 0) {
-                    step_size = st().initial_step;
-                    found = -1;
-                    break;
-                }
-                accept = acc_sum;
-                if (dir > 0) {
-                    if (accept <= st().target_accept || step_size > 1e5) { found = 1; break; }
-                    step_size *= 2.0;
-                } else {
-                    if (accept >= st().target_accept || step_size < 1e-10) { found = 1; break; }
-                    step_size /= 2.0;
-                }
-            }
-            if (found == 0) {
+        int dir = 1;
+        int found = 0;  // 0 searching, 1 settled (new dual average), -1 gave up
+        // iteration 0 is the forward trial step that decides whether to double or halve
+        for (int it = 0; it <= 100 && found == 0; ++it) {
+            acc_sum = 0.0;
+            acc_count = 0;
+            const int rc = leapfrog(point, nxt, dir);
+            if (rc != 0) {
                 step_size = st().initial_step;
-                found = 1;
+                found = -1;
+                break;
             }
-            if (found == 1) da_new(step_size);
+            const double accept = acc_sum;
+            if (it == 0) {
+                dir = accept > st().target_accept ? 1 : -1;
+                continue;
+            }
+            if (dir > 0) {
+                if (accept <= st().target_accept || step_size > 1e5) found = 1;
+                else step_size *= 2.0;
+            } else {
+                if (accept >= st().target_accept || step_size < 1e-10) found = 1;
+                else step_size /= 2.0;
+            }
         }
+        if (found == 0) {
+            step_size = st().initial_step;
+            found = 1;
+        }
+        if (found == 1) da_new(step_size);
         acc_sum = keep_sum;
         acc_sym = keep_sym;
         acc_count = keep_count;

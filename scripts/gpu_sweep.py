@@ -22,12 +22,14 @@ def run(n_chains, tune, draws, tpc, slots, cpb=0, model=model, **upd):
 which = sys.argv[1] if len(sys.argv) > 1 else "radon"
 if which == "radon":
     run(64, 50, 50, 32, -1)
-    for tpc in (32, 64, 128, 256):
-        for slots in (-1, 0, 2, 4, 8):
-            for cpb in ((0, 2, 4) if tpc == 32 else (0,)):
+    for tpc, slots, cpb, unroll in [(32, -1, 0, 1), (32, -1, 0, 0), (32, 8, 0, 1), (32, 2, 0, 1), (64, -1, 0, 1), (64, 8, 0, 1),
+                                    (128, -1, 0, 1), (128, 8, 0, 1), (128, -1, 0, 0), (256, -1, 0, 1)]:
+        _lib.set_unroll(unroll)
+        for _ in (0,):
+            for _ in (0,):
                 try:
                     v, ms, g = run(1024, 300, 200, tpc, slots, cpb)
-                    print(f"radon 1024ch tpc={tpc} slots={slots} cpb={cpb}: {v:.3e} evals/s  {ms:.1f} ms  {g}", flush=True)
+                    print(f"radon 1024ch tpc={tpc} slots={slots} cpb={cpb} unroll={unroll}: {v:.3e} evals/s  {ms:.1f} ms  {g}", flush=True)
                 except Exception as e:
                     print(f"radon tpc={tpc} slots={slots} cpb={cpb}: FAILED {e}", flush=True)
 elif which == "cfg4":

@@ -14,8 +14,8 @@
 
 using namespace nb200;
 
-template <class M>
-static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_t dim,
+template <class M, int NIT>
+static int run_all_nit(const nb200_settings* st, const typename M::Data& md, uint64_t dim,
                    uint64_t n_chains, uint64_t chain_id_offset, const double* q0,
                    const double* init_mean, const double* z_tape, double* draws, double* stats,
                    double* grads, double* mminv, uint64_t* total_steps, int max_per_launch, int smem_slots) {
@@ -55,7 +55,7 @@ static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_
             // the shared-memory tier does not survive a launch: scramble it
             std::fill(spool.begin(), spool.end(), -777.0);
             std::fill(svar.begin(), svar.end(), -777.0);
-            ChainCtx<M, GroupSerial> ctx;
+            ChainCtx<M, GroupSerial, NIT> ctx;
             std::memset((void*)&ctx, 0, sizeof(ctx));
             ctx.P = &P; ctx.sh = &sh; ctx.msm = msm.data();
             ctx.D = P.D; ctx.Dp = P.Dp; ctx.NS = P.NS;
@@ -72,6 +72,18 @@ static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_
     }
     if (total_steps) *total_steps = steps;
     return err;
+}
+
+// the unrolled (NIT > 0) code paths are exercised when one thread's trip count is small
+template <class M, class... A>
+static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_t dim, A... rest) {
+    switch (dim) {
+    case 1: return run_all_nit<M, 1>(st, md, dim, rest...);
+    case 2: return run_all_nit<M, 2>(st, md, dim, rest...);
+    case 5: return run_all_nit<M, 6>(st, md, dim, rest...);  // NIT * T > D: predicated tail
+    case 6: return run_all_nit<M, 6>(st, md, dim, rest...);
+    default: return run_all_nit<M, 0>(st, md, dim, rest...);
+    }
 }
 
 extern "C" int emul_sample(const nb200_settings* st, const nb200_model_desc* model,
@@ -93,8 +105,8 @@ extern "C" int emul_sample(const nb200_settings* st, const nb200_model_desc* mod
     case NB200_MODEL_RADON: {
         RadonLayout L = build_radon_layout(model->n_obs, model->n_county, model->y, model->county,
                                            model->floor, 1);
-        RadonModel::Data d{L.J, L.N, L.n_steps, L.R, L.packed.data(), L.y.data(),
-                           L.run_base.data(), L.run_start.data()};
+        RadonModel::Data d{L.J, L.N, L.n_steps, L.G, L.meta.data(), L.y.data(),
+                           L.group_base.data(), L.group_start.data()};
         return run_all<RadonModel>(st, d, model->dim, n_chains, chain_id_offset, q0, init_mean,
                                    z_tape, draws, stats, grads, mminv, total_steps, max_per_launch, smem_slots);
     }
