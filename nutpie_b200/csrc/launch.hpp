@@ -16,6 +16,6 @@ template <class M>
 cudaError_t launch_component(int W, const KParams<M>& P, int mode, const double* scal, double* out,
                              size_t smem, unsigned n);
 template <class M>
-size_t smem_fixed(int W, const typename M::Data& md);
+size_t smem_fixed(int W, const typename M::Data& md, int Dp);
 
 }  // namespace nb200

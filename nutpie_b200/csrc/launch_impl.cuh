@@ -17,7 +17,13 @@ static size_t chain_smem_fixed(const typename M::Data& md) {
     size_t b = align16(sizeof(ChainShared));
     b += align16(sizeof(double) * (size_t)M::smem_doubles(md, 32 * W));
     if (W > 1) b += align16(sizeof(double) * W * GroupCuda<W>::kMaxRed);
-    return b;
+    return b;  // + staging of q and grad for non-elementwise densities: see stage_bytes()
+}
+
+// shared staging (q, grad) for densities that gather across dimensions
+template <class M>
+__host__ __device__ inline size_t stage_bytes(int Dp) {
+    return M::kElementwise ? 0 : ((2 * sizeof(double) * (size_t)Dp + 15) & ~size_t(15));
 }
 
 template <class M, int W, int NIT>
@@ -31,6 +37,9 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, c
     off += (sizeof(double) * (size_t)M::smem_doubles(P.mdata, 32 * W) + 15) & ~size_t(15);
     ctx.g.red = reinterpret_cast<double*>(smem_chain + off);
     if (W > 1) off += (sizeof(double) * W * GroupCuda<W>::kMaxRed + 15) & ~size_t(15);
+    ctx.mq = reinterpret_cast<double*>(smem_chain + off);
+    ctx.mg = ctx.mq + P.Dp;
+    off += stage_bytes<M>(P.Dp);
     double* svar = reinterpret_cast<double*>(smem_chain + off);
     if (P.var_in_smem) off += (sizeof(double) * P.Dp + 15) & ~size_t(15);
     ctx.spool = reinterpret_cast<double*>(smem_chain + off);
@@ -158,14 +167,15 @@ cudaError_t launch_component(int W, const KParams<M>& P, int mode, const double*
 }
 
 template <class M>
-size_t smem_fixed(int W, const typename M::Data& md) {
+size_t smem_fixed(int W, const typename M::Data& md, int Dp) {
+    const size_t st = stage_bytes<M>(Dp);
     switch (W) {
-    case 1: return chain_smem_fixed<M, 1>(md);
-    case 2: return chain_smem_fixed<M, 2>(md);
-    case 4: return chain_smem_fixed<M, 4>(md);
-    case 8: return chain_smem_fixed<M, 8>(md);
-    case 16: return chain_smem_fixed<M, 16>(md);
-    default: return chain_smem_fixed<M, 32>(md);
+    case 1: return chain_smem_fixed<M, 1>(md) + st;
+    case 2: return chain_smem_fixed<M, 2>(md) + st;
+    case 4: return chain_smem_fixed<M, 4>(md) + st;
+    case 8: return chain_smem_fixed<M, 8>(md) + st;
+    case 16: return chain_smem_fixed<M, 16>(md) + st;
+    default: return chain_smem_fixed<M, 32>(md) + st;
     }
 }
 
@@ -175,6 +185,6 @@ size_t smem_fixed(int W, const typename M::Data& md) {
                                         cudaStream_t);                                          \
     template cudaError_t launch_component<M>(int, const KParams<M>&, int, const double*,        \
                                              double*, size_t, unsigned);                        \
-    template size_t smem_fixed<M>(int, const M::Data&);
+    template size_t smem_fixed<M>(int, const M::Data&, int);
 
 }  // namespace nb200

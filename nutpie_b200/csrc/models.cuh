@@ -19,6 +19,9 @@
 
 namespace nb200 {
 
+struct RadonObs;
+NB_HD RadonObs nb_ldg_obs(const RadonObs* p);
+
 #define NB_LOG_2PI 1.8378770664093454835606594728112
 #define NB_HALF_LOG_2_OVER_PI (-0.22579135264472743236309761494744)
 
@@ -72,26 +75,47 @@ struct FunnelModel {
 //
 // Data layout (built on the host for the group size T, radon_layout.hpp): the
 // observations are sorted by (county, floor) and cut into T contiguous ranges,
-// one per thread, stored transposed ([step][thread]) so a warp's loads
-// coalesce.  Inside a range, a GROUP is a maximal run of equal (county, floor):
-// all its observations share the linear predictor mu[2*county + floor], which
-// every thread reads from a shared table.  A thread keeps one running sum of
-// residuals and stores it into the group's private slot when the group ends
-// (flag bit in the per-observation word).  Because ranges are contiguous the
-// groups of one (county, floor) pair are contiguous in slot order: the
-// per-county gradient is a short fixed-order sum — no atomics, bitwise
-// reproducible (determinism contract, tests/test_stan.py:67-101).
+// one per thread, stored transposed ([step][thread]) as 16-byte records
+// {y, meta} so a warp's loads coalesce into one LDG.128 per observation.  Inside
+// a range, a GROUP is a maximal run of equal (county, floor): all its
+// observations share the linear predictor mu[2*county + floor], which every
+// thread reads from a shared table (meta carries its byte offset).  The walk is
+// branch-free: the running sum of residuals is stored to the group's private
+// slot after EVERY observation and the slot pointer advances when the end-of-
+// group bit is set, so the last store of a group wins.  Because ranges are
+// contiguous, a (county, floor) pair owns at most `kmax` groups; the host lists
+// them (padded with a slot that always holds 0), so the per-county gradient is a
+// fixed-order sum of kmax terms — no atomics, no data-dependent branches,
+// bitwise reproducible (determinism contract, tests/test_stan.py:67-101).
+struct RadonObs {
+    double y;
+    int32_t meta;  // byte offset of mu[2*county+floor] | 1 if last observation of its group
+    int32_t pad;
+};
+
+NB_HD RadonObs nb_ldg_obs(const RadonObs* p) {
+#ifdef __CUDA_ARCH__
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    RadonObs r;
+    r.y = __hiloint2double(v.y, v.x);
+    r.meta = v.z;
+    r.pad = 0;
+    return r;
+#else
+    return *p;
+#endif
+}
+
 struct RadonModel {
     static constexpr bool kElementwise = false;
-    static constexpr int kEndFlag = 1 << 30;
     struct Data {
-        int J, N, n_steps, G;       // counties, observations, steps per thread, total groups
-        const int32_t* meta;        // [n_steps][T]  (2*county + floor) | kEndFlag; -1 = padding
-        const double* y;            // [n_steps][T]
-        const int32_t* group_base;  // [T]     first group slot of each thread
-        const int32_t* group_start; // [2J+1]  first group slot of each (county, floor) pair
+        int J, N, n_steps, G, kmax;  // counties, observations, steps/thread, group slots, pieces per pair
+        const RadonObs* obs;         // [n_steps][T]; padding: y = 0, meta -> mu[2J] (= 0), no end bit
+        const int32_t* group_base;   // [T]   first group slot of each thread (one spare slot each)
+        const uint16_t* group_list;  // [2J][kmax] group slots of each (county, floor); padding -> slot G
     };
-    NB_HD static int smem_doubles(const Data& d, int) { return 2 * d.J + d.G; }
+    // mu[2J+1] (last = 0 for padding) + gsum[G+1] (last = 0 for padding)
+    NB_HD static int smem_doubles(const Data& d, int) { return 2 * d.J + 1 + d.G + 1; }
 
     template <class G>
     NB_HD static double logp_grad(const G& grp, const Data& d, int, const double* q, double* g,
@@ -105,51 +129,54 @@ struct RadonModel {
         const double sd_a = exp(log_sd_a), sd_b = exp(log_sd_b), sigma = exp(log_sigma);
         const double inv_sigma = 1.0 / sigma;
         const double inv_s2 = inv_sigma * inv_sigma;
-        double* mu = sm;            // [2J] linear predictor per (county, floor)
-        double* gsum = sm + 2 * J;  // [G]  per-group sum of residuals
+        double* mu = sm;                // [2J+1] linear predictor per (county, floor)
+        double* gsum = sm + 2 * J + 1;  // [G+1]  per-group sum of residuals
         for (int c = grp.tid; c < J; c += T) {
             const double a = intercept + q[1 + c] * sd_a;
             mu[2 * c] = a;
             mu[2 * c + 1] = a + (floor_eff + q[J + 3 + c] * sd_b);
         }
+        if (grp.tid == 0) {
+            mu[2 * J] = 0.0;
+            gsum[d.G] = 0.0;
+        }
         grp.sync();
-        double ss = 0.0;
+        double ss0 = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
         {
-            int k = nb_ldg(d.group_base + grp.tid);
+            char* kp = reinterpret_cast<char*>(gsum + nb_ldg(d.group_base + grp.tid));
+            const char* mub = reinterpret_cast<const char*>(mu);
+            const RadonObs* ob = d.obs + grp.tid;
             double s1 = 0.0;
-            // n_steps is padded to a multiple of 4 with meta = -1: the loads of four
-            // steps and their mu lookups are independent of the running sums
+            // n_steps is a multiple of 4: four records are loaded before they are consumed
             for (int j0 = 0; j0 < d.n_steps; j0 += 4) {
-                int mt[4];
-                double yv[4];
+                RadonObs rec[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rec[u] = nb_ldg_obs(ob + (size_t)(j0 + u) * T);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    mt[u] = nb_ldg(d.meta + (size_t)(j0 + u) * T + grp.tid);
-                    yv[u] = nb_ldg(d.y + (size_t)(j0 + u) * T + grp.tid);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (mt[u] >= 0) {
-                        const double r = yv[u] - mu[mt[u] & 0xFFFF];
-                        ss += r * r;
-                        s1 += r;
-                        if (mt[u] & kEndFlag) {
-                            gsum[k] = s1;
-                            ++k;
-                            s1 = 0.0;
-                        }
-                    }
+                    const int mt = rec[u].meta;
+                    const double r = rec[u].y - *reinterpret_cast<const double*>(mub + (mt & ~7));
+                    if (u == 0) ss0 += r * r;
+                    else if (u == 1) ss1 += r * r;
+                    else if (u == 2) ss2 += r * r;
+                    else ss3 += r * r;
+                    s1 += r;
+                    *reinterpret_cast<double*>(kp) = s1;
+                    const bool e = mt & 1;
+                    kp += e ? 8 : 0;
+                    s1 = e ? 0.0 : s1;
                 }
             }
         }
         grp.sync();
-        double acc[7] = {ss, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        double acc[7] = {(ss0 + ss1) + (ss2 + ss3), 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         for (int c = grp.tid; c < J; c += T) {
-            const int g0 = nb_ldg(d.group_start + 2 * c), g1 = nb_ldg(d.group_start + 2 * c + 1),
-                      g2 = nb_ldg(d.group_start + 2 * c + 2);
+            const uint16_t* gl = d.group_list + (size_t)(2 * c) * d.kmax;
             double S0 = 0.0, S1 = 0.0;
-            for (int r = g0; r < g1; ++r) S0 += gsum[r];
-            for (int r = g1; r < g2; ++r) S1 += gsum[r];
+            for (int k = 0; k < d.kmax; ++k) {
+                S0 += gsum[nb_ldg(gl + k)];
+                S1 += gsum[nb_ldg(gl + d.kmax + k)];
+            }
             const double E = (S0 + S1) * inv_s2;  // sum over the county of d logp / d mu_i
             const double F = S1 * inv_s2;         // same, floor = 1 observations only
             const double ra = q[1 + c], rb = q[J + 3 + c];

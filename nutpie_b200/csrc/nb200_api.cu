@@ -106,8 +106,8 @@ struct SamplerImpl : nb200_sampler {
 };
 
 template <class M>
-static size_t smem_for(int W, const typename M::Data& md) {
-    return smem_fixed<M>(W, md);
+static size_t smem_for(int W, const typename M::Data& md, int Dp) {
+    return smem_fixed<M>(W, md, Dp);
 }
 
 static int pick_W(const nb200_model_desc& m, uint64_t n_chains) {
@@ -172,15 +172,16 @@ static int build_model_data(const nb200_model_desc&, int, FunnelModel::Data& d,
 static int build_model_data(const nb200_model_desc& m, int T, RadonModel::Data& d,
                             std::vector<void*>& keep) {
     RadonLayout L = build_radon_layout(m.n_obs, m.n_county, m.y, m.county, m.floor, T);
-    d.J = L.J; d.N = L.N; d.n_steps = L.n_steps; d.G = L.G;
-    int32_t *meta, *group_base, *group_start;
-    double* y;
+    if (L.G >= 65535) return fail(NB200_EINVAL, "radon: too many observation groups");
+    d.J = L.J; d.N = L.N; d.n_steps = L.n_steps; d.G = L.G; d.kmax = L.kmax;
+    RadonObs* obs;
+    int32_t* group_base;
+    uint16_t* group_list;
     int rc;
-    if ((rc = to_device(L.meta, &meta, keep))) return rc;
-    if ((rc = to_device(L.y, &y, keep))) return rc;
+    if ((rc = to_device(L.obs, &obs, keep))) return rc;
     if ((rc = to_device(L.group_base, &group_base, keep))) return rc;
-    if ((rc = to_device(L.group_start, &group_start, keep))) return rc;
-    d.meta = meta; d.y = y; d.group_base = group_base; d.group_start = group_start;
+    if ((rc = to_device(L.group_list, &group_list, keep))) return rc;
+    d.obs = obs; d.group_base = group_base; d.group_list = group_list;
     return 0;
 }
 
@@ -217,7 +218,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     std::memset(&P, 0, sizeof(P));
     P.st = *st;
     if (build_model_data(*m, 32 * s->W, P.mdata, s->model_allocs) != 0) return bail();
-    const size_t fixed = smem_for<M>(s->W, P.mdata);
+    const size_t fixed = smem_for<M>(s->W, P.mdata, s->Dp);
     if (s->W == 1) {
         int c = g_chains_per_block.load();
         if (c <= 0) {
@@ -792,7 +793,7 @@ static int component_run(const nb200_model_desc* model, int device, uint64_t n, 
     }
     CU(cudaMemcpy(d_scal, hs.data(), n * 4 * sizeof(double), cudaMemcpyHostToDevice));
     P.pool = d_pool; P.var = d_var;
-    const size_t smem = smem_for<M>(W, P.mdata);
+    const size_t smem = smem_for<M>(W, P.mdata, Dp);
     CU(launch_component<M>(W, P, mode, d_scal, d_out, smem, (unsigned)n));
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());

@@ -112,6 +112,7 @@ struct ChainCtx {
     const KParams<M>* P;
     ChainShared* sh;
     double* msm;  // model scratch (shared)
+    double *mq, *mg;  // shared staging of the position / gradient the density works on
     int D, Dp, NS;
     unsigned long long chain_local;
     uint32_t chain_gid;
@@ -199,11 +200,14 @@ struct ChainCtx {
             lp = M::finish(P->mdata, acc[0], D);
             flag[0] = acc[1];
         } else {
+            for_dims([&](int i) { mq[i] = q[i]; });
             g.sync();
-            lp = M::logp_grad(g, P->mdata, D, q, gr, msm);
+            lp = M::logp_grad(g, P->mdata, D, mq, mg, msm);
             g.sync();
             for_dims([&](int i) {
-                if (!nb_isfinite(gr[i])) flag[0] += 1.0;
+                const double gn = mg[i];
+                gr[i] = gn;
+                if (!nb_isfinite(gn)) flag[0] += 1.0;
             });
             g.reduce(flag);
         }
@@ -260,18 +264,21 @@ struct ChainCtx {
                 if (i < D) {
                     vr[it] = var[i];
                     ph[it] = ps[i] + heps * gs[i];
-                    qd[i] = qs[i] + eps * (vr[it] * ph[it]);
+                    const double qn = qs[i] + eps * (vr[it] * ph[it]);
+                    qd[i] = qn;
+                    mq[i] = qn;
                 }
             }
             g.sync();
-            lp = M::logp_grad(g, P->mdata, D, qd, gd, msm);
+            lp = M::logp_grad(g, P->mdata, D, mq, mg, msm);
             g.sync();
             double acc[2] = {0.0, 0.0};
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int i = g.tid + it * G::kThreads;
                 if (i < D) {
-                    const double gn = gd[i];
+                    const double gn = mg[i];
+                    gd[i] = gn;
                     const double pn = ph[it] + heps * gn;
                     acc[0] += pn * (vr[it] * pn);
                     pd[i] = pn;
@@ -286,14 +293,17 @@ struct ChainCtx {
             for (int i = g.tid; i < D; i += g.size()) {
                 const double ph = ps[i] + heps * gs[i];
                 pd[i] = ph;
-                qd[i] = qs[i] + eps * (var[i] * ph);
+                const double qn = qs[i] + eps * (var[i] * ph);
+                qd[i] = qn;
+                mq[i] = qn;
             }
             g.sync();
-            lp = M::logp_grad(g, P->mdata, D, qd, gd, msm);
+            lp = M::logp_grad(g, P->mdata, D, mq, mg, msm);
             g.sync();
             double acc[2] = {0.0, 0.0};
             for (int i = g.tid; i < D; i += g.size()) {
-                const double gn = gd[i];
+                const double gn = mg[i];
+                gd[i] = gn;
                 const double pn = pd[i] + heps * gn;
                 acc[0] += pn * (var[i] * pn);
                 pd[i] = pn;

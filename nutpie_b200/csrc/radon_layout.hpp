@@ -11,19 +11,19 @@
 #include <numeric>
 #include <vector>
 
+#include "models.cuh"
+
 namespace nb200 {
 
 struct RadonLayout {
-    int J = 0, N = 0, T = 0, n_steps = 0, G = 0;
-    std::vector<int32_t> meta;         // [n_steps][T]  (2*county+floor) | end-of-group flag
-    std::vector<double> y;             // [n_steps][T]
-    std::vector<int32_t> group_base;   // [T]
-    std::vector<int32_t> group_start;  // [2J+1]
+    int J = 0, N = 0, T = 0, n_steps = 0, G = 0, kmax = 1;
+    std::vector<RadonObs> obs;           // [n_steps][T]
+    std::vector<int32_t> group_base;     // [T]
+    std::vector<uint16_t> group_list;    // [2J][kmax]
 };
 
 inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
                                       const int32_t* county, const uint8_t* floor, int T) {
-    constexpr int32_t kEndFlag = 1 << 30;
     RadonLayout L;
     L.J = n_county;
     L.N = n_obs;
@@ -33,14 +33,14 @@ inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
     auto key = [&](int o) { return 2 * county[o] + (floor[o] ? 1 : 0); };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
     const int per = (n_obs + T - 1) / T;  // observations per thread
-    L.n_steps = ((per > 0 ? per : 1) + 3) / 4 * 4;  // padded: the device loop is unrolled by 4
-    L.meta.assign((size_t)L.n_steps * T, -1);
-    L.y.assign((size_t)L.n_steps * T, 0.0);
+    L.n_steps = ((per > 0 ? per : 1) + 3) / 4 * 4;  // the device loop is unrolled by 4
+    const int32_t dummy_mu = (int32_t)(2 * n_county) * 8;  // byte offset of mu[2J] (always 0)
+    L.obs.assign((size_t)L.n_steps * T, RadonObs{0.0, dummy_mu, 0});
     L.group_base.assign(T, 0);
-    L.group_start.assign(2 * n_county + 1, 0);
-    std::vector<int> group_key;
+    std::vector<std::vector<int>> pieces(2 * n_county);
+    int slot = 0;
     for (int t = 0; t < T; ++t) {
-        L.group_base[t] = (int32_t)group_key.size();
+        L.group_base[t] = slot;
         for (int j = 0; j < per; ++j) {
             const int pos = t * per + j;
             if (pos >= n_obs) break;
@@ -48,20 +48,18 @@ inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
             const int kcur = key(o);
             const bool last_of_range = (j + 1 == per) || (pos + 1 >= n_obs);
             const bool ends = last_of_range || key(order[pos + 1]) != kcur;
-            L.meta[(size_t)j * T + t] = kcur | (ends ? kEndFlag : 0);
-            L.y[(size_t)j * T + t] = y[o];
-            if (ends) group_key.push_back(kcur);
+            L.obs[(size_t)j * T + t] = RadonObs{y[o], (int32_t)(kcur * 8) | (ends ? 1 : 0), 0};
+            if (ends) pieces[kcur].push_back(slot++);
         }
+        ++slot;  // spare slot: receives the stores issued after the thread's last group ended
     }
-    L.G = (int)group_key.size();
-    // groups are ordered by key because the observations are; pair k owns the
-    // contiguous slot range [group_start[k], group_start[k+1])
-    size_t r = 0;
-    for (int k = 0; k <= 2 * n_county; ++k) {
-        while (r < group_key.size() && group_key[r] < k) ++r;
-        L.group_start[k] = (int32_t)r;
-    }
-    if (L.G == 0) L.G = 1;
+    L.G = slot;  // slot G itself (one past) always holds 0 and pads the lists
+    L.kmax = 1;
+    for (auto& p : pieces) L.kmax = std::max<int>(L.kmax, (int)p.size());
+    L.group_list.assign((size_t)2 * n_county * L.kmax, (uint16_t)L.G);
+    for (int k = 0; k < 2 * n_county; ++k)
+        for (size_t i = 0; i < pieces[k].size(); ++i)
+            L.group_list[(size_t)k * L.kmax + i] = (uint16_t)pieces[k][i];
     return L;
 }
 
