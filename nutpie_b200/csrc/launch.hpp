@@ -10,8 +10,10 @@ namespace nb200 {
 template <class M>
 int supported_nit(int W, int nit);
 template <class M>
-cudaError_t launch_nuts(int W, int NIT, const KParams<M>& P, size_t smem_per_chain, int cpb,
-                        int grid, int block, cudaStream_t stream);
+cudaError_t launch_nuts(int W, int NIT, const KParams<M>& P, size_t smem_per_chain,
+                        size_t block_data, int cpb, int grid, int block, cudaStream_t stream);
+template <class M>
+size_t model_block_data_bytes(const typename M::Data& md);
 template <class M>
 cudaError_t launch_component(int W, const KParams<M>& P, int mode, const double* scal, double* out,
                              size_t smem, unsigned n);

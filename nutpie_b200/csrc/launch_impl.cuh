@@ -17,13 +17,14 @@ static size_t chain_smem_fixed(const typename M::Data& md) {
     size_t b = align16(sizeof(ChainShared));
     b += align16(sizeof(double) * (size_t)M::smem_doubles(md, 32 * W));
     if (W > 1) b += align16(sizeof(double) * W * GroupCuda<W>::kMaxRed);
-    return b;  // + staging of q and grad for non-elementwise densities: see stage_bytes()
+    return b;  // + the front buffer of non-elementwise densities: see stage_bytes()
 }
 
-// shared staging (q, grad) for densities that gather across dimensions
+// shared-memory front (q, p, grad, p_sum of the newest leaf) for densities that gather
+// across dimensions; elementwise densities stream straight from the pool
 template <class M>
 __host__ __device__ inline size_t stage_bytes(int Dp) {
-    return M::kElementwise ? 0 : ((2 * sizeof(double) * (size_t)Dp + 15) & ~size_t(15));
+    return M::kElementwise ? 0 : ((4 * sizeof(double) * (size_t)Dp + 15) & ~size_t(15));
 }
 
 template <class M, int W, int NIT>
@@ -31,14 +32,15 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, c
                                           unsigned long long chain, unsigned char* smem_chain) {
     ctx.g.tid = (W == 1) ? (threadIdx.x & 31) : threadIdx.x;
     ctx.P = &P;
+    ctx.md = P.mdata;
     ctx.sh = reinterpret_cast<ChainShared*>(smem_chain);
     size_t off = (sizeof(ChainShared) + 15) & ~size_t(15);
     ctx.msm = reinterpret_cast<double*>(smem_chain + off);
     off += (sizeof(double) * (size_t)M::smem_doubles(P.mdata, 32 * W) + 15) & ~size_t(15);
     ctx.g.red = reinterpret_cast<double*>(smem_chain + off);
     if (W > 1) off += (sizeof(double) * W * GroupCuda<W>::kMaxRed + 15) & ~size_t(15);
-    ctx.mq = reinterpret_cast<double*>(smem_chain + off);
-    ctx.mg = ctx.mq + P.Dp;
+    ctx.front = reinterpret_cast<double*>(smem_chain + off);
+    ctx.front_slot = -1;
     off += stage_bytes<M>(P.Dp);
     double* svar = reinterpret_cast<double*>(smem_chain + off);
     if (P.var_in_smem) off += (sizeof(double) * P.Dp + 15) & ~size_t(15);
@@ -61,14 +63,22 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, c
 // One persistent launch advances every chain through all its draws.
 template <class M, int W, int NIT>
 __global__ void __launch_bounds__(W == 1 ? 256 : 32 * W)
-    nuts_kernel(const __grid_constant__ KParams<M> P, size_t smem_per_chain) {
+    nuts_kernel(const __grid_constant__ KParams<M> P, size_t smem_per_chain, size_t block_data) {
     extern __shared__ __align__(16) unsigned char smem[];
+    typename M::Data md = P.mdata;
+    if constexpr (M::kHasBlockData) {
+        if (block_data > 0) {  // CTA-wide copy of the density's constant tables
+            M::load_block_data(md, smem, threadIdx.x, blockDim.x);
+            __syncthreads();
+        }
+    }
     const int local = (W == 1) ? (threadIdx.x >> 5) : 0;
     const int cpb = (W == 1) ? (blockDim.x >> 5) : 1;
     const unsigned long long chain = (unsigned long long)blockIdx.x * cpb + local;
     if (chain >= P.n_chains) return;
     ChainCtx<M, GroupCuda<W>, NIT> ctx;
-    setup_ctx<M, W, NIT>(ctx, P, chain, smem + (size_t)local * smem_per_chain);
+    setup_ctx<M, W, NIT>(ctx, P, chain, smem + block_data + (size_t)local * smem_per_chain);
+    ctx.md = md;
     ctx.run();
 }
 
@@ -115,15 +125,15 @@ __global__ void __launch_bounds__(32 * W)
 }
 
 template <class M, int W, int NIT>
-static cudaError_t launch_one(const KParams<M>& P, size_t smem_per_chain, int cpb, int grid,
-                              int block, cudaStream_t stream) {
-    const size_t smem = smem_per_chain * cpb;
+static cudaError_t launch_one(const KParams<M>& P, size_t smem_per_chain, size_t block_data, int cpb,
+                              int grid, int block, cudaStream_t stream) {
+    const size_t smem = block_data + smem_per_chain * cpb;
     cudaError_t e = cudaFuncSetAttribute(nuts_kernel<M, W, NIT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(nuts_kernel<M, W, NIT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    nuts_kernel<M, W, NIT><<<grid, block, smem, stream>>>(P, smem_per_chain);
+    nuts_kernel<M, W, NIT><<<grid, block, smem, stream>>>(P, smem_per_chain, block_data);
     return cudaGetLastError();
 }
 
@@ -137,10 +147,11 @@ int supported_nit(int W, int nit) {
 }
 
 template <class M>
-cudaError_t launch_nuts(int W, int NIT, const KParams<M>& P, size_t smem_per_chain, int cpb,
-                        int grid, int block, cudaStream_t stream) {
-#define NB_CASE(WW, NN) \
-    if (W == WW && NIT == NN) return launch_one<M, WW, NN>(P, smem_per_chain, cpb, grid, block, stream);
+cudaError_t launch_nuts(int W, int NIT, const KParams<M>& P, size_t smem_per_chain,
+                        size_t block_data, int cpb, int grid, int block, cudaStream_t stream) {
+#define NB_CASE(WW, NN)                                                                       \
+    if (W == WW && NIT == NN)                                                                 \
+        return launch_one<M, WW, NN>(P, smem_per_chain, block_data, cpb, grid, block, stream);
     NB_CASE(1, 1) NB_CASE(1, 2) NB_CASE(1, 3) NB_CASE(1, 4) NB_CASE(1, 6) NB_CASE(1, 8) NB_CASE(1, 0)
     NB_CASE(2, 1) NB_CASE(2, 2) NB_CASE(2, 3) NB_CASE(2, 4) NB_CASE(2, 0)
     NB_CASE(4, 1) NB_CASE(4, 2) NB_CASE(4, 0)
@@ -179,12 +190,19 @@ size_t smem_fixed(int W, const typename M::Data& md, int Dp) {
     }
 }
 
+template <class M>
+size_t model_block_data_bytes(const typename M::Data& md) {
+    if constexpr (M::kHasBlockData) return (M::block_data_bytes(md) + 15) & ~size_t(15);
+    else return 0;
+}
+
 #define NB200_INSTANTIATE_MODEL(M)                                                              \
     template int supported_nit<M>(int, int);                                                    \
-    template cudaError_t launch_nuts<M>(int, int, const KParams<M>&, size_t, int, int, int,     \
-                                        cudaStream_t);                                          \
+    template cudaError_t launch_nuts<M>(int, int, const KParams<M>&, size_t, size_t, int, int,  \
+                                        int, cudaStream_t);                                          \
     template cudaError_t launch_component<M>(int, const KParams<M>&, int, const double*,        \
                                              double*, size_t, unsigned);                        \
-    template size_t smem_fixed<M>(int, const M::Data&, int);
+    template size_t smem_fixed<M>(int, const M::Data&, int);                                    \
+    template size_t model_block_data_bytes<M>(const M::Data&);
 
 }  // namespace nb200

@@ -20,7 +20,11 @@
 namespace nb200 {
 
 struct RadonObs;
-NB_HD RadonObs nb_ldg_obs(const RadonObs* p);
+NB_HD RadonObs nb_ldg_obs(const RadonObs* p, bool in_smem);
+template <class T>
+NB_HD T nb_ld_tab(const T* p, bool in_smem) {
+    return in_smem ? *p : nb_ldg(p);
+}
 
 #define NB_LOG_2PI 1.8378770664093454835606594728112
 #define NB_HALF_LOG_2_OVER_PI (-0.22579135264472743236309761494744)
@@ -29,6 +33,7 @@ NB_HD RadonObs nb_ldg_obs(const RadonObs* p);
 // tests/test_stan.py:16-24) and the D = 10 000 bandwidth-bound config 4.
 struct NormalModel {
     static constexpr bool kElementwise = true;
+    static constexpr bool kHasBlockData = false;
     struct Data {
         double mu, inv_var;
     };
@@ -44,6 +49,7 @@ struct NormalModel {
 // Neal's funnel (docs/sample-stats.qmd:19-21; 9 parameters in BASELINE.json)
 struct FunnelModel {
     static constexpr bool kElementwise = false;
+    static constexpr bool kHasBlockData = false;
     struct Data {
         int unused;
     };
@@ -93,9 +99,16 @@ struct RadonObs {
     int32_t pad;
 };
 
-NB_HD RadonObs nb_ldg_obs(const RadonObs* p) {
+NB_HD RadonObs nb_ldg_obs(const RadonObs* p, bool in_smem) {
 #ifdef __CUDA_ARCH__
-    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    int4 v;
+    if (in_smem) {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"((unsigned)__cvta_generic_to_shared(p)));
+    } else {
+        v = __ldg(reinterpret_cast<const int4*>(p));
+    }
     RadonObs r;
     r.y = __hiloint2double(v.y, v.x);
     r.meta = v.z;
@@ -108,12 +121,41 @@ NB_HD RadonObs nb_ldg_obs(const RadonObs* p) {
 
 struct RadonModel {
     static constexpr bool kElementwise = false;
+    // The observation records and group tables are the same for every chain: a CTA
+    // that hosts several chains copies them into shared memory once (launch_impl.cuh).
+    static constexpr bool kHasBlockData = true;
     struct Data {
         int J, N, n_steps, G, kmax;  // counties, observations, steps/thread, group slots, pieces per pair
+        int T, in_smem;              // group size the layout was built for; tables live in shared memory
         const RadonObs* obs;         // [n_steps][T]; padding: y = 0, meta -> mu[2J] (= 0), no end bit
         const int32_t* group_base;   // [T]   first group slot of each thread (one spare slot each)
         const uint16_t* group_list;  // [2J][kmax] group slots of each (county, floor); padding -> slot G
     };
+    NB_HD static size_t block_data_bytes(const Data& d) {
+        size_t b = sizeof(RadonObs) * (size_t)d.n_steps * d.T;
+        b += (sizeof(uint16_t) * (size_t)2 * d.J * d.kmax + 15) & ~size_t(15);
+        b += (sizeof(int32_t) * (size_t)d.T + 15) & ~size_t(15);
+        return b;
+    }
+#ifdef __CUDACC__
+    // all threads of the CTA copy the tables; the caller synchronises
+    __device__ static void load_block_data(Data& d, unsigned char* dst, int tid, int nthreads) {
+        const int n16 = d.n_steps * d.T;  // 16-byte records
+        int4* o = reinterpret_cast<int4*>(dst);
+        const int4* src = reinterpret_cast<const int4*>(d.obs);
+        for (int i = tid; i < n16; i += nthreads) o[i] = __ldg(src + i);
+        size_t off = sizeof(RadonObs) * (size_t)n16;
+        uint16_t* gl = reinterpret_cast<uint16_t*>(dst + off);
+        for (int i = tid; i < 2 * d.J * d.kmax; i += nthreads) gl[i] = __ldg(d.group_list + i);
+        off += (sizeof(uint16_t) * (size_t)2 * d.J * d.kmax + 15) & ~size_t(15);
+        int32_t* gb = reinterpret_cast<int32_t*>(dst + off);
+        for (int i = tid; i < d.T; i += nthreads) gb[i] = __ldg(d.group_base + i);
+        d.obs = reinterpret_cast<const RadonObs*>(dst);
+        d.group_list = gl;
+        d.group_base = gb;
+        d.in_smem = 1;
+    }
+#endif
     // mu[2J+1] (last = 0 for padding) + gsum[G+1] (last = 0 for padding)
     NB_HD static int smem_doubles(const Data& d, int) { return 2 * d.J + 1 + d.G + 1; }
 
@@ -143,7 +185,7 @@ struct RadonModel {
         grp.sync();
         double ss0 = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
         {
-            char* kp = reinterpret_cast<char*>(gsum + nb_ldg(d.group_base + grp.tid));
+            char* kp = reinterpret_cast<char*>(gsum + nb_ld_tab(d.group_base + grp.tid, d.in_smem));
             const char* mub = reinterpret_cast<const char*>(mu);
             const RadonObs* ob = d.obs + grp.tid;
             double s1 = 0.0;
@@ -151,7 +193,7 @@ struct RadonModel {
             for (int j0 = 0; j0 < d.n_steps; j0 += 4) {
                 RadonObs rec[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) rec[u] = nb_ldg_obs(ob + (size_t)(j0 + u) * T);
+                for (int u = 0; u < 4; ++u) rec[u] = nb_ldg_obs(ob + (size_t)(j0 + u) * T, d.in_smem);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int mt = rec[u].meta;
@@ -174,8 +216,8 @@ struct RadonModel {
             const uint16_t* gl = d.group_list + (size_t)(2 * c) * d.kmax;
             double S0 = 0.0, S1 = 0.0;
             for (int k = 0; k < d.kmax; ++k) {
-                S0 += gsum[nb_ldg(gl + k)];
-                S1 += gsum[nb_ldg(gl + d.kmax + k)];
+                S0 += gsum[nb_ld_tab(gl + k, d.in_smem)];
+                S1 += gsum[nb_ld_tab(gl + d.kmax + k, d.in_smem)];
             }
             const double E = (S0 + S1) * inv_s2;  // sum over the county of d logp / d mu_i
             const double F = S1 * inv_s2;         // same, floor = 1 observations only

@@ -70,7 +70,7 @@ struct nb200_sampler {
     nb200_model_desc model{};
     uint64_t n_chains = 0, chain_id_offset = 0;
     int W = 1, NIT = 0, cpb = 1, grid = 0, block = 0;
-    size_t smem_per_chain = 0;
+    size_t smem_per_chain = 0, block_data = 0;
     cudaStream_t stream = nullptr, side = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     RunState state = RunState::Created;
@@ -99,7 +99,7 @@ struct SamplerImpl : nb200_sampler {
     KParams<M> P;
     int launch() override {
         P.max_draws_per_launch = draws_per_launch;
-        cudaError_t e = launch_nuts<M>(W, NIT, P, smem_per_chain, cpb, grid, block, stream);
+        cudaError_t e = launch_nuts<M>(W, NIT, P, smem_per_chain, block_data, cpb, grid, block, stream);
         if (e != cudaSuccess) return fail(NB200_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
         return 0;
     }
@@ -174,6 +174,7 @@ static int build_model_data(const nb200_model_desc& m, int T, RadonModel::Data& 
     RadonLayout L = build_radon_layout(m.n_obs, m.n_county, m.y, m.county, m.floor, T);
     if (L.G >= 65535) return fail(NB200_EINVAL, "radon: too many observation groups");
     d.J = L.J; d.N = L.N; d.n_steps = L.n_steps; d.G = L.G; d.kmax = L.kmax;
+    d.T = T; d.in_smem = 0;
     RadonObs* obs;
     int32_t* group_base;
     uint16_t* group_list;
@@ -219,16 +220,28 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     P.st = *st;
     if (build_model_data(*m, 32 * s->W, P.mdata, s->model_allocs) != 0) return bail();
     const size_t fixed = smem_for<M>(s->W, P.mdata, s->Dp);
+    size_t bdata = 0;
     if (s->W == 1) {
         int c = g_chains_per_block.load();
+        const size_t bd = model_block_data_bytes<M>(P.mdata);
         if (c <= 0) {
-            c = 1;
-            while (c < 8 && (n_chains + c - 1) / c > 148ull * 24) c *= 2;
+            if (bd > 0) {
+                // densities with constant tables: one CTA per SM hosting all of that SM's
+                // chains, so the tables are staged in shared memory once per SM
+                uint64_t per_sm = (n_chains + 147) / 148;
+                c = (int)(per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+            } else {
+                c = 1;
+                while (c < 8 && (n_chains + c - 1) / c > 148ull * 24) c *= 2;
+            }
         }
+        if (c > 8) c = 8;
         s->cpb = c;
+        if (bd > 0 && c >= 4) bdata = bd;
     } else {
         s->cpb = 1;
     }
+    s->block_data = bdata;
     // Shared-memory budget per chain: the SM's 227 KB divided by the chains that
     // will be co-resident on it (chains spread evenly over the 148 SMs).
     {
@@ -239,7 +252,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         if (per_sm > 32ull * s->cpb) per_sm = 32ull * s->cpb;     // CTA limit per SM
         if (per_sm < 1) per_sm = 1;
         const uint64_t ctas = (per_sm + s->cpb - 1) / s->cpb;
-        size_t budget = (kSmemSM - ctas * kSlack) / (ctas * s->cpb);
+        size_t budget = (kSmemSM - ctas * kSlack - ctas * bdata) / (ctas * s->cpb);
         const size_t slot_b = align16(sizeof(double) * 4 * (size_t)s->Dp);
         const size_t var_b = align16(sizeof(double) * (size_t)s->Dp);
         int slots = 0, var_in = 0;

@@ -110,9 +110,15 @@ template <class M, class G, int NIT = 0>
 struct ChainCtx {
     G g;
     const KParams<M>* P;
+    typename M::Data md;  // density data (a per-CTA copy may point into shared memory)
     ChainShared* sh;
     double* msm;  // model scratch (shared)
-    double *mq, *mg;  // shared staging of the position / gradient the density works on
+    // "front": shared-memory copy (q, p, grad, p_sum) of the newest leaf of the running
+    // trajectory.  Densities that gather across dimensions integrate IN PLACE on it
+    // with plain LDS/STS and only write each new state out to its pool slot; the
+    // U-turn checks read the newest leaf from it.  front_slot = pool slot it mirrors.
+    double* front;
+    int front_slot;
     int D, Dp, NS;
     unsigned long long chain_local;
     uint32_t chain_gid;
@@ -192,24 +198,27 @@ struct ChainCtx {
             double acc[2] = {0.0, 0.0};
             for_dims([&](int i) {
                 double gn;
-                acc[0] += M::term(P->mdata, i, q[i], gn);
+                acc[0] += M::term(md, i, q[i], gn);
                 gr[i] = gn;
                 if (!nb_isfinite(gn)) acc[1] += 1.0;
             });
             g.reduce(acc);
-            lp = M::finish(P->mdata, acc[0], D);
+            lp = M::finish(md, acc[0], D);
             flag[0] = acc[1];
         } else {
-            for_dims([&](int i) { mq[i] = q[i]; });
+            double* fq = front;
+            double* fg = front + 2 * (size_t)Dp;
+            for_dims([&](int i) { fq[i] = q[i]; });
             g.sync();
-            lp = M::logp_grad(g, P->mdata, D, mq, mg, msm);
+            lp = M::logp_grad(g, md, D, fq, fg, msm);
             g.sync();
             for_dims([&](int i) {
-                const double gn = mg[i];
+                const double gn = fg[i];
                 gr[i] = gn;
                 if (!nb_isfinite(gn)) flag[0] += 1.0;
             });
             g.reduce(flag);
+            front_slot = -1;  // momentum part of the front is stale
         }
         bad = flag[0] > 0.0 || !nb_isfinite(lp);
         return lp;
@@ -240,7 +249,7 @@ struct ChainCtx {
                 const double ph = ps[i] + heps * gs[i];
                 const double qn = qs[i] + eps * (vr * ph);
                 double gn;
-                acc[0] += M::term(P->mdata, i, qn, gn);
+                acc[0] += M::term(md, i, qn, gn);
                 const double pn = ph + heps * gn;
                 acc[1] += pn * (vr * pn);
                 const double sn = restart_sum ? pn : ss[i] + pn;
@@ -251,64 +260,83 @@ struct ChainCtx {
                 if (!nb_isfinite(gn)) acc[2] += 1.0;
             });
             g.reduce(acc);
-            lp = M::finish(P->mdata, acc[0], D);
+            lp = M::finish(md, acc[0], D);
             kin = 0.5 * acc[1];
             bad = acc[2] > 0.0;
-        } else if constexpr (NIT > 0) {
-            // half-step momenta and the mass matrix stay in registers across the
-            // density evaluation
-            double ph[NIT], vr[NIT];
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int i = g.tid + it * G::kThreads;
-                if (i < D) {
-                    vr[it] = var[i];
-                    ph[it] = ps[i] + heps * gs[i];
-                    const double qn = qs[i] + eps * (vr[it] * ph[it]);
-                    qd[i] = qn;
-                    mq[i] = qn;
-                }
+        } else {
+            // in place on the shared-memory front; the new state is also written out
+            // to its pool slot (stores only, nothing waits on them)
+            double* fq = front;
+            double* fp = front + (size_t)Dp;
+            double* fg = front + 2 * (size_t)Dp;
+            double* fs = front + 3 * (size_t)Dp;
+            if (front_slot != src) {
+                for_dims([&](int i) {
+                    fq[i] = qs[i];
+                    fp[i] = ps[i];
+                    fg[i] = gs[i];
+                    fs[i] = ss[i];
+                });
             }
-            g.sync();
-            lp = M::logp_grad(g, P->mdata, D, mq, mg, msm);
-            g.sync();
+            front_slot = dst;
             double acc[2] = {0.0, 0.0};
+            if constexpr (NIT > 0) {
+                // half-step momenta and the mass matrix stay in registers across the
+                // density evaluation
+                double ph[NIT], vr[NIT];
 #pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int i = g.tid + it * G::kThreads;
-                if (i < D) {
-                    const double gn = mg[i];
+                for (int it = 0; it < NIT; ++it) {
+                    const int i = g.tid + it * G::kThreads;
+                    if (i < D) {
+                        vr[it] = var[i];
+                        ph[it] = fp[i] + heps * fg[i];
+                        const double qn = fq[i] + eps * (vr[it] * ph[it]);
+                        fq[i] = qn;
+                        qd[i] = qn;
+                    }
+                }
+                g.sync();
+                lp = M::logp_grad(g, md, D, fq, fg, msm);
+                g.sync();
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int i = g.tid + it * G::kThreads;
+                    if (i < D) {
+                        const double gn = fg[i];
+                        const double pn = ph[it] + heps * gn;
+                        acc[0] += pn * (vr[it] * pn);
+                        const double sn = restart_sum ? pn : fs[i] + pn;
+                        fp[i] = pn;
+                        fs[i] = sn;
+                        gd[i] = gn;
+                        pd[i] = pn;
+                        sd[i] = sn;
+                        if (!nb_isfinite(gn)) acc[1] += 1.0;
+                    }
+                }
+            } else {
+                for (int i = g.tid; i < D; i += g.size()) {
+                    const double ph = fp[i] + heps * fg[i];
+                    fp[i] = ph;
+                    const double qn = fq[i] + eps * (var[i] * ph);
+                    fq[i] = qn;
+                    qd[i] = qn;
+                }
+                g.sync();
+                lp = M::logp_grad(g, md, D, fq, fg, msm);
+                g.sync();
+                for (int i = g.tid; i < D; i += g.size()) {
+                    const double gn = fg[i];
+                    const double pn = fp[i] + heps * gn;
+                    acc[0] += pn * (var[i] * pn);
+                    const double sn = restart_sum ? pn : fs[i] + pn;
+                    fp[i] = pn;
+                    fs[i] = sn;
                     gd[i] = gn;
-                    const double pn = ph[it] + heps * gn;
-                    acc[0] += pn * (vr[it] * pn);
                     pd[i] = pn;
-                    sd[i] = restart_sum ? pn : ss[i] + pn;
+                    sd[i] = sn;
                     if (!nb_isfinite(gn)) acc[1] += 1.0;
                 }
-            }
-            g.reduce(acc);
-            kin = 0.5 * acc[0];
-            bad = acc[1] > 0.0;
-        } else {
-            for (int i = g.tid; i < D; i += g.size()) {
-                const double ph = ps[i] + heps * gs[i];
-                pd[i] = ph;
-                const double qn = qs[i] + eps * (var[i] * ph);
-                qd[i] = qn;
-                mq[i] = qn;
-            }
-            g.sync();
-            lp = M::logp_grad(g, P->mdata, D, mq, mg, msm);
-            g.sync();
-            double acc[2] = {0.0, 0.0};
-            for (int i = g.tid; i < D; i += g.size()) {
-                const double gn = mg[i];
-                gd[i] = gn;
-                const double pn = pd[i] + heps * gn;
-                acc[0] += pn * (var[i] * pn);
-                pd[i] = pn;
-                sd[i] = restart_sum ? pn : ss[i] + pn;
-                if (!nb_isfinite(gn)) acc[1] += 1.0;
             }
             g.reduce(acc);
             kin = 0.5 * acc[0];
@@ -343,22 +371,31 @@ struct ChainCtx {
             int t = a; a = b; b = t;
             ss_ = s2; se_ = s1;
         }
-        const double* p_s = vec(ss_, VP);
-        const double* sum_s = vec(ss_, VS);
-        const double* p_e = vec(se_, VP);
-        const double* sum_e = vec(se_, VS);
         const int mode = (a >= 0 && b >= 0) ? 0 : ((b >= 0 && a < 0) ? 1 : 2);
         double acc[2] = {0.0, 0.0};
-        for_dims([&](int i) {
-            const double pse = sum_e[i], pss = sum_s[i], pe = p_e[i], ps = p_s[i];
-            double rho;
-            if (mode == 0) rho = pse - pss + ps;
-            else if (mode == 1) rho = pse + pss;
-            else rho = pss - pse + pe;
-            const double vr = var[i];
-            acc[0] += rho * (vr * pe);
-            acc[1] += rho * (vr * ps);
-        });
+        auto body = [&](const double* p_s, const double* sum_s, const double* p_e,
+                        const double* sum_e) {
+            for_dims([&](int i) {
+                const double pse = sum_e[i], pss = sum_s[i], pe = p_e[i], ps = p_s[i];
+                double rho;
+                if (mode == 0) rho = pse - pss + ps;
+                else if (mode == 1) rho = pse + pss;
+                else rho = pss - pse + pe;
+                const double vr = var[i];
+                acc[0] += rho * (vr * pe);
+                acc[1] += rho * (vr * ps);
+            });
+        };
+        if constexpr (!M::kElementwise) {
+            // the newest leaf is read from the shared-memory front
+            const double* f_p = front + (size_t)Dp;
+            const double* f_s = front + 3 * (size_t)Dp;
+            if (se_ == front_slot) body(vec(ss_, VP), vec(ss_, VS), f_p, f_s);
+            else if (ss_ == front_slot) body(f_p, f_s, vec(se_, VP), vec(se_, VS));
+            else body(vec(ss_, VP), vec(ss_, VS), vec(se_, VP), vec(se_, VS));
+        } else {
+            body(vec(ss_, VP), vec(ss_, VS), vec(se_, VP), vec(se_, VS));
+        }
         g.reduce(acc);
         return (acc[0] < 0.0) | (acc[1] < 0.0);
     }
@@ -368,6 +405,22 @@ struct ChainCtx {
     NB_HD void init_momentum(int slot, uint32_t purpose, uint32_t rng_draw) {
         double* pd = vec(slot, VP);
         double* sd = vec(slot, VS);
+        if constexpr (!M::kElementwise) {
+            // the front takes over (q, grad) of this point; its momentum is written below
+            if (front_slot != slot) {
+                const double* q = vec(slot, VQ);
+                const double* gr = vec(slot, VG);
+                double* fq = front;
+                double* fg = front + 2 * (size_t)Dp;
+                for_dims([&](int i) {
+                    fq[i] = q[i];
+                    fg[i] = gr[i];
+                });
+            }
+            front_slot = slot;
+        }
+        double* fp = M::kElementwise ? pd : front + (size_t)Dp;
+        double* fs = M::kElementwise ? sd : front + 3 * (size_t)Dp;
         const double* tape = nullptr;
         if (purpose == RNG_MOMENTUM && P->z_tape)
             tape = P->z_tape + ((size_t)chain_local * P->n_total + rng_draw) * (size_t)D;
@@ -388,6 +441,10 @@ struct ChainCtx {
                 const double p = sqrt(1.0 / vr) * z0;
                 pd[i0] = p;
                 sd[i0] = p;
+                if (!M::kElementwise) {
+                    fp[i0] = p;
+                    fs[i0] = p;
+                }
                 acc[0] += p * (vr * p);
             }
             if (i1 < D) {
@@ -395,6 +452,10 @@ struct ChainCtx {
                 const double p = sqrt(1.0 / vr) * z1;
                 pd[i1] = p;
                 sd[i1] = p;
+                if (!M::kElementwise) {
+                    fp[i1] = p;
+                    fs[i1] = p;
+                }
                 acc[0] += p * (vr * p);
             }
         }
@@ -817,6 +878,7 @@ struct ChainCtx {
         int cur;
         unsigned long long t = sc.draw;
         last_n_steps = 0;
+        front_slot = -1;
         if (status == 0) {
             const int rc = init_chain();
             g.sync();

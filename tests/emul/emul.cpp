@@ -42,7 +42,7 @@ static int run_all_nit(const nb200_settings* st, const typename M::Data& md, uin
     P.draws = draws; P.stats = stats; P.grads = grads; P.mminv = mminv;
     P.q0 = q0; P.init_mean = init_mean; P.z_tape = z_tape;
     P.stop_flag = nullptr;
-    std::vector<double> msm(M::smem_doubles(md, 1) + 1), stage(2 * (size_t)P.Dp + 1);
+    std::vector<double> msm(M::smem_doubles(md, 1) + 1), stage(4 * (size_t)P.Dp + 1);
     std::vector<double> spool((size_t)P.smem_slots * 4 * P.Dp + 1), svar(P.Dp);
     ChainShared sh;
     uint64_t steps = 0;
@@ -57,8 +57,9 @@ static int run_all_nit(const nb200_settings* st, const typename M::Data& md, uin
             std::fill(svar.begin(), svar.end(), -777.0);
             ChainCtx<M, GroupSerial, NIT> ctx;
             std::memset((void*)&ctx, 0, sizeof(ctx));
-            ctx.P = &P; ctx.sh = &sh; ctx.msm = msm.data();
-            ctx.mq = stage.data(); ctx.mg = stage.data() + P.Dp;
+            ctx.P = &P; ctx.md = P.mdata; ctx.sh = &sh; ctx.msm = msm.data();
+            ctx.front = stage.data(); ctx.front_slot = -1;
+            std::fill(stage.begin(), stage.end(), -555.0);
             ctx.D = P.D; ctx.Dp = P.Dp; ctx.NS = P.NS;
             ctx.chain_local = c;
             ctx.chain_gid = (uint32_t)(chain_id_offset + c);
@@ -106,7 +107,7 @@ extern "C" int emul_sample(const nb200_settings* st, const nb200_model_desc* mod
     case NB200_MODEL_RADON: {
         RadonLayout L = build_radon_layout(model->n_obs, model->n_county, model->y, model->county,
                                            model->floor, 1);
-        RadonModel::Data d{L.J, L.N, L.n_steps, L.G, L.kmax, L.obs.data(), L.group_base.data(),
+        RadonModel::Data d{L.J, L.N, L.n_steps, L.G, L.kmax, 1, 0, L.obs.data(), L.group_base.data(),
                            L.group_list.data()};
         return run_all<RadonModel>(st, d, model->dim, n_chains, chain_id_offset, q0, init_mean,
                                    z_tape, draws, stats, grads, mminv, total_steps, max_per_launch, smem_slots);
