@@ -132,6 +132,7 @@ struct ChainCtx {
     double acc_sum, acc_sym;
     uint32_t acc_count, n_merge, draw;
     double last_de;
+    bool l0_turn;  // U-turn verdict between src and the new leaf, fused into the leapfrog
     // tree bookkeeping (slot ids; -1 = none)
     int mL, mR, mD, tL, tR, tD;
     unsigned lv_valid;
@@ -157,11 +158,15 @@ struct ChainCtx {
         }
     }
 
-    // Slots below smem_slots are the hot tier in shared memory: alloc() hands out
-    // the lowest free slot, so leaves and low tree levels stay on chip; deeper
-    // levels (touched every 2^k leapfrogs) spill to the HBM/L2 tier.
+    // Hot tier in shared memory: only the MOMENTUM half (p, p_sum) of the lowest
+    // 2 * smem_slots pool slots.  That half is what the U-turn checks read from older
+    // states; positions and gradients of older states are read back only when a
+    // trajectory restarts from a tree end or a draw is written out, so they always
+    // live in the HBM/L2 tier.  alloc() hands out the lowest free slot, so recent
+    // leaves and low tree levels land in the hot tier.
     NB_HD double* vec(int slot, int comp) const {
-        if (slot < smem_slots) return spool + ((size_t)slot * 4 + comp) * (size_t)Dp;
+        if ((comp & 1) && slot < 2 * smem_slots)  // VP = 1, VS = 3
+            return spool + ((size_t)slot * 2 + (comp >> 1)) * (size_t)Dp;
         return pool + ((size_t)slot * 4 + comp) * (size_t)Dp;
     }
     NB_HD double* gvec(int slot, int comp) const {
@@ -226,7 +231,10 @@ struct ChainCtx {
 
     // ---------------------------------------------------------------- leapfrog
     // src -> dst (dst is a fresh slot).  Returns 0 ok, 1 divergence.
-    NB_HD int leapfrog(int src, int dst, int dir) {
+    // want_l0: also evaluate is_turning(src, dst) inside the pass (both states are at
+    // hand there); the verdict lands in l0_turn.  Only the unrolled front path fuses.
+    static constexpr bool kFuseL0 = !M::kElementwise && NIT > 0;
+    NB_HD int leapfrog(int src, int dst, int dir, bool want_l0 = false) {
         const double eps = (double)dir * step_size;
         const double heps = 0.5 * eps;
         const double* qs = vec(src, VQ);
@@ -298,6 +306,13 @@ struct ChainCtx {
                 g.sync();
                 lp = M::logp_grad(g, md, D, fq, fg, msm);
                 g.sync();
+                // U-turn between src (old front) and the new leaf: same arithmetic as
+                // is_turning(), on values that are in registers / the front right here
+                const int idx_src = new_idx - dir;
+                const bool src_is_start = idx_src < new_idx;
+                const int ia = src_is_start ? idx_src : new_idx, ib = src_is_start ? new_idx : idx_src;
+                const int mode = (ia >= 0 && ib >= 0) ? 0 : ((ib >= 0 && ia < 0) ? 1 : 2);
+                double tacc[2] = {0.0, 0.0};
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
                     const int i = g.tid + it * G::kThreads;
@@ -305,7 +320,18 @@ struct ChainCtx {
                         const double gn = fg[i];
                         const double pn = ph[it] + heps * gn;
                         acc[0] += pn * (vr[it] * pn);
-                        const double sn = restart_sum ? pn : fs[i] + pn;
+                        const double p_old = fp[i], s_old = fs[i];
+                        const double sn = restart_sum ? pn : s_old + pn;
+                        if (want_l0) {
+                            const double ps_ = src_is_start ? p_old : pn, pss = src_is_start ? s_old : sn;
+                            const double pe = src_is_start ? pn : p_old, pse = src_is_start ? sn : s_old;
+                            double rho;
+                            if (mode == 0) rho = pse - pss + ps_;
+                            else if (mode == 1) rho = pse + pss;
+                            else rho = pss - pse + pe;
+                            tacc[0] += rho * (vr[it] * pe);
+                            tacc[1] += rho * (vr[it] * ps_);
+                        }
                         fp[i] = pn;
                         fs[i] = sn;
                         gd[i] = gn;
@@ -313,6 +339,15 @@ struct ChainCtx {
                         sd[i] = sn;
                         if (!nb_isfinite(gn)) acc[1] += 1.0;
                     }
+                }
+                if (want_l0) {
+                    double all[4] = {acc[0], acc[1], tacc[0], tacc[1]};
+                    g.reduce(all);
+                    acc[0] = all[0];
+                    acc[1] = all[1];
+                    l0_turn = (all[2] < 0.0) | (all[3] < 0.0);
+                } else {
+                    g.reduce(acc);
                 }
             } else {
                 for (int i = g.tid; i < D; i += g.size()) {
@@ -337,8 +372,8 @@ struct ChainCtx {
                     sd[i] = sn;
                     if (!nb_isfinite(gn)) acc[1] += 1.0;
                 }
+                g.reduce(acc);
             }
-            g.reduce(acc);
             kin = 0.5 * acc[0];
             bad = acc[1] > 0.0;
         }
@@ -497,7 +532,10 @@ struct ChainCtx {
             bool stop = false;  // the new sub-tree is discarded and the transition ends
             for (unsigned j = 0; j < n_leaf && !stop && !done; ++j) {
                 const int dst = alloc();
-                const int rc = leapfrog(prev, dst, dir);
+                // the first check after this leaf pairs it with its predecessor (level-0
+                // sibling, or the initial point when depth == 0): fused into the leapfrog
+                const bool fuse_l0 = kFuseL0 && check && ((j & 1u) || depth == 0);
+                const int rc = leapfrog(prev, dst, dir, fuse_l0);
                 if (rc != 0) {
                     info.diverging = 1;
                     stop = true;
@@ -522,10 +560,14 @@ struct ChainCtx {
                         // full span, then the two cross-junction checks (depth > 0 only)
                         const int pa0 = dir > 0 ? sL : tL, pb0 = dir > 0 ? tR : sR;
                         const int n_checks = k > 0 ? 3 : 1;
-                        for (int c = 0; c < n_checks && !turn; ++c) {
-                            const int pa = c == 0 ? pa0 : (c == 1 ? sR : sL);
-                            const int pb = c == 0 ? pb0 : (c == 1 ? tR : tL);
-                            turn = is_turning(pa, pb);
+                        if (k == 0 && fuse_l0) {
+                            turn = l0_turn;
+                        } else {
+                            for (int c = 0; c < n_checks && !turn; ++c) {
+                                const int pa = c == 0 ? pa0 : (c == 1 ? sR : sL);
+                                const int pb = c == 0 ? pb0 : (c == 1 ? tR : tL);
+                                turn = is_turning(pa, pb);
+                            }
                         }
                     }
                     const double new_ls = nb_logaddexp(s_ls, t_ls);
@@ -893,14 +935,6 @@ struct ChainCtx {
             cur = sc.cur_slot;
             if (varg != var)
                 for (int i = g.tid; i < D; i += g.size()) var[i] = varg[i];
-            if (cur < smem_slots) {  // the current point was parked in the HBM tier
-                const double *gq = gvec(cur, VQ), *gg = gvec(cur, VG);
-                double *q = vec(cur, VQ), *gr = vec(cur, VG);
-                for (int i = g.tid; i < D; i += g.size()) {
-                    q[i] = gq[i];
-                    gr[i] = gg[i];
-                }
-            }
             if (g.tid == 0) {
                 sh->U[cur] = sc.cur_U;
                 sh->idx[cur] = 0;
@@ -973,14 +1007,6 @@ struct ChainCtx {
             }
         }
         g.sync();
-        if (cur < smem_slots && t < n_total) {  // park the current point for a later resume
-            double *gq = gvec(cur, VQ), *gg = gvec(cur, VG);
-            const double *q = vec(cur, VQ), *gr = vec(cur, VG);
-            for (int i = g.tid; i < D; i += g.size()) {
-                gq[i] = q[i];
-                gg[i] = gr[i];
-            }
-        }
         if (g.tid == 0) store(sc, t, cur, t >= n_total ? 2 : 1);
     }
 };

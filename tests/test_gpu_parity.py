@@ -265,7 +265,7 @@ def test_config4_leapfrog_properties():
     ref = O.sample(om, so, 12)
     for k in ("depth", "n_steps", "index_in_trajectory"):
         assert np.array_equal(tr.stats[..., STAT[k]], ref["stats"][..., STAT[k]]), k
-    np.testing.assert_allclose(tr.draws[:, :3], ref["draws"][:, :3], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(tr.draws[:, :3], ref["draws"][:, :3], rtol=0, atol=1e-8)  # sums over 10^4 terms
     np.testing.assert_allclose(tr.draws, ref["draws"], rtol=0, atol=1e-3)
     post = tr.draws[:, 120:]
     assert abs(post.std() - 1.0) < 0.08
