@@ -110,6 +110,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_cores() -> int:
+    """CPUs this process may actually use: affinity mask capped by the cgroup CPU quota
+    (the GPU boxes expose 128 logical CPUs but grant a 16-CPU quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -128,7 +141,7 @@ def cpu_run(n_chains: int, seed: int, n_threads: int = 0):
     m = O.Model("radon", DIM, y=d["y"], county=d["county"], floor=d["floor"], n_county=N_COUNTY)
     s = O.default_settings(seed=seed, num_tune=TUNE, num_draws=DRAWS, init_radius=1.0)
     t0 = time.perf_counter()
-    r = O.sample(m, s, n_chains, n_threads=n_threads)
+    r = O.sample(m, s, n_chains, n_threads=n_threads or host_cores())
     dt = time.perf_counter() - t0
     return r["total_steps"], dt
 
@@ -137,8 +150,8 @@ def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    n_chains = min(CHAINS_PER_GPU, 4 * cores)
+    cores = host_cores()
+    n_chains = min(CHAINS_PER_GPU, 16 * cores)
     for i in range(args.warmup):
         cpu_run(min(n_chains, cores), 1000 + i)
     steps_total, t_total = 0, 0.0
@@ -148,7 +161,7 @@ def run_reference(args):
         t_total += dt
     value = steps_total / t_total
     sample_desc = (f"{n_chains} chains x ({TUNE} tune + {DRAWS} draws) of the same radon model per "
-                   f"step on {cores} host threads")
+                   f"step on {cores} host threads (cgroup quota; {os.cpu_count()} logical CPUs visible)")
     line = {
         "impl": "reference", "metric": "gradient_evals_per_sec_all_chains", "value": value,
         "unit": "grad_evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -184,7 +197,9 @@ def run_gpu(args):
     data = nutpie_b200.make_radon_data()
     model = nutpie_b200.radon_model(data["y"], data["county"], data["floor"], N_COUNTY)
     n_chains = CHAINS_PER_GPU
-    offset = rank * n_chains
+    from nutpie_b200.distributed import shard
+
+    n_chains, offset = shard(CHAINS_PER_GPU * world, rank, world)
     n_rows = TUNE + DRAWS
 
     def make_settings(seed):
@@ -202,19 +217,20 @@ def run_gpu(args):
     bufs = {"draws": pinned_d.array, "stats": pinned_s.array}
 
     def gather_stats(smp):
-        """trace collection across GPUs: NCCL all-gather of the sample-stats buffers"""
+        """trace collection across GPUs: NCCL all-gather of the device-resident
+        sample-stats buffers (nutpie_b200.distributed.all_gather_chains)"""
         if not multi:
             return
+        from nutpie_b200.distributed import all_gather_chains
+
         _, sptr = smp.device_buffers()
 
         class _Wrap:
-            __cuda_array_interface__ = {"shape": (n_chains * n_rows * _lib.NSTAT,), "typestr": "<f8",
+            __cuda_array_interface__ = {"shape": (n_chains, n_rows * _lib.NSTAT), "typestr": "<f8",
                                         "data": (sptr, False), "version": 2}
 
         local_t = torch.as_tensor(_Wrap(), device=f"cuda:{local}")
-        out = torch.empty((world,) + tuple(local_t.shape), dtype=torch.float64,
-                          device=f"cuda:{local}")
-        dist.all_gather_into_tensor(out, local_t)
+        all_gather_chains(local_t, n_chains * world)
         torch.cuda.synchronize()
 
     # ---- device-resident arm: samplers (model data, init state) created up front
@@ -305,8 +321,8 @@ def run_gpu(args):
     value = steps / (kernel_ms / 1e3)
     algo_bytes = 72.0 * DIM * (steps / world)  # per GPU
     achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
-    cores = os.cpu_count() or 1
-    cpu_chains = min(CHAINS_PER_GPU, 4 * cores)
+    cores = host_cores()
+    cpu_chains = min(CHAINS_PER_GPU, 16 * cores)
     cpu_steps, cpu_dt = cpu_run(cpu_chains, 31337)
     line = {
         "metric": "gradient_evals_per_sec_all_chains", "value": value, "unit": "grad_evals/s",
