@@ -61,8 +61,11 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, c
 
 // The sampler: W warps per chain, CPB chains per CTA (CPB > 1 only for W == 1).
 // One persistent launch advances every chain through all its draws.
+// Streaming regime (W >= 8): cap registers at 64 so that 1024 threads — up to four chains —
+// are resident per SM and one chain's reductions / tree bookkeeping overlap another's
+// streaming pass.
 template <class M, int W, int NIT>
-__global__ void __launch_bounds__(W == 1 ? 256 : 32 * W)
+__global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, W >= 8 ? 1024 / (32 * W) : 1)
     nuts_kernel(const __grid_constant__ KParams<M> P, size_t smem_per_chain, size_t block_data) {
     extern __shared__ __align__(16) unsigned char smem[];
     typename M::Data md = P.mdata;

@@ -113,7 +113,12 @@ static size_t smem_for(int W, const typename M::Data& md, int Dp) {
 static int pick_W(const nb200_model_desc& m, uint64_t n_chains) {
     int t = g_threads_per_chain.load();
     if (t > 0) return t / 32;
-    if (m.dim >= 2048) return 32;  // streaming regime (config 4): a full CTA per chain
+    if (m.dim >= 2048) {  // streaming regime (config 4): a CTA per chain; prefer CTAs small
+        // enough that every chain is resident at once (2048 threads per SM)
+        if (n_chains > 148ull * 2) return 8;
+        if (n_chains > 148ull) return 16;
+        return 32;
+    }
     if (m.dim <= 256) return 1;    // a warp per chain with fully unrolled per-dimension loops
                                    // (measured best on radon: profiles/sweep_radon_r1.txt)
     const uint64_t work = m.kind == NB200_MODEL_RADON ? (uint64_t)m.n_obs : m.dim;

@@ -232,8 +232,8 @@ struct ChainCtx {
     // ---------------------------------------------------------------- leapfrog
     // src -> dst (dst is a fresh slot).  Returns 0 ok, 1 divergence.
     // want_l0: also evaluate is_turning(src, dst) inside the pass (both states are at
-    // hand there); the verdict lands in l0_turn.  Only the unrolled front path fuses.
-    static constexpr bool kFuseL0 = !M::kElementwise && NIT > 0;
+    // hand there); the verdict lands in l0_turn.  (The run-time-loop front path does not fuse.)
+    static constexpr bool kFuseL0 = M::kElementwise || NIT > 0;  // not the run-time-loop front path
     NB_HD int leapfrog(int src, int dst, int dir, bool want_l0 = false) {
         const double eps = (double)dir * step_size;
         const double heps = 0.5 * eps;
@@ -250,24 +250,85 @@ struct ChainCtx {
         double lp, kin;
         bool bad;
         if constexpr (M::kElementwise) {
-            // one streaming pass: 5 loads + 4 stores per dimension
-            double acc[3] = {0.0, 0.0, 0.0};
-            for_dims([&](int i) {
-                const double vr = var[i];
-                const double ph = ps[i] + heps * gs[i];
-                const double qn = qs[i] + eps * (vr * ph);
-                double gn;
+            // one streaming pass: 5 loads + 4 stores per dimension (72 B), reductions for
+            // logp, kinetic energy and — when asked — the U-turn pair (src, dst) fused in
+            const int idx_src = new_idx - dir;
+            const bool src_is_start = idx_src < new_idx;
+            const int ia = src_is_start ? idx_src : new_idx, ib = src_is_start ? new_idx : idx_src;
+            const int mode = (ia >= 0 && ib >= 0) ? 0 : ((ib >= 0 && ia < 0) ? 1 : 2);
+            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            auto elem = [&](int i, double q0, double p0, double g0, double vr, double s0, double& qn,
+                            double& pn, double& gn, double& sn) {
+                const double ph = p0 + heps * g0;
+                qn = q0 + eps * (vr * ph);
                 acc[0] += M::term(md, i, qn, gn);
-                const double pn = ph + heps * gn;
+                pn = ph + heps * gn;
                 acc[1] += pn * (vr * pn);
-                const double sn = restart_sum ? pn : ss[i] + pn;
-                qd[i] = qn;
-                pd[i] = pn;
-                gd[i] = gn;
-                sd[i] = sn;
+                sn = restart_sum ? pn : s0 + pn;
                 if (!nb_isfinite(gn)) acc[2] += 1.0;
-            });
-            g.reduce(acc);
+                if (want_l0) {
+                    const double ps_ = src_is_start ? p0 : pn, pss = src_is_start ? s0 : sn;
+                    const double pe = src_is_start ? pn : p0, pse = src_is_start ? sn : s0;
+                    double rho;
+                    if (mode == 0) rho = pse - pss + ps_;
+                    else if (mode == 1) rho = pse + pss;
+                    else rho = pss - pse + pe;
+                    acc[3] += rho * (vr * pe);
+                    acc[4] += rho * (vr * ps_);
+                }
+            };
+            if constexpr (NIT == 0) {
+                // 16-byte accesses: two dimensions per thread and iteration (slots are 32-byte
+                // aligned, Dp is a multiple of 4); an odd last dimension is handled alone
+                const int D2 = D >> 1;
+                const double2* qs2 = reinterpret_cast<const double2*>(qs);
+                const double2* ps2 = reinterpret_cast<const double2*>(ps);
+                const double2* gs2 = reinterpret_cast<const double2*>(gs);
+                const double2* ss2 = reinterpret_cast<const double2*>(ss);
+                const double2* vr2 = reinterpret_cast<const double2*>(var);
+                double2* qd2 = reinterpret_cast<double2*>(qd);
+                double2* pd2 = reinterpret_cast<double2*>(pd);
+                double2* gd2 = reinterpret_cast<double2*>(gd);
+                double2* sd2 = reinterpret_cast<double2*>(sd);
+                for (int k = g.tid; k < D2; k += g.size()) {
+                    const double2 q0 = qs2[k], p0 = ps2[k], g0 = gs2[k], v0 = vr2[k], s0 = ss2[k];
+                    double2 qn, pn, gn, sn;
+                    elem(2 * k, q0.x, p0.x, g0.x, v0.x, s0.x, qn.x, pn.x, gn.x, sn.x);
+                    elem(2 * k + 1, q0.y, p0.y, g0.y, v0.y, s0.y, qn.y, pn.y, gn.y, sn.y);
+                    qd2[k] = qn;
+                    pd2[k] = pn;
+                    gd2[k] = gn;
+                    sd2[k] = sn;
+                }
+                if ((D & 1) && g.tid == 0) {
+                    const int i = D - 1;
+                    double qn, pn, gn, sn;
+                    elem(i, qs[i], ps[i], gs[i], var[i], ss[i], qn, pn, gn, sn);
+                    qd[i] = qn;
+                    pd[i] = pn;
+                    gd[i] = gn;
+                    sd[i] = sn;
+                }
+            } else {
+                for_dims([&](int i) {
+                    double qn, pn, gn, sn;
+                    elem(i, qs[i], ps[i], gs[i], var[i], ss[i], qn, pn, gn, sn);
+                    qd[i] = qn;
+                    pd[i] = pn;
+                    gd[i] = gn;
+                    sd[i] = sn;
+                });
+            }
+            if (want_l0) {
+                g.reduce(acc);
+                l0_turn = (acc[3] < 0.0) | (acc[4] < 0.0);
+            } else {
+                double a3[3] = {acc[0], acc[1], acc[2]};
+                g.reduce(a3);
+                acc[0] = a3[0];
+                acc[1] = a3[1];
+                acc[2] = a3[2];
+            }
             lp = M::finish(md, acc[0], D);
             kin = 0.5 * acc[1];
             bad = acc[2] > 0.0;

@@ -16,6 +16,12 @@
 #define NB_D inline
 #endif
 
+#ifndef __CUDACC__
+struct alignas(16) double2 {
+    double x, y;
+};
+#endif
+
 namespace nb200 {
 
 NB_HD void nb_sincos_2pi(double u, double& s, double& c) {
