@@ -18,7 +18,7 @@ struct GroupCuda {
     static constexpr int kThreads = 32 * W;
     int tid;       // thread index inside the chain's group
     double* red;   // shared scratch, W * kMaxRed doubles (only W > 1)
-    static constexpr int kMaxRed = 8;
+    static constexpr int kMaxRed = 12;
 
     NB_D int size() const { return kThreads; }
     NB_D void sync() const {

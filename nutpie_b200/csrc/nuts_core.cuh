@@ -132,7 +132,8 @@ struct ChainCtx {
     double acc_sum, acc_sym;
     uint32_t acc_count, n_merge, draw;
     double last_de;
-    bool l0_turn;  // U-turn verdict between src and the new leaf, fused into the leapfrog
+    bool l0_turn;          // U-turn verdict between src and the new leaf, fused into the leapfrog
+    unsigned fused_bits;   // verdicts of the other pairs planned for this leapfrog (bit c = plist[c])
     // tree bookkeeping (slot ids; -1 = none)
     int mL, mR, mD, tL, tR, tD;
     unsigned lv_valid;
@@ -229,12 +230,49 @@ struct ChainCtx {
         return lp;
     }
 
+    // ------------------------------------------------- fused U-turn bookkeeping
+    // The checks that pair the NEW leaf with an older state are evaluated inside the
+    // leapfrog's own pass over the dimensions (the new p, p_sum are in registers there):
+    //   * the pair (src, new) costs nothing extra — src's vectors are loaded anyway;
+    //   * up to kMaxFused further partners cost two vector reads each instead of a
+    //     separate five-vector pass plus its own reduction.
+    // All verdicts share one reduction with logp / kinetic energy.
+    static constexpr bool kFuseL0 = M::kElementwise || NIT > 0;  // not the run-time-loop front path
+    static constexpr int kMaxFused = M::kElementwise ? 3 : (NIT > 0 ? 2 : 0);
+    static constexpr int kFusedDim = kMaxFused > 0 ? kMaxFused : 1;
+
+    // orientation of the pair (x, new leaf): which one is the trajectory's earlier state
+    struct PairMode {
+        int mode;       // 0 both on the forward side, 1 spans the origin, 2 both backward
+        bool n_is_end;  // the new leaf has the larger index
+    };
+    NB_HD static PairMode pair_mode(int idx_x, int idx_n) {
+        const bool n_is_end = idx_x < idx_n;
+        const int a = n_is_end ? idx_x : idx_n, b = n_is_end ? idx_n : idx_x;
+        PairMode m;
+        m.mode = (a >= 0 && b >= 0) ? 0 : ((b >= 0 && a < 0) ? 1 : 2);
+        m.n_is_end = n_is_end;
+        return m;
+    }
+    // same arithmetic, term by term, as is_turning()
+    NB_HD static void turn_terms(const PairMode& m, double px, double sx, double pn, double sn,
+                                 double vr, double& acc_e, double& acc_s) {
+        const double ps_ = m.n_is_end ? px : pn, pss = m.n_is_end ? sx : sn;
+        const double pe = m.n_is_end ? pn : px, pse = m.n_is_end ? sn : sx;
+        double rho;
+        if (m.mode == 0) rho = pse - pss + ps_;
+        else if (m.mode == 1) rho = pse + pss;
+        else rho = pss - pse + pe;
+        acc_e += rho * (vr * pe);
+        acc_s += rho * (vr * ps_);
+    }
+
     // ---------------------------------------------------------------- leapfrog
     // src -> dst (dst is a fresh slot).  Returns 0 ok, 1 divergence.
-    // want_l0: also evaluate is_turning(src, dst) inside the pass (both states are at
-    // hand there); the verdict lands in l0_turn.  (The run-time-loop front path does not fuse.)
-    static constexpr bool kFuseL0 = M::kElementwise || NIT > 0;  // not the run-time-loop front path
-    NB_HD int leapfrog(int src, int dst, int dir, bool want_l0 = false) {
+    // want_l0: also evaluate is_turning(src, dst); verdict in l0_turn.
+    // plist[0..np): older states to pair with the new leaf; verdicts in fused_bits.
+    NB_HD int leapfrog(int src, int dst, int dir, bool want_l0 = false, const int* plist = nullptr,
+                       int np = 0) {
         const double eps = (double)dir * step_size;
         const double heps = 0.5 * eps;
         const double* qs = vec(src, VQ);
@@ -247,16 +285,27 @@ struct ChainCtx {
         double* sd = vec(dst, VS);
         const int new_idx = sh->idx[src] + dir;
         const bool restart_sum = new_idx == -1;
+        const PairMode m_src = pair_mode(new_idx - dir, new_idx);
+        const double* Pp[kFusedDim];
+        const double* Sp[kFusedDim];
+        PairMode Pm[kFusedDim];
+#pragma unroll
+        for (int c = 0; c < kFusedDim; ++c) {
+            const int sl = (c < np) ? plist[c] : src;
+            Pp[c] = vec(sl, VP);
+            Sp[c] = vec(sl, VS);
+            Pm[c] = pair_mode(sh->idx[sl], new_idx);
+        }
+        fused_bits = 0;
         double lp, kin;
         bool bad;
         if constexpr (M::kElementwise) {
-            // one streaming pass: 5 loads + 4 stores per dimension (72 B), reductions for
-            // logp, kinetic energy and — when asked — the U-turn pair (src, dst) fused in
-            const int idx_src = new_idx - dir;
-            const bool src_is_start = idx_src < new_idx;
-            const int ia = src_is_start ? idx_src : new_idx, ib = src_is_start ? new_idx : idx_src;
-            const int mode = (ia >= 0 && ib >= 0) ? 0 : ((ib >= 0 && ia < 0) ? 1 : 2);
-            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            // one streaming pass: 5 loads + 4 stores per dimension (72 B); logp, kinetic
+            // energy and the planned U-turn pairs are reduced together
+            constexpr int NA = 5 + 2 * kMaxFused;
+            double acc[NA];
+#pragma unroll
+            for (int c = 0; c < NA; ++c) acc[c] = 0.0;
             auto elem = [&](int i, double q0, double p0, double g0, double vr, double s0, double& qn,
                             double& pn, double& gn, double& sn) {
                 const double ph = p0 + heps * g0;
@@ -266,16 +315,10 @@ struct ChainCtx {
                 acc[1] += pn * (vr * pn);
                 sn = restart_sum ? pn : s0 + pn;
                 if (!nb_isfinite(gn)) acc[2] += 1.0;
-                if (want_l0) {
-                    const double ps_ = src_is_start ? p0 : pn, pss = src_is_start ? s0 : sn;
-                    const double pe = src_is_start ? pn : p0, pse = src_is_start ? sn : s0;
-                    double rho;
-                    if (mode == 0) rho = pse - pss + ps_;
-                    else if (mode == 1) rho = pse + pss;
-                    else rho = pss - pse + pe;
-                    acc[3] += rho * (vr * pe);
-                    acc[4] += rho * (vr * ps_);
-                }
+                if (want_l0) turn_terms(m_src, p0, s0, pn, sn, vr, acc[3], acc[4]);
+#pragma unroll
+                for (int c = 0; c < kMaxFused; ++c)
+                    if (c < np) turn_terms(Pm[c], Pp[c][i], Sp[c][i], pn, sn, vr, acc[5 + 2 * c], acc[6 + 2 * c]);
             };
             if constexpr (NIT == 0) {
                 // 16-byte accesses: two dimensions per thread and iteration (slots are 32-byte
@@ -319,9 +362,12 @@ struct ChainCtx {
                     sd[i] = sn;
                 });
             }
-            if (want_l0) {
+            if (want_l0 || np > 0) {
                 g.reduce(acc);
                 l0_turn = (acc[3] < 0.0) | (acc[4] < 0.0);
+#pragma unroll
+                for (int c = 0; c < kMaxFused; ++c)
+                    if (c < np && ((acc[5 + 2 * c] < 0.0) | (acc[6 + 2 * c] < 0.0))) fused_bits |= 1u << c;
             } else {
                 double a3[3] = {acc[0], acc[1], acc[2]};
                 g.reduce(a3);
@@ -367,13 +413,9 @@ struct ChainCtx {
                 g.sync();
                 lp = M::logp_grad(g, md, D, fq, fg, msm);
                 g.sync();
-                // U-turn between src (old front) and the new leaf: same arithmetic as
-                // is_turning(), on values that are in registers / the front right here
-                const int idx_src = new_idx - dir;
-                const bool src_is_start = idx_src < new_idx;
-                const int ia = src_is_start ? idx_src : new_idx, ib = src_is_start ? new_idx : idx_src;
-                const int mode = (ia >= 0 && ib >= 0) ? 0 : ((ib >= 0 && ia < 0) ? 1 : 2);
-                double tacc[2] = {0.0, 0.0};
+                double tacc[2 + 2 * kFusedDim];
+#pragma unroll
+                for (int c = 0; c < 2 + 2 * kFusedDim; ++c) tacc[c] = 0.0;
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
                     const int i = g.tid + it * G::kThreads;
@@ -383,16 +425,12 @@ struct ChainCtx {
                         acc[0] += pn * (vr[it] * pn);
                         const double p_old = fp[i], s_old = fs[i];
                         const double sn = restart_sum ? pn : s_old + pn;
-                        if (want_l0) {
-                            const double ps_ = src_is_start ? p_old : pn, pss = src_is_start ? s_old : sn;
-                            const double pe = src_is_start ? pn : p_old, pse = src_is_start ? sn : s_old;
-                            double rho;
-                            if (mode == 0) rho = pse - pss + ps_;
-                            else if (mode == 1) rho = pse + pss;
-                            else rho = pss - pse + pe;
-                            tacc[0] += rho * (vr[it] * pe);
-                            tacc[1] += rho * (vr[it] * ps_);
-                        }
+                        if (want_l0) turn_terms(m_src, p_old, s_old, pn, sn, vr[it], tacc[0], tacc[1]);
+#pragma unroll
+                        for (int c = 0; c < kMaxFused; ++c)
+                            if (c < np)
+                                turn_terms(Pm[c], Pp[c][i], Sp[c][i], pn, sn, vr[it], tacc[2 + 2 * c],
+                                           tacc[3 + 2 * c]);
                         fp[i] = pn;
                         fs[i] = sn;
                         gd[i] = gn;
@@ -401,12 +439,19 @@ struct ChainCtx {
                         if (!nb_isfinite(gn)) acc[1] += 1.0;
                     }
                 }
-                if (want_l0) {
-                    double all[4] = {acc[0], acc[1], tacc[0], tacc[1]};
+                if (want_l0 || np > 0) {
+                    double all[4 + 2 * kFusedDim];
+                    all[0] = acc[0];
+                    all[1] = acc[1];
+#pragma unroll
+                    for (int c = 0; c < 2 + 2 * kFusedDim; ++c) all[2 + c] = tacc[c];
                     g.reduce(all);
                     acc[0] = all[0];
                     acc[1] = all[1];
                     l0_turn = (all[2] < 0.0) | (all[3] < 0.0);
+#pragma unroll
+                    for (int c = 0; c < kMaxFused; ++c)
+                        if (c < np && ((all[4 + 2 * c] < 0.0) | (all[5 + 2 * c] < 0.0))) fused_bits |= 1u << c;
                 } else {
                     g.reduce(acc);
                 }
@@ -577,6 +622,7 @@ struct ChainCtx {
         lv_valid = 0;
         double m_ls = 0.0;
         int depth = 0;
+        unsigned spec_bits = 0;  // speculative C verdicts per level (bit 31: main tree)
         info.diverging = 0;
         info.maxdepth_reached = 0;
         bool done = false;
@@ -593,15 +639,55 @@ struct ChainCtx {
             bool stop = false;  // the new sub-tree is discarded and the transition ends
             for (unsigned j = 0; j < n_leaf && !stop && !done; ++j) {
                 const int dst = alloc();
-                // the first check after this leaf pairs it with its predecessor (level-0
-                // sibling, or the initial point when depth == 0): fused into the leapfrog
+                // ---- plan the U-turn checks that pair the new leaf N with older states.
+                // Merging sub-tree s (earlier) with t (later, ending in N) needs three pairs:
+                //   A = (far end of s, N),  B = (near end of s, N)  [depth > 0],
+                //   C = (far end of s, first leaf of t)             [depth > 0].
+                // A and B are evaluated in the leapfrog that creates N (the pair with N's
+                // predecessor is free); C was evaluated speculatively in the leapfrog that
+                // created t's first leaf and is kept in spec_bits until the merge.
+                const bool last = j + 1 == n_leaf;
+                const int cascade = nb_ffsll((unsigned long long)(~j)) - 1;  // trailing ones of j
                 const bool fuse_l0 = kFuseL0 && check && ((j & 1u) || depth == 0);
-                const int rc = leapfrog(prev, dst, dir, fuse_l0);
+                int plist[kFusedDim];
+                int np = 0;
+                int spec_level = -1;
+                if (check && kMaxFused > 0) {
+                    if (j == 0) {
+                        if (depth > 0) {
+                            spec_level = 31;
+                            plist[np++] = dir > 0 ? mL : mR;
+                        }
+                    } else if (!(j & 1u)) {
+                        spec_level = nb_ffsll((unsigned long long)j) - 1;
+                        plist[np++] = dir > 0 ? sh->lvL[spec_level] : sh->lvR[spec_level];
+                    }
+                    for (int k = 1; k < cascade && np < kMaxFused; ++k) {
+                        plist[np++] = dir > 0 ? sh->lvL[k] : sh->lvR[k];
+                        if (np < kMaxFused) plist[np++] = dir > 0 ? sh->lvR[k] : sh->lvL[k];
+                    }
+                    if (last && depth > 0 && np < kMaxFused) {
+                        plist[np++] = dir > 0 ? mL : mR;
+                        if (np < kMaxFused) plist[np++] = dir > 0 ? mR : mL;
+                    }
+                }
+                const int rc = leapfrog(prev, dst, dir, fuse_l0, plist, np);
                 if (rc != 0) {
                     info.diverging = 1;
                     stop = true;
                     break;
                 }
+                int fi = 0;  // next fused verdict to consume, in planning order
+                if (spec_level >= 0) {
+                    const unsigned bit = 1u << spec_level;
+                    spec_bits = (fused_bits & 1u) ? (spec_bits | bit) : (spec_bits & ~bit);
+                    fi = 1;
+                }
+                // verdict of the pair (x, N): fused if it was planned, else a separate pass
+                auto pair_with_new = [&](int x, int n_slot) -> bool {
+                    if (fi < np) return (fused_bits >> fi++) & 1u;
+                    return is_turning(x, n_slot);
+                };
                 tL = tR = tD = dst;
                 double t_ls = -last_de;
                 int k = 0;
@@ -610,7 +696,7 @@ struct ChainCtx {
                 for (;;) {
                     bool with_main;
                     if ((j >> k) & 1u) with_main = false;
-                    else if (j + 1 == n_leaf && k == depth) with_main = true;
+                    else if (last && k == depth) with_main = true;
                     else break;
                     const int sL = with_main ? mL : sh->lvL[k];
                     const int sR = with_main ? mR : sh->lvR[k];
@@ -618,17 +704,20 @@ struct ChainCtx {
                     const double s_ls = with_main ? m_ls : sh->lvLS[k];
                     bool turn = false;
                     if (check) {
-                        // full span, then the two cross-junction checks (depth > 0 only)
-                        const int pa0 = dir > 0 ? sL : tL, pb0 = dir > 0 ? tR : sR;
-                        const int n_checks = k > 0 ? 3 : 1;
-                        if (k == 0 && fuse_l0) {
-                            turn = l0_turn;
+                        const int far_s = dir > 0 ? sL : sR, near_s = dir > 0 ? sR : sL;
+                        if (k == 0) {
+                            // the single pair (s, N); s is N's predecessor
+                            turn = fuse_l0 ? l0_turn : is_turning(far_s, dst);
                         } else {
-                            for (int c = 0; c < n_checks && !turn; ++c) {
-                                const int pa = c == 0 ? pa0 : (c == 1 ? sR : sL);
-                                const int pb = c == 0 ? pb0 : (c == 1 ? tR : tL);
-                                turn = is_turning(pa, pb);
+                            const bool a = pair_with_new(far_s, dst);
+                            const bool b = pair_with_new(near_s, dst);
+                            bool c;
+                            if constexpr (kMaxFused > 0) {
+                                c = (spec_bits >> (with_main ? 31 : k)) & 1u;
+                            } else {
+                                c = is_turning(far_s, dir > 0 ? tL : tR);
                             }
+                            turn = a | b | c;
                         }
                     }
                     const double new_ls = nb_logaddexp(s_ls, t_ls);
