@@ -238,7 +238,10 @@ struct ChainCtx {
     //     separate five-vector pass plus its own reduction.
     // All verdicts share one reduction with logp / kinetic energy.
     static constexpr bool kFuseL0 = M::kElementwise || NIT > 0;  // not the run-time-loop front path
-    static constexpr int kMaxFused = M::kElementwise ? 3 : (NIT > 0 ? 2 : 0);
+    // Measured (profiles/r1_sweep_*): planning + extra partner loads pay off only in the
+    // streaming regime (large D, run-time loops), where each separate check is a pass over
+    // HBM; for small D they cost more than the on-chip is_turning() they replace.
+    static constexpr int kMaxFused = (M::kElementwise && NIT == 0) ? 3 : 0;
     static constexpr int kFusedDim = kMaxFused > 0 ? kMaxFused : 1;
 
     // orientation of the pair (x, new leaf): which one is the trajectory's earlier state
