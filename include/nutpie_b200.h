@@ -216,6 +216,11 @@ int nb200_sampler_trace(nb200_sampler *s, nb200_trace_view *out);
 int nb200_sampler_trace_into(nb200_sampler *s, double *draws, double *stats,
                              double *gradients, double *mass_matrix_inv,
                              uint64_t *rows_filled);
+/* Register host buffers ([n_chains][n_rows][store_dims] and [n_chains][n_rows][NB200_NSTAT],
+ * ideally pinned) BEFORE start: nb200_sampler_wait then streams finished rows into them
+ * while the kernel is still sampling, so the D2H copy of the trace overlaps the run;
+ * nb200_sampler_trace_into with the same pointers afterwards copies nothing twice. */
+int nb200_sampler_set_trace_target(nb200_sampler *s, double *draws, double *stats);
 int nb200_sampler_destroy(nb200_sampler *s);
 
 /* ---- measurement hooks --------------------------------------------------

@@ -140,6 +140,8 @@ def load_library() -> C.CDLL:
                                                    C.POINTER(C.c_void_p)]
         L.nb200_sampler_set_draws_per_launch.restype = C.c_int
         L.nb200_sampler_set_draws_per_launch.argtypes = [C.c_void_p, C.c_uint64]
+        L.nb200_sampler_set_trace_target.restype = C.c_int
+        L.nb200_sampler_set_trace_target.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.nb200_sampler_set_z_tape.restype = C.c_int
         L.nb200_sampler_set_z_tape.argtypes = [C.c_void_p, C.c_void_p]
         L.nb200_settings_default.restype = None
@@ -474,7 +476,7 @@ class PySampler:
 
     def __init__(self, settings: PyNutsSettings, model, *, n_chains=None, chain_id_offset=0,
                  device=0, progress_type=None, init_mean=None, q0=None, z_tape=None,
-                 draws_per_launch=0, autostart=True):
+                 draws_per_launch=0, autostart=True, trace_buffers=None):
         L = load_library()
         self._L = L
         self._settings = settings
@@ -498,6 +500,10 @@ class PySampler:
             _check(L.nb200_sampler_set_z_tape(self._h, _ptr(z_tape)))
         if draws_per_launch:
             _check(L.nb200_sampler_set_draws_per_launch(self._h, int(draws_per_launch)))
+        self._trace_buffers = trace_buffers
+        if trace_buffers is not None:  # rows are streamed into these while sampling runs
+            _check(L.nb200_sampler_set_trace_target(self._h, _ptr(trace_buffers["draws"]),
+                                                    _ptr(trace_buffers["stats"])))
         self.n_total = int(self._c.num_tune + self._c.num_draws)
         self.n_rows = self.n_total if self._c.save_warmup else int(self._c.num_draws)
         sd = int(self._c.store_dims)
@@ -589,6 +595,8 @@ class PySampler:
         shape_d = (self.n_chains, self.n_rows, self.sdim)
         shape_s = (self.n_chains, self.n_rows, NSTAT)
         keep = []
+        if out is None:
+            out = self._trace_buffers
         if out is not None:
             draws, stats = out["draws"], out["stats"]
         else:

@@ -92,6 +92,10 @@ struct nb200_sampler {
     std::vector<void*> model_allocs;
     virtual int launch() = 0;
     int sampler_error = 0;
+    // streaming of finished trace rows to host buffers while the kernel runs
+    double *tgt_draws = nullptr, *tgt_stats = nullptr;
+    uint64_t streamed_rows = 0;
+    std::chrono::steady_clock::time_point last_stream{};
 };
 
 template <class M>
@@ -322,10 +326,6 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     CHK(cudaEventCreate(&s->ev1));
     CHK(cudaMemsetAsync(s->d_sc, 0, n_chains * sizeof(ChainScalars), s->stream));
     CHK(cudaMemsetAsync(s->d_stop, 0, sizeof(int), s->stream));
-    CHK(cudaMemsetAsync(s->d_pool, 0, n_chains * (size_t)s->NS * 4 * vecb, s->stream));
-    CHK(cudaMemsetAsync(s->d_var, 0, n_chains * vecb, s->stream));
-    CHK(cudaMemsetAsync(s->d_wf, 0, n_chains * 8 * vecb, s->stream));
-    CHK(cudaMemsetAsync(s->d_stats, 0, n_chains * s->n_rows * NB200_NSTAT * sizeof(double), s->stream));
     CHK(cudaHostAlloc((void**)&s->h_sc, n_chains * sizeof(ChainScalars), cudaHostAllocDefault));
     std::memset(s->h_sc, 0, n_chains * sizeof(ChainScalars));
     if (q0) {
@@ -443,6 +443,15 @@ nb200_sampler* nb200_sampler_create(const nb200_settings* settings, const nb200_
     return nullptr;
 }
 
+int nb200_sampler_set_trace_target(nb200_sampler* s, double* draws, double* stats) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state != RunState::Created) return fail(NB200_ESTATE, "trace target must be set before start");
+    s->tgt_draws = draws;
+    s->tgt_stats = stats;
+    return 0;
+}
+
 int nb200_sampler_set_draws_per_launch(nb200_sampler* s, uint64_t n) {
     if (!s) return fail(NB200_EINVAL, "null sampler");
     std::lock_guard<std::mutex> lk(s->mu);
@@ -499,11 +508,50 @@ int nb200_sampler_start(nb200_sampler* s) {
 }
 
 // refresh h_sc from the device on the side stream (safe while the kernel runs)
+static int fetch_scalars(nb200_sampler* s);
+static int stream_rows(nb200_sampler* s, uint64_t from, uint64_t to);
 static int fetch_scalars(nb200_sampler* s) {
     CU(cudaSetDevice(s->device));
     CU(cudaMemcpyAsync(s->h_sc, s->d_sc, s->n_chains * sizeof(ChainScalars), cudaMemcpyDeviceToHost,
                        s->side));
     CU(cudaStreamSynchronize(s->side));
+    return 0;
+}
+
+// rows [from, to) of every chain -> the registered host buffers (2-D copies: one row block
+// per chain, pitch = a chain's full trace)
+static int stream_rows(nb200_sampler* s, uint64_t from, uint64_t to) {
+    if (to <= from) return 0;
+    CU(cudaSetDevice(s->device));
+    const size_t dpitch = s->n_rows * s->sdim * sizeof(double);
+    const size_t spitch = s->n_rows * NB200_NSTAT * sizeof(double);
+    if (s->tgt_draws)
+        CU(cudaMemcpy2DAsync(s->tgt_draws + from * s->sdim, dpitch, s->d_draws + from * s->sdim, dpitch,
+                             (to - from) * s->sdim * sizeof(double), s->n_chains,
+                             cudaMemcpyDeviceToHost, s->side));
+    if (s->tgt_stats)
+        CU(cudaMemcpy2DAsync(s->tgt_stats + from * NB200_NSTAT, spitch, s->d_stats + from * NB200_NSTAT,
+                             spitch, (to - from) * NB200_NSTAT * sizeof(double), s->n_chains,
+                             cudaMemcpyDeviceToHost, s->side));
+    CU(cudaStreamSynchronize(s->side));
+    s->streamed_rows = to;
+    return 0;
+}
+
+// while the kernel runs: copy out the rows every chain has already published
+static int stream_progress(nb200_sampler* s) {
+    if (!s->tgt_draws && !s->tgt_stats) return 0;
+    auto now = std::chrono::steady_clock::now();
+    if (std::chrono::duration<double>(now - s->last_stream).count() < 0.004) return 0;
+    s->last_stream = now;
+    int rc = fetch_scalars(s);
+    if (rc != 0) return rc;
+    uint64_t m = ~0ull;
+    for (uint64_t c = 0; c < s->n_chains; ++c)
+        if (s->h_sc[c].published < m) m = s->h_sc[c].published;
+    uint64_t rows = s->st.save_warmup ? m : (m > s->st.num_tune ? m - s->st.num_tune : 0);
+    if (rows > s->n_rows) rows = s->n_rows;
+    if (rows >= s->streamed_rows + 32) return stream_rows(s, s->streamed_rows, rows);
     return 0;
 }
 
@@ -527,6 +575,10 @@ static int on_launch_done(nb200_sampler* s) {
         if (s->h_sc[c].status != 2) all_done = false;
     }
     if (all_done) {
+        if (s->tgt_draws || s->tgt_stats) {
+            rc = stream_rows(s, s->streamed_rows, s->n_rows);
+            if (rc != 0) return rc;
+        }
         s->state = RunState::Finished;
         return 0;
     }
@@ -558,7 +610,10 @@ int nb200_sampler_wait(nb200_sampler* s, double timeout_seconds) {
                         s->sampler_error = rc;
                         return rc;
                     }
-                } else if (q != cudaErrorNotReady) {
+                } else if (q == cudaErrorNotReady) {
+                    int rc = stream_progress(s);
+                    if (rc < 0) return rc;
+                } else {
                     s->state = RunState::Error;
                     s->sampler_error = NB200_ECUDA;
                     return fail(NB200_ECUDA, std::string("kernel failed: ") + cudaGetErrorString(q));
@@ -666,8 +721,11 @@ static int copy_trace(nb200_sampler* s, double* draws, double* stats, double* gr
     }
     const size_t nd = s->n_chains * s->n_rows * s->sdim * sizeof(double);
     const size_t ns = s->n_chains * s->n_rows * NB200_NSTAT * sizeof(double);
-    if (draws) CU(cudaMemcpyAsync(draws, s->d_draws, nd, cudaMemcpyDeviceToHost, s->side));
-    if (stats) CU(cudaMemcpyAsync(stats, s->d_stats, ns, cudaMemcpyDeviceToHost, s->side));
+    const bool streamed = s->streamed_rows >= s->n_rows;  // already landed in the target buffers
+    if (draws && !(streamed && draws == s->tgt_draws))
+        CU(cudaMemcpyAsync(draws, s->d_draws, nd, cudaMemcpyDeviceToHost, s->side));
+    if (stats && !(streamed && stats == s->tgt_stats))
+        CU(cudaMemcpyAsync(stats, s->d_stats, ns, cudaMemcpyDeviceToHost, s->side));
     if (grads && s->d_grads) CU(cudaMemcpyAsync(grads, s->d_grads, nd, cudaMemcpyDeviceToHost, s->side));
     if (mm && s->d_mm) CU(cudaMemcpyAsync(mm, s->d_mm, nd, cudaMemcpyDeviceToHost, s->side));
     CU(cudaStreamSynchronize(s->side));

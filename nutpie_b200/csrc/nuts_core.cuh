@@ -51,6 +51,7 @@ struct ChainScalars {
     unsigned long long total_steps;
     unsigned long long divergences;
     unsigned long long latest_n_steps;
+    unsigned long long published;  // rows < published are complete in HBM (fenced): safe to copy out
     double cur_U;                // potential energy (-logp) of the current point
     int fg_sel;                  // which Welford set is the foreground
     int has_initial_mm;
@@ -1150,6 +1151,13 @@ struct ChainCtx {
             cur = sel;
             t += 1;
             done_here += 1;
+            // every 16 draws (and at the end) fence the trace rows written so far and publish
+            // the count: the host streams published rows to its buffers while sampling runs
+            if ((t & 15ull) == 0 || t == n_total) {
+                nb_threadfence();
+                g.sync();
+                if (g.tid == 0) sc.published = t;
+            }
             if (g.tid == 0) {  // progress record, polled by the host on a side stream
                 sc.draw = t;
                 sc.total_steps = total_steps;

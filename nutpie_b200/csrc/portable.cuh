@@ -51,6 +51,12 @@ NB_HD int nb_ffsll(unsigned long long x) {
 #endif
 }
 
+NB_HD void nb_threadfence() {
+#ifdef __CUDA_ARCH__
+    __threadfence();
+#endif
+}
+
 NB_HD bool nb_isfinite(double x) {
 #ifdef __CUDA_ARCH__
     return isfinite(x);

@@ -123,7 +123,7 @@ class _BackgroundSampler:
             progress_type = _lib.ProgressType.none()
         self._sampler = compiled_model._make_sampler(
             settings, init_mean, cores, progress_type, device=device,
-            chain_id_offset=chain_id_offset, **sampler_kw)
+            chain_id_offset=chain_id_offset, trace_buffers=trace_buffers, **sampler_kw)
         self._html = None
 
     def wait(self, *, timeout=None):

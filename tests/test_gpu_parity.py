@@ -351,3 +351,22 @@ def test_init_failure_is_reported():
     with pytest.raises(RuntimeError, match="initial point"):
         smp.wait()
     smp.close()
+
+
+def test_streamed_trace_equals_final_copy(radon_data):
+    """Rows streamed to (pinned) host buffers while the kernel runs == one copy at the end."""
+    gm, _ = models(radon_data)["radon"]
+    mk = lambda: settings_pair(seed=6, num_tune=300, num_draws=300, init_radius=1.0)[0]
+    ref = run_gpu(mk(), gm, 64)
+    n_rows, D = 600, gm.n_dim
+    pd_, ps_ = _lib.PinnedArray((64, n_rows, D)), _lib.PinnedArray((64, n_rows, _lib.NSTAT))
+    pd_.array[:] = -1.0
+    bufs = {"draws": pd_.array, "stats": ps_.array}
+    smp = _lib.PySampler(mk(), gm, n_chains=64, trace_buffers=bufs)
+    try:
+        smp.wait()
+        tr = smp.take_results()
+    finally:
+        smp.close()
+    assert tr.draws is bufs["draws"]
+    assert np.array_equal(tr.draws, ref.draws) and np.array_equal(tr.stats, ref.stats)
