@@ -286,6 +286,8 @@ def run_gpu(args):
     for i in range(args.warmup + args.steps):
         barrier()
         t1 = time.perf_counter()
+        # the user's call: host data in, raw trace (draws + stats of every chain) landed in
+        # pinned host memory when it returns; finished rows are streamed out while sampling
         tr = nutpie_b200.sample(model, draws=DRAWS, tune=TUNE, chains=n_chains, seed=500 + i,
                                 init_radius=1.0, return_raw_trace=True, progress_bar=False,
                                 device=device, chain_id_offset=offset, trace_buffers=bufs)
@@ -295,7 +297,7 @@ def run_gpu(args):
         dt = time.perf_counter() - t1
         if i >= args.warmup:
             e2e_wall += dt
-            e2e_steps += int(tr.stats[..., 9].sum())
+            e2e_steps += int(tr.stats[..., 9].sum())  # metric bookkeeping, outside the timed call
     h2d = int(data["y"].nbytes + data["county"].nbytes + data["floor"].nbytes + DIM * 8)
     d2h = int(bufs["draws"].nbytes + bufs["stats"].nbytes)
 
