@@ -25,14 +25,67 @@ struct GroupCuda {
         if (W == 1) __syncwarp();
         else __syncthreads();
     }
+    // Warp sum of N values with recursive halving: at every level a lane keeps half of its
+    // values and hands the other half to its xor-partner, so the shuffle count is
+    // ~N + log2(32) instead of N * log2(32); the final value i lives in the lanes whose
+    // low bits spell i and is broadcast from the lowest such lane, so every lane ends up with
+    // bit-identical sums (fixed association order).
+    template <int N>
+    NB_D static void warp_reduce(double (&v)[N]) {
+        if constexpr (N < 4) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+            }
+        } else {
+            constexpr int P = N <= 4 ? 4 : (N <= 8 ? 8 : 16);  // padded to a power of two
+            constexpr int LV = P == 4 ? 2 : (P == 8 ? 3 : 4);  // halving levels
+            const int lane = threadIdx.x & 31;
+            double w[P];
+#pragma unroll
+            for (int i = 0; i < P; ++i) w[i] = i < N ? v[i] : 0.0;
+            // level l pairs lanes differing in bit l; the lane with bit l set keeps the upper half
+            int cnt = P;
+#pragma unroll
+            for (int l = 0; l < LV; ++l) {
+                const int half = cnt >> 1;
+                const bool up = (lane >> l) & 1;
+#pragma unroll
+                for (int i = 0; i < P / 2; ++i) {
+                    if (i < half) {
+                        const double keep = up ? w[half + i] : w[i];
+                        const double give = up ? w[i] : w[half + i];
+                        w[i] = keep + __shfl_xor_sync(0xffffffffu, give, 1 << l);
+                    }
+                }
+                cnt = half;
+            }
+            // w[0] now holds the partial sum of value id(lane) = bit-reversed low LV bits order
+            double r = w[0];
+#pragma unroll
+            for (int off = 1 << LV; off < 32; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+            // value index held by a lane: bit l of lane selects the upper half at level l
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                int src = 0, lo = 0, span = P;
+#pragma unroll
+                for (int l = 0; l < LV; ++l) {
+                    span >>= 1;
+                    if (i >= lo + span) {
+                        src |= 1 << l;
+                        lo += span;
+                    }
+                }
+                v[i] = __shfl_sync(0xffffffffu, r, src);
+            }
+        }
+    }
+
     // sum N values over the group; result identical on all threads
     template <int N>
     NB_D void reduce(double (&v)[N]) const {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
-        }
+        warp_reduce(v);
         if (W > 1) {
             const int warp = tid >> 5;
             __syncthreads();  // previous users of `red` are done

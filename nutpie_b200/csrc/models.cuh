@@ -86,9 +86,9 @@ struct FunnelModel {
 // a range, a GROUP is a maximal run of equal (county, floor): all its
 // observations share the linear predictor mu[2*county + floor], which every
 // thread reads from a shared table (meta carries its byte offset).  The walk is
-// branch-free: the running sum of residuals is stored to the group's private
-// slot after EVERY observation and the slot pointer advances when the end-of-
-// group bit is set, so the last store of a group wins.  Because ranges are
+// a running PREFIX sum of residuals over the thread's range is stored to the group's
+// private slot when the end-of-group bit is set (a group's sum is the difference of two
+// consecutive prefixes of the same thread).  Because ranges are
 // contiguous, a (county, floor) pair owns at most `kmax` groups; the host lists
 // them (padded with a slot that always holds 0), so the per-county gradient is a
 // fixed-order sum of kmax terms — no atomics, no data-dependent branches,
@@ -119,6 +119,25 @@ NB_HD RadonObs nb_ldg_obs(const RadonObs* p, bool in_smem) {
 #endif
 }
 
+// three exponentials: on the device lanes 0..2 of each warp evaluate one each and the
+// results are broadcast (same instruction count as ONE exp for the warp); bit-identical on
+// every lane because each value is computed exactly once
+template <class G>
+NB_HD void nb_exp3(const G&, double a, double b, double c, double& ea, double& eb, double& ec) {
+#ifdef __CUDA_ARCH__
+    const int lane = threadIdx.x & 31;
+    const double x = lane == 0 ? a : (lane == 1 ? b : c);
+    const double e = exp(x);
+    ea = __shfl_sync(0xffffffffu, e, 0);
+    eb = __shfl_sync(0xffffffffu, e, 1);
+    ec = __shfl_sync(0xffffffffu, e, 2);
+#else
+    ea = exp(a);
+    eb = exp(b);
+    ec = exp(c);
+#endif
+}
+
 struct RadonModel {
     static constexpr bool kElementwise = false;
     // The observation records and group tables are the same for every chain: a CTA
@@ -129,11 +148,12 @@ struct RadonModel {
         int T, in_smem;              // group size the layout was built for; tables live in shared memory
         const RadonObs* obs;         // [n_steps][T]; padding: y = 0, meta -> mu[2J] (= 0), no end bit
         const int32_t* group_base;   // [T]   first group slot of each thread (one spare slot each)
-        const uint16_t* group_list;  // [2J][kmax] group slots of each (county, floor); padding -> slot G
+        const uint32_t* group_list;  // [2J][kmax] (slot | prev_slot << 16) of each (county, floor) piece;
+                                     // prev = previous group of the same thread, or G; padding = (G, G)
     };
     NB_HD static size_t block_data_bytes(const Data& d) {
         size_t b = sizeof(RadonObs) * (size_t)d.n_steps * d.T;
-        b += (sizeof(uint16_t) * (size_t)2 * d.J * d.kmax + 15) & ~size_t(15);
+        b += (sizeof(uint32_t) * (size_t)2 * d.J * d.kmax + 15) & ~size_t(15);
         b += (sizeof(int32_t) * (size_t)d.T + 15) & ~size_t(15);
         return b;
     }
@@ -145,9 +165,9 @@ struct RadonModel {
         const int4* src = reinterpret_cast<const int4*>(d.obs);
         for (int i = tid; i < n16; i += nthreads) o[i] = __ldg(src + i);
         size_t off = sizeof(RadonObs) * (size_t)n16;
-        uint16_t* gl = reinterpret_cast<uint16_t*>(dst + off);
+        uint32_t* gl = reinterpret_cast<uint32_t*>(dst + off);
         for (int i = tid; i < 2 * d.J * d.kmax; i += nthreads) gl[i] = __ldg(d.group_list + i);
-        off += (sizeof(uint16_t) * (size_t)2 * d.J * d.kmax + 15) & ~size_t(15);
+        off += (sizeof(uint32_t) * (size_t)2 * d.J * d.kmax + 15) & ~size_t(15);
         int32_t* gb = reinterpret_cast<int32_t*>(dst + off);
         for (int i = tid; i < d.T; i += nthreads) gb[i] = __ldg(d.group_base + i);
         d.obs = reinterpret_cast<const RadonObs*>(dst);
@@ -168,7 +188,8 @@ struct RadonModel {
         const double floor_eff = q[J + 2];
         const double log_sd_b = q[2 * J + 3];
         const double log_sigma = q[2 * J + 4];
-        const double sd_a = exp(log_sd_a), sd_b = exp(log_sd_b), sigma = exp(log_sigma);
+        double sd_a, sd_b, sigma;
+        nb_exp3(grp, log_sd_a, log_sd_b, log_sigma, sd_a, sd_b, sigma);
         const double inv_sigma = 1.0 / sigma;
         const double inv_s2 = inv_sigma * inv_sigma;
         double* mu = sm;                // [2J+1] linear predictor per (county, floor)
@@ -188,7 +209,7 @@ struct RadonModel {
             char* kp = reinterpret_cast<char*>(gsum + nb_ld_tab(d.group_base + grp.tid, d.in_smem));
             const char* mub = reinterpret_cast<const char*>(mu);
             const RadonObs* ob = d.obs + grp.tid;
-            double s1 = 0.0;
+            double pre = 0.0;  // running PREFIX sum of residuals over the thread's whole range
             // n_steps is a multiple of 4: four records are loaded before they are consumed
             for (int j0 = 0; j0 < d.n_steps; j0 += 4) {
                 RadonObs rec[4];
@@ -202,22 +223,26 @@ struct RadonModel {
                     else if (u == 1) ss1 += r * r;
                     else if (u == 2) ss2 += r * r;
                     else ss3 += r * r;
-                    s1 += r;
-                    *reinterpret_cast<double*>(kp) = s1;
-                    const bool e = mt & 1;
-                    kp += e ? 8 : 0;
-                    s1 = e ? 0.0 : s1;
+                    pre += r;
+                    if (mt & 1) {  // last observation of its group: publish the prefix sum
+                        *reinterpret_cast<double*>(kp) = pre;
+                        kp += 8;
+                    }
                 }
             }
         }
         grp.sync();
         double acc[7] = {(ss0 + ss1) + (ss2 + ss3), 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         for (int c = grp.tid; c < J; c += T) {
-            const uint16_t* gl = d.group_list + (size_t)(2 * c) * d.kmax;
+            const uint32_t* gl = d.group_list + (size_t)(2 * c) * d.kmax;
             double S0 = 0.0, S1 = 0.0;
+            // a group's sum = prefix at its end - prefix at the end of the previous group of
+            // the same thread (slot G, always 0, for a thread's first group and for padding)
             for (int k = 0; k < d.kmax; ++k) {
-                S0 += gsum[nb_ld_tab(gl + k, d.in_smem)];
-                S1 += gsum[nb_ld_tab(gl + d.kmax + k, d.in_smem)];
+                const uint32_t e0 = nb_ld_tab(gl + k, d.in_smem);
+                const uint32_t e1 = nb_ld_tab(gl + d.kmax + k, d.in_smem);
+                S0 += gsum[e0 & 0xFFFFu] - gsum[e0 >> 16];
+                S1 += gsum[e1 & 0xFFFFu] - gsum[e1 >> 16];
             }
             const double E = (S0 + S1) * inv_s2;  // sum over the county of d logp / d mu_i
             const double F = S1 * inv_s2;         // same, floor = 1 observations only

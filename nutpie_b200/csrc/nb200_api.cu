@@ -188,7 +188,7 @@ static int build_model_data(const nb200_model_desc& m, int T, RadonModel::Data& 
     d.T = T; d.in_smem = 0;
     RadonObs* obs;
     int32_t* group_base;
-    uint16_t* group_list;
+    uint32_t* group_list;
     int rc;
     if ((rc = to_device(L.obs, &obs, keep))) return rc;
     if ((rc = to_device(L.group_base, &group_base, keep))) return rc;

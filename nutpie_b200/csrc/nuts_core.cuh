@@ -153,7 +153,8 @@ struct ChainCtx {
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int i = g.tid + it * G::kThreads;
-                if (i < D) f(i);
+                // NIT = ceil(D / group size): only the last iteration can run past D
+                if (it + 1 < NIT || i < D) f(i);
             }
         } else {
             for (int i = g.tid; i < D; i += g.size()) f(i);
@@ -406,7 +407,7 @@ struct ChainCtx {
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
                     const int i = g.tid + it * G::kThreads;
-                    if (i < D) {
+                    if (it + 1 < NIT || i < D) {
                         vr[it] = var[i];
                         ph[it] = fp[i] + heps * fg[i];
                         const double qn = fq[i] + eps * (vr[it] * ph[it]);
@@ -423,7 +424,7 @@ struct ChainCtx {
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
                     const int i = g.tid + it * G::kThreads;
-                    if (i < D) {
+                    if (it + 1 < NIT || i < D) {
                         const double gn = fg[i];
                         const double pn = ph[it] + heps * gn;
                         acc[0] += pn * (vr[it] * pn);

@@ -19,7 +19,7 @@ struct RadonLayout {
     int J = 0, N = 0, T = 0, n_steps = 0, G = 0, kmax = 1;
     std::vector<RadonObs> obs;           // [n_steps][T]
     std::vector<int32_t> group_base;     // [T]
-    std::vector<uint16_t> group_list;    // [2J][kmax]
+    std::vector<uint32_t> group_list;    // [2J][kmax]  slot | prev_slot << 16
 };
 
 inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
@@ -37,10 +37,11 @@ inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
     const int32_t dummy_mu = (int32_t)(2 * n_county) * 8;  // byte offset of mu[2J] (always 0)
     L.obs.assign((size_t)L.n_steps * T, RadonObs{0.0, dummy_mu, 0});
     L.group_base.assign(T, 0);
-    std::vector<std::vector<int>> pieces(2 * n_county);
+    std::vector<std::vector<std::pair<int, int>>> pieces(2 * n_county);  // (slot, prev or -1)
     int slot = 0;
     for (int t = 0; t < T; ++t) {
         L.group_base[t] = slot;
+        int prev = -1;
         for (int j = 0; j < per; ++j) {
             const int pos = t * per + j;
             if (pos >= n_obs) break;
@@ -49,17 +50,22 @@ inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
             const bool last_of_range = (j + 1 == per) || (pos + 1 >= n_obs);
             const bool ends = last_of_range || key(order[pos + 1]) != kcur;
             L.obs[(size_t)j * T + t] = RadonObs{y[o], (int32_t)(kcur * 8) | (ends ? 1 : 0), 0};
-            if (ends) pieces[kcur].push_back(slot++);
+            if (ends) {
+                pieces[kcur].push_back({slot, prev});
+                prev = slot++;
+            }
         }
-        ++slot;  // spare slot: receives the stores issued after the thread's last group ended
     }
     L.G = slot;  // slot G itself (one past) always holds 0 and pads the lists
     L.kmax = 1;
     for (auto& p : pieces) L.kmax = std::max<int>(L.kmax, (int)p.size());
-    L.group_list.assign((size_t)2 * n_county * L.kmax, (uint16_t)L.G);
+    const uint32_t pad = (uint32_t)L.G | ((uint32_t)L.G << 16);
+    L.group_list.assign((size_t)2 * n_county * L.kmax, pad);
     for (int k = 0; k < 2 * n_county; ++k)
-        for (size_t i = 0; i < pieces[k].size(); ++i)
-            L.group_list[(size_t)k * L.kmax + i] = (uint16_t)pieces[k][i];
+        for (size_t i = 0; i < pieces[k].size(); ++i) {
+            const int pv = pieces[k][i].second < 0 ? L.G : pieces[k][i].second;
+            L.group_list[(size_t)k * L.kmax + i] = (uint32_t)pieces[k][i].first | ((uint32_t)pv << 16);
+        }
     return L;
 }
 
