@@ -33,11 +33,10 @@ struct GroupCuda {
     template <int N>
     NB_D static void warp_reduce(double (&v)[N]) {
         if constexpr (N < 4) {
-            // levels as a real loop (code size), values unrolled inside (independent shuffles)
-#pragma unroll 1
-            for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
             }
         } else {
             constexpr int P = N <= 4 ? 4 : (N <= 8 ? 8 : 16);  // padded to a power of two
@@ -64,7 +63,7 @@ struct GroupCuda {
             }
             // w[0] now holds the partial sum of value id(lane) = bit-reversed low LV bits order
             double r = w[0];
-#pragma unroll 1
+#pragma unroll
             for (int off = 1 << LV; off < 32; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
             // value index held by a lane: bit l of lane selects the upper half at level l
 #pragma unroll

@@ -127,7 +127,7 @@ NB_HD void nb_exp3(const G&, double a, double b, double c, double& ea, double& e
 #ifdef __CUDA_ARCH__
     const int lane = threadIdx.x & 31;
     const double x = lane == 0 ? a : (lane == 1 ? b : c);
-    const double e = nb_exp(x);
+    const double e = exp(x);
     ea = __shfl_sync(0xffffffffu, e, 0);
     eb = __shfl_sync(0xffffffffu, e, 1);
     ec = __shfl_sync(0xffffffffu, e, 2);

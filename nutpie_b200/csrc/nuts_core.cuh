@@ -96,7 +96,7 @@ struct SampleInfo {
     int depth, diverging, maxdepth_reached;
 };
 
-NB_HD_NOINLINE double nb_logaddexp(double a, double b) {
+NB_HD double nb_logaddexp(double a, double b) {
     if (a == b) return a + 0.69314718055994530941723212145818;
     double diff = a - b;
     if (diff > 0) return a + log1p(exp(-diff));
@@ -500,7 +500,7 @@ struct ChainCtx {
         g.sync();
         acc_count += 1;
         if (rc == 0) {
-            const double w = nb_exp(-de);
+            const double w = exp(-de);
             const double a = w < 1.0 ? w : 1.0;
             acc_sum += a;
             acc_sym += 2.0 * a / (1.0 + w);
@@ -731,7 +731,7 @@ struct ChainCtx {
                     const double u = rng_u01(ra);
                     // multinomial pick inside a sub-tree, biased progressive for the main tree
                     const double ref_ls = with_main ? s_ls : new_ls;
-                    const bool take_new = t_ls >= ref_ls || u < nb_exp(t_ls - ref_ls);
+                    const bool take_new = t_ls >= ref_ls || u < exp(t_ls - ref_ls);
                     if (with_main) {
                         if (take_new) mD = tD;
                         if (dir > 0) mR = tR;
@@ -961,14 +961,14 @@ struct ChainCtx {
                 has_initial_mm = 0;
                 step_size_search(dslot, (uint32_t)t);
             } else if (!fixed) {
-                step_size = clamp_step(nb_exp(da_log_step));
+                step_size = clamp_step(exp(da_log_step));
             }
             return;
         }
         if (fixed) return;
         da_advance(last_sym);
-        if (t == num_tune - 1) step_size = clamp_step(nb_exp(da_log_step_adapted));
-        else step_size = clamp_step(nb_exp(da_log_step));
+        if (t == num_tune - 1) step_size = clamp_step(exp(da_log_step_adapted));
+        else step_size = clamp_step(exp(da_log_step));
     }
 
     // -------------------------------------------------------------- chain init
@@ -1139,7 +1139,7 @@ struct ChainCtx {
                     s[NB200_STAT_ENERGY_ERROR] = (K + U) - E0t;
                     s[NB200_STAT_DIVERGING] = info.diverging;
                     s[NB200_STAT_STEP_SIZE] = step_used;
-                    s[NB200_STAT_STEP_SIZE_BAR] = nb_exp(da_log_step_adapted);
+                    s[NB200_STAT_STEP_SIZE_BAR] = exp(da_log_step_adapted);
                     s[NB200_STAT_N_STEPS] = (double)last_n_steps;
                     s[NB200_STAT_MEAN_TREE_ACCEPT] = last_mean;
                     s[NB200_STAT_MEAN_TREE_ACCEPT_SYM] = last_sym;

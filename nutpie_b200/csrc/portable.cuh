@@ -11,13 +11,9 @@
 #ifdef __CUDACC__
 #define NB_HD __host__ __device__ __forceinline__
 #define NB_D __device__ __forceinline__
-// one shared copy of a bulky helper (libm expansions) instead of one per call site: the hot
-// path of the sampler is instruction-cache bound (profiles/r1_radon_nuts_kernel_latest.txt)
-#define NB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define NB_HD inline
 #define NB_D inline
-#define NB_HD_NOINLINE inline
 #endif
 
 #ifndef __CUDACC__
@@ -54,8 +50,6 @@ NB_HD int nb_ffsll(unsigned long long x) {
     return __builtin_ffsll((long long)x);
 #endif
 }
-
-NB_HD_NOINLINE double nb_exp(double x) { return exp(x); }
 
 NB_HD void nb_threadfence() {
 #ifdef __CUDA_ARCH__
