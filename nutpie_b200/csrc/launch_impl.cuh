@@ -119,6 +119,17 @@ __global__ void __launch_bounds__(32 * W)
         ctx.step_size = eps;
         ctx.E0 = 0.0;
         const int rc = ctx.leapfrog(0, 1, dir);
+        if constexpr (M::kElementwise) {
+            // elementwise gradients are recomputed on use, not stored with the state: materialise
+            // it for the caller of this component entry point
+            const double* qn = ctx.vec(1, VQ);
+            double* gn = ctx.vec(1, VG);
+            for (int i = ctx.g.tid; i < ctx.D; i += ctx.g.size()) {
+                double gi;
+                (void)M::term(ctx.md, i, qn[i], gi);
+                gn[i] = gi;
+            }
+        }
         if (ctx.g.tid == 0) {
             out_scal[chain * 4 + 0] = -ctx.sh->U[1];
             out_scal[chain * 4 + 1] = ctx.sh->K[1];

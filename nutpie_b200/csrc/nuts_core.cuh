@@ -311,8 +311,13 @@ struct ChainCtx {
             double acc[NA];
 #pragma unroll
             for (int c = 0; c < NA; ++c) acc[c] = 0.0;
-            auto elem = [&](int i, double q0, double p0, double g0, double vr, double s0, double& qn,
-                            double& pn, double& gn, double& sn) {
+            // An elementwise gradient is a function of q_i alone: it is recomputed from the
+            // source position instead of being stored with every state, which removes one
+            // vector read and one vector write per gradient evaluation (72 -> 56 B/dim moved).
+            auto elem = [&](int i, double q0, double p0, double vr, double s0, double& qn, double& pn,
+                            double& sn) {
+                double g0, gn;
+                (void)M::term(md, i, q0, g0);
                 const double ph = p0 + heps * g0;
                 qn = q0 + eps * (vr * ph);
                 acc[0] += M::term(md, i, qn, gn);
@@ -331,39 +336,34 @@ struct ChainCtx {
                 const int D2 = D >> 1;
                 const double2* qs2 = reinterpret_cast<const double2*>(qs);
                 const double2* ps2 = reinterpret_cast<const double2*>(ps);
-                const double2* gs2 = reinterpret_cast<const double2*>(gs);
                 const double2* ss2 = reinterpret_cast<const double2*>(ss);
                 const double2* vr2 = reinterpret_cast<const double2*>(var);
                 double2* qd2 = reinterpret_cast<double2*>(qd);
                 double2* pd2 = reinterpret_cast<double2*>(pd);
-                double2* gd2 = reinterpret_cast<double2*>(gd);
                 double2* sd2 = reinterpret_cast<double2*>(sd);
                 for (int k = g.tid; k < D2; k += g.size()) {
-                    const double2 q0 = qs2[k], p0 = ps2[k], g0 = gs2[k], v0 = vr2[k], s0 = ss2[k];
-                    double2 qn, pn, gn, sn;
-                    elem(2 * k, q0.x, p0.x, g0.x, v0.x, s0.x, qn.x, pn.x, gn.x, sn.x);
-                    elem(2 * k + 1, q0.y, p0.y, g0.y, v0.y, s0.y, qn.y, pn.y, gn.y, sn.y);
+                    const double2 q0 = qs2[k], p0 = ps2[k], v0 = vr2[k], s0 = ss2[k];
+                    double2 qn, pn, sn;
+                    elem(2 * k, q0.x, p0.x, v0.x, s0.x, qn.x, pn.x, sn.x);
+                    elem(2 * k + 1, q0.y, p0.y, v0.y, s0.y, qn.y, pn.y, sn.y);
                     qd2[k] = qn;
                     pd2[k] = pn;
-                    gd2[k] = gn;
                     sd2[k] = sn;
                 }
                 if ((D & 1) && g.tid == 0) {
                     const int i = D - 1;
-                    double qn, pn, gn, sn;
-                    elem(i, qs[i], ps[i], gs[i], var[i], ss[i], qn, pn, gn, sn);
+                    double qn, pn, sn;
+                    elem(i, qs[i], ps[i], var[i], ss[i], qn, pn, sn);
                     qd[i] = qn;
                     pd[i] = pn;
-                    gd[i] = gn;
                     sd[i] = sn;
                 }
             } else {
                 for_dims([&](int i) {
-                    double qn, pn, gn, sn;
-                    elem(i, qs[i], ps[i], gs[i], var[i], ss[i], qn, pn, gn, sn);
+                    double qn, pn, sn;
+                    elem(i, qs[i], ps[i], var[i], ss[i], qn, pn, sn);
                     qd[i] = qn;
                     pd[i] = pn;
-                    gd[i] = gn;
                     sd[i] = sn;
                 });
             }
@@ -863,7 +863,10 @@ struct ChainCtx {
         for (int i = g.tid; i < D; i += g.size()) {
             double fq = 0.0, fg = 0.0;  // m2 of draws / grads in the (post-switch) foreground set
             if (add) {
-                const double x = q[i], y = gr[i];
+                const double x = q[i];
+                double y;
+                if constexpr (M::kElementwise) (void)M::term(md, i, x, y);  // gradients are not stored
+                else y = gr[i];
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     double* w = s ? w1 : w0;
@@ -1126,7 +1129,12 @@ struct ChainCtx {
                 if (P->grads) {
                     const double* gr = vec(sel, VG);
                     double* og = P->grads + row_off * P->sdim;
-                    for (int i = g.tid; i < (int)P->sdim; i += g.size()) og[i] = gr[i];
+                    for (int i = g.tid; i < (int)P->sdim; i += g.size()) {
+                        double gi;
+                        if constexpr (M::kElementwise) (void)M::term(md, i, q[i], gi);
+                        else gi = gr[i];
+                        og[i] = gi;
+                    }
                 }
                 if (g.tid == 0) {
                     double* s = P->stats + row_off * NB200_NSTAT;
