@@ -60,6 +60,24 @@ static size_t chain_smem_total(size_t fixed, int Dp, int var_in_smem, int smem_s
            align16(sizeof(double) * 4 * (size_t)Dp * smem_slots);
 }
 
+// Device buffers of a sampler come from the stream-ordered memory pool with an unbounded
+// release threshold: destroying a sampler returns its ~3.4 GB to the pool instead of
+// unmapping it (cudaFree of that much memory was measured at 100-180 ms), and the next
+// sampler's allocations are served from the pool.
+static void pool_keep_memory(int device) {
+    static std::mutex mu;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lk(mu);
+    for (int d : done)
+        if (d == device) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done.push_back(device);
+}
+
 // ------------------------------------------------------------------ sampler
 enum class RunState { Created, Running, Paused, Finished, Aborted, Error };
 
@@ -296,7 +314,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     P.n_rows = s->n_rows; P.sdim = s->sdim; P.n_total = s->n_total;
 #define ALLOC(ptr, bytes)                                                               \
     do {                                                                                \
-        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes) ? (bytes) : 8);             \
+        cudaError_t e_ = cudaMallocAsync((void**)&(ptr), (bytes) ? (bytes) : 8, s->stream); \
         if (e_ != cudaSuccess) {                                                        \
             fail(NB200_ECUDA, std::string("cudaMalloc ") + #ptr + ": " + cudaGetErrorString(e_)); \
             return bail();                                                              \
@@ -311,6 +329,9 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         }                                                                               \
     } while (0)
     const size_t vecb = sizeof(double) * (size_t)s->Dp;
+    pool_keep_memory(device);
+    CHK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CHK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
     ALLOC(s->d_pool, n_chains * (size_t)s->NS * 4 * vecb);
     ALLOC(s->d_var, n_chains * vecb);
     ALLOC(s->d_wf, n_chains * 8 * vecb);
@@ -320,8 +341,6 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     if (st->store_gradient) ALLOC(s->d_grads, n_chains * s->n_rows * s->sdim * sizeof(double));
     if (st->store_mass_matrix) ALLOC(s->d_mm, n_chains * s->n_rows * s->sdim * sizeof(double));
     ALLOC(s->d_stop, sizeof(int));
-    CHK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CHK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
     CHK(cudaEventCreate(&s->ev0));
     CHK(cudaEventCreate(&s->ev1));
     CHK(cudaMemsetAsync(s->d_sc, 0, n_chains * sizeof(ChainScalars), s->stream));
@@ -808,9 +827,14 @@ int nb200_sampler_destroy(nb200_sampler* s) {
         if (s->stream) cudaStreamSynchronize(s->stream);
     }
     void* dev[] = {s->d_pool, s->d_var, s->d_wf, s->d_sc, s->d_draws, s->d_stats, s->d_grads,
-                   s->d_mm, s->d_q0, s->d_init_mean, s->d_tape, s->d_stop};
-    for (void* p : dev)
-        if (p) cudaFree(p);
+                   s->d_mm, s->d_q0, s->d_init_mean, s->d_stop};
+    for (void* p : dev) {
+        if (!p) continue;
+        if (s->stream) cudaFreeAsync(p, s->stream);  // back to the pool
+        else cudaFree(p);
+    }
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->d_tape) cudaFree(s->d_tape);
     for (void* p : s->model_allocs) cudaFree(p);
     void* host[] = {s->h_sc, s->h_draws, s->h_stats, s->h_grads, s->h_mm};
     for (void* p : host)
