@@ -314,8 +314,8 @@ struct ChainCtx {
             // An elementwise gradient is a function of q_i alone: it is recomputed from the
             // source position instead of being stored with every state, which removes one
             // vector read and one vector write per gradient evaluation (72 -> 56 B/dim moved).
-            auto elem = [&](int i, double q0, double p0, double vr, double s0, const double* ppx,
-                            const double* psx, double& qn, double& pn, double& sn) {
+            auto elem = [&](int i, double q0, double p0, double vr, double s0, double& qn, double& pn,
+                            double& sn) {
                 double g0, gn;
                 (void)M::term(md, i, q0, g0);
                 const double ph = p0 + heps * g0;
@@ -328,7 +328,7 @@ struct ChainCtx {
                 if (want_l0) turn_terms(m_src, p0, s0, pn, sn, vr, acc[3], acc[4]);
 #pragma unroll
                 for (int c = 0; c < kMaxFused; ++c)
-                    if (c < np) turn_terms(Pm[c], ppx[c], psx[c], pn, sn, vr, acc[5 + 2 * c], acc[6 + 2 * c]);
+                    if (c < np) turn_terms(Pm[c], Pp[c][i], Sp[c][i], pn, sn, vr, acc[5 + 2 * c], acc[6 + 2 * c]);
             };
             if constexpr (NIT == 0) {
                 // 16-byte accesses: two dimensions per thread and iteration (slots are 32-byte
@@ -343,41 +343,25 @@ struct ChainCtx {
                 double2* sd2 = reinterpret_cast<double2*>(sd);
                 for (int k = g.tid; k < D2; k += g.size()) {
                     const double2 q0 = qs2[k], p0 = ps2[k], v0 = vr2[k], s0 = ss2[k];
-                    double px0[kFusedDim], px1[kFusedDim], sx0[kFusedDim], sx1[kFusedDim];
-#pragma unroll
-                    for (int c = 0; c < kMaxFused; ++c) {
-                        if (c < np) {  // partners of the planned U-turn pairs: 16-byte loads too
-                            const double2 pp = reinterpret_cast<const double2*>(Pp[c])[k];
-                            const double2 sp = reinterpret_cast<const double2*>(Sp[c])[k];
-                            px0[c] = pp.x; px1[c] = pp.y;
-                            sx0[c] = sp.x; sx1[c] = sp.y;
-                        }
-                    }
                     double2 qn, pn, sn;
-                    elem(2 * k, q0.x, p0.x, v0.x, s0.x, px0, sx0, qn.x, pn.x, sn.x);
-                    elem(2 * k + 1, q0.y, p0.y, v0.y, s0.y, px1, sx1, qn.y, pn.y, sn.y);
+                    elem(2 * k, q0.x, p0.x, v0.x, s0.x, qn.x, pn.x, sn.x);
+                    elem(2 * k + 1, q0.y, p0.y, v0.y, s0.y, qn.y, pn.y, sn.y);
                     qd2[k] = qn;
                     pd2[k] = pn;
                     sd2[k] = sn;
                 }
                 if ((D & 1) && g.tid == 0) {
                     const int i = D - 1;
-                    double qn, pn, sn, px[kFusedDim], sx[kFusedDim];
-#pragma unroll
-                    for (int c = 0; c < kMaxFused; ++c)
-                        if (c < np) { px[c] = Pp[c][i]; sx[c] = Sp[c][i]; }
-                    elem(i, qs[i], ps[i], var[i], ss[i], px, sx, qn, pn, sn);
+                    double qn, pn, sn;
+                    elem(i, qs[i], ps[i], var[i], ss[i], qn, pn, sn);
                     qd[i] = qn;
                     pd[i] = pn;
                     sd[i] = sn;
                 }
             } else {
                 for_dims([&](int i) {
-                    double qn, pn, sn, px[kFusedDim], sx[kFusedDim];
-#pragma unroll
-                    for (int c = 0; c < kMaxFused; ++c)
-                        if (c < np) { px[c] = Pp[c][i]; sx[c] = Sp[c][i]; }
-                    elem(i, qs[i], ps[i], var[i], ss[i], px, sx, qn, pn, sn);
+                    double qn, pn, sn;
+                    elem(i, qs[i], ps[i], var[i], ss[i], qn, pn, sn);
                     qd[i] = qn;
                     pd[i] = pn;
                     sd[i] = sn;
