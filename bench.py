@@ -50,6 +50,13 @@ DIM = 2 * N_COUNTY + 5
 WORKLOAD = "radon_hierarchical_D175_1024chains_per_gpu_1000tune_1000draws"
 
 
+# DRAM bytes per gradient evaluation of nuts_kernel, from the committed `ncu --set full`
+# captures (dram__bytes_read.sum + dram__bytes_write.sum over the capture's leapfrog count):
+#   profiles/r1_radon_nuts_kernel_latest.txt   : 712.0 MB / 1 323 333 evaluations
+#   profiles/r1_config4_nuts_kernel_latest.txt : 836.5 GB / 1 138 581 evaluations
+NCU_DRAM_BYTES_PER_EVAL = {"radon": 712.0e6 / 1323333, "config4": 836.5e9 / 1138581}
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -212,7 +219,10 @@ def run_gpu(args):
             torch.cuda.synchronize()
             dist.barrier()
 
-    pinned_d = _lib.PinnedArray((n_chains, n_rows, DIM))
+    # the e2e trace is what the reference returns: expanded draws (constrained values +
+    # deterministics, computed on the device), 4J+5 = 345 doubles per draw
+    EXP_DIM = 4 * N_COUNTY + 5
+    pinned_d = _lib.PinnedArray((n_chains, n_rows, EXP_DIM))
     pinned_s = _lib.PinnedArray((n_chains, n_rows, _lib.NSTAT))
     bufs = {"draws": pinned_d.array, "stats": pinned_s.array}
 
@@ -258,7 +268,7 @@ def run_gpu(args):
     ess_min = None
     geom = samplers[-1].geometry()
     for i in range(args.warmup, total):
-        tr = samplers[i].take_results(bufs)
+        tr = samplers[i].take_results()
         steps += int(tr.stats[..., _lib.STAT_NAMES.index("n_steps")].sum())
         if i == total - 1 and rank == 0:
             post = tr.draws[:, TUNE:, :]
@@ -343,7 +353,13 @@ def run_gpu(args):
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": NCU_DRAM_BYTES_PER_EVAL["radon"] * (steps / world) / args.steps,
+                     "traffic_note": "DRAM bytes per launch = ncu-measured bytes per gradient evaluation "
+                                     "(profiles/r1_radon_nuts_kernel_latest.txt) x evaluations in one launch; "
+                                     "4% of the algorithmic bytes, almost all of it the trace being written",
+                     "algorithmic_bytes_per_launch": algo_bytes / args.steps,
+                     "peak_source": peak_src,
                      "note": "radon keeps chain state in shared memory: algorithmic bytes are "
                              "served on chip, see roofline_hbm_config4 for the HBM-bound kernel"},
         "roofline_hbm_config4": cfg4,
@@ -387,7 +403,10 @@ def run_config4(device):
     return {"workload": "iid_normal_D10000_512chains_200tune_200draws", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "grad_evals_per_sec": steps / (ms / 1e3), "kernel_ms": ms, "geometry": geom,
-            "peak_source": src, "traffic": None}
+            "peak_source": src, "algorithmic_bytes_per_launch": 72.0 * D * steps,
+            "traffic": NCU_DRAM_BYTES_PER_EVAL["config4"] * steps,
+            "traffic_note": "ncu-measured DRAM bytes per gradient evaluation "
+                            "(profiles/r1_config4_nuts_kernel_latest.txt) x evaluations in this launch"}
 
 
 def main():

@@ -83,7 +83,12 @@ typedef struct nb200_settings {
     uint64_t store_dims;       /* store only the first store_dims coordinates  */
                                /* of each draw; 0 = all                        */
     int32_t save_warmup;       /* sample.py:831; 1 = keep tuning draws         */
-    int32_t _pad1;
+    int32_t expand_draws;      /* 1 = each stored draw is the model's EXPANDED  */
+                               /* vector (constrained value variables followed  */
+                               /* by deterministics), computed on the device:   */
+                               /* CpuLogpFunc::expand_vector, src/pymc.rs:217-  */
+                               /* 286; row width = nb200_model_expanded_dim().  */
+                               /* Ignored when store_dims thins the draws.      */
 } nb200_settings;
 
 /* ---- model density plug-in ---------------------------------------------
@@ -176,6 +181,8 @@ typedef struct nb200_sampler nb200_sampler;
 int nb200_abi_version(void);
 const char *nb200_last_error(void);
 int nb200_device_count(void);
+/* width of an expanded draw (ExpandFunc's expanded_dim, src/pymc.rs:78-94); 0 on error */
+uint64_t nb200_model_expanded_dim(const nb200_model_desc *model);
 /* nuts_rs::DiagNutsSettings::default() as surfaced by
  * PyNutsSettings::new_diag (src/wrapper.rs:525-533). */
 void nb200_settings_default(nb200_settings *out);

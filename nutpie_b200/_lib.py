@@ -63,7 +63,7 @@ class Settings(C.Structure):
         ("init_kind", C.c_int32), ("num_try_init", C.c_int32),
         ("init_radius", C.c_double),
         ("store_dims", C.c_uint64),
-        ("save_warmup", C.c_int32), ("_pad1", C.c_int32),
+        ("save_warmup", C.c_int32), ("expand_draws", C.c_int32),
     ]
 
 
@@ -116,6 +116,8 @@ def load_library() -> C.CDLL:
         L.nb200_abi_version.restype = C.c_int
         L.nb200_last_error.restype = C.c_char_p
         L.nb200_device_count.restype = C.c_int
+        L.nb200_model_expanded_dim.restype = C.c_uint64
+        L.nb200_model_expanded_dim.argtypes = [C.POINTER(ModelDesc)]
         L.nb200_sampler_create.restype = C.c_void_p
         L.nb200_sampler_create.argtypes = [C.POINTER(Settings), C.POINTER(ModelDesc), C.c_uint64,
                                            C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
@@ -403,8 +405,10 @@ class PyTrace:
     which is what the end-to-end path uses to avoid a per-chain Arrow hop."""
 
     def __init__(self, draws, stats, rows_filled, gradients=None, mass_matrix_inv=None,
-                 variables=None, expand=None, keep=None):
+                 variables=None, expand=None, keep=None, expanded=False):
         self.draws, self.stats, self.rows_filled = draws, stats, rows_filled
+        self.expanded = expanded  # draws hold expanded vectors (constrained + deterministics)
+        self.expand_fn = expand
         self.gradients, self.mass_matrix_inv = gradients, mass_matrix_inv
         self.variables, self._expand, self._keep = variables, expand, keep
         self._taken = False
@@ -507,7 +511,9 @@ class PySampler:
         self.n_total = int(self._c.num_tune + self._c.num_draws)
         self.n_rows = self.n_total if self._c.save_warmup else int(self._c.num_draws)
         sd = int(self._c.store_dims)
-        self.sdim = sd if 0 < sd < self.dim else self.dim
+        self.grad_dim = sd if 0 < sd < self.dim else self.dim
+        self.expanded = bool(self._c.expand_draws) and not (0 < sd < self.dim)
+        self.sdim = int(L.nb200_model_expanded_dim(C.byref(self._desc))) if self.expanded else self.grad_dim
         self._lock = threading.Lock()
         self._taken = False
         self._t_start = None
@@ -601,13 +607,20 @@ class PySampler:
             draws, stats = out["draws"], out["stats"]
         else:
             draws, stats = np.empty(shape_d), np.empty(shape_s)
-        grads = np.empty(shape_d) if self._c.store_gradient else None
-        mm = np.empty(shape_d) if self._c.store_mass_matrix else None
+        shape_g = (self.n_chains, self.n_rows, self.grad_dim)
+        grads = np.empty(shape_g) if self._c.store_gradient else None
+        mm = np.empty(shape_g) if self._c.store_mass_matrix else None
         rows = np.zeros(self.n_chains, dtype=np.uint64)
         _check(self._L.nb200_sampler_trace_into(self._h, _ptr(draws), _ptr(stats), _ptr(grads),
                                                 _ptr(mm), _ptr(rows)))
+        if self.expanded:  # rows already hold the expanded vector: slice it into variables
+            expand = self._model._split_expanded
+        elif self.sdim == self.dim:
+            expand = self._model._expand
+        else:
+            expand = None
         return PyTrace(draws, stats, rows, grads, mm, variables=self._model._variable_dims(),
-                       expand=self._model._expand if self.sdim == self.dim else None, keep=keep)
+                       expand=expand, keep=keep, expanded=self.expanded)
 
     def inspect(self, out=None):
         return self._trace(out)

@@ -44,6 +44,12 @@ struct NormalModel {
         return r * r;
     }
     NB_HD static double finish(const Data& d, double acc, int) { return -0.5 * acc * d.inv_var; }
+    // expand_vector (src/pymc.rs:217-286): no transforms, no deterministics
+    NB_HD static int expanded_dim(int D) { return D; }
+    template <class G>
+    NB_HD static void expand(const G& grp, const Data&, int D, const double* q, double* out) {
+        for (int i = grp.tid; i < D; i += grp.size()) out[i] = q[i];
+    }
 };
 
 // Neal's funnel (docs/sample-stats.qmd:19-21; 9 parameters in BASELINE.json)
@@ -71,6 +77,11 @@ struct FunnelModel {
         const double n = (double)(D - 1);
         if (grp.tid == 0) g[0] = -v + acc[0] * e - n;
         return -0.5 * v * v - 0.5 * acc[0] * e - n * v;
+    }
+    NB_HD static int expanded_dim(int D) { return D; }
+    template <class G>
+    NB_HD static void expand(const G& grp, const Data&, int D, const double* q, double* out) {
+        for (int i = grp.tid; i < D; i += grp.size()) out[i] = q[i];
     }
 };
 
@@ -151,6 +162,28 @@ struct RadonModel {
         const uint32_t* group_list;  // [2J][kmax] (slot | prev_slot << 16) of each (county, floor) piece;
                                      // prev = previous group of the same thread, or G; padding = (G, G)
     };
+    // expand_vector for the radon model (src/pymc.rs:217-286; producer
+    // python/nutpie/compile_pymc.py:816-861): value variables on the constrained scale
+    // (the three log-transformed scales exponentiated) followed by the Deterministics
+    // county_effect = county_raw * county_sd and county_floor_effect likewise: 4J + 5 values,
+    // same order as oracle_expand_radon.
+    NB_HD static int expanded_dim(int D) { return 2 * D - 5; }
+    template <class G>
+    NB_HD static void expand(const G& grp, const Data& d, int D, const double* q, double* out) {
+        const int J = d.J;
+        const double sd_a = exp(q[J + 1]), sd_b = exp(q[2 * J + 3]);
+        for (int i = grp.tid; i < D; i += grp.size()) {
+            double v = q[i];
+            if (i == J + 1) v = sd_a;
+            else if (i == 2 * J + 3) v = sd_b;
+            else if (i == 2 * J + 4) v = exp(v);
+            out[i] = v;
+        }
+        for (int c = grp.tid; c < J; c += grp.size()) {
+            out[D + c] = q[1 + c] * sd_a;
+            out[D + J + c] = q[J + 3 + c] * sd_b;
+        }
+    }
     NB_HD static size_t block_data_bytes(const Data& d) {
         size_t b = sizeof(RadonObs) * (size_t)d.n_steps * d.T;
         b += (sizeof(uint32_t) * (size_t)2 * d.J * d.kmax + 15) & ~size_t(15);

@@ -106,6 +106,7 @@ struct nb200_sampler {
     double *h_draws = nullptr, *h_stats = nullptr, *h_grads = nullptr, *h_mm = nullptr;
     std::vector<uint64_t> rows_filled;
     uint64_t n_rows = 0, sdim = 0, n_total = 0;
+    uint64_t grad_dim = 0;  // row width of the gradient / mass-matrix traces (never expanded)
     int Dp = 0, NS = 0, smem_slots = 0;
     std::vector<void*> model_allocs;
     virtual int launch() = 0;
@@ -243,7 +244,10 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     s->NS = 3 * ((int)st->maxdepth + 1) + 3;
     s->n_total = st->num_tune + st->num_draws;
     s->n_rows = st->save_warmup ? s->n_total : st->num_draws;
-    s->sdim = (st->store_dims && st->store_dims < m->dim) ? st->store_dims : m->dim;
+    const bool thinned = st->store_dims && st->store_dims < m->dim;
+    const bool expand = st->expand_draws && !thinned;
+    s->sdim = thinned ? st->store_dims : (expand ? (uint64_t)M::expanded_dim((int)m->dim) : m->dim);
+    s->grad_dim = thinned ? st->store_dims : m->dim;
     KParams<M>& P = s->P;
     std::memset(&P, 0, sizeof(P));
     P.st = *st;
@@ -312,6 +316,8 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     P.D = D; P.Dp = s->Dp; P.NS = s->NS;
     P.n_chains = n_chains; P.chain_id_offset = chain_id_offset;
     P.n_rows = s->n_rows; P.sdim = s->sdim; P.n_total = s->n_total;
+    P.expand = expand ? 1 : 0;
+    P.gdim = s->grad_dim;
 #define ALLOC(ptr, bytes)                                                               \
     do {                                                                                \
         cudaError_t e_ = cudaMallocAsync((void**)&(ptr), (bytes) ? (bytes) : 8, s->stream); \
@@ -338,8 +344,8 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     ALLOC(s->d_sc, n_chains * sizeof(ChainScalars));
     ALLOC(s->d_draws, n_chains * s->n_rows * s->sdim * sizeof(double));
     ALLOC(s->d_stats, n_chains * s->n_rows * NB200_NSTAT * sizeof(double));
-    if (st->store_gradient) ALLOC(s->d_grads, n_chains * s->n_rows * s->sdim * sizeof(double));
-    if (st->store_mass_matrix) ALLOC(s->d_mm, n_chains * s->n_rows * s->sdim * sizeof(double));
+    if (st->store_gradient) ALLOC(s->d_grads, n_chains * s->n_rows * s->grad_dim * sizeof(double));
+    if (st->store_mass_matrix) ALLOC(s->d_mm, n_chains * s->n_rows * s->grad_dim * sizeof(double));
     ALLOC(s->d_stop, sizeof(int));
     CHK(cudaEventCreate(&s->ev0));
     CHK(cudaEventCreate(&s->ev1));
@@ -371,6 +377,15 @@ extern "C" {
 
 int nb200_abi_version(void) { return NB200_ABI_VERSION; }
 const char* nb200_last_error(void) { return g_err.c_str(); }
+uint64_t nb200_model_expanded_dim(const nb200_model_desc* model) {
+    if (!model) return 0;
+    switch (model->kind) {
+    case NB200_MODEL_NORMAL: return (uint64_t)NormalModel::expanded_dim((int)model->dim);
+    case NB200_MODEL_FUNNEL: return (uint64_t)FunnelModel::expanded_dim((int)model->dim);
+    case NB200_MODEL_RADON: return (uint64_t)RadonModel::expanded_dim((int)model->dim);
+    }
+    return 0;
+}
 int nb200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -411,6 +426,7 @@ void nb200_settings_default(nb200_settings* s) {
     s->init_radius = 2.0;
     s->store_dims = 0;
     s->save_warmup = 1;
+    s->expand_draws = 0;
 }
 
 void* nb200_host_alloc(size_t bytes) {
@@ -745,8 +761,9 @@ static int copy_trace(nb200_sampler* s, double* draws, double* stats, double* gr
         CU(cudaMemcpyAsync(draws, s->d_draws, nd, cudaMemcpyDeviceToHost, s->side));
     if (stats && !(streamed && stats == s->tgt_stats))
         CU(cudaMemcpyAsync(stats, s->d_stats, ns, cudaMemcpyDeviceToHost, s->side));
-    if (grads && s->d_grads) CU(cudaMemcpyAsync(grads, s->d_grads, nd, cudaMemcpyDeviceToHost, s->side));
-    if (mm && s->d_mm) CU(cudaMemcpyAsync(mm, s->d_mm, nd, cudaMemcpyDeviceToHost, s->side));
+    const size_t ng = s->n_chains * s->n_rows * s->grad_dim * sizeof(double);
+    if (grads && s->d_grads) CU(cudaMemcpyAsync(grads, s->d_grads, ng, cudaMemcpyDeviceToHost, s->side));
+    if (mm && s->d_mm) CU(cudaMemcpyAsync(mm, s->d_mm, ng, cudaMemcpyDeviceToHost, s->side));
     CU(cudaStreamSynchronize(s->side));
     return 0;
 }
@@ -768,8 +785,9 @@ int nb200_sampler_trace(nb200_sampler* s, nb200_trace_view* out) {
     const size_t ns = s->n_chains * s->n_rows * NB200_NSTAT * sizeof(double);
     if (!s->h_draws) CU(cudaHostAlloc((void**)&s->h_draws, nd ? nd : 8, cudaHostAllocDefault));
     if (!s->h_stats) CU(cudaHostAlloc((void**)&s->h_stats, ns ? ns : 8, cudaHostAllocDefault));
-    if (s->d_grads && !s->h_grads) CU(cudaHostAlloc((void**)&s->h_grads, nd ? nd : 8, cudaHostAllocDefault));
-    if (s->d_mm && !s->h_mm) CU(cudaHostAlloc((void**)&s->h_mm, nd ? nd : 8, cudaHostAllocDefault));
+    const size_t ng = s->n_chains * s->n_rows * s->grad_dim * sizeof(double);
+    if (s->d_grads && !s->h_grads) CU(cudaHostAlloc((void**)&s->h_grads, ng ? ng : 8, cudaHostAllocDefault));
+    if (s->d_mm && !s->h_mm) CU(cudaHostAlloc((void**)&s->h_mm, ng ? ng : 8, cudaHostAllocDefault));
     int rc = copy_trace(s, s->h_draws, s->h_stats, s->h_grads, s->h_mm, nullptr);
     if (rc != 0) return rc;
     out->n_chains = s->n_chains;

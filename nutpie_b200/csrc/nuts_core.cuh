@@ -75,8 +75,10 @@ struct KParams {
     int D, Dp, NS;
     int smem_slots;    // pool slots 0..smem_slots-1 live in shared memory (hot tier)
     int var_in_smem;   // working copy of the mass matrix in shared memory
+    int expand;        // stored draws are expanded vectors (sdim = expanded dimension)
     unsigned long long n_chains, chain_id_offset;
     unsigned long long n_rows, sdim, n_total;
+    unsigned long long gdim;  // row width of the gradient / mass-matrix traces
     unsigned long long max_draws_per_launch;  // 0 = run to the end
     double* pool;      // [n_chains][NS][4][Dp]
     double* var;       // [n_chains][Dp]        diagonal of M^-1
@@ -1110,8 +1112,8 @@ struct ChainCtx {
             const unsigned long long row = st().save_warmup ? t : t - num_tune;
             const size_t row_off = ((size_t)chain_local * P->n_rows + row);
             if (keep && P->mminv) {
-                double* o = P->mminv + row_off * P->sdim;
-                for (int i = g.tid; i < (int)P->sdim; i += g.size()) o[i] = var[i];
+                double* o = P->mminv + row_off * P->gdim;
+                for (int i = g.tid; i < (int)P->gdim; i += g.size()) o[i] = var[i];
             }
             SampleInfo info;
             const int sel = transition(cur, (uint32_t)t, info);
@@ -1125,11 +1127,13 @@ struct ChainCtx {
             if (keep) {
                 const double* q = vec(sel, VQ);
                 double* o = P->draws + row_off * P->sdim;
-                for (int i = g.tid; i < (int)P->sdim; i += g.size()) o[i] = q[i];
+                if (P->expand) M::expand(g, md, D, q, o);  // constrained values + deterministics
+                else
+                    for (int i = g.tid; i < (int)P->sdim; i += g.size()) o[i] = q[i];
                 if (P->grads) {
                     const double* gr = vec(sel, VG);
-                    double* og = P->grads + row_off * P->sdim;
-                    for (int i = g.tid; i < (int)P->sdim; i += g.size()) {
+                    double* og = P->grads + row_off * P->gdim;
+                    for (int i = g.tid; i < (int)P->gdim; i += g.size()) {
                         double gi;
                         if constexpr (M::kElementwise) (void)M::term(md, i, q[i], gi);
                         else gi = gr[i];

@@ -74,6 +74,29 @@ class CompiledDeviceModel:
             }
         raise ValueError(self.kind)
 
+    def expanded_layout(self):
+        """[(name, start, end, shape)] over the device-side expanded vector — the role of
+        PyVariable.start_idx/end_idx (src/common.rs:283-300)."""
+        if self.kind == "normal":
+            return [("x", 0, self.n_dim, (self.n_dim,) if self.n_dim > 1 else ())]
+        if self.kind == "funnel":
+            return [("log_sigma", 0, 1, ()), ("x", 1, self.n_dim, (self.n_dim - 1,))]
+        if self.kind == "radon":
+            J, D = int(self.params["n_county"]), self.n_dim
+            return [("intercept", 0, 1, ()), ("county_raw", 1, J + 1, (J,)),
+                    ("county_sd", J + 1, J + 2, ()), ("floor_effect", J + 2, J + 3, ()),
+                    ("county_floor_raw", J + 3, 2 * J + 3, (J,)),
+                    ("county_floor_sd", 2 * J + 3, 2 * J + 4, ()), ("sigma", 2 * J + 4, D, ()),
+                    ("county_effect", D, D + J, (J,)), ("county_floor_effect", D + J, D + 2 * J, (J,))]
+        raise ValueError(self.kind)
+
+    def _split_expanded(self, e: np.ndarray) -> dict:
+        """expanded draws [..., n_expanded] (computed on the device) -> {variable: values}"""
+        out = {}
+        for name, a, b, shape in self.expanded_layout():
+            out[name] = e[..., a:b] if shape else e[..., a]
+        return out
+
     # names of value variables that are stored transformed (compile_pymc.py:810-814)
     @property
     def reparameterized_names(self):

@@ -55,8 +55,13 @@ def _trace_to_groups(trace: _lib.PyTrace, compiled_model, settings, save_warmup,
     n_rows = int(rows.min()) if len(rows) else 0  # equal for finished runs
     draws = trace.draws[:, :n_rows]
     n_tune_rows = min(num_tune, n_rows)
-    full = draws.shape[-1] == compiled_model.n_dim
-    values = compiled_model._expand(draws) if full else {"unconstrained_draw": draws}
+    full = trace.expanded or draws.shape[-1] == compiled_model.n_dim
+    if trace.expanded:  # expand_vector ran on the device
+        values = compiled_model._split_expanded(draws)
+    elif full:
+        values = compiled_model._expand(draws)
+    else:
+        values = {"unconstrained_draw": draws}
     if var_names is not None:
         values = {k: v for k, v in values.items() if k in var_names}
     out = Trace(dims={k: list(v) for k, v in compiled_model.dims.items()},
@@ -73,7 +78,7 @@ def _trace_to_groups(trace: _lib.PyTrace, compiled_model, settings, save_warmup,
             out.warmup_sample_stats[name] = arr[:, :n_tune_rows]
             out.sample_stats[name] = arr[:, n_tune_rows:n_rows]
             out.dims[name] = ["unconstrained_parameter"]
-    if store_unconstrained and full:
+    if store_unconstrained and full and not trace.expanded:
         out.sample_stats["unconstrained_draw"] = draws[:, n_tune_rows:]
         out.warmup_sample_stats["unconstrained_draw"] = draws[:, :n_tune_rows]
         out.dims["unconstrained_draw"] = ["unconstrained_parameter"]
@@ -203,6 +208,7 @@ def sample(
     device: int = 0,
     chain_id_offset: int = 0,
     trace_buffers=None,
+    expand_on_device: bool | None = None,
     **kwargs,
 ):
     """Sample the posterior of a compiled device model on a B200.
@@ -262,6 +268,9 @@ def sample(
     settings.update(updates)
     if store_unconstrained:
         settings.store_unconstrained = True
+    # the trace holds expanded draws (constrained values + deterministics) computed on the
+    # device, like the reference's posterior; unconstrained draws on request
+    settings._c.expand_draws = 0 if (store_unconstrained or expand_on_device is False) else 1
     if init_mean is None:
         init_mean = np.zeros(compiled_model.n_dim)
 

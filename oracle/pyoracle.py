@@ -44,7 +44,7 @@ class Settings(C.Structure):
         ("init_kind", C.c_int32), ("num_try_init", C.c_int32),
         ("init_radius", C.c_double),
         ("store_dims", C.c_uint64),
-        ("save_warmup", C.c_int32), ("_pad1", C.c_int32),
+        ("save_warmup", C.c_int32), ("expand_draws", C.c_int32),
     ]
 
 

@@ -32,6 +32,8 @@ static int run_all_nit(const nb200_settings* st, const typename M::Data& md, uin
     P.n_total = st->num_tune + st->num_draws;
     P.n_rows = st->save_warmup ? P.n_total : st->num_draws;
     P.sdim = (st->store_dims && st->store_dims < dim) ? st->store_dims : dim;
+    P.gdim = P.sdim;
+    P.expand = 0;
     P.max_draws_per_launch = max_per_launch;
     P.smem_slots = smem_slots < P.NS ? smem_slots : P.NS;
     P.var_in_smem = smem_slots > 0;

@@ -370,3 +370,27 @@ def test_streamed_trace_equals_final_copy(radon_data):
         smp.close()
     assert tr.draws is bufs["draws"]
     assert np.array_equal(tr.draws, ref.draws) and np.array_equal(tr.stats, ref.stats)
+
+
+def test_device_expand_matches_host_expand(radon_data):
+    """expand_vector on the device (src/pymc.rs:217-286): the expanded trace equals the host
+    expansion of the unconstrained trace of the same run, and the oracle's expand twin."""
+    import ctypes as C
+
+    gm, om = models(radon_data)["radon"]
+    J = radon_data["n_county"]
+    mk = lambda e: settings_pair(seed=8, num_tune=60, num_draws=40, init_radius=1.0, expand_draws=e)[0]
+    raw = run_gpu(mk(0), gm, 8)
+    exp_ = run_gpu(mk(1), gm, 8)
+    assert exp_.expanded and exp_.draws.shape == (8, 100, 4 * J + 5)
+    host = gm._expand(raw.draws)
+    dev = gm._split_expanded(exp_.draws)
+    for k in host:
+        np.testing.assert_allclose(dev[k], host[k], rtol=1e-15, atol=0, err_msg=k)
+    assert np.array_equal(exp_.stats, raw.stats)
+    # oracle twin on one draw
+    out = np.zeros(4 * J + 5)
+    q = np.ascontiguousarray(raw.draws[3, 57])
+    assert O.lib().oracle_expand_radon(C.c_size_t(2 * J + 5), C.c_size_t(4 * J + 5), q.ctypes.data_as(C.c_void_p),
+                                       out.ctypes.data_as(C.c_void_p), om.ud_ptr) == 0
+    np.testing.assert_allclose(exp_.draws[3, 57], out, rtol=1e-15)
