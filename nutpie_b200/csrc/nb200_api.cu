@@ -98,7 +98,9 @@ struct nb200_sampler {
     uint64_t draws_per_launch = 0;
     int* d_stop = nullptr;
     ChainScalars* d_sc = nullptr;
-    ChainScalars* h_sc = nullptr;  // pinned
+    ChainScalars* h_sc = nullptr;  // host copy of the progress records (pageable: pinning and
+                                   // unpinning per sampler cost 10-400 ms in cudaHostAlloc/FreeHost)
+    std::vector<ChainScalars> h_sc_store;
     double *d_pool = nullptr, *d_var = nullptr, *d_wf = nullptr;
     double *d_draws = nullptr, *d_stats = nullptr, *d_grads = nullptr, *d_mm = nullptr;
     double *d_q0 = nullptr, *d_init_mean = nullptr, *d_tape = nullptr;
@@ -351,7 +353,8 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     CHK(cudaEventCreate(&s->ev1));
     CHK(cudaMemsetAsync(s->d_sc, 0, n_chains * sizeof(ChainScalars), s->stream));
     CHK(cudaMemsetAsync(s->d_stop, 0, sizeof(int), s->stream));
-    CHK(cudaHostAlloc((void**)&s->h_sc, n_chains * sizeof(ChainScalars), cudaHostAllocDefault));
+    s->h_sc_store.resize(n_chains);
+    s->h_sc = s->h_sc_store.data();
     std::memset(s->h_sc, 0, n_chains * sizeof(ChainScalars));
     if (q0) {
         ALLOC(s->d_q0, n_chains * D * sizeof(double));
@@ -854,7 +857,7 @@ int nb200_sampler_destroy(nb200_sampler* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->d_tape) cudaFree(s->d_tape);
     for (void* p : s->model_allocs) cudaFree(p);
-    void* host[] = {s->h_sc, s->h_draws, s->h_stats, s->h_grads, s->h_mm};
+    void* host[] = {s->h_draws, s->h_stats, s->h_grads, s->h_mm};
     for (void* p : host)
         if (p) cudaFreeHost(p);
     if (s->ev0) cudaEventDestroy(s->ev0);

@@ -34,7 +34,7 @@ if which == "radon":
                     print(f"radon tpc={tpc} slots={slots} cpb={cpb}: FAILED {e}", flush=True)
 elif which == "cfg4":
     m4 = nutpie_b200.normal_model(10000)
-    for tpc in (256, 512, 1024):
+    for tpc in (128, 256):
         v, ms, g = run(512, 200, 200, tpc, -1, model=m4, store_dims=16)
         print(f"cfg4 tpc={tpc}: {v:.3e} evals/s -> {v*72*10000/1e9:.0f} GB/s algorithmic  {ms:.1f} ms {g}", flush=True)
 elif which == "funnel":
