@@ -111,6 +111,7 @@ struct nb200_sampler {
     uint64_t grad_dim = 0;  // row width of the gradient / mass-matrix traces (never expanded)
     int Dp = 0, NS = 0, smem_slots = 0;
     std::vector<void*> model_allocs;
+    bool model_allocs_pooled = false;
     virtual int launch() = 0;
     int sampler_error = 0;
     // streaming of finished trace rows to host buffers while the kernel runs
@@ -181,11 +182,23 @@ static int validate(const nb200_settings* st, const nb200_model_desc* m) {
     return 0;
 }
 
+// small constant tables of a density: pool-backed (stream-ordered) when a stream is given
+static thread_local cudaStream_t g_upload_stream = nullptr;
 template <class T>
 static int to_device(const std::vector<T>& v, T** out, std::vector<void*>& keep) {
-    CU(cudaMalloc((void**)out, sizeof(T) * (v.size() ? v.size() : 1)));
-    keep.push_back(*out);
-    if (!v.empty()) CU(cudaMemcpy(*out, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    const size_t bytes = sizeof(T) * (v.size() ? v.size() : 1);
+    if (g_upload_stream) {
+        CU(cudaMallocAsync((void**)out, bytes, g_upload_stream));
+        keep.push_back(*out);
+        if (!v.empty()) {
+            CU(cudaMemcpyAsync(*out, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, g_upload_stream));
+            CU(cudaStreamSynchronize(g_upload_stream));  // v may be a temporary
+        }
+    } else {
+        CU(cudaMalloc((void**)out, bytes));
+        keep.push_back(*out);
+        if (!v.empty()) CU(cudaMemcpy(*out, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -253,7 +266,17 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     KParams<M>& P = s->P;
     std::memset(&P, 0, sizeof(P));
     P.st = *st;
-    if (build_model_data(*m, 32 * s->W, P.mdata, s->model_allocs) != 0) return bail();
+    pool_keep_memory(device);
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(NB200_ECUDA, "cudaStreamCreate failed");
+        return bail();
+    }
+    g_upload_stream = s->stream;
+    const int mrc = build_model_data(*m, 32 * s->W, P.mdata, s->model_allocs);
+    g_upload_stream = nullptr;
+    s->model_allocs_pooled = true;
+    if (mrc != 0) return bail();
     const size_t fixed = smem_for<M>(s->W, P.mdata, s->Dp);
     size_t bdata = 0;
     if (s->W == 1) {
@@ -337,9 +360,6 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         }                                                                               \
     } while (0)
     const size_t vecb = sizeof(double) * (size_t)s->Dp;
-    pool_keep_memory(device);
-    CHK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CHK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
     ALLOC(s->d_pool, n_chains * (size_t)s->NS * 4 * vecb);
     ALLOC(s->d_var, n_chains * vecb);
     ALLOC(s->d_wf, n_chains * 8 * vecb);
@@ -854,9 +874,13 @@ int nb200_sampler_destroy(nb200_sampler* s) {
         if (s->stream) cudaFreeAsync(p, s->stream);  // back to the pool
         else cudaFree(p);
     }
+    for (void* p : s->model_allocs) {
+        if (s->model_allocs_pooled && s->stream) cudaFreeAsync(p, s->stream);
+        else cudaFree(p);
+    }
+    s->model_allocs.clear();
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->d_tape) cudaFree(s->d_tape);
-    for (void* p : s->model_allocs) cudaFree(p);
     void* host[] = {s->h_draws, s->h_stats, s->h_grads, s->h_mm};
     for (void* p : host)
         if (p) cudaFreeHost(p);
