@@ -291,6 +291,11 @@ def run_gpu(args):
     for s in samplers:
         s.close()
     samplers.clear()
+    # release the device arm's (pageable, multi-GB) result arrays now, not inside a timed call
+    tr = post = st = None
+    import gc
+
+    gc.collect()
 
     # ---- end-to-end arm: public API with host data, trace into pinned host memory
     e2e_steps, e2e_wall = 0, 0.0
