@@ -223,8 +223,9 @@ def run_gpu(args):
     # CPU arm produces (sample(expand_on_device=True), the default, writes 4J+5 = 345 expanded
     # values per draw instead; measured this round: 667 ms/step e2e because the strided D2H of
     # 5.9 GB is not yet hidden behind the 327 ms kernel — see DESIGN.md §7)
-    pinned_d = _lib.PinnedArray((n_chains, n_rows, DIM))
-    pinned_s = _lib.PinnedArray((n_chains, n_rows, _lib.NSTAT))
+    # row-major host buffers, as the engine streams them: [row][chain][width]
+    pinned_d = _lib.PinnedArray((n_rows, n_chains, DIM))
+    pinned_s = _lib.PinnedArray((n_rows, n_chains, _lib.NSTAT))
     bufs = {"draws": pinned_d.array, "stats": pinned_s.array}
 
     def gather_stats(smp):
@@ -237,11 +238,11 @@ def run_gpu(args):
         _, sptr = smp.device_buffers()
 
         class _Wrap:
-            __cuda_array_interface__ = {"shape": (n_chains, n_rows * _lib.NSTAT), "typestr": "<f8",
+            __cuda_array_interface__ = {"shape": (n_rows, n_chains, _lib.NSTAT), "typestr": "<f8",
                                         "data": (sptr, False), "version": 2}
 
         local_t = torch.as_tensor(_Wrap(), device=f"cuda:{local}")
-        all_gather_chains(local_t, n_chains * world)
+        all_gather_chains(local_t, n_chains * world, chain_axis=1)
         torch.cuda.synchronize()
 
     # ---- device-resident arm: samplers (model data, init state) created up front

@@ -160,18 +160,20 @@ typedef struct nb200_progress {
 /* View into the library's pinned host copy of the trace.  Valid until the
  * next nb200_sampler_trace() call or nb200_sampler_destroy().
  * Replaces PySampler::{inspect,take_results,abort} → Vec<ArrowTrace>
- * (src/wrapper.rs:1332-1456): chain c's rows are contiguous, so each chain
- * maps 1:1 onto the (posterior, sample_stats) RecordBatch pair of
- * src/wrapper.rs:1477-1494. */
+ * (src/wrapper.rs:1332-1456).  Layout is ROW-major: element (row r, chain c)
+ * starts at (r * n_chains + c) * width, so the rows that every chain has
+ * finished are one contiguous block (they are streamed to the host with linear
+ * copies while sampling runs); chain c's (posterior, sample_stats) RecordBatch
+ * pair of src/wrapper.rs:1477-1494 is the strided slice [:, c, :]. */
 typedef struct nb200_trace_view {
     uint64_t n_chains;
     uint64_t n_rows;         /* rows allocated per chain (tune+draws, or draws) */
     uint64_t dim;            /* model dimension                                 */
     uint64_t store_dims;     /* coordinates stored per draw                     */
-    const double *draws;     /* [n_chains][n_rows][store_dims] unconstrained    */
-    const double *stats;     /* [n_chains][n_rows][NB200_NSTAT]                 */
-    const double *gradients; /* [n_chains][n_rows][store_dims] or NULL          */
-    const double *mass_matrix_inv; /* [n_chains][n_rows][store_dims] or NULL    */
+    const double *draws;     /* [n_rows][n_chains][store_dims]                  */
+    const double *stats;     /* [n_rows][n_chains][NB200_NSTAT]                 */
+    const double *gradients; /* [n_rows][n_chains][dim or store_dims] or NULL   */
+    const double *mass_matrix_inv; /* same shape as gradients, or NULL          */
     const uint64_t *rows_filled;   /* [n_chains] rows valid so far              */
 } nb200_trace_view;
 
@@ -223,7 +225,7 @@ int nb200_sampler_trace(nb200_sampler *s, nb200_trace_view *out);
 int nb200_sampler_trace_into(nb200_sampler *s, double *draws, double *stats,
                              double *gradients, double *mass_matrix_inv,
                              uint64_t *rows_filled);
-/* Register host buffers ([n_chains][n_rows][store_dims] and [n_chains][n_rows][NB200_NSTAT],
+/* Register host buffers ([n_rows][n_chains][width] and [n_rows][n_chains][NB200_NSTAT],
  * ideally pinned) BEFORE start: nb200_sampler_wait then streams finished rows into them
  * while the kernel is still sampling, so the D2H copy of the trace overlaps the run;
  * nb200_sampler_trace_into with the same pointers afterwards copies nothing twice. */

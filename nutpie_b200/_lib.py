@@ -400,6 +400,8 @@ class PyStorage:
 class PyTrace:
     """Mirror of PyTrace (src/wrapper.rs:1467-1494): the trace of all chains.
 
+    `draws` / `stats` are [chain, row, ...] views of the engine's row-major buffers.
+
     Besides the reference's `get_arrow_trace()` (one (posterior, sample_stats)
     RecordBatch pair per chain) it exposes the raw arrays (`draws`, `stats`),
     which is what the end-to-end path uses to avoid a per-chain Arrow hop."""
@@ -506,6 +508,10 @@ class PySampler:
             _check(L.nb200_sampler_set_draws_per_launch(self._h, int(draws_per_launch)))
         self._trace_buffers = trace_buffers
         if trace_buffers is not None:  # rows are streamed into these while sampling runs
+            for k in ("draws", "stats"):
+                a = trace_buffers[k]
+                if not a.flags["C_CONTIGUOUS"] or a.dtype != np.float64:
+                    raise ValueError("trace buffers must be C-contiguous float64 arrays")
             _check(L.nb200_sampler_set_trace_target(self._h, _ptr(trace_buffers["draws"]),
                                                     _ptr(trace_buffers["stats"])))
         self.n_total = int(self._c.num_tune + self._c.num_draws)
@@ -597,19 +603,24 @@ class PySampler:
         return None
 
     # -- results (src/wrapper.rs:1401-1456) --------------------------------
+    def trace_shapes(self):
+        """Shapes of the engine's ROW-major host buffers: [row][chain][width]."""
+        return {"draws": (self.n_rows, self.n_chains, self.sdim),
+                "stats": (self.n_rows, self.n_chains, NSTAT),
+                "gradients": (self.n_rows, self.n_chains, self.grad_dim)}
+
     def _trace(self, out=None) -> PyTrace:
-        shape_d = (self.n_chains, self.n_rows, self.sdim)
-        shape_s = (self.n_chains, self.n_rows, NSTAT)
-        keep = []
+        sh = self.trace_shapes()
         if out is None:
             out = self._trace_buffers
         if out is not None:
             draws, stats = out["draws"], out["stats"]
+            if draws.shape != sh["draws"] or stats.shape != sh["stats"]:
+                raise ValueError(f"trace buffers must be row-major arrays of shape {sh['draws']} / {sh['stats']}")
         else:
-            draws, stats = np.empty(shape_d), np.empty(shape_s)
-        shape_g = (self.n_chains, self.n_rows, self.grad_dim)
-        grads = np.empty(shape_g) if self._c.store_gradient else None
-        mm = np.empty(shape_g) if self._c.store_mass_matrix else None
+            draws, stats = np.empty(sh["draws"]), np.empty(sh["stats"])
+        grads = np.empty(sh["gradients"]) if self._c.store_gradient else None
+        mm = np.empty(sh["gradients"]) if self._c.store_mass_matrix else None
         rows = np.zeros(self.n_chains, dtype=np.uint64)
         _check(self._L.nb200_sampler_trace_into(self._h, _ptr(draws), _ptr(stats), _ptr(grads),
                                                 _ptr(mm), _ptr(rows)))
@@ -619,8 +630,11 @@ class PySampler:
             expand = self._model._expand
         else:
             expand = None
-        return PyTrace(draws, stats, rows, grads, mm, variables=self._model._variable_dims(),
-                       expand=expand, keep=keep, expanded=self.expanded)
+        # chain-major VIEWS ([chain, row, ...]) of the row-major buffers
+        tv = lambda a: None if a is None else a.transpose(1, 0, 2)
+        return PyTrace(tv(draws), tv(stats), rows, tv(grads), tv(mm),
+                       variables=self._model._variable_dims(), expand=expand,
+                       keep=[draws, stats, grads, mm], expanded=self.expanded)
 
     def inspect(self, out=None):
         return self._trace(out)

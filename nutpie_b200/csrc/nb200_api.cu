@@ -576,21 +576,18 @@ static int fetch_scalars(nb200_sampler* s) {
     return 0;
 }
 
-// rows [from, to) of every chain -> the registered host buffers (2-D copies: one row block
-// per chain, pitch = a chain's full trace)
+// rows [from, to) of every chain -> the registered host buffers: with the [row][chain][...]
+// layout this is one contiguous block per buffer
 static int stream_rows(nb200_sampler* s, uint64_t from, uint64_t to) {
     if (to <= from) return 0;
     CU(cudaSetDevice(s->device));
-    const size_t dpitch = s->n_rows * s->sdim * sizeof(double);
-    const size_t spitch = s->n_rows * NB200_NSTAT * sizeof(double);
+    const size_t drow = s->n_chains * s->sdim, srow = s->n_chains * NB200_NSTAT;  // doubles per row
     if (s->tgt_draws)
-        CU(cudaMemcpy2DAsync(s->tgt_draws + from * s->sdim, dpitch, s->d_draws + from * s->sdim, dpitch,
-                             (to - from) * s->sdim * sizeof(double), s->n_chains,
-                             cudaMemcpyDeviceToHost, s->side));
+        CU(cudaMemcpyAsync(s->tgt_draws + from * drow, s->d_draws + from * drow,
+                           (to - from) * drow * sizeof(double), cudaMemcpyDeviceToHost, s->side));
     if (s->tgt_stats)
-        CU(cudaMemcpy2DAsync(s->tgt_stats + from * NB200_NSTAT, spitch, s->d_stats + from * NB200_NSTAT,
-                             spitch, (to - from) * NB200_NSTAT * sizeof(double), s->n_chains,
-                             cudaMemcpyDeviceToHost, s->side));
+        CU(cudaMemcpyAsync(s->tgt_stats + from * srow, s->d_stats + from * srow,
+                           (to - from) * srow * sizeof(double), cudaMemcpyDeviceToHost, s->side));
     CU(cudaStreamSynchronize(s->side));
     s->streamed_rows = to;
     return 0;

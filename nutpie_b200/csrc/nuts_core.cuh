@@ -84,8 +84,8 @@ struct KParams {
     double* var;       // [n_chains][Dp]        diagonal of M^-1
     double* welford;   // [n_chains][2][4][Dp]  (mean_q, m2_q, mean_g, m2_g) x 2 sets
     ChainScalars* sc;  // [n_chains]
-    double* draws;     // [n_chains][n_rows][sdim]
-    double* stats;     // [n_chains][n_rows][NB200_NSTAT]
+    double* draws;     // [n_rows][n_chains][sdim]
+    double* stats;     // [n_rows][n_chains][NB200_NSTAT]
     double* grads;     // optional, like draws
     double* mminv;     // optional, like draws
     const double* q0;        // optional [n_chains][D]
@@ -1110,7 +1110,9 @@ struct ChainCtx {
             const double step_used = step_size;
             const bool keep = st().save_warmup || t >= num_tune;
             const unsigned long long row = st().save_warmup ? t : t - num_tune;
-            const size_t row_off = ((size_t)chain_local * P->n_rows + row);
+            // trace layout [row][chain][...]: the rows every chain has finished form one
+            // contiguous block, so the host streams them out with linear copies
+            const size_t row_off = ((size_t)row * P->n_chains + chain_local);
             if (keep && P->mminv) {
                 double* o = P->mminv + row_off * P->gdim;
                 for (int i = g.tid; i < (int)P->gdim; i += g.size()) o[i] = var[i];

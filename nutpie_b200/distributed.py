@@ -25,16 +25,21 @@ def shard(n_chains_total: int, rank: int, world: int):
     return n_local, offset
 
 
-def all_gather_chains(local, n_chains_total: int, group=None):
-    """All-gather per-chain arrays ([n_local, ...], chain-major) from every rank into
-    [n_chains_total, ...] in global chain order.  Accepts a numpy array (gathered over
-    the group's default device: CPU for gloo) or a torch tensor (gathered where it lives)."""
+def all_gather_chains(local, n_chains_total: int, group=None, chain_axis: int = 0):
+    """All-gather per-chain arrays from every rank into global chain order along
+    `chain_axis` (0 for chain-major [n_local, ...] arrays; 1 for the engine's row-major
+    [row, n_local, ...] trace buffers).  Accepts a numpy array (gathered over the group's
+    default device: CPU for gloo) or a torch tensor (gathered where it lives)."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     is_np = isinstance(local, np.ndarray)
+    if chain_axis != 0:
+        moved = np.moveaxis(local, chain_axis, 0) if is_np else local.movedim(chain_axis, 0)
+        out = all_gather_chains(moved, n_chains_total, group, 0)
+        return np.moveaxis(out, 0, chain_axis) if is_np else out.movedim(0, chain_axis)
     t = torch.from_numpy(np.ascontiguousarray(local)) if is_np else local.contiguous()
     if dist.get_backend(group) == "nccl" and not t.is_cuda:
         t = t.cuda()

@@ -8,7 +8,7 @@ d = nutpie_b200.make_radon_data(); model = nutpie_b200.radon_model(d["y"], d["co
 n, rows, D = 1024, 2000, 175
 def mk(seed):
     s = _lib.PyNutsSettings.Diag(seed); s.update({"num_tune": 1000, "num_draws": 1000, "num_chains": n, "init_radius": 1.0}); return s
-pd_, ps_ = _lib.PinnedArray((n, rows, D)), _lib.PinnedArray((n, rows, 16))
+pd_, ps_ = _lib.PinnedArray((rows, n, D)), _lib.PinnedArray((rows, n, 16))
 bufs = {"draws": pd_.array, "stats": ps_.array}
 variant = sys.argv[1] if len(sys.argv) > 1 else "full"
 if variant in ("full", "noess"):

@@ -6,7 +6,7 @@ import nutpie_b200
 from nutpie_b200 import _lib
 d = nutpie_b200.make_radon_data(); model = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], 85)
 n, rows, D = 1024, 2000, 175
-pd_, ps_ = _lib.PinnedArray((n, rows, D)), _lib.PinnedArray((n, rows, 16))
+pd_, ps_ = _lib.PinnedArray((rows, n, D)), _lib.PinnedArray((rows, n, 16))
 bufs = {"draws": pd_.array, "stats": ps_.array}
 orig_init = _lib.PySampler.__init__; orig_wait = _lib.PySampler.wait; orig_take = _lib.PySampler.take_results; orig_close = _lib.PySampler.close
 T = {}

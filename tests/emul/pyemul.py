@@ -60,10 +60,11 @@ def sample(kind, dim, settings, n_chains, chain_id_offset=0, q0=None, init_mean=
     n_total = settings.num_tune + settings.num_draws
     n_rows = n_total if settings.save_warmup else settings.num_draws
     sdim = settings.store_dims if 0 < settings.store_dims < dim else dim
-    draws = np.zeros((n_chains, n_rows, sdim))
-    stats = np.zeros((n_chains, n_rows, 16))
-    grads = np.zeros((n_chains, n_rows, sdim)) if settings.store_gradient else None
-    mm = np.zeros((n_chains, n_rows, sdim)) if settings.store_mass_matrix else None
+    # the engine's trace is row-major ([row][chain][...]); hand back chain-major views
+    draws = np.zeros((n_rows, n_chains, sdim))
+    stats = np.zeros((n_rows, n_chains, 16))
+    grads = np.zeros((n_rows, n_chains, sdim)) if settings.store_gradient else None
+    mm = np.zeros((n_rows, n_chains, sdim)) if settings.store_mass_matrix else None
     if q0 is not None:
         q0 = np.ascontiguousarray(q0, dtype=np.float64)
     if init_mean is not None:
@@ -77,5 +78,6 @@ def sample(kind, dim, settings, n_chains, chain_id_offset=0, q0=None, init_mean=
                        C.c_int(max_per_launch), C.c_int(smem_slots))
     if rc != 0:
         raise RuntimeError(f"emul_sample failed: {rc}")
-    return dict(draws=draws, stats=stats, gradients=grads, mass_matrix_inv=mm,
+    tv = lambda a: None if a is None else a.transpose(1, 0, 2)
+    return dict(draws=tv(draws), stats=tv(stats), gradients=tv(grads), mass_matrix_inv=tv(mm),
                 total_steps=int(steps.value))

@@ -50,8 +50,14 @@ def _worker(rank, world, port, total, q):
 
         _, stats, draws = sample_sharded(None, chains=total, gather_draws=True,
                                          sampler_fn=oracle_sampler)
+        # the engine's own buffers are row-major [row][chain][...]: gather along axis 1
+        from nutpie_b200.distributed import all_gather_chains, shard
+
+        n_local, offset = shard(total, rank, world)
+        local_rm = np.ascontiguousarray(stats[offset:offset + n_local].transpose(1, 0, 2))
+        stats_rm = all_gather_chains(local_rm, total, chain_axis=1)
         if rank == 0:
-            q.put((stats, draws))
+            q.put((stats, draws, stats_rm))
     finally:
         dist.destroy_process_group()
 
@@ -68,7 +74,7 @@ def test_sharded_run_equals_single_run(total):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, total, q)) for r in range(2)]
     for p in procs:
         p.start()
-    stats, draws = q.get(timeout=120)
+    stats, draws, stats_rm = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -76,3 +82,4 @@ def test_sharded_run_equals_single_run(total):
     ref = O.sample(O.Model("funnel", 5), s, total)
     assert np.array_equal(stats, ref["stats"])
     assert np.array_equal(draws, ref["draws"])
+    assert np.array_equal(stats_rm.transpose(1, 0, 2), ref["stats"])

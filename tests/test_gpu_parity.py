@@ -359,7 +359,8 @@ def test_streamed_trace_equals_final_copy(radon_data):
     mk = lambda: settings_pair(seed=6, num_tune=300, num_draws=300, init_radius=1.0)[0]
     ref = run_gpu(mk(), gm, 64)
     n_rows, D = 600, gm.n_dim
-    pd_, ps_ = _lib.PinnedArray((64, n_rows, D)), _lib.PinnedArray((64, n_rows, _lib.NSTAT))
+    # the engine's buffers are row-major: [row][chain][width]
+    pd_, ps_ = _lib.PinnedArray((n_rows, 64, D)), _lib.PinnedArray((n_rows, 64, _lib.NSTAT))
     pd_.array[:] = -1.0
     bufs = {"draws": pd_.array, "stats": ps_.array}
     smp = _lib.PySampler(mk(), gm, n_chains=64, trace_buffers=bufs)
@@ -368,7 +369,7 @@ def test_streamed_trace_equals_final_copy(radon_data):
         tr = smp.take_results()
     finally:
         smp.close()
-    assert tr.draws is bufs["draws"]
+    assert np.shares_memory(tr.draws, bufs["draws"]) and tr.draws.shape == (64, n_rows, D)
     assert np.array_equal(tr.draws, ref.draws) and np.array_equal(tr.stats, ref.stats)
 
 
