@@ -219,12 +219,11 @@ def run_gpu(args):
             torch.cuda.synchronize()
             dist.barrier()
 
-    # e2e trace = unconstrained draws + sampler stats of every chain, the same content the
-    # CPU arm produces (sample(expand_on_device=True), the default, writes 4J+5 = 345 expanded
-    # values per draw instead; measured this round: 667 ms/step e2e because the strided D2H of
-    # 5.9 GB is not yet hidden behind the 327 ms kernel — see DESIGN.md §7)
+    # e2e trace = what nutpie returns: EXPANDED draws (constrained value variables + the two
+    # Deterministics, 4J+5 = 345 doubles per draw, computed by the kernel) + sampler stats
+    EXP_DIM = 4 * N_COUNTY + 5
     # row-major host buffers, as the engine streams them: [row][chain][width]
-    pinned_d = _lib.PinnedArray((n_rows, n_chains, DIM))
+    pinned_d = _lib.PinnedArray((n_rows, n_chains, EXP_DIM))
     pinned_s = _lib.PinnedArray((n_rows, n_chains, _lib.NSTAT))
     bufs = {"draws": pinned_d.array, "stats": pinned_s.array}
 
@@ -307,8 +306,7 @@ def run_gpu(args):
         # pinned host memory when it returns; finished rows are streamed out while sampling
         tr = nutpie_b200.sample(model, draws=DRAWS, tune=TUNE, chains=n_chains, seed=500 + i,
                                 init_radius=1.0, return_raw_trace=True, progress_bar=False,
-                                device=device, chain_id_offset=offset, trace_buffers=bufs,
-                                expand_on_device=False)
+                                device=device, chain_id_offset=offset, trace_buffers=bufs)
         if multi:
             torch.cuda.synchronize()
         barrier()
