@@ -62,7 +62,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         obj = OBJ / (src.stem + ".o")
         if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, newest_hdr):
             return obj, 0, f"[up to date] {src.name}\n"
-        cmd = [nvcc, *ccbin, *NVCC_FLAGS, "-c", "-o", str(obj), str(src)]
+        extra = os.environ.get("NB200_EXTRA_NVCC_FLAGS", "").split()
+        cmd = [nvcc, *ccbin, *NVCC_FLAGS, *extra, "-c", "-o", str(obj), str(src)]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         return obj, res.returncode, " ".join(cmd) + "\n" + res.stdout
 

@@ -32,6 +32,12 @@
 #include "philox.cuh"
 #include "portable.cuh"
 
+// partners (besides the predecessor) whose U-turn pair is evaluated inside the streaming
+// leapfrog pass; tunable at build time for register-pressure experiments
+#ifndef NB200_MAX_FUSED
+#define NB200_MAX_FUSED 3
+#endif
+
 namespace nb200 {
 
 constexpr int kMaxSlots = 64;
@@ -245,7 +251,7 @@ struct ChainCtx {
     // Measured (profiles/r1_sweep_*): planning + extra partner loads pay off only in the
     // streaming regime (large D, run-time loops), where each separate check is a pass over
     // HBM; for small D they cost more than the on-chip is_turning() they replace.
-    static constexpr int kMaxFused = (M::kElementwise && NIT == 0) ? 3 : 0;
+    static constexpr int kMaxFused = (M::kElementwise && NIT == 0) ? NB200_MAX_FUSED : 0;
     static constexpr int kFusedDim = kMaxFused > 0 ? kMaxFused : 1;
 
     // orientation of the pair (x, new leaf): which one is the trajectory's earlier state
