@@ -35,7 +35,7 @@
 // partners (besides the predecessor) whose U-turn pair is evaluated inside the streaming
 // leapfrog pass; tunable at build time for register-pressure experiments
 #ifndef NB200_MAX_FUSED
-#define NB200_MAX_FUSED 3
+#define NB200_MAX_FUSED 1  // measured best for config 4: profiles/r1_sweep_fused_partners.txt
 #endif
 
 namespace nb200 {
