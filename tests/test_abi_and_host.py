@@ -142,3 +142,44 @@ def test_ess_estimator():
     x = rng.normal(size=(8, 1000, 2))
     e = ess(x, None, device="cpu")
     assert (e > 6000).all() and (e < 10500).all()
+
+
+def test_with_data_wrong_shape_raises_runtime_error(radon_data):
+    """tests/test_pymc.py:418-420: wrong-shape with_data surfaces as RuntimeError."""
+    import nutpie_b200
+
+    d = radon_data
+    cm = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], d["n_county"])
+    ok = cm.with_data(y=d["y"] + 1.0)
+    assert ok.params["y"][0] == d["y"][0] + 1.0 and cm.params["y"][0] == d["y"][0]
+    with pytest.raises(RuntimeError):
+        cm.with_data(y=d["y"][:-1])
+    with pytest.raises(KeyError):
+        cm.with_data(nope=np.zeros(3))
+
+
+def test_unsupported_samplers_and_adaptations_are_explicit():
+    """Out-of-scope variants fail loudly instead of silently running something else."""
+    import nutpie_b200
+
+    m = nutpie_b200.normal_model(2)
+    for kw in (dict(adaptation="low_rank"), dict(adaptation="flow"), dict(sampler="mclmc")):
+        with pytest.raises(NotImplementedError):
+            nutpie_b200.sample(m, chains=1, draws=1, tune=1, **kw)
+    with pytest.raises(ValueError):
+        nutpie_b200.sample(m, chains=1, draws=1, tune=1, adaptation="bogus")
+    with pytest.raises(NotImplementedError):
+        nutpie_b200.compile_stan_model(code="parameters { real x; } model { x ~ normal(0, 1); }")
+
+
+def test_expanded_layout_covers_every_variable(radon_data):
+    import nutpie_b200
+
+    d = radon_data
+    J = d["n_county"]
+    cm = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], J)
+    lay = cm.expanded_layout()
+    assert lay[0][1] == 0 and lay[-1][2] == 4 * J + 5
+    for (_, a, b, shape), (_, a2, _, _) in zip(lay, lay[1:]):
+        assert b == a2 and (b - a) == (int(np.prod(shape)) if shape else 1)
+    assert {n for n, *_ in lay} == set(cm.dims)

@@ -11,6 +11,8 @@ Tolerances (fp64, BASELINE.json north_star "stated fp64 tolerance"):
     first draws, then statistical parity — means within 4 MCSE, sds within 5 %,
     step size within 10 % (SURVEY.md §8d "Parity report").
 """
+import json
+
 import numpy as np
 import pytest
 
@@ -395,3 +397,27 @@ def test_device_expand_matches_host_expand(radon_data):
     assert O.lib().oracle_expand_radon(C.c_size_t(2 * J + 5), C.c_size_t(4 * J + 5), q.ctypes.data_as(C.c_void_p),
                                        out.ctypes.data_as(C.c_void_p), om.ud_ptr) == 0
     np.testing.assert_allclose(exp_.draws[3, 57], out, rtol=1e-15)
+
+
+def test_pymc_model_shared_pin_on_gpu():
+    """tests/test_pymc.py:397-416 through the public API: posterior mean of N(-0.1, 1)^3
+    within 0.05 and of N(10, 3)^3 within 0.5."""
+    tr = nutpie_b200.sample(nutpie_b200.normal_model(3, -0.1, 1.0), chains=4, draws=1000, tune=400, seed=1)
+    np.testing.assert_allclose(tr.posterior["x"].mean(), -0.1, atol=0.05)
+    tr = nutpie_b200.sample(nutpie_b200.normal_model(3, 10.0, 3.0), chains=4, draws=1000, tune=400, seed=1)
+    np.testing.assert_allclose(tr.posterior["x"].mean(), 10.0, atol=0.5)
+
+
+def test_draw_diag_adaptation_and_var_names(radon_data):
+    """adaptation="draw_diag" (python/nutpie/sample.py:1015-1023) and var_names filtering
+    (tests/test_pymc.py:423-468)."""
+    d = radon_data
+    J = d["n_county"]
+    cm = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], J)
+    tr = nutpie_b200.sample(cm, chains=16, draws=200, tune=300, seed=3, adaptation="draw_diag",
+                            init_radius=1.0, var_names=["sigma", "county_effect"])
+    assert set(tr.posterior) == {"sigma", "county_effect"}
+    assert tr.posterior["county_effect"].shape == (16, 200, J)
+    assert abs(tr.posterior["sigma"].mean() - d["truth"]["sigma"]) < 0.1
+    assert tr.dims["county_effect"] == ["county"] and len(tr.coords["county"]) == J
+    assert json.loads(tr.attrs["_settings"])["settings"]["use_grad_based_estimate"] == 0
