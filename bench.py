@@ -195,6 +195,8 @@ def run_gpu(args):
 
     multi = world > 1
     if multi:
+        # keep stdout for the one JSON line: NCCL's version banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
 
@@ -323,7 +325,12 @@ def run_gpu(args):
         cfg4 = run_config4(device)
 
     # ---- reduce over ranks
+    per_rank_ms = [kernel_ms / args.steps]
     if multi:
+        mine = torch.tensor([kernel_ms / args.steps], dtype=torch.float64, device=f"cuda:{local}")
+        allr = torch.empty(world, dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank_ms = [float(x) for x in allr.tolist()]
         t = torch.tensor([kernel_ms, wall, e2e_wall], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         kernel_ms, wall, e2e_wall = (float(x) for x in t.tolist())
@@ -346,6 +353,7 @@ def run_gpu(args):
         "metric": "gradient_evals_per_sec_all_chains", "value": value, "unit": "grad_evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": kernel_ms / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
+        "kernel_ms_per_step_per_rank": per_rank_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "chains_total": n_chains * world, "dim": DIM,
