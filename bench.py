@@ -265,6 +265,15 @@ def run_gpu(args):
     barrier()
     wall = time.perf_counter() - t0
     clk = clocks.stop()
+    if multi:  # every rank samples its own GPU: report the slowest clock as well
+        mhz = torch.tensor([clk["sm_mhz"] or 0.0], dtype=torch.float64, device=f"cuda:{local}")
+        allm = torch.empty(world, dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_gather_into_tensor(allm, mhz)
+        clk["sm_mhz_per_rank"] = [float(x) for x in allm.tolist()]
+        flags = [clk["reasons"]]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, clk["reasons"])
+        clk["reasons"] = sorted({r for rs in gathered for r in rs})
     kernel_ms = sum(samplers[i].kernel_ms() for i in range(args.warmup, total))
     launches = sum(samplers[i].launch_count() for i in range(args.warmup, total))
     steps = 0
