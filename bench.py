@@ -195,8 +195,11 @@ def run_gpu(args):
 
     multi = world > 1
     if multi:
-        # keep stdout for the one JSON line: NCCL's version banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # keep stdout for the one JSON line: NCCL prints its version banner to fd 1 when it
+        # initialises, so fd 1 points at stderr until the result line is printed
+        sys.stdout.flush()
+        saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch
         import torch.distributed as dist
 
@@ -394,8 +397,12 @@ def run_gpu(args):
         "ess_min_per_step_per_gpu": ess_min,
         "sampler_summary": summary,
     }
+    if multi:
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
     print(json.dumps(line), flush=True)
     if multi:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
