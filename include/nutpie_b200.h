@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NB200_ABI_VERSION 1
+#define NB200_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define NB200_OK 0
@@ -40,6 +40,7 @@ extern "C" {
 #define NB200_ELOGP (-4)    /* fatal (non-recoverable) logp error, cf.      */
                             /* src/pymc.rs:166-181 (rc < 0 is fatal)        */
 #define NB200_EINIT (-5)    /* no finite initial point found for a chain    */
+#define NB200_ECOMPILE (-6) /* NVRTC missing or custom density failed to build */
 #define NB200_ETIMEOUT 1    /* nb200_sampler_wait: still running            */
 
 /* ---- settings ----------------------------------------------------------
@@ -96,7 +97,26 @@ typedef struct nb200_settings {
  * python/nutpie/compile_pymc.py:970-1006) is a HOST function pointer.  The
  * device engine cannot call it per leapfrog, so a model is either one of the
  * built-in device densities below (hand-written CUDA, host twin in oracle/)
- * or — next row, SURVEY §8f-3 — a host callback.
+ * or NB200_MODEL_CUSTOM: the DEVICE analogue of that plug-in ABI (SURVEY
+ * §8b2 / §8f-3), CUDA source compiled at run time with NVRTC into the same
+ * persistent sampler kernel.  The source must define, at global scope,
+ *
+ *   __device__ int nb200_user_logp(const nb200_group &grp, int dim,
+ *                                  const double *q, double *grad,
+ *                                  double *logp_partial, const double *data);
+ *
+ * It is called by ALL grp.nthreads threads that own the chain (tid =
+ * grp.tid): q [dim] and grad [dim] live in shared memory; every grad[i] must
+ * be written by exactly one thread; *logp_partial receives this thread's
+ * share of the log-density (the engine sums the shares in a fixed order);
+ * grp.sum(x) is a bit-reproducible sum over the group that every thread
+ * must call, grp.sync() a barrier over the group, grp.scratch [n_user_scratch]
+ * the chain's private shared-memory scratch (contents do not persist between
+ * calls); data [n_user_data] is the model's read-only device copy of
+ * `user_data`.  Return code as in the
+ * reference ABI (src/pymc.rs:178): 0 ok, > 0 recoverable (the trajectory
+ * diverges there); non-finite logp / gradient are detected by the engine.
+ * A serial density is `if (grp.tid == 0) { ... }`.
  */
 typedef int (*nb200_logp_fn)(size_t dim, const double *x, double *grad_out,
                              double *logp_out, const void *user_data);
@@ -108,6 +128,7 @@ typedef int (*nb200_expand_fn)(size_t dim, size_t expanded_dim, const double *x,
 #define NB200_MODEL_RADON 3  /* README.md:53-88 / notebooks/pytensor_logp.md    */
                              /* :57-88 hierarchical radon, plain-Normal raws,   */
                              /* dim = 2*n_county + 5                            */
+#define NB200_MODEL_CUSTOM 4 /* run-time compiled CUDA source (see above)       */
 
 typedef struct nb200_model_desc {
     int32_t kind;
@@ -118,6 +139,11 @@ typedef struct nb200_model_desc {
     const double *y;         /* [n_obs] log_radon                              */
     const int32_t *county;   /* [n_obs] county index, any order                */
     const uint8_t *floor;    /* [n_obs] 0/1                                    */
+    const char *cuda_source; /* NB200_MODEL_CUSTOM: NUL-terminated CUDA C++     */
+    const double *user_data; /* NB200_MODEL_CUSTOM: [n_user_data] host doubles  */
+    uint64_t n_user_data;
+    uint64_t n_user_scratch; /* NB200_MODEL_CUSTOM: doubles of per-chain shared    */
+                             /* memory handed to the density as grp.scratch     */
 } nb200_model_desc;
 
 /* ---- per-draw sampler statistics ---------------------------------------
@@ -259,6 +285,18 @@ int nb200_sampler_set_draws_per_launch(nb200_sampler *s, uint64_t n);
  * of standard normals; must precede start() */
 int nb200_sampler_set_z_tape(nb200_sampler *s, const double *z_tape);
 /* pinned host memory for trace buffers handed to nb200_sampler_trace_into */
+/* ---- run-time compiled densities ------------------------------------------
+ * Compile `model->cuda_source` (kind NB200_MODEL_CUSTOM) for sm_100a into the
+ * sampler kernel specialised for `threads_per_chain` (32..1024, power of two)
+ * and `dims_per_thread` unrolled dimensions per thread (0 = run-time loop).
+ * Needs libnvrtc but no GPU; nb200_sampler_create does the same lazily for
+ * the geometry it picks.  On failure returns NB200_ECOMPILE and copies the
+ * NVRTC log into log[0..log_len).  ⇔ the role of numba's cfunc compile in
+ * python/nutpie/compile_pymc.py:970-1006.                                   */
+int nb200_custom_model_compile(const nb200_model_desc *model,
+                               int threads_per_chain, int dims_per_thread,
+                               char *log, size_t log_len);
+
 void *nb200_host_alloc(size_t bytes);
 void nb200_host_free(void *p);
 

@@ -39,7 +39,8 @@ _STAT_DTYPES = {
 }
 
 NB200_ETIMEOUT = 1
-_ERRORS = {-1: ValueError, -2: RuntimeError, -3: ValueError, -4: RuntimeError, -5: RuntimeError}
+_ERRORS = {-1: ValueError, -2: RuntimeError, -3: ValueError, -4: RuntimeError, -5: RuntimeError,
+           -6: RuntimeError}
 
 
 class Settings(C.Structure):
@@ -73,7 +74,9 @@ class ModelDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("dim", C.c_uint64),
                 ("mu", C.c_double), ("sigma", C.c_double),
                 ("n_obs", C.c_int32), ("n_county", C.c_int32),
-                ("y", C.c_void_p), ("county", C.c_void_p), ("floor", C.c_void_p)]
+                ("y", C.c_void_p), ("county", C.c_void_p), ("floor", C.c_void_p),
+                ("cuda_source", C.c_char_p), ("user_data", C.c_void_p),
+                ("n_user_data", C.c_uint64), ("n_user_scratch", C.c_uint64)]
 
 
 class Progress(C.Structure):
@@ -85,7 +88,7 @@ class Progress(C.Structure):
                 ("tuning", C.c_int32), ("started", C.c_int32)]
 
 
-MODEL_KINDS = {"normal": 1, "funnel": 2, "radon": 3}
+MODEL_KINDS = {"normal": 1, "funnel": 2, "radon": 3, "custom": 4}
 
 
 def library_path() -> Path:
@@ -166,7 +169,10 @@ def load_library() -> C.CDLL:
         L.nb200_logp_grad.argtypes = [C.POINTER(ModelDesc), C.c_int, C.c_uint64] + [C.c_void_p] * 4
         L.nb200_leapfrog.restype = C.c_int
         L.nb200_leapfrog.argtypes = [C.POINTER(ModelDesc), C.c_int, C.c_uint64] + [C.c_void_p] * 15
-        if L.nb200_abi_version() != 1:
+        L.nb200_custom_model_compile.restype = C.c_int
+        L.nb200_custom_model_compile.argtypes = [C.POINTER(ModelDesc), C.c_int, C.c_int,
+                                                 C.c_char_p, C.c_size_t]
+        if L.nb200_abi_version() != 2:
             raise RuntimeError("libnutpie_b200.so ABI version mismatch")
         _lib = L
         return L
@@ -692,6 +698,19 @@ def PySamplerDeferred(*args, **kwargs):
 # --------------------------------------------------------------------------
 # component entry points (parity tests)
 # --------------------------------------------------------------------------
+def compile_custom(model, threads_per_chain=32, dims_per_thread=0):
+    """NVRTC-compile a custom CUDA density for one kernel geometry (no GPU needed);
+    raises RuntimeError carrying the compiler log on failure."""
+    L = load_library()
+    desc, keep = model._descriptor()
+    log = C.create_string_buffer(1 << 16)
+    rc = L.nb200_custom_model_compile(C.byref(desc), threads_per_chain, dims_per_thread, log,
+                                      len(log))
+    if rc != 0:
+        _check(rc)
+    return True
+
+
 def logp_grad(model, q, device=0):
     L = load_library()
     desc, keep = model._descriptor()

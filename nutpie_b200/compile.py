@@ -5,7 +5,8 @@
 BridgeStan library (compile_stan.py:133-386); both yield HOST densities.  The
 B200 engine evaluates densities on the device (nutpie_b200/csrc/models.cuh), and
 neither pymc/pytensor nor bridgestan/stanc exist in this image, so the graph →
-CUDA lowering is not part of this round.  The functions
+CUDA lowering is not part of this round; `from_cuda_source` is the hook it would target
+(SURVEY.md §8f-3).  The functions
 recognise the models that have a device density and otherwise explain what to
 use instead — they never fall back to CPU sampling.
 """
@@ -34,5 +35,15 @@ def compile_stan_model(*, code=None, filename=None, **kwargs):
 
 def from_pyfunc(*args, **kwargs):
     raise NotImplementedError(
-        "Python-callable densities run on the host; the B200 engine has no host-callback "
-        "path yet (SURVEY.md §8f-3). Use a device density from nutpie_b200.models.")
+        "Python-callable densities run on the host and the B200 engine never calls back into "
+        "the host per gradient. Hand the density over as CUDA source instead: "
+        "nutpie_b200.from_cuda_source(ndim, cuda_source, data=...).")
+
+
+def from_cuda_source(ndim, cuda_source, data=None, *, scratch=0, shapes=None, dims=None,
+                     coords=None):
+    """The device counterpart of `from_pyfunc` (python/nutpie/compiled_pyfunc.py:108-155): the
+    user supplies the log-density as CUDA C++ (`nb200_user_logp`, see include/nutpie_b200.h);
+    it is compiled with NVRTC into the sampler kernel when the sampler is created."""
+    return models.custom_model(ndim, cuda_source, data, scratch=scratch, shapes=shapes, dims=dims,
+                               coords=coords)

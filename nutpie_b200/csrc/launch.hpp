@@ -20,4 +20,10 @@ cudaError_t launch_component(int W, const KParams<M>& P, int mode, const double*
 template <class M>
 size_t smem_fixed(int W, const typename M::Data& md, int Dp);
 
+// NB200_MODEL_CUSTOM (kernels_custom.cu): register a CUDA source (identical text -> same slot),
+// compile it with NVRTC for one geometry (no GPU needed), text of the last failure on this thread
+int custom_register(const char* source);
+int custom_compile(int program, int W, int NIT);
+const char* custom_last_log();
+
 }  // namespace nb200

@@ -4,8 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "kernels.cuh"
 #include "launch.hpp"
-#include "nuts_core.cuh"
 
 namespace nb200 {
 
@@ -18,124 +18,6 @@ static size_t chain_smem_fixed(const typename M::Data& md) {
     b += align16(sizeof(double) * (size_t)M::smem_doubles(md, 32 * W));
     if (W > 1) b += align16(sizeof(double) * W * GroupCuda<W>::kMaxRed);
     return b;  // + the front buffer of non-elementwise densities: see stage_bytes()
-}
-
-// shared-memory front (q, p, grad, p_sum of the newest leaf) for densities that gather
-// across dimensions; elementwise densities stream straight from the pool
-template <class M>
-__host__ __device__ inline size_t stage_bytes(int Dp) {
-    return M::kElementwise ? 0 : ((4 * sizeof(double) * (size_t)Dp + 15) & ~size_t(15));
-}
-
-template <class M, int W, int NIT>
-__device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, const KParams<M>& P,
-                                          unsigned long long chain, unsigned char* smem_chain) {
-    ctx.g.tid = (W == 1) ? (threadIdx.x & 31) : threadIdx.x;
-    ctx.P = &P;
-    ctx.md = P.mdata;
-    ctx.sh = reinterpret_cast<ChainShared*>(smem_chain);
-    size_t off = (sizeof(ChainShared) + 15) & ~size_t(15);
-    ctx.msm = reinterpret_cast<double*>(smem_chain + off);
-    off += (sizeof(double) * (size_t)M::smem_doubles(P.mdata, 32 * W) + 15) & ~size_t(15);
-    ctx.g.red = reinterpret_cast<double*>(smem_chain + off);
-    if (W > 1) off += (sizeof(double) * W * GroupCuda<W>::kMaxRed + 15) & ~size_t(15);
-    ctx.front = reinterpret_cast<double*>(smem_chain + off);
-    ctx.front_slot = -1;
-    off += stage_bytes<M>(P.Dp);
-    double* svar = reinterpret_cast<double*>(smem_chain + off);
-    if (P.var_in_smem) off += (sizeof(double) * P.Dp + 15) & ~size_t(15);
-    ctx.spool = reinterpret_cast<double*>(smem_chain + off);
-    ctx.smem_slots = P.smem_slots;
-    ctx.D = P.D;
-    ctx.Dp = P.Dp;
-    ctx.NS = P.NS;
-    ctx.chain_local = chain;
-    ctx.chain_gid = (uint32_t)(P.chain_id_offset + chain);
-    ctx.pool = P.pool + (size_t)chain * P.NS * 4 * (size_t)P.Dp;
-    ctx.varg = P.var + (size_t)chain * P.Dp;
-    ctx.var = P.var_in_smem ? svar : ctx.varg;
-    ctx.wf = P.welford + (size_t)chain * 8 * (size_t)P.Dp;
-    ctx.mL = ctx.mR = ctx.mD = ctx.tL = ctx.tR = ctx.tD = -1;
-    ctx.lv_valid = 0;
-}
-
-// The sampler: W warps per chain, CPB chains per CTA (CPB > 1 only for W == 1).
-// One persistent launch advances every chain through all its draws.
-// Streaming regime (W >= 8): cap registers at 64 so that 1024 threads — up to four chains —
-// are resident per SM and one chain's reductions / tree bookkeeping overlap another's
-// streaming pass.
-template <class M, int W, int NIT>
-__global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, W >= 8 ? 1024 / (32 * W) : 1)
-    nuts_kernel(const __grid_constant__ KParams<M> P, size_t smem_per_chain, size_t block_data) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    typename M::Data md = P.mdata;
-    if constexpr (M::kHasBlockData) {
-        if (block_data > 0) {  // CTA-wide copy of the density's constant tables
-            M::load_block_data(md, smem, threadIdx.x, blockDim.x);
-            __syncthreads();
-        }
-    }
-    const int local = (W == 1) ? (threadIdx.x >> 5) : 0;
-    const int cpb = (W == 1) ? (blockDim.x >> 5) : 1;
-    const unsigned long long chain = (unsigned long long)blockIdx.x * cpb + local;
-    if (chain >= P.n_chains) return;
-    ChainCtx<M, GroupCuda<W>, NIT> ctx;
-    setup_ctx<M, W, NIT>(ctx, P, chain, smem + block_data + (size_t)local * smem_per_chain);
-    ctx.md = md;
-    ctx.run();
-}
-
-// Component kernel: mode 0 = density at q (slot 0); mode 1 = one leapfrog
-// slot 0 -> slot 1 with per-state eps/dir/idx.  scal: [n][4] = eps, dir, idx, unused;
-// out_scal: [n][4] = logp, kinetic, rc, unused.
-template <class M, int W>
-__global__ void __launch_bounds__(32 * W)
-    component_kernel(const __grid_constant__ KParams<M> P, int mode, const double* scal,
-                     double* out_scal) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const unsigned long long chain = blockIdx.x;
-    if (chain >= P.n_chains) return;
-    ChainCtx<M, GroupCuda<W>, 0> ctx;
-    setup_ctx<M, W, 0>(ctx, P, chain, smem);
-    ctx.acc_sum = ctx.acc_sym = 0.0;
-    ctx.acc_count = 0;
-    if (mode == 0) {
-        bool bad;
-        const double lp = ctx.eval_logp(0, bad);
-        if (ctx.g.tid == 0) {
-            out_scal[chain * 4 + 0] = lp;
-            out_scal[chain * 4 + 1] = 0.0;
-            out_scal[chain * 4 + 2] = bad ? (isfinite(lp) ? 3.0 : 4.0) : 0.0;
-        }
-    } else {
-        const double eps = scal[chain * 4 + 0];
-        const int dir = scal[chain * 4 + 1] > 0 ? 1 : -1;
-        if (ctx.g.tid == 0) {
-            ctx.sh->idx[0] = (int)scal[chain * 4 + 2];
-            ctx.sh->U[0] = 0.0;
-            ctx.sh->K[0] = 0.0;
-        }
-        ctx.g.sync();
-        ctx.step_size = eps;
-        ctx.E0 = 0.0;
-        const int rc = ctx.leapfrog(0, 1, dir);
-        if constexpr (M::kElementwise) {
-            // elementwise gradients are recomputed on use, not stored with the state: materialise
-            // it for the caller of this component entry point
-            const double* qn = ctx.vec(1, VQ);
-            double* gn = ctx.vec(1, VG);
-            for (int i = ctx.g.tid; i < ctx.D; i += ctx.g.size()) {
-                double gi;
-                (void)M::term(ctx.md, i, qn[i], gi);
-                gn[i] = gi;
-            }
-        }
-        if (ctx.g.tid == 0) {
-            out_scal[chain * 4 + 0] = -ctx.sh->U[1];
-            out_scal[chain * 4 + 1] = ctx.sh->K[1];
-            out_scal[chain * 4 + 2] = (double)rc;
-        }
-    }
 }
 
 template <class M, int W, int NIT>

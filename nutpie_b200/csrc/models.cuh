@@ -313,3 +313,64 @@ struct RadonModel {
 };
 
 }  // namespace nb200
+
+// ---- run-time compiled densities (NB200_MODEL_CUSTOM, include/nutpie_b200.h) ----
+// The user's CUDA source defines nb200_user_logp(); kernels_custom.cu appends it to an
+// amalgamation of these headers and compiles the sampler kernel with NVRTC for the (threads
+// per chain, dimensions per thread) geometry the host picked, so a custom density runs inside
+// the same persistent kernel as the built-in ones — the device analogue of the reference's
+// numba-compiled LogpFunc (src/pymc.rs:50-62, compile_pymc.py:970-1006).
+#ifdef NB200_RTC
+struct nb200_group {
+    int tid, nthreads;
+    double* scratch;  // nb200_model_desc::n_user_scratch doubles of shared memory, private to the chain
+    const void* impl_;
+    // bit-reproducible sum over the chain's threads; every thread must call it
+    __device__ double sum(double x) const {
+        double a[1] = {x};
+        static_cast<const nb200::GroupCuda<NB200_RTC_W>*>(impl_)->reduce(a);
+        return a[0];
+    }
+    __device__ void sync() const { static_cast<const nb200::GroupCuda<NB200_RTC_W>*>(impl_)->sync(); }
+};
+__device__ int nb200_user_logp(const nb200_group& grp, int dim, const double* q, double* grad,
+                               double* logp_partial, const double* data);
+#endif
+
+namespace nb200 {
+
+struct CustomModel {
+    static constexpr bool kElementwise = false;
+    static constexpr bool kHasBlockData = false;
+    struct Data {
+        const double* data;  // device copy of nb200_model_desc::user_data
+        int n_data;
+        int program;         // host-side registry slot of the compiled source
+        int n_scratch;       // doubles of per-chain shared scratch the density asked for
+    };
+    NB_HD static int smem_doubles(const Data& d, int) { return d.n_scratch; }
+    template <class G>
+    NB_HD static double logp_grad(const G& grp, const Data& d, int D, const double* q, double* g,
+                                  double* sm) {
+#ifdef NB200_RTC
+        nb200_group ug{grp.tid, grp.size(), sm, &grp};
+        double part = 0.0;
+        const int rc = nb200_user_logp(ug, D, q, g, &part, d.data);
+        double acc[2] = {part, rc != 0 ? 1.0 : 0.0};
+        grp.reduce(acc);
+        // rc > 0 is the reference's recoverable error (src/pymc.rs:178): the engine treats a
+        // non-finite logp as exactly that (divergent transition / rejected initial point)
+        return acc[1] > 0.0 ? __longlong_as_double(0x7ff8000000000000ll) : acc[0];
+#else
+        (void)grp; (void)d; (void)D; (void)q; (void)g; (void)sm;
+        return 0.0;  // only ever instantiated by NVRTC
+#endif
+    }
+    NB_HD static int expanded_dim(int D) { return D; }
+    template <class G>
+    NB_HD static void expand(const G& grp, const Data&, int D, const double* q, double* out) {
+        for (int i = grp.tid; i < D; i += grp.size()) out[i] = q[i];
+    }
+};
+
+}  // namespace nb200

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "launch.hpp"
@@ -25,7 +26,7 @@ using namespace nb200;
 
 // the Python/Rust bindings mirror these layouts field by field
 static_assert(sizeof(nb200_settings) == 192, "nb200_settings ABI layout changed");
-static_assert(sizeof(nb200_model_desc) == 64, "nb200_model_desc ABI layout changed");
+static_assert(sizeof(nb200_model_desc) == 96, "nb200_model_desc ABI layout changed");
 static_assert(sizeof(nb200_progress) == 56, "nb200_progress ABI layout changed");
 
 // ------------------------------------------------------------------ errors
@@ -176,6 +177,13 @@ static int validate(const nb200_settings* st, const nb200_model_desc* m) {
         if (!(m->sigma > 0)) return fail(NB200_EINVAL, "normal: sigma must be > 0");
     } else if (m->kind == NB200_MODEL_FUNNEL) {
         if (m->dim < 2) return fail(NB200_EINVAL, "funnel: dim must be >= 2");
+    } else if (m->kind == NB200_MODEL_CUSTOM) {
+        if (!m->cuda_source || !m->cuda_source[0])
+            return fail(NB200_EINVAL, "custom: cuda_source is empty");
+        if (m->n_user_data > 0 && !m->user_data)
+            return fail(NB200_EINVAL, "custom: user_data is null but n_user_data > 0");
+        if (m->n_user_data > (1ull << 31)) return fail(NB200_EINVAL, "custom: user_data too large");
+        if (m->n_user_scratch > 16384) return fail(NB200_EINVAL, "custom: at most 16384 doubles of scratch");
     } else {
         return fail(NB200_EINVAL, "unknown model kind");
     }
@@ -228,6 +236,19 @@ static int build_model_data(const nb200_model_desc& m, int T, RadonModel::Data& 
     if ((rc = to_device(L.group_base, &group_base, keep))) return rc;
     if ((rc = to_device(L.group_list, &group_list, keep))) return rc;
     d.obs = obs; d.group_base = group_base; d.group_list = group_list;
+    return 0;
+}
+
+static int build_model_data(const nb200_model_desc& m, int, CustomModel::Data& d,
+                            std::vector<void*>& keep) {
+    std::vector<double> v(m.user_data, m.user_data + m.n_user_data);
+    double* dev;
+    int rc;
+    if ((rc = to_device(v, &dev, keep))) return rc;
+    d.data = dev;
+    d.n_data = (int)m.n_user_data;
+    d.n_scratch = (int)m.n_user_scratch;
+    d.program = custom_register(m.cuda_source);
     return 0;
 }
 
@@ -338,6 +359,18 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     }
     s->block = 32 * s->W * s->cpb;
     s->grid = (int)((n_chains + s->cpb - 1) / s->cpb);
+    if (bdata + s->smem_per_chain * s->cpb > 227 * 1024) {
+        fail(NB200_EINVAL, "model dimension too large: a density that gathers across dimensions "
+                           "keeps 4 vectors of the chain in shared memory (227 KB per SM)");
+        return bail();
+    }
+    if constexpr (std::is_same<M, CustomModel>::value) {
+        // compile now so that errors in the user's source surface here, with the NVRTC log
+        if (custom_compile(P.mdata.program, s->W, s->NIT) != 0) {
+            fail(NB200_ECOMPILE, custom_last_log());
+            return bail();
+        }
+    }
     P.D = D; P.Dp = s->Dp; P.NS = s->NS;
     P.n_chains = n_chains; P.chain_id_offset = chain_id_offset;
     P.n_rows = s->n_rows; P.sdim = s->sdim; P.n_total = s->n_total;
@@ -406,6 +439,7 @@ uint64_t nb200_model_expanded_dim(const nb200_model_desc* model) {
     case NB200_MODEL_NORMAL: return (uint64_t)NormalModel::expanded_dim((int)model->dim);
     case NB200_MODEL_FUNNEL: return (uint64_t)FunnelModel::expanded_dim((int)model->dim);
     case NB200_MODEL_RADON: return (uint64_t)RadonModel::expanded_dim((int)model->dim);
+    case NB200_MODEL_CUSTOM: return (uint64_t)CustomModel::expanded_dim((int)model->dim);
     }
     return 0;
 }
@@ -496,6 +530,8 @@ nb200_sampler* nb200_sampler_create(const nb200_settings* settings, const nb200_
         return create_impl<FunnelModel>(settings, model, n_chains, chain_id_offset, device, q0, init_mean);
     case NB200_MODEL_RADON:
         return create_impl<RadonModel>(settings, model, n_chains, chain_id_offset, device, q0, init_mean);
+    case NB200_MODEL_CUSTOM:
+        return create_impl<CustomModel>(settings, model, n_chains, chain_id_offset, device, q0, init_mean);
     }
     fail(NB200_EINVAL, "unknown model kind");
     return nullptr;
@@ -537,6 +573,7 @@ int nb200_sampler_set_z_tape(nb200_sampler* s, const double* z_tape) {
     case NB200_MODEL_NORMAL: set_tape<NormalModel>(s); break;
     case NB200_MODEL_FUNNEL: set_tape<FunnelModel>(s); break;
     case NB200_MODEL_RADON: set_tape<RadonModel>(s); break;
+    case NB200_MODEL_CUSTOM: set_tape<CustomModel>(s); break;
     }
     return 0;
 }
@@ -969,8 +1006,29 @@ extern "C" {
     case NB200_MODEL_NORMAL: return CALL(NormalModel);                         \
     case NB200_MODEL_FUNNEL: return CALL(FunnelModel);                         \
     case NB200_MODEL_RADON: return CALL(RadonModel);                           \
+    case NB200_MODEL_CUSTOM: return CALL(CustomModel);                         \
     }                                                                          \
     return fail(NB200_EINVAL, "unknown model kind");
+
+int nb200_custom_model_compile(const nb200_model_desc* model, int threads_per_chain,
+                               int dims_per_thread, char* log, size_t log_len) {
+    if (log && log_len) log[0] = 0;
+    nb200_settings st;
+    nb200_settings_default(&st);
+    if (validate(&st, model) != 0) return NB200_EINVAL;
+    if (model->kind != NB200_MODEL_CUSTOM) return fail(NB200_EINVAL, "not a custom model");
+    const int W = threads_per_chain / 32;
+    if (threads_per_chain % 32 || W < 1 || W > 32 || (W & (W - 1)))
+        return fail(NB200_EINVAL, "threads per chain must be 32..1024, power of two");
+    const int nit = dims_per_thread > 0 ? supported_nit<CustomModel>(W, dims_per_thread) : 0;
+    if (nit != dims_per_thread)
+        return fail(NB200_EINVAL, "no unrolled kernel for this (threads, dims per thread) pair");
+    if (custom_compile(custom_register(model->cuda_source), W, nit) != 0) {
+        if (log && log_len) std::snprintf(log, log_len, "%s", custom_last_log());
+        return fail(NB200_ECOMPILE, custom_last_log());
+    }
+    return 0;
+}
 
 int nb200_logp_grad(const nb200_model_desc* model, int device, uint64_t n, const double* q,
                     double* logp, double* grad, int32_t* rc) {

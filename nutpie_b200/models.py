@@ -44,6 +44,14 @@ class CompiledDeviceModel:
             keep = [y, county, floor]
             d.n_obs, d.n_county = len(y), int(self.params["n_county"])
             d.y, d.county, d.floor = y.ctypes.data, county.ctypes.data, floor.ctypes.data
+        if self.kind == "custom":
+            src = self.params["cuda_source"].encode("utf-8")
+            data = np.ascontiguousarray(self.params.get("data", ()), dtype=np.float64).ravel()
+            keep = [src, data]
+            d.cuda_source = src
+            d.user_data = data.ctypes.data if data.size else None
+            d.n_user_data = data.size
+            d.n_user_scratch = int(self.params.get("scratch", 0))
         self._keep = keep
         return d, keep
 
@@ -57,6 +65,8 @@ class CompiledDeviceModel:
             return {"x": q if self.n_dim > 1 else q[..., 0]}
         if self.kind == "funnel":
             return {"log_sigma": q[..., 0], "x": q[..., 1:]}
+        if self.kind == "custom":
+            return self._split_expanded(q)
         if self.kind == "radon":
             J = int(self.params["n_county"])
             sd_a, sd_b = np.exp(q[..., J + 1]), np.exp(q[..., 2 * J + 3])
@@ -81,6 +91,13 @@ class CompiledDeviceModel:
             return [("x", 0, self.n_dim, (self.n_dim,) if self.n_dim > 1 else ())]
         if self.kind == "funnel":
             return [("log_sigma", 0, 1, ()), ("x", 1, self.n_dim, (self.n_dim - 1,))]
+        if self.kind == "custom":
+            out, pos = [], 0
+            for name, shape in self.shapes.items():
+                n = int(np.prod(shape)) if shape else 1
+                out.append((name, pos, pos + n, tuple(shape)))
+                pos += n
+            return out
         if self.kind == "radon":
             J, D = int(self.params["n_county"]), self.n_dim
             return [("intercept", 0, 1, ()), ("county_raw", 1, J + 1, (J,)),
@@ -94,7 +111,12 @@ class CompiledDeviceModel:
         """expanded draws [..., n_expanded] (computed on the device) -> {variable: values}"""
         out = {}
         for name, a, b, shape in self.expanded_layout():
-            out[name] = e[..., a:b] if shape else e[..., a]
+            if not shape:
+                out[name] = e[..., a]
+            elif len(shape) == 1:
+                out[name] = e[..., a:b]
+            else:
+                out[name] = e[..., a:b].reshape(e.shape[:-1] + tuple(shape))
         return out
 
     # names of value variables that are stored transformed (compile_pymc.py:810-814)
@@ -150,3 +172,30 @@ def radon_model(y, county, floor, n_county: int, county_names=None) -> CompiledD
                                dict(y=np.asarray(y, dtype=np.float64),
                                     county=np.asarray(county, dtype=np.int32),
                                     floor=np.asarray(floor, dtype=np.uint8), n_county=J))
+
+
+def custom_model(ndim: int, cuda_source: str, data=None, *, scratch: int = 0, shapes=None,
+                 dims=None, coords=None) -> CompiledDeviceModel:
+    """A density given as CUDA source (NB200_MODEL_CUSTOM, include/nutpie_b200.h): the device
+    counterpart of `nutpie.compiled_pyfunc.from_pyfunc` (python/nutpie/compiled_pyfunc.py:108-155),
+    where the user hands over a function instead of a PyMC / Stan model.  `cuda_source` defines
+
+        __device__ int nb200_user_logp(const nb200_group& grp, int dim, const double* q,
+                                       double* grad, double* logp_partial, const double* data);
+
+    `data` is a flat float64 array the density reads on the device, `scratch` the number of
+    doubles of per-chain shared memory it gets as `grp.scratch`.  `shapes` maps variable
+    names to shapes that partition the `ndim` unconstrained coordinates in order (default: one
+    vector "x"); custom densities have no transforms, so the trace holds q itself."""
+    ndim = int(ndim)
+    if shapes is None:
+        shapes = {"x": (ndim,)}
+    shapes = {k: tuple(int(n) for n in v) for k, v in shapes.items()}
+    total = sum(int(np.prod(v)) if v else 1 for v in shapes.values())
+    if total != ndim:
+        raise ValueError(f"variable shapes cover {total} coordinates, the density has {ndim}")
+    if dims is None:
+        dims = {k: tuple(f"{k}_dim_{i}" for i in range(len(v))) for k, v in shapes.items()}
+    params = dict(cuda_source=str(cuda_source), scratch=int(scratch),
+                  data=np.ascontiguousarray(() if data is None else data, dtype=np.float64).ravel())
+    return CompiledDeviceModel("custom", ndim, dict(dims), dict(coords or {}), shapes, params)

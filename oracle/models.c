@@ -66,6 +66,31 @@ int oracle_logp_funnel(size_t dim, const double *x, double *grad, double *logp_o
     return finish(dim, grad, logp, logp_out);
 }
 
+/* Bayesian logistic regression, beta ~ N(0, 1), y_n ~ Bernoulli(logit^-1(X_n . beta)) — the
+ * host twin of the run-time compiled CUDA density in tests/custom_densities.py (the device
+ * analogue of a `from_pyfunc` user model, python/nutpie/compiled_pyfunc.py:108-155).
+ * user_data: doubles [N, D, X row-major N*D, y N]. */
+int oracle_logp_logreg(size_t dim, const double *x, double *grad, double *logp_out,
+                       const void *user_data) {
+    const double *d = (const double *)user_data;
+    const size_t N = (size_t)d[0], D = (size_t)d[1];
+    if (dim != D) return -1;
+    const double *X = d + 2, *y = d + 2 + N * D;
+    double logp = 0.0;
+    for (size_t i = 0; i < D; ++i) {
+        grad[i] = -x[i];
+        logp += -0.5 * x[i] * x[i];
+    }
+    for (size_t n = 0; n < N; ++n) {
+        double eta = 0.0;
+        for (size_t i = 0; i < D; ++i) eta += X[n * D + i] * x[i];
+        const double r = y[n] - 1.0 / (1.0 + exp(-eta));
+        logp += y[n] * eta - (eta > 0.0 ? eta + log1p(exp(-eta)) : log1p(exp(eta)));
+        for (size_t i = 0; i < D; ++i) grad[i] += X[n * D + i] * r;
+    }
+    return finish(dim, grad, logp, logp_out);
+}
+
 /* Radon, parameter order = PyMC value-variable order:
  *   [0] intercept, [1..J] county_raw, [J+1] log county_sd, [J+2] floor_effect,
  *   [J+3..2J+2] county_floor_raw, [2J+3] log county_floor_sd, [2J+4] log sigma */

@@ -48,6 +48,7 @@ typedef struct oracle_radon_data {
 int oracle_logp_normal(size_t dim, const double *x, double *grad, double *logp, const void *ud);
 int oracle_logp_funnel(size_t dim, const double *x, double *grad, double *logp, const void *ud);
 int oracle_logp_radon(size_t dim, const double *x, double *grad, double *logp, const void *ud);
+int oracle_logp_logreg(size_t dim, const double *x, double *grad, double *logp, const void *ud);
 int oracle_expand_radon(size_t dim, size_t expanded_dim, const double *x, double *out,
                         const void *ud);
 

@@ -143,10 +143,19 @@ class Model:
             self.fn = L.oracle_logp_radon
             self.ud = RadonData(len(y), int(kw["n_county"]), _ptr(y), _ptr(county), _ptr(floor))
             assert self.dim == 2 * int(kw["n_county"]) + 5
+        elif kind == "logreg":  # user_data = flat doubles [N, D, X, y]
+            flat = np.ascontiguousarray(kw["data"], dtype=np.float64)
+            self._keep.append(flat)
+            self.fn = L.oracle_logp_logreg
+            self.ud = None
+            assert self.dim == int(flat[1])
         else:
             raise ValueError(kind)
         self.fn_ptr = C.cast(self.fn, C.c_void_p)
-        self.ud_ptr = C.cast(C.pointer(self.ud), C.c_void_p)
+        if kind == "logreg":
+            self.ud_ptr = C.c_void_p(self._keep[0].ctypes.data)
+        else:
+            self.ud_ptr = C.cast(C.pointer(self.ud), C.c_void_p)
 
     def logp_grad(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64)

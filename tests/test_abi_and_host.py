@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for n in names:
         assert hasattr(L, n), f"missing export {n}"
-    assert L.nb200_abi_version() == 1
+    assert L.nb200_abi_version() == 2
 
 
 def test_settings_struct_layout_matches_header():
@@ -183,3 +183,72 @@ def test_expanded_layout_covers_every_variable(radon_data):
     for (_, a, b, shape), (_, a2, _, _) in zip(lay, lay[1:]):
         assert b == a2 and (b - a) == (int(np.prod(shape)) if shape else 1)
     assert {n for n, *_ in lay} == set(cm.dims)
+
+
+# ------------------------------------------------- run-time compiled densities (no GPU needed)
+def test_model_desc_layout():
+    from nutpie_b200 import _lib
+
+    assert C.sizeof(_lib.ModelDesc) == 96
+    assert _lib.ModelDesc.cuda_source.offset == 64 and _lib.ModelDesc.n_user_scratch.offset == 88
+
+
+@pytest.mark.parametrize("tpc,nit", [(32, 1), (32, 0), (256, 0)])
+def test_custom_density_compiles_for_sm100a(tpc, nit):
+    """NVRTC builds the sampler kernel around each test density for several geometries."""
+    import nutpie_b200
+    from nutpie_b200 import _lib
+    from tests import custom_densities as CD
+
+    for src, kw in ((CD.NORMAL, dict(data=[0.0, 1.0])), (CD.FUNNEL, {}),
+                    (CD.LOGREG, dict(data=CD.logreg_data(20, 5), scratch=20)), (CD.WALL, {})):
+        assert _lib.compile_custom(nutpie_b200.from_cuda_source(5, src, **kw), tpc, nit)
+
+
+def test_custom_density_compile_errors_carry_the_nvrtc_log():
+    import nutpie_b200
+    from nutpie_b200 import _lib
+    from tests import custom_densities as CD
+
+    bad = nutpie_b200.from_cuda_source(5, CD.WALL.replace("acc += q[i] * q[i];", "acc += q[i] * nope;"))
+    with pytest.raises(RuntimeError, match=r"nb200_user_density\.cu\(\d+\): error: identifier \"nope\""):
+        _lib.compile_custom(bad, 32, 0)
+    with pytest.raises(ValueError):   # no unrolled kernel with 5 dims per thread
+        _lib.compile_custom(nutpie_b200.from_cuda_source(5, CD.WALL), 32, 5)
+    with pytest.raises(ValueError):   # variable shapes must partition the coordinates
+        nutpie_b200.from_cuda_source(5, CD.WALL, shapes={"a": (2,), "b": (2,)})
+    with pytest.raises(ValueError):
+        _lib.compile_custom(nutpie_b200.normal_model(3), 32, 0)
+
+
+def test_custom_model_layout_and_with_data():
+    import nutpie_b200
+    from tests import custom_densities as CD
+
+    m = nutpie_b200.from_cuda_source(12, CD.LOGREG, data=CD.logreg_data(20, 12), scratch=20,
+                                     shapes={"intercept": (), "beta": (11,)})
+    assert m.expanded_layout() == [("intercept", 0, 1, ()), ("beta", 1, 12, (11,))]
+    e = np.arange(24.0).reshape(2, 12)
+    out = m._split_expanded(e)
+    assert out["intercept"].shape == (2,) and out["beta"].shape == (2, 11)
+    m2 = m.with_data(data=CD.logreg_data(20, 12, seed=9))
+    assert m2.kind == "custom" and not np.array_equal(m2.params["data"], m.params["data"])
+    d, keep = m2._descriptor()
+    assert d.kind == 4 and d.n_user_data == 2 + 20 * 12 + 20 and d.n_user_scratch == 20
+
+
+def test_oracle_logreg_gradient_by_finite_differences():
+    from oracle import pyoracle as O
+    from tests import custom_densities as CD
+
+    data = CD.logreg_data(50, 6)
+    om = O.Model("logreg", 6, data=data)
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=6)
+    lp, g, rc = om.logp_grad(q)
+    assert rc == 0
+    for i in range(6):
+        h = 1e-6
+        e = np.zeros(6); e[i] = h
+        fd = (om.logp_grad(q + e)[0] - om.logp_grad(q - e)[0]) / (2 * h)
+        assert abs(fd - g[i]) < 1e-6 * max(1.0, abs(g[i]))

@@ -20,7 +20,10 @@ import nutpie_b200
 from nutpie_b200 import _lib
 from oracle import pyoracle as O
 
+from tests import custom_densities as CD
+
 pytestmark = pytest.mark.gpu
+LOGREG_DATA = CD.logreg_data(200, 12)
 
 STAT = {n: i for i, n in enumerate(_lib.STAT_NAMES)}
 
@@ -60,11 +63,18 @@ def models(radon_data):
         "funnel": (nutpie_b200.funnel_model(9), O.Model("funnel", 9)),
         "radon": (nutpie_b200.radon_model(d["y"], d["county"], d["floor"], J),
                   O.Model("radon", 2 * J + 5, y=d["y"], county=d["county"], floor=d["floor"], n_county=J)),
+        # run-time compiled CUDA densities (NB200_MODEL_CUSTOM) against their host twins
+        "c_normal37": (nutpie_b200.from_cuda_source(37, CD.NORMAL, data=[2.0, 4.0]),
+                       O.Model("normal", 37, mu=2.0, sigma=0.5)),
+        "c_funnel": (nutpie_b200.from_cuda_source(9, CD.FUNNEL), O.Model("funnel", 9)),
+        "c_logreg": (nutpie_b200.from_cuda_source(12, CD.LOGREG, data=LOGREG_DATA, scratch=200),
+                     O.Model("logreg", 12, data=LOGREG_DATA)),
     }
 
 
 @pytest.mark.parametrize("tpc", [32, 128, 1024])
-@pytest.mark.parametrize("name", ["normal1", "normal37", "funnel", "radon"])
+@pytest.mark.parametrize("name", ["normal1", "normal37", "funnel", "radon", "c_normal37", "c_funnel",
+                                  "c_logreg"])
 def test_logp_grad_matches_oracle(radon_data, name, tpc):
     gm, om = models(radon_data)[name]
     _lib.set_threads_per_chain(tpc)
@@ -84,7 +94,7 @@ def test_logp_nonfinite_codes():
 
 
 @pytest.mark.parametrize("tpc", [32, 256])
-@pytest.mark.parametrize("name", ["normal37", "funnel", "radon"])
+@pytest.mark.parametrize("name", ["normal37", "funnel", "radon", "c_funnel", "c_logreg"])
 def test_leapfrog_matches_oracle(radon_data, name, tpc):
     import ctypes as C
 
@@ -421,3 +431,83 @@ def test_draw_diag_adaptation_and_var_names(radon_data):
     assert abs(tr.posterior["sigma"].mean() - d["truth"]["sigma"]) < 0.1
     assert tr.dims["county_effect"] == ["county"] and len(tr.coords["county"]) == J
     assert json.loads(tr.attrs["_settings"])["settings"]["use_grad_based_estimate"] == 0
+
+
+# ------------------------------------------------- run-time compiled densities (NVRTC)
+@pytest.mark.parametrize("tpc", [0, 64])
+def test_custom_normal_sampler_matches_oracle_draw_for_draw(radon_data, tpc):
+    """The NVRTC-compiled sampler kernel around a user density reproduces the oracle run on the
+    twin host density: identical tree shapes, positions to rounding."""
+    gm, om = models(radon_data)["c_normal37"]
+    _lib.set_threads_per_chain(tpc)
+    s, so = settings_pair(seed=5, num_tune=300, num_draws=200)
+    tr = run_gpu(s, gm, 16)
+    ref = O.sample(om, so, 16)
+    for k in ("depth", "n_steps", "index_in_trajectory", "diverging", "maxdepth_reached", "tuning"):
+        assert np.array_equal(tr.stats[..., STAT[k]], ref["stats"][..., STAT[k]]), k
+    np.testing.assert_allclose(tr.draws[:, :3], ref["draws"][:, :3], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(tr.draws, ref["draws"], rtol=0, atol=1e-3)
+
+
+def test_custom_equals_builtin_density_bitwise_shapes(radon_data):
+    """Same density, built-in elementwise kernel vs run-time compiled gather kernel."""
+    gm, _ = models(radon_data)["c_normal37"]
+    bm, _ = models(radon_data)["normal37"]
+    s, _ = settings_pair(seed=11, num_tune=200, num_draws=100)
+    a = run_gpu(s, gm, 32)
+    b = run_gpu(s, bm, 32)
+    for k in ("depth", "n_steps", "index_in_trajectory", "diverging"):
+        assert np.array_equal(a.stats[..., STAT[k]], b.stats[..., STAT[k]]), k
+    np.testing.assert_allclose(a.draws, b.draws, rtol=0, atol=1e-3)
+
+
+def test_custom_logreg_parity(radon_data):
+    """A user model with no built-in counterpart: logistic regression from CUDA source vs the
+    oracle on the host twin — identical start, then statistical parity."""
+    gm, om = models(radon_data)["c_logreg"]
+    s, so = settings_pair(seed=2, num_tune=300, num_draws=300)
+    C = 64
+    tr = run_gpu(s, gm, C)
+    ref = O.sample(om, so, C)
+    np.testing.assert_allclose(tr.draws[:, 0], ref["draws"][:, 0], rtol=0, atol=1e-9)
+    assert np.array_equal(tr.stats[:, :20, STAT["n_steps"]], ref["stats"][:, :20, STAT["n_steps"]])
+    a, b = tr.draws[:, 300:], ref["draws"][:, 300:]
+    z, ratio = _mcse_compare(a, b)
+    assert z.max() < 4.5, z
+    assert np.all(np.abs(ratio - 1) < 0.08), ratio
+    sa = tr.stats[:, -1, STAT["step_size_bar"]].mean()
+    sb = ref["stats"][:, -1, STAT["step_size_bar"]].mean()
+    assert abs(sa / sb - 1) < 0.1
+    dg, do = tr.stats[..., STAT["diverging"]], ref["stats"][..., STAT["diverging"]]
+    assert dg[:, 300:].sum() == do[:, 300:].sum() == 0          # none after warm-up
+    assert np.array_equal(dg[:, :10], do[:, :10])               # same early-warm-up divergences
+    assert abs(dg.sum() - do.sum()) <= 0.2 * max(do.sum(), 10)
+
+
+def test_custom_recoverable_error_is_a_divergence():
+    """rc > 0 from the density is the reference's recoverable error (src/pymc.rs:178): the
+    trajectory ends there as a divergence and no draw lands in the forbidden region."""
+    gm = nutpie_b200.from_cuda_source(4, CD.WALL)
+    s, _ = settings_pair(seed=3, num_tune=100, num_draws=200)
+    tr = run_gpu(s, gm, 32, q0=np.full((32, 4), 0.2))
+    assert tr.draws[..., 0].max() <= 1.0
+    assert tr.stats[..., STAT["diverging"]].sum() > 0
+    lp, g, rc = _lib.logp_grad(gm, np.array([[2.0, 0, 0, 0], [0.5, 0, 0, 0]]))
+    assert rc[0] != 0 and rc[1] == 0
+
+
+def test_custom_compile_error_surfaces_at_create():
+    gm = nutpie_b200.from_cuda_source(4, CD.WALL.replace("acc += q[i] * q[i];", "acc += q[i] * nope;"))
+    s, _ = settings_pair(seed=3, num_tune=10, num_draws=10)
+    with pytest.raises(RuntimeError, match="nope"):
+        run_gpu(s, gm, 4)
+
+
+def test_custom_public_api_variables():
+    tr = nutpie_b200.sample(
+        nutpie_b200.from_cuda_source(12, CD.LOGREG, data=LOGREG_DATA, scratch=200,
+                                     shapes={"intercept": (), "beta": (11,)}),
+        chains=8, draws=50, tune=100, seed=4, progress_bar=False)
+    post = tr.posterior
+    assert np.asarray(post["intercept"]).shape == (8, 50)
+    assert np.asarray(post["beta"]).shape == (8, 50, 11)
