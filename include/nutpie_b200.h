@@ -278,6 +278,8 @@ void nb200_set_smem_slots(int32_t n);
 int nb200_sampler_smem(nb200_sampler *s, int32_t *smem_slots, int32_t *bytes_per_chain);
 /* 0 = always use the run-time-trip-count kernels (testing); 1 = auto */
 void nb200_set_unroll(int32_t on);
+/* 1 (default): the streaming leapfrog (256 threads per chain) reads through bulk-copy staging */
+void nb200_set_stage_loads(int32_t on);
 /* limit the draws one kernel launch may advance each chain by (0 = run to the
  * end in one persistent launch); the host relaunches until done */
 int nb200_sampler_set_draws_per_launch(nb200_sampler *s, uint64_t n);

@@ -157,6 +157,8 @@ def load_library() -> C.CDLL:
         L.nb200_set_chains_per_block.argtypes = [C.c_int32]
         L.nb200_set_smem_slots.restype = None
         L.nb200_set_smem_slots.argtypes = [C.c_int32]
+        L.nb200_set_stage_loads.restype = None
+        L.nb200_set_stage_loads.argtypes = [C.c_int32]
         L.nb200_set_unroll.restype = None
         L.nb200_set_unroll.argtypes = [C.c_int32]
         L.nb200_sampler_smem.restype = C.c_int
@@ -753,6 +755,10 @@ def set_smem_slots(n: int):
 
 def set_unroll(on: bool):
     load_library().nb200_set_unroll(1 if on else 0)
+
+
+def set_stage_loads(on: bool):
+    load_library().nb200_set_stage_loads(1 if on else 0)
 
 
 def device_count() -> int:

@@ -25,6 +25,17 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, c
     off += (sizeof(double) * (size_t)M::smem_doubles(P.mdata, 32 * W) + 15) & ~size_t(15);
     ctx.g.red = reinterpret_cast<double*>(smem_chain + off);
     if (W > 1) off += (sizeof(double) * W * GroupCuda<W>::kMaxRed + 15) & ~size_t(15);
+    ctx.stage = smem_chain + off;
+    ctx.stage_phase = 0;
+    if constexpr (stage_smem_bytes<M, 32 * W>() > 0) {
+        if (ctx.g.tid == 0) {
+            nb_mbar_init(ctx.stage + 2 * kStageBufBytes, 1);
+            nb_mbar_init(ctx.stage + 2 * kStageBufBytes + 8, 1);
+            nb_mbar_init_fence();
+        }
+        __syncthreads();
+        off += stage_smem_bytes<M, 32 * W>();
+    }
     ctx.front = reinterpret_cast<double*>(smem_chain + off);
     ctx.front_slot = -1;
     off += stage_bytes<M>(P.Dp);

@@ -17,6 +17,7 @@ static size_t chain_smem_fixed(const typename M::Data& md) {
     size_t b = align16(sizeof(ChainShared));
     b += align16(sizeof(double) * (size_t)M::smem_doubles(md, 32 * W));
     if (W > 1) b += align16(sizeof(double) * W * GroupCuda<W>::kMaxRed);
+    b += (size_t)stage_smem_bytes<M, 32 * W>();  // bulk-copy staging of the streaming leapfrog
     return b;  // + the front buffer of non-elementwise densities: see stage_bytes()
 }
 

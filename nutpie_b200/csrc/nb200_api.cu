@@ -54,6 +54,7 @@ static std::atomic<int> g_threads_per_chain{0};
 static std::atomic<int> g_chains_per_block{0};
 static std::atomic<int> g_smem_slots{-1};
 static std::atomic<int> g_force_nit{-1};
+static std::atomic<int> g_stage_loads{1};
 static inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 // + working mass matrix + hot tier of the pool
 static size_t chain_smem_total(size_t fixed, int Dp, int var_in_smem, int smem_slots) {
@@ -376,6 +377,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     P.n_rows = s->n_rows; P.sdim = s->sdim; P.n_total = s->n_total;
     P.expand = expand ? 1 : 0;
     P.gdim = s->grad_dim;
+    P.stage_loads = g_stage_loads.load();
 #define ALLOC(ptr, bytes)                                                               \
     do {                                                                                \
         cudaError_t e_ = cudaMallocAsync((void**)&(ptr), (bytes) ? (bytes) : 8, s->stream); \
@@ -452,6 +454,7 @@ void nb200_set_threads_per_chain(int32_t t) { g_threads_per_chain.store(t); }
 void nb200_set_chains_per_block(int32_t c) { g_chains_per_block.store(c); }
 void nb200_set_smem_slots(int32_t n) { g_smem_slots.store(n); }
 void nb200_set_unroll(int32_t on) { g_force_nit.store(on ? -1 : 0); }
+void nb200_set_stage_loads(int32_t on) { g_stage_loads.store(on ? 1 : 0); }
 
 void nb200_settings_default(nb200_settings* s) {
     std::memset(s, 0, sizeof(*s));
@@ -946,6 +949,7 @@ static int component_run(const nb200_model_desc* model, int device, uint64_t n, 
     int rc = build_model_data(*model, 32 * W, P.mdata, keep);
     if (rc != 0) return rc;
     P.D = D; P.Dp = Dp; P.NS = NS; P.n_chains = n;
+    P.stage_loads = g_stage_loads.load();
     const size_t vecb = sizeof(double) * (size_t)Dp;
     double *d_pool, *d_var, *d_scal, *d_out;
     CU(cudaMalloc((void**)&d_pool, n * NS * 4 * vecb)); keep.push_back(d_pool);

@@ -40,6 +40,17 @@
 
 namespace nb200 {
 
+// Streaming leapfrog staging (CTA-per-chain geometry with 256 threads): double-buffered
+// chunks of kStageChunk double2 per vector, 4 source vectors + 2 per fused partner.
+constexpr int kStageChunk = 256;
+constexpr int kStageVecs = 4 + 2 * NB200_MAX_FUSED;
+constexpr int kStageBufBytes = kStageVecs * kStageChunk * 16;   // one stage
+constexpr int kStageBytes = 2 * kStageBufBytes + 16;             // two stages + two mbarriers
+template <class M, int T>
+NB_HD constexpr int stage_smem_bytes() {
+    return (M::kElementwise && T == kStageChunk) ? kStageBytes : 0;
+}
+
 constexpr int kMaxSlots = 64;
 constexpr int kMaxLevels = 20;
 constexpr double kVarLower = 1e-20, kVarUpper = 1e20;
@@ -98,6 +109,7 @@ struct KParams {
     const double* init_mean; // optional [D]
     const double* z_tape;    // optional [n_chains][n_total][D] (tests)
     const volatile int* stop_flag;
+    int stage_loads;   // streaming leapfrog reads its inputs through bulk-copy staging
 };
 
 struct SampleInfo {
@@ -132,6 +144,8 @@ struct ChainCtx {
     unsigned long long chain_local;
     uint32_t chain_gid;
     double *pool, *var, *wf;
+    unsigned char* stage;   // bulk-copy staging buffers + mbarriers (streaming geometry only)
+    unsigned stage_phase;   // parity bit per stage barrier
     double* spool;     // shared-memory tier of the pool (slots < smem_slots)
     double* varg;      // persistent (global) copy of the mass matrix; var may alias it
     int smem_slots;
@@ -280,6 +294,59 @@ struct ChainCtx {
         acc_s += rho * (vr * ps_);
     }
 
+    // ------------------------------------------------- bulk-copy staged streaming pass
+    // body(k, b) is called once for every double2 index k < D2 owned by this thread, with
+    // b[v * kStageChunk] = srcs[v][k] read from the shared-memory stage.  Thread 0 asks the copy
+    // engine for chunk c+1 (c+2 after the hand-over barrier) of every source vector while the
+    // CTA works on chunk c, so a whole stage per chain is in flight regardless of registers.
+    // All sources must be in global memory; the pass starts with a proxy fence + barrier
+    // because the sources were written with ordinary stores by this CTA.
+    NB_HD bool can_stage() const {
+#ifdef __CUDA_ARCH__
+        if constexpr (stage_smem_bytes<M, G::kThreads>() > 0)
+            return P->stage_loads && smem_slots == 0 && var == varg;
+#endif
+        return false;
+    }
+#ifdef __CUDA_ARCH__
+    template <class F>
+    NB_D void staged_pass(const double2* const (&srcs)[kStageVecs], int nv, int D2, F&& body) {
+        unsigned char* buf0 = stage;
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage + 2 * kStageBufBytes);
+        const int nchunk = (D2 + kStageChunk - 1) / kStageChunk;
+        auto issue = [&](int c) {
+            const int sidx = c & 1;
+            const int first = c * kStageChunk;
+            const int n = (D2 - first) < kStageChunk ? (D2 - first) : kStageChunk;
+            const unsigned bytes = (unsigned)n * 16u;
+            unsigned char* b = buf0 + (size_t)sidx * kStageBufBytes;
+            void* bar = bars + sidx;
+            nb_mbar_expect_tx(bar, bytes * (unsigned)nv);
+#pragma unroll
+            for (int v = 0; v < kStageVecs; ++v)
+                if (v < nv) nb_bulk_g2s(b + v * kStageChunk * 16, srcs[v] + first, bytes, bar);
+        };
+        nb_fence_proxy_async();
+        g.sync();
+        if (g.tid == 0) {
+            issue(0);
+            if (nchunk > 1) issue(1);
+        }
+        for (int c = 0; c < nchunk; ++c) {
+            const int sidx = c & 1;
+            nb_mbar_wait(bars + sidx, (stage_phase >> sidx) & 1u);
+            stage_phase ^= 1u << sidx;
+            const int k = c * kStageChunk + g.tid;
+            if (k < D2)
+                body(k, reinterpret_cast<const double2*>(buf0 + (size_t)sidx * kStageBufBytes) + g.tid);
+            if (c + 2 < nchunk) {
+                g.sync();  // every thread is done reading this stage
+                if (g.tid == 0) issue(c + 2);
+            }
+        }
+    }
+#endif
+
     // ---------------------------------------------------------------- leapfrog
     // src -> dst (dst is a fresh slot).  Returns 0 ok, 1 divergence.
     // want_l0: also evaluate is_turning(src, dst); verdict in l0_turn.
@@ -322,8 +389,9 @@ struct ChainCtx {
             // An elementwise gradient is a function of q_i alone: it is recomputed from the
             // source position instead of being stored with every state, which removes one
             // vector read and one vector write per gradient evaluation (72 -> 56 B/dim moved).
-            auto elem = [&](int i, double q0, double p0, double vr, double s0, double& qn, double& pn,
-                            double& sn) {
+            // px / sx: momentum and p_sum of the planned partners at dimension i
+            auto elem = [&](int i, double q0, double p0, double vr, double s0, const double (&px)[kFusedDim],
+                            const double (&sx)[kFusedDim], double& qn, double& pn, double& sn) {
                 double g0, gn;
                 (void)M::term(md, i, q0, g0);
                 const double ph = p0 + heps * g0;
@@ -336,7 +404,16 @@ struct ChainCtx {
                 if (want_l0) turn_terms(m_src, p0, s0, pn, sn, vr, acc[3], acc[4]);
 #pragma unroll
                 for (int c = 0; c < kMaxFused; ++c)
-                    if (c < np) turn_terms(Pm[c], Pp[c][i], Sp[c][i], pn, sn, vr, acc[5 + 2 * c], acc[6 + 2 * c]);
+                    if (c < np) turn_terms(Pm[c], px[c], sx[c], pn, sn, vr, acc[5 + 2 * c], acc[6 + 2 * c]);
+            };
+            auto elem1 = [&](int i, double& qn, double& pn, double& sn) {  // scalar accesses
+                double px[kFusedDim], sx[kFusedDim];
+#pragma unroll
+                for (int c = 0; c < kFusedDim; ++c) {
+                    px[c] = (c < kMaxFused && c < np) ? Pp[c][i] : 0.0;
+                    sx[c] = (c < kMaxFused && c < np) ? Sp[c][i] : 0.0;
+                }
+                elem(i, qs[i], ps[i], var[i], ss[i], px, sx, qn, pn, sn);
             };
             if constexpr (NIT == 0) {
                 // 16-byte accesses: two dimensions per thread and iteration (slots are 32-byte
@@ -349,19 +426,70 @@ struct ChainCtx {
                 double2* qd2 = reinterpret_cast<double2*>(qd);
                 double2* pd2 = reinterpret_cast<double2*>(pd);
                 double2* sd2 = reinterpret_cast<double2*>(sd);
-                for (int k = g.tid; k < D2; k += g.size()) {
-                    const double2 q0 = qs2[k], p0 = ps2[k], v0 = vr2[k], s0 = ss2[k];
-                    double2 qn, pn, sn;
-                    elem(2 * k, q0.x, p0.x, v0.x, s0.x, qn.x, pn.x, sn.x);
-                    elem(2 * k + 1, q0.y, p0.y, v0.y, s0.y, qn.y, pn.y, sn.y);
-                    qd2[k] = qn;
-                    pd2[k] = pn;
-                    sd2[k] = sn;
+                bool staged = false;
+#ifdef __CUDA_ARCH__
+                if constexpr (stage_smem_bytes<M, G::kThreads>() > 0) {
+                    // Bulk-copy staging: thread 0 asks the copy engine for chunk c+1 of every
+                    // source vector while the CTA integrates chunk c out of shared memory, so
+                    // the bytes in flight are a whole stage (kStageBufBytes) per chain instead of
+                    // what 64 registers per thread can hold.  Needs every source in global memory.
+                    staged = can_stage() && D2 > 0;
+                    if (staged) {
+                        const double2* srcs[kStageVecs];
+                        srcs[0] = qs2; srcs[1] = ps2; srcs[2] = vr2; srcs[3] = ss2;
+#pragma unroll
+                        for (int cc = 0; cc < kMaxFused; ++cc) {
+                            srcs[4 + 2 * cc] = reinterpret_cast<const double2*>(Pp[cc]);
+                            srcs[5 + 2 * cc] = reinterpret_cast<const double2*>(Sp[cc]);
+                        }
+                        staged_pass(srcs, 4 + 2 * np, D2, [&](int k, const double2* b) {
+                            const double2 q0 = b[0 * kStageChunk], p0 = b[1 * kStageChunk];
+                            const double2 v0 = b[2 * kStageChunk], s0 = b[3 * kStageChunk];
+                            double pxa[kFusedDim], sxa[kFusedDim], pxb[kFusedDim], sxb[kFusedDim];
+#pragma unroll
+                            for (int cc = 0; cc < kFusedDim; ++cc) {
+                                pxa[cc] = sxa[cc] = pxb[cc] = sxb[cc] = 0.0;
+                                if (cc < kMaxFused && cc < np) {
+                                    const double2 pp = b[(4 + 2 * cc) * kStageChunk];
+                                    const double2 sp = b[(5 + 2 * cc) * kStageChunk];
+                                    pxa[cc] = pp.x; pxb[cc] = pp.y;
+                                    sxa[cc] = sp.x; sxb[cc] = sp.y;
+                                }
+                            }
+                            double2 qn, pn, sn;
+                            elem(2 * k, q0.x, p0.x, v0.x, s0.x, pxa, sxa, qn.x, pn.x, sn.x);
+                            elem(2 * k + 1, q0.y, p0.y, v0.y, s0.y, pxb, sxb, qn.y, pn.y, sn.y);
+                            qd2[k] = qn;
+                            pd2[k] = pn;
+                            sd2[k] = sn;
+                        });
+                    }
+                }
+#endif
+                if (!staged) {
+                    for (int k = g.tid; k < D2; k += g.size()) {
+                        const double2 q0 = qs2[k], p0 = ps2[k], v0 = vr2[k], s0 = ss2[k];
+                        double pxa[kFusedDim], sxa[kFusedDim], pxb[kFusedDim], sxb[kFusedDim];
+#pragma unroll
+                        for (int cc = 0; cc < kFusedDim; ++cc) {
+                            pxa[cc] = sxa[cc] = pxb[cc] = sxb[cc] = 0.0;
+                            if (cc < kMaxFused && cc < np) {
+                                pxa[cc] = Pp[cc][2 * k]; pxb[cc] = Pp[cc][2 * k + 1];
+                                sxa[cc] = Sp[cc][2 * k]; sxb[cc] = Sp[cc][2 * k + 1];
+                            }
+                        }
+                        double2 qn, pn, sn;
+                        elem(2 * k, q0.x, p0.x, v0.x, s0.x, pxa, sxa, qn.x, pn.x, sn.x);
+                        elem(2 * k + 1, q0.y, p0.y, v0.y, s0.y, pxb, sxb, qn.y, pn.y, sn.y);
+                        qd2[k] = qn;
+                        pd2[k] = pn;
+                        sd2[k] = sn;
+                    }
                 }
                 if ((D & 1) && g.tid == 0) {
                     const int i = D - 1;
                     double qn, pn, sn;
-                    elem(i, qs[i], ps[i], var[i], ss[i], qn, pn, sn);
+                    elem1(i, qn, pn, sn);
                     qd[i] = qn;
                     pd[i] = pn;
                     sd[i] = sn;
@@ -369,7 +497,7 @@ struct ChainCtx {
             } else {
                 for_dims([&](int i) {
                     double qn, pn, sn;
-                    elem(i, qs[i], ps[i], var[i], ss[i], qn, pn, sn);
+                    elem1(i, qn, pn, sn);
                     qd[i] = qn;
                     pd[i] = pn;
                     sd[i] = sn;
@@ -540,6 +668,43 @@ struct ChainCtx {
                 acc[1] += rho * (vr * ps);
             });
         };
+#ifdef __CUDA_ARCH__
+        if constexpr (stage_smem_bytes<M, G::kThreads>() > 0) {
+            if (can_stage() && D >= 2) {
+                // same pass through the bulk-copy stage (two dimensions per thread and chunk)
+                const int D2 = D >> 1;
+                const double2* srcs[kStageVecs];
+                srcs[0] = reinterpret_cast<const double2*>(vec(ss_, VP));
+                srcs[1] = reinterpret_cast<const double2*>(vec(ss_, VS));
+                srcs[2] = reinterpret_cast<const double2*>(vec(se_, VP));
+                srcs[3] = reinterpret_cast<const double2*>(vec(se_, VS));
+                srcs[4] = reinterpret_cast<const double2*>(var);
+#pragma unroll
+                for (int v = 5; v < kStageVecs; ++v) srcs[v] = srcs[0];
+                auto term = [&](double ps, double pss, double pe, double pse, double vr) {
+                    double rho;
+                    if (mode == 0) rho = pse - pss + ps;
+                    else if (mode == 1) rho = pse + pss;
+                    else rho = pss - pse + pe;
+                    acc[0] += rho * (vr * pe);
+                    acc[1] += rho * (vr * ps);
+                };
+                const_cast<ChainCtx*>(this)->staged_pass(srcs, 5, D2, [&](int, const double2* b) {
+                    const double2 ps = b[0 * kStageChunk], pss = b[1 * kStageChunk];
+                    const double2 pe = b[2 * kStageChunk], pse = b[3 * kStageChunk];
+                    const double2 vr = b[4 * kStageChunk];
+                    term(ps.x, pss.x, pe.x, pse.x, vr.x);
+                    term(ps.y, pss.y, pe.y, pse.y, vr.y);
+                });
+                if ((D & 1) && g.tid == 0) {
+                    const int i = D - 1;
+                    term(vec(ss_, VP)[i], vec(ss_, VS)[i], vec(se_, VP)[i], vec(se_, VS)[i], var[i]);
+                }
+                g.reduce(acc);
+                return (acc[0] < 0.0) | (acc[1] < 0.0);
+            }
+        }
+#endif
         if constexpr (!M::kElementwise) {
             // the newest leaf is read from the shared-memory front
             const double* f_p = front + (size_t)Dp;

@@ -65,4 +65,40 @@ NB_HD bool nb_isfinite(double x) {
 #endif
 }
 
+// ---- bulk-copy staging (TMA 1-D bulk copies completing on an mbarrier) ----
+// Used by the streaming leapfrog: one elected thread asks the copy engine for the next
+// chunk of every vector, so the bytes in flight no longer depend on registers per thread.
+#ifdef __CUDACC__
+NB_D uint32_t nb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+NB_D void nb_mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nb_smem_u32(bar)), "r"(count) : "memory");
+}
+NB_D void nb_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+NB_D void nb_mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nb_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+NB_D void nb_mbar_wait(void* bar, unsigned parity) {
+    unsigned ok;
+    const unsigned a = nb_smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+NB_D void nb_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     nb_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(nb_smem_u32(bar))
+                 : "memory");
+}
+// order this thread's earlier generic-proxy writes before later async-proxy (bulk copy) reads
+NB_D void nb_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#endif
+
 }  // namespace nb200

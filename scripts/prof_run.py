@@ -10,7 +10,7 @@ if which == "radon":
     d = nutpie_b200.make_radon_data()
     model = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], 85); n = 1024; upd = {"num_tune": 30, "num_draws": 10, "init_radius": 1.0}
 elif which == "cfg4":
-    model = nutpie_b200.normal_model(10000); n = 512; upd = {"num_tune": 6, "num_draws": 4, "store_dims": 16}
+    model = nutpie_b200.normal_model(10000); n = 512; upd = {"num_tune": 40, "num_draws": 10, "store_dims": 16}
 else:
     model = nutpie_b200.funnel_model(9); n = 4096; upd = {"num_tune": 30, "num_draws": 10, "maxdepth": 12}
 s = _lib.PyNutsSettings.Diag(3); s.update(upd)
