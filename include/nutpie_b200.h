@@ -278,8 +278,10 @@ void nb200_set_smem_slots(int32_t n);
 int nb200_sampler_smem(nb200_sampler *s, int32_t *smem_slots, int32_t *bytes_per_chain);
 /* 0 = always use the run-time-trip-count kernels (testing); 1 = auto */
 void nb200_set_unroll(int32_t on);
-/* 1 (default): the streaming leapfrog (256 threads per chain) reads through bulk-copy staging */
-void nb200_set_stage_loads(int32_t on);
+/* streaming leapfrog (256 threads per chain), bit mask: 1 = inputs read through bulk-copy
+ * staging, 2 = successive passes sweep the dimensions in alternating directions (the tail a
+ * pass wrote is the first thing the next one reads), 4 = L2 eviction hints on the bulk copies */
+void nb200_set_stage_loads(int32_t mode);
 /* limit the draws one kernel launch may advance each chain by (0 = run to the
  * end in one persistent launch); the host relaunches until done */
 int nb200_sampler_set_draws_per_launch(nb200_sampler *s, uint64_t n);

@@ -23,6 +23,8 @@ __version__ = "0.1.0"
 
 _PKG = Path(__file__).resolve().parent
 _SO = _PKG / "libnutpie_b200.so"
+if os.environ.get("NB200_LIB"):  # a build variant of the same sources (scripts/build_variants.py)
+    _SO = Path(os.environ["NB200_LIB"]).resolve()
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -102,7 +104,7 @@ def load_library() -> C.CDLL:
     with _lib_lock:
         if _lib is not None:
             return _lib
-        if os.environ.get("NUTPIE_B200_NO_BUILD") != "1":
+        if os.environ.get("NUTPIE_B200_NO_BUILD") != "1" and not os.environ.get("NB200_LIB"):
             try:
                 from . import build as _build
 
@@ -757,8 +759,10 @@ def set_unroll(on: bool):
     load_library().nb200_set_unroll(1 if on else 0)
 
 
-def set_stage_loads(on: bool):
-    load_library().nb200_set_stage_loads(1 if on else 0)
+def set_stage_loads(mode):
+    """Streaming-leapfrog mode bits: 1 bulk-copy staging, 2 alternating sweep direction,
+    4 L2 eviction hints (True = 1, False = 0)."""
+    load_library().nb200_set_stage_loads(int(mode))
 
 
 def device_count() -> int:

@@ -27,10 +27,11 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, c
     if (W > 1) off += (sizeof(double) * W * GroupCuda<W>::kMaxRed + 15) & ~size_t(15);
     ctx.stage = smem_chain + off;
     ctx.stage_phase = 0;
+    ctx.sweep_rev = false;
     if constexpr (stage_smem_bytes<M, 32 * W>() > 0) {
         if (ctx.g.tid == 0) {
-            nb_mbar_init(ctx.stage + 2 * kStageBufBytes, 1);
-            nb_mbar_init(ctx.stage + 2 * kStageBufBytes + 8, 1);
+            for (int st = 0; st < stage_count<32 * W>(); ++st)
+                nb_mbar_init(ctx.stage + stage_count<32 * W>() * stage_buf_bytes<32 * W>() + 8 * st, 1);
             nb_mbar_init_fence();
         }
         __syncthreads();
@@ -58,11 +59,18 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, c
 
 // The sampler: W warps per chain, CPB chains per CTA (CPB > 1 only for W == 1).
 // One persistent launch advances every chain through all its draws.
-// Streaming regime (W >= 8): cap registers at 64 so that 1024 threads — up to four chains —
-// are resident per SM and one chain's reductions / tree bookkeeping overlap another's
-// streaming pass.
+// Streaming regime: four chains resident per SM, so that one chain's reductions / tree
+// bookkeeping overlap another's streaming pass — 256 threads per chain with registers capped at
+// 64, or 128 threads per chain with 128 registers (bulk-copy staging keeps the bytes in flight
+// independent of the thread count, and half as many warps repeat the chain's scalar work).
 template <class M, int W, int NIT>
-__global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, W >= 8 ? 1024 / (32 * W) : 1)
+constexpr int kernel_min_blocks() {
+    if (W >= 8) return 1024 / (32 * W);
+    if (W == 4 && M::kElementwise && NIT == 0) return 4;
+    return 1;
+}
+template <class M, int W, int NIT>
+__global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, kernel_min_blocks<M, W, NIT>())
     nuts_kernel(const __grid_constant__ KParams<M> P, size_t smem_per_chain, size_t block_data) {
     extern __shared__ __align__(16) unsigned char smem[];
     typename M::Data md = P.mdata;

@@ -34,6 +34,9 @@ NB_HD T nb_ld_tab(const T* p, bool in_smem) {
 struct NormalModel {
     static constexpr bool kElementwise = true;
     static constexpr bool kHasBlockData = false;
+    // g_i = -(q_i - mu) / var is non-finite only if q_i - mu is, and then so is the term
+    // (q_i - mu)^2 of logp: the leapfrog needs no separate per-dimension gradient check
+    static constexpr bool kLogpFlagsBadGrad = true;
     struct Data {
         double mu, inv_var;
     };

@@ -54,7 +54,7 @@ static std::atomic<int> g_threads_per_chain{0};
 static std::atomic<int> g_chains_per_block{0};
 static std::atomic<int> g_smem_slots{-1};
 static std::atomic<int> g_force_nit{-1};
-static std::atomic<int> g_stage_loads{1};
+static std::atomic<int> g_stage_loads{3};  // staging + alternating sweep (nb200_set_stage_loads)
 static inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 // + working mass matrix + hot tier of the pool
 static size_t chain_smem_total(size_t fixed, int Dp, int var_in_smem, int smem_slots) {
@@ -142,8 +142,11 @@ static int pick_W(const nb200_model_desc& m, uint64_t n_chains) {
     int t = g_threads_per_chain.load();
     if (t > 0) return t / 32;
     if (m.dim >= 2048) {  // streaming regime (config 4): a CTA per chain; prefer CTAs small
-        // enough that every chain is resident at once (2048 threads per SM)
-        if (n_chains > 148ull * 2) return 8;
+        // enough that every chain is resident at once.  With bulk-copy staging the bytes in
+        // flight do not depend on the thread count: 128 threads x 128 registers per chain beat
+        // 256 x 64 (no spills in the streaming loop, half the redundant scalar work; measured
+        // +13 %, profiles/r1_sweep_config4_variants.txt)
+        if (n_chains > 148ull * 2) return m.kind == NB200_MODEL_NORMAL ? 4 : 8;
         if (n_chains > 148ull) return 16;
         return 32;
     }
@@ -454,7 +457,7 @@ void nb200_set_threads_per_chain(int32_t t) { g_threads_per_chain.store(t); }
 void nb200_set_chains_per_block(int32_t c) { g_chains_per_block.store(c); }
 void nb200_set_smem_slots(int32_t n) { g_smem_slots.store(n); }
 void nb200_set_unroll(int32_t on) { g_force_nit.store(on ? -1 : 0); }
-void nb200_set_stage_loads(int32_t on) { g_stage_loads.store(on ? 1 : 0); }
+void nb200_set_stage_loads(int32_t mode) { g_stage_loads.store(mode & 7); }
 
 void nb200_settings_default(nb200_settings* s) {
     std::memset(s, 0, sizeof(*s));

@@ -40,15 +40,27 @@
 
 namespace nb200 {
 
-// Streaming leapfrog staging (CTA-per-chain geometry with 256 threads): double-buffered
-// chunks of kStageChunk double2 per vector, 4 source vectors + 2 per fused partner.
-constexpr int kStageChunk = 256;
+// Streaming leapfrog staging (CTA-per-chain geometry with T = 128 or 256 threads): kStages
+// buffers of one chunk each; a chunk is T double2 (one per thread) of every source vector,
+// 4 source vectors + 2 per fused partner; one mbarrier per stage behind the buffers.
+#ifndef NB200_STAGES
+#define NB200_STAGES 4  // at 128 threads per chain; measured: profiles/r1_sweep_config4_variants.txt
+#endif
 constexpr int kStageVecs = 4 + 2 * NB200_MAX_FUSED;
-constexpr int kStageBufBytes = kStageVecs * kStageChunk * 16;   // one stage
-constexpr int kStageBytes = 2 * kStageBufBytes + 16;             // two stages + two mbarriers
+// stages are sized so that four chains fit one SM's shared memory (<= 48 KB of staging each)
+template <int T>
+NB_HD constexpr int stage_count() {
+    return T == 256 ? 2 : NB200_STAGES;
+}
+template <int T>
+NB_HD constexpr int stage_buf_bytes() {
+    return kStageVecs * T * 16;  // one stage
+}
 template <class M, int T>
 NB_HD constexpr int stage_smem_bytes() {
-    return (M::kElementwise && T == kStageChunk) ? kStageBytes : 0;
+    return (M::kElementwise && (T == 128 || T == 256))
+               ? stage_count<T>() * stage_buf_bytes<T>() + ((8 * stage_count<T>() + 15) & ~15)
+               : 0;
 }
 
 constexpr int kMaxSlots = 64;
@@ -109,7 +121,11 @@ struct KParams {
     const double* init_mean; // optional [D]
     const double* z_tape;    // optional [n_chains][n_total][D] (tests)
     const volatile int* stop_flag;
-    int stage_loads;   // streaming leapfrog reads its inputs through bulk-copy staging
+    // streaming leapfrog (bit mask): 1 = inputs come through bulk-copy staging; 2 = successive
+    // passes sweep the dimensions in alternating directions, so the tail a pass has just written
+    // is the first thing the next pass reads (still in L2); 4 = the bulk copies carry L2
+    // eviction hints (consumed state leaves first, the mass matrix stays)
+    int stage_loads;
 };
 
 struct SampleInfo {
@@ -146,6 +162,7 @@ struct ChainCtx {
     double *pool, *var, *wf;
     unsigned char* stage;   // bulk-copy staging buffers + mbarriers (streaming geometry only)
     unsigned stage_phase;   // parity bit per stage barrier
+    bool sweep_rev;         // direction of the last streaming leapfrog over the dimensions
     double* spool;     // shared-memory tier of the pool (slots < smem_slots)
     double* varg;      // persistent (global) copy of the mass matrix; var may alias it
     int smem_slots;
@@ -268,81 +285,119 @@ struct ChainCtx {
     static constexpr int kMaxFused = (M::kElementwise && NIT == 0) ? NB200_MAX_FUSED : 0;
     static constexpr int kFusedDim = kMaxFused > 0 ? kMaxFused : 1;
 
-    // orientation of the pair (x, new leaf): which one is the trajectory's earlier state
+    // The pair (x, new leaf N) in is_turning()'s terms: with (s, e) = the earlier / later of
+    // the two, rho is one of three forms depending on where the pair sits relative to the
+    // trajectory's origin — (S_e - S_s) + p_s, S_e + S_s, or (S_s - S_e) + p_e.  Written on
+    // (x, N) these are (S_n - S_x) + p_x, S_n + S_x and (S_x - S_n) + p_n; the form is uniform
+    // over the pass, so it is applied as exact +-1 / 0 coefficients in a chain of fused
+    // multiply-adds — the same roundings, in the same order, as the branches of is_turning(),
+    // without per-dimension selects.  The verdict (either projection negative) is symmetric in
+    // the two projections, so they need not be told apart either.
     struct PairMode {
-        int mode;       // 0 both on the forward side, 1 spans the origin, 2 both backward
-        bool n_is_end;  // the new leaf has the larger index
+        double cn, cx, cpx, cpn;  // rho = fma(cpn, p_n, fma(cpx, p_x, fma(cx, S_x, cn * S_n)))
     };
     NB_HD static PairMode pair_mode(int idx_x, int idx_n) {
         const bool n_is_end = idx_x < idx_n;
         const int a = n_is_end ? idx_x : idx_n, b = n_is_end ? idx_n : idx_x;
+        const int mode = (a >= 0 && b >= 0) ? 0 : ((b >= 0 && a < 0) ? 1 : 2);
         PairMode m;
-        m.mode = (a >= 0 && b >= 0) ? 0 : ((b >= 0 && a < 0) ? 1 : 2);
-        m.n_is_end = n_is_end;
+        if (mode == 1) {
+            m.cn = 1.0; m.cx = 1.0; m.cpx = 0.0; m.cpn = 0.0;
+        } else if ((mode == 0) == n_is_end) {  // (S_n - S_x) + p_x
+            m.cn = 1.0; m.cx = -1.0; m.cpx = 1.0; m.cpn = 0.0;
+        } else {                               // (S_x - S_n) + p_n
+            m.cn = -1.0; m.cx = 1.0; m.cpx = 0.0; m.cpn = 1.0;
+        }
         return m;
     }
-    // same arithmetic, term by term, as is_turning()
+    // vpn = vr * pn (shared with the kinetic energy)
     NB_HD static void turn_terms(const PairMode& m, double px, double sx, double pn, double sn,
-                                 double vr, double& acc_e, double& acc_s) {
-        const double ps_ = m.n_is_end ? px : pn, pss = m.n_is_end ? sx : sn;
-        const double pe = m.n_is_end ? pn : px, pse = m.n_is_end ? sn : sx;
-        double rho;
-        if (m.mode == 0) rho = pse - pss + ps_;
-        else if (m.mode == 1) rho = pse + pss;
-        else rho = pss - pse + pe;
-        acc_e += rho * (vr * pe);
-        acc_s += rho * (vr * ps_);
+                                 double vr, double vpn, double& acc_n, double& acc_x) {
+        const double rho = fma(m.cpn, pn, fma(m.cpx, px, fma(m.cx, sx, m.cn * sn)));
+        acc_n += rho * vpn;
+        acc_x += rho * (vr * px);
     }
 
     // ------------------------------------------------- bulk-copy staged streaming pass
     // body(k, b) is called once for every double2 index k < D2 owned by this thread, with
-    // b[v * kStageChunk] = srcs[v][k] read from the shared-memory stage.  Thread 0 asks the copy
-    // engine for chunk c+1 (c+2 after the hand-over barrier) of every source vector while the
-    // CTA works on chunk c, so a whole stage per chain is in flight regardless of registers.
+    // b[v * T] = srcs[v][k] read from the shared-memory stage (T = threads of the chain).  Thread 0
+    // keeps the copy engine kStages chunks ahead (chunk c + kStages is requested at the hand-over
+    // barrier of chunk c), so whole stages per chain are in flight regardless of registers.
     // All sources must be in global memory; the pass starts with a proxy fence + barrier
     // because the sources were written with ordinary stores by this CTA.
     NB_HD bool can_stage() const {
 #ifdef __CUDA_ARCH__
         if constexpr (stage_smem_bytes<M, G::kThreads>() > 0)
-            return P->stage_loads && smem_slots == 0 && var == varg;
+            return (P->stage_loads & 1) && smem_slots == 0 && var == varg;
+#endif
+        return false;
+    }
+    // direction of the next streaming pass: opposite to the last leapfrog's (see stage_loads)
+    NB_HD bool next_sweep_rev() const {
+#ifdef __CUDA_ARCH__
+        if constexpr (M::kElementwise && NIT == 0) return (P->stage_loads & 2) ? !sweep_rev : false;
 #endif
         return false;
     }
 #ifdef __CUDA_ARCH__
+    // rev: visit the chunks from the last to the first.  dead_mask / keep_mask: source vectors
+    // whose lines are dead once read (L2 evict_first) / re-read by every pass (evict_last).
     template <class F>
-    NB_D void staged_pass(const double2* const (&srcs)[kStageVecs], int nv, int D2, F&& body) {
-        unsigned char* buf0 = stage;
-        unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage + 2 * kStageBufBytes);
-        const int nchunk = (D2 + kStageChunk - 1) / kStageChunk;
+    NB_D void staged_pass(const double2* const (&srcs)[kStageVecs], int nv, int D2, bool rev,
+                          unsigned dead_mask, unsigned keep_mask, F&& body) {
+        constexpr int CH = G::kThreads;              // double2 per vector and chunk
+        constexpr int BUF = stage_buf_bytes<CH>();   // bytes per stage
+        constexpr int kStages = stage_count<CH>();
+        const uint32_t buf0 = nb_smem_u32(stage);
+        const uint32_t bar0 = buf0 + kStages * BUF;
+        const int nchunk = (D2 + CH - 1) / CH;
+        const bool hints = (P->stage_loads & 4) != 0;
+        unsigned long long pol_dead = 0, pol_keep = 0;
+        if (hints && g.tid == 0) {
+            pol_dead = nb_policy_evict_first();
+            pol_keep = nb_policy_evict_last();
+        }
+        if (!hints) dead_mask = keep_mask = 0;
+        const int first0 = rev ? (nchunk - 1) * CH : 0, dfirst = rev ? -CH : CH;
         auto issue = [&](int c) {
-            const int sidx = c & 1;
-            const int first = c * kStageChunk;
-            const int n = (D2 - first) < kStageChunk ? (D2 - first) : kStageChunk;
+            const int sidx = c % kStages;
+            const int first = first0 + c * dfirst;
+            const int n = (D2 - first) < CH ? (D2 - first) : CH;
             const unsigned bytes = (unsigned)n * 16u;
-            unsigned char* b = buf0 + (size_t)sidx * kStageBufBytes;
-            void* bar = bars + sidx;
+            const uint32_t b = buf0 + sidx * BUF;
+            const uint32_t bar = bar0 + 8 * sidx;
             nb_mbar_expect_tx(bar, bytes * (unsigned)nv);
 #pragma unroll
-            for (int v = 0; v < kStageVecs; ++v)
-                if (v < nv) nb_bulk_g2s(b + v * kStageChunk * 16, srcs[v] + first, bytes, bar);
+            for (int v = 0; v < kStageVecs; ++v) {
+                if (v < nv) {
+                    if ((dead_mask >> v) & 1u)
+                        nb_bulk_g2s_hint(b + v * CH * 16, srcs[v] + first, bytes, bar, pol_dead);
+                    else if ((keep_mask >> v) & 1u)
+                        nb_bulk_g2s_hint(b + v * CH * 16, srcs[v] + first, bytes, bar, pol_keep);
+                    else
+                        nb_bulk_g2s(b + v * CH * 16, srcs[v] + first, bytes, bar);
+                }
+            }
         };
         nb_fence_proxy_async();
         g.sync();
         if (g.tid == 0) {
-            issue(0);
-            if (nchunk > 1) issue(1);
+#pragma unroll
+            for (int c = 0; c < kStages; ++c)
+                if (c < nchunk) issue(c);
         }
+        int k = first0 + g.tid;
+        int sidx = 0;
         for (int c = 0; c < nchunk; ++c) {
-            const int sidx = c & 1;
-            nb_mbar_wait(bars + sidx, (stage_phase >> sidx) & 1u);
+            nb_mbar_wait(bar0 + 8 * sidx, (stage_phase >> sidx) & 1u);
             stage_phase ^= 1u << sidx;
-            const int k = c * kStageChunk + g.tid;
-            if (k < D2)
-                body(k, reinterpret_cast<const double2*>(buf0 + (size_t)sidx * kStageBufBytes) + g.tid);
-            if (c + 2 < nchunk) {
+            if (k < D2) body(k, reinterpret_cast<const double2*>(stage + (size_t)sidx * BUF) + g.tid);
+            if (c + kStages < nchunk) {
                 g.sync();  // every thread is done reading this stage
-                if (g.tid == 0) issue(c + 2);
+                if (g.tid == 0) issue(c + kStages);
             }
+            k += dfirst;
+            sidx = sidx + 1 == kStages ? 0 : sidx + 1;
         }
     }
 #endif
@@ -398,13 +453,17 @@ struct ChainCtx {
                 qn = q0 + eps * (vr * ph);
                 acc[0] += M::term(md, i, qn, gn);
                 pn = ph + heps * gn;
-                acc[1] += pn * (vr * pn);
+                const double vpn = vr * pn;
+                acc[1] += pn * vpn;
                 sn = restart_sum ? pn : s0 + pn;
-                if (!nb_isfinite(gn)) acc[2] += 1.0;
-                if (want_l0) turn_terms(m_src, p0, s0, pn, sn, vr, acc[3], acc[4]);
+                // (a density may promise that a non-finite gradient shows in logp as well)
+                if constexpr (!M::kLogpFlagsBadGrad)
+                    if (!nb_isfinite(gn)) acc[2] += 1.0;
+                if (want_l0) turn_terms(m_src, p0, s0, pn, sn, vr, vpn, acc[3], acc[4]);
 #pragma unroll
                 for (int c = 0; c < kMaxFused; ++c)
-                    if (c < np) turn_terms(Pm[c], px[c], sx[c], pn, sn, vr, acc[5 + 2 * c], acc[6 + 2 * c]);
+                    if (c < np)
+                        turn_terms(Pm[c], px[c], sx[c], pn, sn, vr, vpn, acc[5 + 2 * c], acc[6 + 2 * c]);
             };
             auto elem1 = [&](int i, double& qn, double& pn, double& sn) {  // scalar accesses
                 double px[kFusedDim], sx[kFusedDim];
@@ -427,11 +486,13 @@ struct ChainCtx {
                 double2* pd2 = reinterpret_cast<double2*>(pd);
                 double2* sd2 = reinterpret_cast<double2*>(sd);
                 bool staged = false;
+                const bool rev = next_sweep_rev();
+                sweep_rev = rev;
 #ifdef __CUDA_ARCH__
                 if constexpr (stage_smem_bytes<M, G::kThreads>() > 0) {
                     // Bulk-copy staging: thread 0 asks the copy engine for chunk c+1 of every
                     // source vector while the CTA integrates chunk c out of shared memory, so
-                    // the bytes in flight are a whole stage (kStageBufBytes) per chain instead of
+                    // the bytes in flight are whole stages (stage_buf_bytes) per chain instead of
                     // what 64 registers per thread can hold.  Needs every source in global memory.
                     staged = can_stage() && D2 > 0;
                     if (staged) {
@@ -442,16 +503,19 @@ struct ChainCtx {
                             srcs[4 + 2 * cc] = reinterpret_cast<const double2*>(Pp[cc]);
                             srcs[5 + 2 * cc] = reinterpret_cast<const double2*>(Sp[cc]);
                         }
-                        staged_pass(srcs, 4 + 2 * np, D2, [&](int k, const double2* b) {
-                            const double2 q0 = b[0 * kStageChunk], p0 = b[1 * kStageChunk];
-                            const double2 v0 = b[2 * kStageChunk], s0 = b[3 * kStageChunk];
+                        // the source state and the partners are read once (dead afterwards for
+                        // all but tree ends); the mass matrix is read by every pass
+                        constexpr int CH = G::kThreads;
+                        staged_pass(srcs, 4 + 2 * np, D2, rev, ~4u, 4u, [&](int k, const double2* b) {
+                            const double2 q0 = b[0 * CH], p0 = b[1 * CH];
+                            const double2 v0 = b[2 * CH], s0 = b[3 * CH];
                             double pxa[kFusedDim], sxa[kFusedDim], pxb[kFusedDim], sxb[kFusedDim];
 #pragma unroll
                             for (int cc = 0; cc < kFusedDim; ++cc) {
                                 pxa[cc] = sxa[cc] = pxb[cc] = sxb[cc] = 0.0;
                                 if (cc < kMaxFused && cc < np) {
-                                    const double2 pp = b[(4 + 2 * cc) * kStageChunk];
-                                    const double2 sp = b[(5 + 2 * cc) * kStageChunk];
+                                    const double2 pp = b[(4 + 2 * cc) * CH];
+                                    const double2 sp = b[(5 + 2 * cc) * CH];
                                     pxa[cc] = pp.x; pxb[cc] = pp.y;
                                     sxa[cc] = sp.x; sxb[cc] = sp.y;
                                 }
@@ -467,7 +531,10 @@ struct ChainCtx {
                 }
 #endif
                 if (!staged) {
-                    for (int k = g.tid; k < D2; k += g.size()) {
+                    const int nth = g.size(), nchunk = (D2 + nth - 1) / nth;
+                    for (int c = 0; c < nchunk; ++c) {
+                        const int k = (rev ? nchunk - 1 - c : c) * nth + g.tid;
+                        if (k >= D2) continue;
                         const double2 q0 = qs2[k], p0 = ps2[k], v0 = vr2[k], s0 = ss2[k];
                         double pxa[kFusedDim], sxa[kFusedDim], pxb[kFusedDim], sxb[kFusedDim];
 #pragma unroll
@@ -563,14 +630,15 @@ struct ChainCtx {
                     if (it + 1 < NIT || i < D) {
                         const double gn = fg[i];
                         const double pn = ph[it] + heps * gn;
-                        acc[0] += pn * (vr[it] * pn);
+                        const double vpn = vr[it] * pn;
+                        acc[0] += pn * vpn;
                         const double p_old = fp[i], s_old = fs[i];
                         const double sn = restart_sum ? pn : s_old + pn;
-                        if (want_l0) turn_terms(m_src, p_old, s_old, pn, sn, vr[it], tacc[0], tacc[1]);
+                        if (want_l0) turn_terms(m_src, p_old, s_old, pn, sn, vr[it], vpn, tacc[0], tacc[1]);
 #pragma unroll
                         for (int c = 0; c < kMaxFused; ++c)
                             if (c < np)
-                                turn_terms(Pm[c], Pp[c][i], Sp[c][i], pn, sn, vr[it], tacc[2 + 2 * c],
+                                turn_terms(Pm[c], Pp[c][i], Sp[c][i], pn, sn, vr[it], vpn, tacc[2 + 2 * c],
                                            tacc[3 + 2 * c]);
                         fp[i] = pn;
                         fs[i] = sn;
@@ -681,18 +749,21 @@ struct ChainCtx {
                 srcs[4] = reinterpret_cast<const double2*>(var);
 #pragma unroll
                 for (int v = 5; v < kStageVecs; ++v) srcs[v] = srcs[0];
+                // the three forms of rho as exact +-1 / 0 coefficients (same roundings as `body`)
+                const double c_se = mode == 2 ? -1.0 : 1.0, c_ss = mode == 0 ? -1.0 : 1.0;
+                const double c_ps = mode == 0 ? 1.0 : 0.0, c_pe = mode == 2 ? 1.0 : 0.0;
                 auto term = [&](double ps, double pss, double pe, double pse, double vr) {
-                    double rho;
-                    if (mode == 0) rho = pse - pss + ps;
-                    else if (mode == 1) rho = pse + pss;
-                    else rho = pss - pse + pe;
+                    const double rho = fma(c_pe, pe, fma(c_ps, ps, fma(c_ss, pss, c_se * pse)));
                     acc[0] += rho * (vr * pe);
                     acc[1] += rho * (vr * ps);
                 };
-                const_cast<ChainCtx*>(this)->staged_pass(srcs, 5, D2, [&](int, const double2* b) {
-                    const double2 ps = b[0 * kStageChunk], pss = b[1 * kStageChunk];
-                    const double2 pe = b[2 * kStageChunk], pse = b[3 * kStageChunk];
-                    const double2 vr = b[4 * kStageChunk];
+                // sweep against the last leapfrog: the newest leaf's tail is still in L2
+                const_cast<ChainCtx*>(this)->staged_pass(srcs, 5, D2, next_sweep_rev(), 0u, 16u,
+                                                         [&](int, const double2* b) {
+                    constexpr int CH = G::kThreads;
+                    const double2 ps = b[0 * CH], pss = b[1 * CH];
+                    const double2 pe = b[2 * CH], pse = b[3 * CH];
+                    const double2 vr = b[4 * CH];
                     term(ps.x, pss.x, pe.x, pse.x, vr.x);
                     term(ps.y, pss.y, pe.y, pse.y, vr.y);
                 });

@@ -74,28 +74,47 @@ NB_D void nb_mbar_init(void* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nb_smem_u32(bar)), "r"(count) : "memory");
 }
 NB_D void nb_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-NB_D void nb_mbar_expect_tx(void* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nb_smem_u32(bar)), "r"(bytes)
-                 : "memory");
+// (shared-memory operands are 32-bit shared-window addresses, computed once per pass)
+NB_D void nb_mbar_expect_tx(uint32_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-NB_D void nb_mbar_wait(void* bar, unsigned parity) {
+NB_D void nb_mbar_wait(uint32_t bar, unsigned parity) {
     unsigned ok;
-    const unsigned a = nb_smem_u32(bar);
     do {
         asm volatile(
             "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             " selp.u32 %0, 1, 0, p;\n}"
             : "=r"(ok)
-            : "r"(a), "r"(parity)
+            : "r"(bar), "r"(parity)
             : "memory");
     } while (!ok);
 }
 // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
-NB_D void nb_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, void* bar) {
+NB_D void nb_bulk_g2s(uint32_t dst_smem, const void* src_gmem, unsigned bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     nb_smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(nb_smem_u32(bar))
+                     dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// the same copy with an L2 eviction-priority hint (createpolicy handle)
+NB_D void nb_bulk_g2s_hint(uint32_t dst_smem, const void* src_gmem, unsigned bytes, uint32_t bar,
+                           unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            dst_smem),
+        "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+// L2 eviction-priority policies: streamed-once data leaves first, re-read tables stay
+NB_D unsigned long long nb_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+NB_D unsigned long long nb_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 // order this thread's earlier generic-proxy writes before later async-proxy (bulk copy) reads
 NB_D void nb_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }

@@ -28,6 +28,9 @@ LOGREG_DATA = CD.logreg_data(200, 12)
 STAT = {n: i for i, n in enumerate(_lib.STAT_NAMES)}
 
 
+DEFAULT_STAGE_MODE = 3  # bulk-copy staging + alternating sweep direction (nb200_set_stage_loads)
+
+
 def settings_pair(seed=1, **kw):
     s = _lib.PyNutsSettings.Diag(seed)
     so = O.default_settings(seed=seed)
@@ -52,6 +55,7 @@ def _reset_geometry():
     _lib.set_threads_per_chain(0)
     _lib.set_chains_per_block(0)
     _lib.set_smem_slots(-1)
+    _lib.set_stage_loads(DEFAULT_STAGE_MODE)
 
 
 def models(radon_data):
@@ -285,6 +289,33 @@ def test_config4_leapfrog_properties():
     assert abs(tr.stats[:, 120:, STAT["mean_tree_accept"]].mean() - 0.8) < 0.1
     # logp of a D-dim standard normal draw: -chi2_D/2 ~ -D/2 +- sqrt(D/2)
     assert abs(tr.stats[:, 120:, STAT["logp"]].mean() + D / 2) < 5 * np.sqrt(D / 2)
+
+
+@pytest.mark.parametrize("tpc", [128, 256])
+def test_streaming_leapfrog_staging_modes(tpc):
+    """The streaming leapfrog of config 4 (bulk-copy staging through shared memory, 128 or 256
+    threads per chain) on an odd, ragged dimension: every mode reproduces the oracle's tree
+    shapes; staging on/off is bit-identical for the same sweep order, and L2 hints never change
+    a bit."""
+    D = 4099  # odd (scalar tail) and not a multiple of the chunk size
+    gm, om = nutpie_b200.normal_model(D, mu=0.3, sigma=1.7), O.Model("normal", D, mu=0.3, sigma=1.7)
+    mk = lambda: settings_pair(seed=5, num_tune=70, num_draws=30, store_dims=24)
+    ref = O.sample(om, mk()[1], 6)
+    _lib.set_threads_per_chain(tpc)
+    out = {}
+    for mode in (0, 1, 2, 3, 7):
+        _lib.set_stage_loads(mode)
+        tr = run_gpu(mk()[0], gm, 6)
+        out[mode] = tr
+        for k in ("depth", "n_steps", "index_in_trajectory", "diverging"):
+            assert np.array_equal(tr.stats[..., STAT[k]], ref["stats"][..., STAT[k]]), (mode, k)
+        np.testing.assert_allclose(tr.draws[:, :3], ref["draws"][:, :3], rtol=0, atol=1e-9, err_msg=str(mode))
+        np.testing.assert_allclose(tr.draws, ref["draws"], rtol=0, atol=1e-4, err_msg=str(mode))  # rounding growth
+        np.testing.assert_allclose(tr.stats[..., STAT["energy"]], ref["stats"][..., STAT["energy"]],
+                                   rtol=0, atol=1e-3)
+    for a, b in ((0, 1), (2, 3), (3, 7)):
+        assert np.array_equal(out[a].draws, out[b].draws), (a, b)
+        assert np.array_equal(out[a].stats, out[b].stats), (a, b)
 
 
 def test_config1_through_public_api():
