@@ -54,7 +54,9 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, c
     ctx.var = P.var_in_smem ? svar : ctx.varg;
     ctx.wf = P.welford + (size_t)chain * 8 * (size_t)P.Dp;
     ctx.mL = ctx.mR = ctx.mD = ctx.tL = ctx.tR = ctx.tD = -1;
-    ctx.lv_valid = 0;
+    ctx.lv_live = 0;
+    ctx.n_parked = 0;
+    ctx.defer_acc = false;
 }
 
 // The sampler: W warps per chain, CPB chains per CTA (CPB > 1 only for W == 1).

@@ -246,34 +246,40 @@ struct RadonModel {
             const char* mub = reinterpret_cast<const char*>(mu);
             const RadonObs* ob = d.obs + grp.tid;
             double pre = 0.0;  // running PREFIX sum of residuals over the thread's whole range
-            // n_steps is a multiple of 4: four records are loaded before they are consumed
-            for (int j0 = 0; j0 < d.n_steps; j0 += 4) {
+            auto step = [&](const RadonObs& rc, double& ss) {
+                const int mt = rc.meta;
+                const double r = rc.y - *reinterpret_cast<const double*>(mub + (mt & ~7));
+                ss += r * r;
+                pre += r;
+                if (mt & 1) {  // last observation of its group: publish the prefix sum
+                    *reinterpret_cast<double*>(kp) = pre;
+                    kp += 8;
+                }
+            };
+            // four records are loaded before they are consumed; the 0..3 left over go one by one
+            int j0 = 0;
+            for (; j0 + 4 <= d.n_steps; j0 += 4) {
                 RadonObs rec[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) rec[u] = nb_ldg_obs(ob + (size_t)(j0 + u) * T, d.in_smem);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int mt = rec[u].meta;
-                    const double r = rec[u].y - *reinterpret_cast<const double*>(mub + (mt & ~7));
-                    if (u == 0) ss0 += r * r;
-                    else if (u == 1) ss1 += r * r;
-                    else if (u == 2) ss2 += r * r;
-                    else ss3 += r * r;
-                    pre += r;
-                    if (mt & 1) {  // last observation of its group: publish the prefix sum
-                        *reinterpret_cast<double*>(kp) = pre;
-                        kp += 8;
-                    }
-                }
+                step(rec[0], ss0);
+                step(rec[1], ss1);
+                step(rec[2], ss2);
+                step(rec[3], ss3);
             }
+            for (; j0 < d.n_steps; ++j0) step(nb_ldg_obs(ob + (size_t)j0 * T, d.in_smem), ss0);
         }
         grp.sync();
         double acc[7] = {(ss0 + ss1) + (ss2 + ss3), 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        // kept rolled (as is the piece loop inside): the kernel is bound by instruction fetch, and
+        // unrolling these two cost 660 SASS instructions for nothing (+3 % rolled, measured)
+#pragma unroll 1
         for (int c = grp.tid; c < J; c += T) {
             const uint32_t* gl = d.group_list + (size_t)(2 * c) * d.kmax;
             double S0 = 0.0, S1 = 0.0;
             // a group's sum = prefix at its end - prefix at the end of the previous group of
             // the same thread (slot G, always 0, for a thread's first group and for padding)
+#pragma unroll 1
             for (int k = 0; k < d.kmax; ++k) {
                 const uint32_t e0 = nb_ld_tab(gl + k, d.in_smem);
                 const uint32_t e1 = nb_ld_tab(gl + d.kmax + k, d.in_smem);

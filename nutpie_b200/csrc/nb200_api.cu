@@ -165,6 +165,7 @@ static int validate(const nb200_settings* st, const nb200_model_desc* m) {
     if (st->maxdepth < 1 || 3 * ((int)st->maxdepth + 1) + 3 > kMaxSlots)
         return fail(NB200_EINVAL, "maxdepth must be in 1..19");
     if (m->dim < 1) return fail(NB200_EINVAL, "model dimension must be >= 1");
+    if (m->dim > (1u << 22)) return fail(NB200_EINVAL, "model dimension must be <= 2^22");
     if (st->step_size_method != 0 && st->step_size_method != 2)
         return fail(NB200_EINVAL, "step_size_adapt_method: only dual_average and fixed are supported");
     if (m->kind == NB200_MODEL_RADON) {

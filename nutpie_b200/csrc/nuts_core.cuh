@@ -140,6 +140,27 @@ NB_HD double nb_logaddexp(double a, double b) {
     return diff;
 }
 
+#ifdef __CUDACC__
+// Acceptance statistics of up to 32 parked leaves (ChainCtx::flush_acc): lane k holds leaf k's
+// energy error; returns (sum of min(1, w), sum of 2 min(1, w) / (1 + w)) added to the running
+// sums in leaf order.  One out-of-line copy: it runs once per transition, and inlining its exp /
+// division at every call site only grows the hot loop's instruction footprint.
+static __device__ __noinline__ double2 nb_flush_parked(double de, unsigned n, double sum, double sym) {
+    double a = 0.0, sy = 0.0;
+    if ((threadIdx.x & 31u) < n) {
+        const double w = exp(-de);
+        a = w < 1.0 ? w : 1.0;
+        sy = 2.0 * a / (1.0 + w);
+    }
+    __syncwarp();
+    for (unsigned k = 0; k < n; ++k) {
+        sum += __shfl_sync(0xffffffffu, a, (int)k);
+        sym += __shfl_sync(0xffffffffu, sy, (int)k);
+    }
+    return make_double2(sum, sym);
+}
+#endif
+
 // NIT > 0: every per-dimension loop runs exactly NIT predicated iterations
 // (NIT * group size >= D), fully unrolled so independent loads overlap;
 // NIT == 0: run-time trip count (any D).
@@ -172,11 +193,19 @@ struct ChainCtx {
     double acc_sum, acc_sym;
     uint32_t acc_count, n_merge, draw;
     double last_de;
+    // Warp-per-chain geometry: the acceptance statistics of a transition's leaves are evaluated
+    // lane-parallel.  Leaf n parks its energy error in lane n % 32; every 32 leaves and at the
+    // end of the transition each lane evaluates exp / the symmetric ratio for ITS leaf and the
+    // values are added in leaf order (same sums, bit for bit, as adding them leaf by leaf — but
+    // one exp + one division per 32 leaves instead of per leaf on the warp's critical path).
+    double de_parked;
+    unsigned n_parked;
+    bool defer_acc;
     bool l0_turn;          // U-turn verdict between src and the new leaf, fused into the leapfrog
     unsigned fused_bits;   // verdicts of the other pairs planned for this leapfrog (bit c = plist[c])
     // tree bookkeeping (slot ids; -1 = none)
     int mL, mR, mD, tL, tR, tD;
-    unsigned lv_valid;
+    unsigned long long lv_live;  // slots referenced by the parked sub-trees of the level stack
     // strategy state
     double da_log_step, da_log_step_adapted, da_hbar, da_mu;
     unsigned long long da_count;
@@ -206,14 +235,13 @@ struct ChainCtx {
     // trajectory restarts from a tree end or a draw is written out, so they always
     // live in the HBM/L2 tier.  alloc() hands out the lowest free slot, so recent
     // leaves and low tree levels land in the hot tier.
+    // (a chain's pool is at most 64 slots x 4 vectors: offsets fit 32 bits for any D < 2^23)
     NB_HD double* vec(int slot, int comp) const {
         if ((comp & 1) && slot < 2 * smem_slots)  // VP = 1, VS = 3
-            return spool + ((size_t)slot * 2 + (comp >> 1)) * (size_t)Dp;
-        return pool + ((size_t)slot * 4 + comp) * (size_t)Dp;
+            return spool + (unsigned)((slot * 2 + (comp >> 1)) * Dp);
+        return pool + (unsigned)((slot * 4 + comp) * Dp);
     }
-    NB_HD double* gvec(int slot, int comp) const {
-        return pool + ((size_t)slot * 4 + comp) * (size_t)Dp;
-    }
+    NB_HD double* gvec(int slot, int comp) const { return pool + (unsigned)((slot * 4 + comp) * Dp); }
     NB_HD const nb200_settings& st() const { return P->st; }
 
     // ------------------------------------------------------------ slot pool
@@ -225,12 +253,7 @@ struct ChainCtx {
         if (tL >= 0) live |= 1ull << tL;
         if (tR >= 0) live |= 1ull << tR;
         if (tD >= 0) live |= 1ull << tD;
-        unsigned v = lv_valid;
-        while (v) {
-            int k = nb_ffsll(v) - 1;
-            v &= v - 1;
-            live |= (1ull << sh->lvL[k]) | (1ull << sh->lvR[k]) | (1ull << sh->lvD[k]);
-        }
+        live |= lv_live;
         const unsigned long long all = NS >= 64 ? ~0ull : ((1ull << NS) - 1ull);
         return nb_ffsll(~live & all) - 1;  // lowest free slot: keeps the hot set small
     }
@@ -621,9 +644,9 @@ struct ChainCtx {
                 g.sync();
                 lp = M::logp_grad(g, md, D, fq, fg, msm);
                 g.sync();
-                double tacc[2 + 2 * kFusedDim];
+                double tacc[2 + 2 * kMaxFused];
 #pragma unroll
-                for (int c = 0; c < 2 + 2 * kFusedDim; ++c) tacc[c] = 0.0;
+                for (int c = 0; c < 2 + 2 * kMaxFused; ++c) tacc[c] = 0.0;
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
                     const int i = g.tid + it * G::kThreads;
@@ -649,11 +672,11 @@ struct ChainCtx {
                     }
                 }
                 if (want_l0 || np > 0) {
-                    double all[4 + 2 * kFusedDim];
+                    double all[4 + 2 * kMaxFused];
                     all[0] = acc[0];
                     all[1] = acc[1];
 #pragma unroll
-                    for (int c = 0; c < 2 + 2 * kFusedDim; ++c) all[2 + c] = tacc[c];
+                    for (int c = 0; c < 2 + 2 * kMaxFused; ++c) all[2 + c] = tacc[c];
                     g.reduce(all);
                     acc[0] = all[0];
                     acc[1] = all[1];
@@ -704,13 +727,34 @@ struct ChainCtx {
         g.sync();
         acc_count += 1;
         if (rc == 0) {
-            const double w = exp(-de);
-            const double a = w < 1.0 ? w : 1.0;
-            acc_sum += a;
-            acc_sym += 2.0 * a / (1.0 + w);
+#ifdef __CUDA_ARCH__
+            if (G::kThreads == 32 && defer_acc) {
+                if ((unsigned)g.tid == n_parked) de_parked = de;
+                if (++n_parked == 32u) flush_acc();
+            } else
+#endif
+            {
+                const double w = exp(-de);
+                const double a = w < 1.0 ? w : 1.0;
+                acc_sum += a;
+                acc_sym += 2.0 * a / (1.0 + w);
+            }
         }
         last_de = de;
         return rc;
+    }
+
+    // add the parked leaves' acceptance statistics to the collectors, in leaf order
+    NB_HD void flush_acc() {
+#ifdef __CUDA_ARCH__
+        if constexpr (G::kThreads == 32) {
+            if (n_parked == 0) return;
+            const double2 r = nb_flush_parked(de_parked, n_parked, acc_sum, acc_sym);
+            acc_sum = r.x;
+            acc_sym = r.y;
+            n_parked = 0;
+        }
+#endif
     }
 
     // ------------------------------------------------------------------ U-turn
@@ -780,9 +824,25 @@ struct ChainCtx {
             // the newest leaf is read from the shared-memory front
             const double* f_p = front + (size_t)Dp;
             const double* f_s = front + 3 * (size_t)Dp;
-            if (se_ == front_slot) body(vec(ss_, VP), vec(ss_, VS), f_p, f_s);
-            else if (ss_ == front_slot) body(f_p, f_s, vec(se_, VP), vec(se_, VS));
-            else body(vec(ss_, VP), vec(ss_, VS), vec(se_, VP), vec(se_, VS));
+            // One copy of the loop behind selected (generic) pointers: the three
+            // address-space-specialised copies it replaces were 3x the code for a saved
+            // generic-address decode, and this kernel is bound by instruction fetch
+            // (profiles/r1_sweep_radon_codesize.txt: +6 %; an out-of-line single copy for the
+            // four call sites of transition() measured no better).
+            const double* p_s = ss_ == front_slot ? f_p : vec(ss_, VP);
+            const double* s_s = ss_ == front_slot ? f_s : vec(ss_, VS);
+            const double* p_e = se_ == front_slot ? f_p : vec(se_, VP);
+            const double* s_e = se_ == front_slot ? f_s : vec(se_, VS);
+            // the three forms of rho as exact +-1 / 0 coefficients (same roundings as `body`)
+            const double c_se = mode == 2 ? -1.0 : 1.0, c_ss = mode == 0 ? -1.0 : 1.0;
+            const double c_ps = mode == 0 ? 1.0 : 0.0, c_pe = mode == 2 ? 1.0 : 0.0;
+            for_dims([&](int i) {
+                const double pse = s_e[i], pss = s_s[i], pe = p_e[i], ps = p_s[i];
+                const double rho = fma(c_pe, pe, fma(c_ps, ps, fma(c_ss, pss, c_se * pse)));
+                const double vr = var[i];
+                acc[0] += rho * (vr * pe);
+                acc[1] += rho * (vr * ps);
+            });
         } else {
             body(vec(ss_, VP), vec(ss_, VS), vec(se_, VP), vec(se_, VS));
         }
@@ -865,10 +925,12 @@ struct ChainCtx {
         n_merge = 0;
         acc_sum = acc_sym = 0.0;
         acc_count = 0;
+        n_parked = 0;
+        defer_acc = true;
         init_momentum(cur, RNG_MOMENTUM, t);
         mL = mR = mD = cur;
         tL = tR = tD = -1;
-        lv_valid = 0;
+        lv_live = 0;
         double m_ls = 0.0;
         int depth = 0;
         unsigned spec_bits = 0;  // speculative C verdicts per level (bit 31: main tree)
@@ -883,7 +945,7 @@ struct ChainCtx {
             const bool check = st().check_turning && depth >= (int)st().mindepth;
             const unsigned n_leaf = 1u << depth;
             int prev = dir > 0 ? mR : mL;
-            lv_valid = 0;
+            lv_live = 0;
             tL = tR = tD = -1;
             bool stop = false;  // the new sub-tree is discarded and the transition ends
             for (unsigned j = 0; j < n_leaf && !stop && !done; ++j) {
@@ -990,7 +1052,9 @@ struct ChainCtx {
                     if (dir > 0) tL = sL;
                     else tR = sR;
                     t_ls = new_ls;
-                    lv_valid &= ~(1u << k);
+                    // level k is consumed: its slots live on only through (tL, tR, tD).  Parked
+                    // sub-trees are disjoint sets of leaves, so clearing cannot hit another level.
+                    lv_live &= ~((1ull << sL) | (1ull << sR) | (1ull << sD));
                     ++k;
                     if (turn) {
                         stop = true;
@@ -1007,15 +1071,17 @@ struct ChainCtx {
                     sh->lvLS[k] = t_ls;
                 }
                 g.sync();
-                lv_valid |= 1u << k;
+                lv_live |= (1ull << tL) | (1ull << tR) | (1ull << tD);
                 tL = tR = tD = -1;
                 prev = dst;
             }
             if (stop) done = true;
         }
+        flush_acc();
+        defer_acc = false;
         if (!done) info.maxdepth_reached = 1;
         info.depth = depth;
-        lv_valid = 0;
+        lv_live = 0;
         tL = tR = tD = -1;
         return mD;
     }
@@ -1053,7 +1119,7 @@ struct ChainCtx {
         const uint32_t keep_count = acc_count;
         mL = mR = mD = point;
         tL = tR = tD = -1;
-        lv_valid = 0;
+        lv_live = 0;
         init_momentum(point, RNG_STEP_INIT, rng_draw);
         const int nxt = alloc();
         step_size = st().initial_step;

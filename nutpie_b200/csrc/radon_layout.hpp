@@ -33,7 +33,7 @@ inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
     auto key = [&](int o) { return 2 * county[o] + (floor[o] ? 1 : 0); };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
     const int per = (n_obs + T - 1) / T;  // observations per thread
-    L.n_steps = ((per > 0 ? per : 1) + 3) / 4 * 4;  // the device loop is unrolled by 4
+    L.n_steps = per > 0 ? per : 1;  // the device loop takes four at a time, then the remainder
     const int32_t dummy_mu = (int32_t)(2 * n_county) * 8;  // byte offset of mu[2J] (always 0)
     L.obs.assign((size_t)L.n_steps * T, RadonObs{0.0, dummy_mu, 0});
     L.group_base.assign(T, 0);

@@ -60,7 +60,7 @@ static int run_all_nit(const nb200_settings* st, const typename M::Data& md, uin
             ChainCtx<M, GroupSerial, NIT> ctx;
             std::memset((void*)&ctx, 0, sizeof(ctx));
             ctx.P = &P; ctx.md = P.mdata; ctx.sh = &sh; ctx.msm = msm.data();
-            ctx.front = stage.data(); ctx.front_slot = -1; ctx.sweep_rev = false;
+            ctx.front = stage.data(); ctx.front_slot = -1; ctx.sweep_rev = false; ctx.n_parked = 0; ctx.defer_acc = false;
             std::fill(stage.begin(), stage.end(), -555.0);
             ctx.D = P.D; ctx.Dp = P.Dp; ctx.NS = P.NS;
             ctx.chain_local = c;
