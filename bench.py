@@ -52,9 +52,9 @@ WORKLOAD = "radon_hierarchical_D175_1024chains_per_gpu_1000tune_1000draws"
 
 # DRAM bytes per gradient evaluation of nuts_kernel, from the committed `ncu --set full`
 # captures (dram__bytes_read.sum + dram__bytes_write.sum over the capture's leapfrog count):
-#   profiles/r1_radon_nuts_kernel_latest.txt   : 720.7 MB / 1 323 933 evaluations
+#   profiles/r1_radon_nuts_kernel_latest.txt   : 729.7 MB / 1 323 933 evaluations
 #   profiles/r1_config4_nuts_kernel_latest.txt : 1055.9 GB / 1 383 687 evaluations
-NCU_DRAM_BYTES_PER_EVAL = {"radon": 720.66e6 / 1323933, "config4": 1055.889e9 / 1383687}
+NCU_DRAM_BYTES_PER_EVAL = {"radon": 729.67e6 / 1323933, "config4": 1055.889e9 / 1383687}
 
 
 def _peaks():
