@@ -89,6 +89,86 @@ def _trace_to_groups(trace: _lib.PyTrace, compiled_model, settings, save_warmup,
     return out
 
 
+def _add_arrow_data(data_dict, max_length, batch, chain, n_chains, dims, skip_vars):
+    """python/nutpie/sample.py:167-214 on the pyarrow API: write one chain's RecordBatch into
+    [chain, draw, *shape] arrays padded to `max_length` draws (NaN / None / 0 by dtype)."""
+    import pyarrow
+
+    num_draws = batch.num_rows
+    for name in batch.schema.names:
+        if name in skip_vars:
+            continue
+        meta = batch.schema.field(name).metadata or {}
+        item_dims = meta.get(b"dims", b"").decode("utf-8")
+        item_dims = item_dims.split(",") if item_dims else []
+        item_shape = meta.get(b"shape", b"").decode("utf-8")
+        item_shape = [int(x) for x in item_shape.split(",")] if item_shape else []
+        total_shape = [n_chains, max_length, *item_shape]
+        col = batch.column(name)
+        if isinstance(col, pyarrow.ChunkedArray):
+            col = col.combine_chunks()
+        is_null = col.is_null()
+        while hasattr(col, "flatten") and pyarrow.types.is_nested(col.type):
+            col = col.flatten()
+        dtype = col.type.to_pandas_dtype()
+        if name not in data_dict:
+            if dtype in (np.float64, np.float32):
+                data = np.full(total_shape, np.nan, dtype=dtype)
+            elif dtype == np.dtype("O"):
+                data = np.full(total_shape, None, dtype=dtype)
+            else:
+                data = np.zeros(total_shape, dtype=dtype)
+            data_dict[name] = data
+            dims[name] = item_dims
+        values = col.to_numpy(zero_copy_only=False)
+        if is_null.sum().as_py() == 0:
+            data_dict[name][chain, :num_draws] = values.reshape((num_draws,) + tuple(item_shape))
+        else:
+            mask = ~is_null.to_numpy(zero_copy_only=False)
+            if values.shape[0] == num_draws:
+                values = values[mask]
+            data_dict[name][chain, :num_draws][mask] = values.reshape((mask.sum(),) + tuple(item_shape))
+
+
+def _arrow_to_groups(draw_batches, stat_batches, skip_vars=None, reparameterized_names=None,
+                     keep_unconstrained_draw=False, coords=None, save_warmup=True, attrs=None):
+    """`_arrow_to_arviz` (python/nutpie/sample.py:62-164) for per-chain Arrow RecordBatch pairs —
+    the form `PyTrace.get_arrow_trace()` and the Rust shim hand over (src/wrapper.rs:1477-1494):
+    split every chain at its own number of tuning rows (the `tuning` column), pad ragged chains,
+    move reparameterized value variables to `unconstrained_posterior`.  Returns the `Trace`
+    groups (converted by `_maybe_arviz` when arviz is importable)."""
+    skip_vars = list(skip_vars or [])
+    reparameterized_names = list(reparameterized_names or [])
+    n_chains = len(draw_batches)
+    assert n_chains == len(stat_batches)
+    max_tuning = max_posterior = 0
+    num_tuning = []
+    for draw, stat in zip(draw_batches, stat_batches):
+        n_tune = int(np.asarray(stat.column("tuning").to_numpy(zero_copy_only=False)).sum())
+        assert draw.num_rows == stat.num_rows
+        max_tuning = max(max_tuning, n_tune)
+        max_posterior = max(max_posterior, draw.num_rows - n_tune)
+        num_tuning.append(n_tune)
+    data_tune, data_post, stats_tune, stats_post, dims = {}, {}, {}, {}, {}
+    for i, draw in enumerate(draw_batches):
+        _add_arrow_data(data_tune, max_tuning, draw.slice(0, num_tuning[i]), i, n_chains, dims, [])
+        _add_arrow_data(data_post, max_posterior, draw.slice(num_tuning[i], draw.num_rows - num_tuning[i]),
+                        i, n_chains, dims, [])
+    for i, stat in enumerate(stat_batches):
+        _add_arrow_data(stats_tune, max_tuning, stat.slice(0, num_tuning[i]), i, n_chains, dims, skip_vars)
+        _add_arrow_data(stats_post, max_posterior, stat.slice(num_tuning[i], stat.num_rows - num_tuning[i]),
+                        i, n_chains, dims, skip_vars)
+    uc_post = {n: data_post.pop(n) for n in reparameterized_names if n in data_post}
+    uc_tune = {n: data_tune.pop(n) for n in reparameterized_names if n in data_tune}
+    out = Trace(posterior=data_post, sample_stats=stats_post, dims=dims, coords=dict(coords or {}),
+                attrs=dict(attrs or {}))
+    if save_warmup:
+        out.warmup_posterior, out.warmup_sample_stats = data_tune, stats_tune
+    if keep_unconstrained_draw and uc_post:
+        out.unconstrained_posterior = uc_post
+    return out
+
+
 def _maybe_arviz(tr: Trace):
     try:
         import arviz  # noqa: F401

@@ -252,3 +252,72 @@ def test_oracle_logreg_gradient_by_finite_differences():
         e = np.zeros(6); e[i] = h
         fd = (om.logp_grad(q + e)[0] - om.logp_grad(q - e)[0]) / (2 * h)
         assert abs(fd - g[i]) < 1e-6 * max(1.0, abs(g[i]))
+
+
+def test_arrow_batches_round_trip_through_the_reference_consumer():
+    """`PyTrace.get_arrow_trace()` (src/wrapper.rs:1477-1494) hands one
+    (posterior, sample_stats) RecordBatch pair per chain with `dims` / `shape` field metadata;
+    `_arrow_to_groups` — `_arrow_to_arviz` / `_add_arrow_data` of python/nutpie/sample.py:62-214
+    on the pyarrow API — must rebuild exactly what the dense path (`_trace_to_groups`) builds,
+    including ragged chains (a run aborted mid-way) padded with NaN / 0."""
+    pytest.importorskip("pyarrow")
+    import nutpie_b200
+    from nutpie_b200 import _lib
+    import importlib
+
+    S = importlib.import_module("nutpie_b200.sample")  # (the package re-exports the function `sample`)
+
+    J, n_chains, tune, draws = 5, 3, 4, 6
+    rng = np.random.default_rng(0)
+    cm = nutpie_b200.radon_model(np.zeros(7), np.arange(7) % J, np.zeros(7), J)
+    n_rows = tune + draws
+    q = rng.normal(size=(n_chains, n_rows, cm.n_dim))
+    stats = rng.normal(size=(n_chains, n_rows, _lib.NSTAT))
+    stats[..., _lib.STAT_NAMES.index("tuning")] = (np.arange(n_rows) < tune)[None, :]
+    for nm in ("depth", "n_steps", "draw", "chain"):
+        stats[..., _lib.STAT_NAMES.index(nm)] = rng.integers(0, 9, size=(n_chains, n_rows))
+    for nm in ("diverging", "maxdepth_reached"):
+        stats[..., _lib.STAT_NAMES.index(nm)] = rng.integers(0, 2, size=(n_chains, n_rows))
+    stats[..., _lib.STAT_NAMES.index("index_in_trajectory")] = rng.integers(-5, 5, size=(n_chains, n_rows))
+    grads = rng.normal(size=(n_chains, n_rows, cm.n_dim))
+
+    def trace(rows):
+        return _lib.PyTrace(q, stats, np.asarray(rows, dtype=np.uint64), gradients=grads,
+                            variables=cm._variable_dims(), expand=cm._expand)
+
+    class _S:  # the settings fields _trace_to_groups reads
+        num_tune = tune
+
+        def as_dict(self):
+            return {}
+
+    # complete run: identical to the dense path, variable by variable
+    dense = S._trace_to_groups(trace([n_rows] * n_chains), cm, _S(), True)
+    pairs = trace([n_rows] * n_chains).get_arrow_trace()
+    post, st = [p for p, _ in pairs], [s for _, s in pairs]
+    assert post[0].schema.field("county_effect").metadata == {b"dims": b"county", b"shape": str(J).encode()}
+    via = S._arrow_to_groups(post, st, skip_vars=["tuning", "draw", "chain"], coords=cm.coords)
+    assert set(via.posterior) == set(dense.posterior)
+    for name, a in dense.posterior.items():
+        np.testing.assert_array_equal(via.posterior[name], a)
+        np.testing.assert_array_equal(via.warmup_posterior[name], dense.warmup_posterior[name])
+        assert via.dims[name] == list(cm.dims[name])
+    for name, a in dense.sample_stats.items():
+        np.testing.assert_array_equal(via.sample_stats[name], a)
+        assert via.sample_stats[name].dtype == a.dtype, name
+        np.testing.assert_array_equal(via.warmup_sample_stats[name], dense.warmup_sample_stats[name])
+    assert via.dims["gradient"] == ["unconstrained_parameter"]
+    assert "tuning" not in via.sample_stats
+    # reparameterized value variables move out of the posterior (compile_pymc.py:810-814)
+    uc = S._arrow_to_groups(post, st, reparameterized_names=["sigma"], keep_unconstrained_draw=True)
+    assert "sigma" not in uc.posterior and uc.unconstrained_posterior["sigma"].shape == (n_chains, draws)
+    # ragged chains: chain 1 stopped inside warm-up, chain 2 after two posterior draws
+    rows = [n_rows, 3, tune + 2]
+    pairs = trace(rows).get_arrow_trace()
+    rag = S._arrow_to_groups([p for p, _ in pairs], [s for _, s in pairs])
+    sig = rag.posterior["sigma"]
+    assert sig.shape == (n_chains, draws) and rag.warmup_posterior["sigma"].shape == (n_chains, tune)
+    assert np.isnan(sig[1]).all() and np.isnan(sig[2, 2:]).all() and not np.isnan(sig[2, :2]).any()
+    assert np.isnan(rag.warmup_posterior["sigma"][1, 3:]).all()
+    np.testing.assert_array_equal(sig[0], np.exp(q[0, tune:, 2 * J + 4]))
+    assert rag.sample_stats["n_steps"][1].sum() == 0  # integer columns pad with 0
