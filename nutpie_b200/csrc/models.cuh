@@ -230,6 +230,7 @@ struct RadonModel {
         const double inv_s2 = inv_sigma * inv_sigma;
         double* mu = sm;                // [2J+1] linear predictor per (county, floor)
         double* gsum = sm + 2 * J + 1;  // [G+1]  per-group sum of residuals
+#pragma unroll 1
         for (int c = grp.tid; c < J; c += T) {
             const double a = intercept + q[1 + c] * sd_a;
             mu[2 * c] = a;

@@ -1016,19 +1016,31 @@ struct ChainCtx {
                     bool turn = false;
                     if (check) {
                         const int far_s = dir > 0 ? sL : sR, near_s = dir > 0 ? sR : sL;
-                        if (k == 0) {
-                            // the single pair (s, N); s is N's predecessor
-                            turn = fuse_l0 ? l0_turn : is_turning(far_s, dst);
-                        } else {
-                            const bool a = pair_with_new(far_s, dst);
-                            const bool b = pair_with_new(near_s, dst);
-                            bool c;
-                            if constexpr (kMaxFused > 0) {
-                                c = (spec_bits >> (with_main ? 31 : k)) & 1u;
+                        if constexpr (kMaxFused > 0) {
+                            if (k == 0) {
+                                // the single pair (s, N); s is N's predecessor
+                                turn = fuse_l0 ? l0_turn : is_turning(far_s, dst);
                             } else {
-                                c = is_turning(far_s, dir > 0 ? tL : tR);
+                                const bool a = pair_with_new(far_s, dst);
+                                const bool b = pair_with_new(near_s, dst);
+                                const bool c = (spec_bits >> (with_main ? 31 : k)) & 1u;
+                                turn = a | b | c;
                             }
-                            turn = a | b | c;
+                        } else {
+                            // No fused partners: every pair is a separate pass.  ONE inlined
+                            // copy of is_turning() walked by a rolled loop over the (up to
+                            // three) pairs — four copies were 420 more instructions in a loop
+                            // that is bound by instruction fetch.  The verdict is an OR, so
+                            // stopping at the first turning pair changes nothing.
+                            int n_pairs = 3;
+                            if (k == 0) {
+                                n_pairs = fuse_l0 ? 0 : 1;  // (s, N) with s = N's predecessor
+                                turn = fuse_l0 && l0_turn;
+                            }
+                            const int t_first = dir > 0 ? tL : tR;
+#pragma unroll 1
+                            for (int w = 0; w < n_pairs && !turn; ++w)
+                                turn = is_turning(w == 1 ? near_s : far_s, w == 2 ? t_first : dst);
                         }
                     }
                     const double new_ls = nb_logaddexp(s_ls, t_ls);
