@@ -132,12 +132,14 @@ struct SampleInfo {
     int depth, diverging, maxdepth_reached;
 };
 
+// log(exp(a) + exp(b)); one inlined exp / log1p pair for both orderings (the two-branch form of
+// the oracle computes the same values with twice the code in the merge loop)
 NB_HD double nb_logaddexp(double a, double b) {
     if (a == b) return a + 0.69314718055994530941723212145818;
-    double diff = a - b;
-    if (diff > 0) return a + log1p(exp(-diff));
-    if (diff < 0) return b + log1p(exp(diff));
-    return diff;
+    const double diff = a - b;
+    if (diff != diff) return diff;  // NaN
+    const double hi = diff > 0 ? a : b;
+    return hi + log1p(exp(-fabs(diff)));
 }
 
 #ifdef __CUDACC__
