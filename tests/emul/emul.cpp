@@ -90,6 +90,237 @@ static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-lane emulation: T logical threads of ONE chain run the very code the GPU runs for a
+// T-thread group (per-thread ChainCtx, shared pool / front / scratch), as cooperative fibers that
+// hand over at every sync() / reduce() in lane order.  Between two hand-overs a lane runs alone,
+// which is one of the schedules independent thread scheduling allows: a missing barrier in the
+// core shows up as a wrong result here.  reduce() adds in the association order of
+// GroupCuda::warp_reduce (xor butterfly) followed by the fixed-order cross-warp sum.
+#include <ucontext.h>
+
+struct LaneSched {
+    int T = 0, cur = 0;
+    std::vector<ucontext_t> ctx;
+    ucontext_t main_ctx;
+    std::vector<std::vector<char>> stacks;
+    std::vector<char> alive;
+    std::vector<double> red;  // [T][kMaxRed]
+    static constexpr int kMaxRed = 16;
+    void (*body)(int lane, void* arg) = nullptr;
+    void* arg = nullptr;
+    // Order in which the lanes run between two barriers: 0 ascending, 1 descending, >= 2 a new
+    // pseudo-random permutation after every barrier (seeded by the value).  Every order is a legal
+    // schedule, so the results must not depend on it.
+    int order = 0;
+    std::vector<int> perm;
+    int pos = 0;
+    uint64_t lcg = 0;
+    void new_epoch() {
+        if (order < 2) return;
+        for (int i = T - 1; i > 0; --i) {
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            std::swap(perm[i], perm[(int)((lcg >> 33) % (uint64_t)(i + 1))]);
+        }
+    }
+    void yield() {
+        int n_alive = 0;
+        for (int l = 0; l < T; ++l) n_alive += alive[l];
+        if (n_alive <= 1) return;
+        do {
+            if (++pos >= T) {
+                pos = 0;
+                new_epoch();
+            }
+        } while (!alive[perm[pos]]);
+        const int to = perm[pos];
+        if (to == cur) return;
+        const int from = cur;
+        cur = to;
+        swapcontext(&ctx[from], &ctx[to]);
+    }
+};
+static LaneSched* g_sched = nullptr;
+static void lane_trampoline(int lane) {
+    g_sched->body(lane, g_sched->arg);
+    g_sched->alive[lane] = 0;  // back to run_lanes() through uc_link
+}
+static void run_lanes(LaneSched& S, int T, void (*body)(int, void*), void* arg) {
+    S.T = T; S.body = body; S.arg = arg;
+    S.ctx.assign(T, ucontext_t());
+    S.stacks.assign(T, std::vector<char>(256 * 1024));
+    S.alive.assign(T, 1);
+    S.red.assign((size_t)T * LaneSched::kMaxRed, 0.0);
+    S.perm.resize(T);
+    for (int l = 0; l < T; ++l) S.perm[l] = S.order == 1 ? T - 1 - l : l;
+    S.lcg = 0x9E3779B97F4A7C15ull * (uint64_t)(S.order + 1);
+    S.new_epoch();
+    S.pos = 0;
+    g_sched = &S;
+    for (int l = 0; l < T; ++l) {
+        getcontext(&S.ctx[l]);
+        S.ctx[l].uc_stack.ss_sp = S.stacks[l].data();
+        S.ctx[l].uc_stack.ss_size = S.stacks[l].size();
+        S.ctx[l].uc_link = &S.main_ctx;
+        makecontext(&S.ctx[l], (void (*)())lane_trampoline, 1, l);
+    }
+    for (;;) {
+        int next = -1;
+        for (int i = 0; i < T; ++i)
+            if (S.alive[S.perm[i]]) { next = S.perm[i]; S.pos = i; break; }
+        if (next < 0) break;
+        S.cur = next;
+        swapcontext(&S.main_ctx, &S.ctx[next]);
+    }
+    g_sched = nullptr;
+}
+
+template <int T>
+struct GroupLanes {
+    static constexpr int kThreads = T;
+    int tid;
+    LaneSched* s;
+    int size() const { return T; }
+    void sync() const { s->yield(); }
+    template <int N>
+    void reduce(double (&v)[N]) const {
+        static_assert(N <= LaneSched::kMaxRed, "reduction too wide for the emulation");
+        double* red = s->red.data();
+        for (int i = 0; i < N; ++i) red[(size_t)tid * LaneSched::kMaxRed + i] = v[i];
+        s->yield();  // every lane has published its partials
+        for (int i = 0; i < N; ++i) {
+            double total = 0.0;
+            for (int w = 0; w < T / 32; ++w) {  // fixed-order sum over the warps of the group
+                double x[32], y[32];
+                for (int l = 0; l < 32; ++l) x[l] = red[(size_t)(w * 32 + l) * LaneSched::kMaxRed + i];
+                for (int lv = 0; lv < 5; ++lv) {
+                    // N < 4: offsets 16, 8, 4, 2, 1; N >= 4 (recursive halving): 1, 2, 4, 8, 16
+                    const int off = N < 4 ? (16 >> lv) : (1 << lv);
+                    for (int l = 0; l < 32; ++l) y[l] = x[l] + x[l ^ off];
+                    for (int l = 0; l < 32; ++l) x[l] = y[l];
+                }
+                total = (T == 32) ? x[0] : total + x[0];
+            }
+            v[i] = total;
+        }
+        s->yield();  // every lane has read: the scratch may be reused
+    }
+};
+
+template <class M, int T, int NIT>
+struct LaneLaunch {
+    const KParams<M>* P;
+    ChainShared* sh;
+    double *msm, *front, *pool, *var, *wf, *spool, *svar;
+    uint64_t chain, chain_id_offset;
+    LaneSched* sched;
+    static void body(int lane, void* arg) {
+        LaneLaunch& L = *static_cast<LaneLaunch*>(arg);
+        const KParams<M>& P = *L.P;
+        ChainCtx<M, GroupLanes<T>, NIT> ctx;
+        std::memset((void*)&ctx, 0, sizeof(ctx));
+        ctx.g.tid = lane;
+        ctx.g.s = L.sched;
+        ctx.P = &P; ctx.md = P.mdata; ctx.sh = L.sh; ctx.msm = L.msm;
+        ctx.front = L.front; ctx.front_slot = -1; ctx.sweep_rev = false; ctx.n_parked = 0; ctx.defer_acc = false;
+        ctx.D = P.D; ctx.Dp = P.Dp; ctx.NS = P.NS;
+        ctx.chain_local = L.chain;
+        ctx.chain_gid = (uint32_t)(L.chain_id_offset + L.chain);
+        ctx.pool = L.pool; ctx.varg = L.var; ctx.wf = L.wf;
+        ctx.var = P.var_in_smem ? L.svar : L.var;
+        ctx.spool = L.spool; ctx.smem_slots = P.smem_slots;
+        ctx.mL = ctx.mR = ctx.mD = ctx.tL = ctx.tR = ctx.tD = -1;
+        ctx.run();
+    }
+};
+
+template <class M, int T, int NIT>
+static int run_lanes_nit(const nb200_settings* st, const typename M::Data& md, uint64_t dim,
+                         uint64_t n_chains, uint64_t chain_id_offset, double* draws, double* stats,
+                         uint64_t* total_steps, int max_per_launch, int smem_slots, int lane_order) {
+    KParams<M> P;
+    std::memset(&P, 0, sizeof(P));
+    P.st = *st;
+    P.mdata = md;
+    P.D = (int)dim;
+    P.Dp = (int)((dim + 3) / 4 * 4);
+    P.NS = 3 * ((int)st->maxdepth + 1) + 3;
+    if (P.NS > kMaxSlots) return NB200_EINVAL;
+    P.n_chains = n_chains;
+    P.chain_id_offset = chain_id_offset;
+    P.n_total = st->num_tune + st->num_draws;
+    P.n_rows = st->save_warmup ? P.n_total : st->num_draws;
+    P.sdim = dim; P.gdim = dim;
+    P.max_draws_per_launch = max_per_launch;
+    P.smem_slots = smem_slots < P.NS ? smem_slots : P.NS;
+    P.var_in_smem = smem_slots > 0;
+    std::vector<double> pool((size_t)P.NS * 4 * P.Dp), var(P.Dp), wf(8 * (size_t)P.Dp);
+    std::vector<ChainScalars> sc(n_chains);
+    std::memset(sc.data(), 0, sizeof(ChainScalars) * n_chains);
+    P.sc = sc.data();
+    P.draws = draws; P.stats = stats;
+    std::vector<double> msm(M::smem_doubles(md, T) + 1), front(4 * (size_t)P.Dp + 1);
+    std::vector<double> spool((size_t)P.smem_slots * 4 * P.Dp + 1), svar(P.Dp);
+    ChainShared sh;
+    uint64_t steps = 0;
+    int err = 0;
+    for (uint64_t c = 0; c < n_chains; ++c) {
+        std::fill(pool.begin(), pool.end(), 0.0);
+        for (;;) {
+            std::fill(spool.begin(), spool.end(), -777.0);
+            std::fill(svar.begin(), svar.end(), -777.0);
+            std::fill(front.begin(), front.end(), -555.0);
+            LaneSched sched;
+            sched.order = lane_order;
+            LaneLaunch<M, T, NIT> L{&P, &sh, msm.data(), front.data(), pool.data(), var.data(), wf.data(),
+                                    spool.data(), svar.data(), c, chain_id_offset, &sched};
+            run_lanes(sched, T, &LaneLaunch<M, T, NIT>::body, &L);
+            if (sc[c].status == 2 || sc[c].status < 0) break;
+        }
+        if (sc[c].status < 0) err = sc[c].status;
+        steps += sc[c].total_steps;
+    }
+    if (total_steps) *total_steps = steps;
+    return err;
+}
+
+// T lanes per chain with the trip count the product picks for (T, dim): ceil(dim / T), unrolled
+extern "C" int emul_sample_lanes(const nb200_settings* st, const nb200_model_desc* model, int T,
+                                 uint64_t n_chains, uint64_t chain_id_offset, double* draws,
+                                 double* stats, uint64_t* total_steps, int max_per_launch,
+                                 int smem_slots, int lane_order) {
+    const uint64_t dim = model->dim;
+    const int nit = (int)((dim + T - 1) / T);
+#define LANES_CASE(MODEL, DATA, TT, NN)                                                          \
+    if (T == TT && nit == NN)                                                                    \
+        return run_lanes_nit<MODEL, TT, NN>(st, DATA, dim, n_chains, chain_id_offset, draws, stats, \
+                                            total_steps, max_per_launch, smem_slots, lane_order);
+    switch (model->kind) {
+    case NB200_MODEL_NORMAL: {
+        NormalModel::Data d{model->mu, 1.0 / (model->sigma * model->sigma)};
+        LANES_CASE(NormalModel, d, 32, 1) LANES_CASE(NormalModel, d, 32, 2) LANES_CASE(NormalModel, d, 64, 1)
+        if (T == 32) return run_lanes_nit<NormalModel, 32, 0>(st, d, dim, n_chains, chain_id_offset, draws, stats,
+                                                              total_steps, max_per_launch, smem_slots, lane_order);
+        break;
+    }
+    case NB200_MODEL_FUNNEL: {
+        FunnelModel::Data d{0};
+        LANES_CASE(FunnelModel, d, 32, 1)
+        break;
+    }
+    case NB200_MODEL_RADON: {
+        RadonLayout L = build_radon_layout(model->n_obs, model->n_county, model->y, model->county,
+                                           model->floor, T);
+        RadonModel::Data d{L.J, L.N, L.n_steps, L.G, L.kmax, T, 0, L.obs.data(), L.group_base.data(),
+                           L.group_list.data()};
+        LANES_CASE(RadonModel, d, 32, 6) LANES_CASE(RadonModel, d, 64, 3) LANES_CASE(RadonModel, d, 128, 2)
+        break;
+    }
+    }
+#undef LANES_CASE
+    return NB200_EINVAL;
+}
+
 extern "C" int emul_sample(const nb200_settings* st, const nb200_model_desc* model,
                            uint64_t n_chains, uint64_t chain_id_offset, const double* q0,
                            const double* init_mean, const double* z_tape, double* draws,

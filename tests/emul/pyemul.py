@@ -9,6 +9,7 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 _LIB = None
+_LIB_NOBARRIER = None
 
 
 class ModelDesc(C.Structure):
@@ -49,6 +50,16 @@ def lib():
     return _LIB
 
 
+def lib_nobarrier():
+    """The core with ONE barrier of the leapfrog removed (negative control of the race check)."""
+    global _LIB_NOBARRIER
+    if _LIB_NOBARRIER is None:
+        subprocess.run(["make", "-C", str(_HERE), "libnuts_emul_nobarrier.so"], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        _LIB_NOBARRIER = C.CDLL(str(_HERE / "libnuts_emul_nobarrier.so"))
+    return _LIB_NOBARRIER
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -81,3 +92,25 @@ def sample(kind, dim, settings, n_chains, chain_id_offset=0, q0=None, init_mean=
     tv = lambda a: None if a is None else a.transpose(1, 0, 2)
     return dict(draws=tv(draws), stats=tv(stats), gradients=tv(grads), mass_matrix_inv=tv(mm),
                 total_steps=int(steps.value))
+
+
+def sample_lanes(kind, dim, settings, n_chains, threads_per_chain=32, chain_id_offset=0, max_per_launch=0,
+                 smem_slots=0, lane_order=0, drop_barrier=False, **model_kw):
+    """The same core run by `threads_per_chain` cooperative lanes per chain (GroupLanes in
+    emul.cpp): the geometry, per-thread loops, shared-memory tier and density layouts the GPU uses.
+    lane_order: 0 lanes run in ascending order between barriers, 1 descending, >= 2 a fresh
+    pseudo-random order after every barrier."""
+    L = lib_nobarrier() if drop_barrier else lib()
+    L.emul_sample_lanes.restype = C.c_int
+    desc, keep = make_desc(kind, dim, **model_kw)
+    n_total = settings.num_tune + settings.num_draws
+    n_rows = n_total if settings.save_warmup else settings.num_draws
+    draws = np.zeros((n_rows, n_chains, dim))
+    stats = np.zeros((n_rows, n_chains, 16))
+    steps = C.c_uint64(0)
+    rc = L.emul_sample_lanes(C.byref(settings), C.byref(desc), C.c_int(threads_per_chain), C.c_uint64(n_chains),
+                             C.c_uint64(chain_id_offset), _ptr(draws), _ptr(stats), C.byref(steps),
+                             C.c_int(max_per_launch), C.c_int(smem_slots), C.c_int(lane_order))
+    if rc != 0:
+        raise RuntimeError(f"emul_sample_lanes failed: {rc}")
+    return dict(draws=draws.transpose(1, 0, 2), stats=stats.transpose(1, 0, 2), total_steps=int(steps.value))

@@ -66,3 +66,82 @@ def test_emulated_radon_tracks_oracle(radon_data):
     dd = np.abs(a["draws"] - b["draws"]).max(axis=(0, 2))
     assert dd[0] < 1e-12 and dd[:5].max() < 1e-8
     assert abs(a["total_steps"] - b["total_steps"]) / a["total_steps"] < 0.25  # 3 short chaotic chains
+
+
+# ---- the same core run by T cooperative lanes per chain (GroupLanes, tests/emul/emul.cpp): the
+# ---- per-thread loops (NIT), shared-memory tier, reductions and density layouts of the GPU geometry
+
+STAT = {n: i for i, n in enumerate(O.STAT_NAMES)}
+
+
+@pytest.mark.parametrize("kind,dim,kw,tpc", [
+    ("normal", 37, dict(mu=1.0, sigma=2.0), 32),   # NIT = 2, predicated tail
+    ("normal", 100, {}, 32),                      # run-time trip count
+    ("normal", 40, {}, 64),                       # two warps per chain: cross-warp reduction
+])
+def test_lane_emulation_reproduces_oracle_trees(kind, dim, kw, tpc):
+    """A warp (or two) per chain: every lane owns dimensions tid, tid + T, ...; sums are taken in
+    the butterfly order of GroupCuda::warp_reduce.  The trees must be the oracle's, draw for
+    draw; positions differ by the rounding of the differently ordered sums."""
+    s = O.default_settings(seed=5, num_tune=80, num_draws=40)
+    a = O.sample(O.Model(kind, dim, **kw), s, 2)
+    b = E.sample_lanes(kind, dim, s, 2, threads_per_chain=tpc, smem_slots=3, **kw)
+    for k in ("depth", "n_steps", "index_in_trajectory", "diverging", "maxdepth_reached"):
+        assert np.array_equal(a["stats"][..., STAT[k]], b["stats"][..., STAT[k]]), k
+    np.testing.assert_allclose(b["draws"][:, :3], a["draws"][:, :3], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(b["draws"], a["draws"], rtol=0, atol=1e-5)  # rounding growth over 120 draws
+    np.testing.assert_allclose(b["stats"][..., STAT["step_size"]], a["stats"][..., STAT["step_size"]], rtol=1e-6)
+
+
+def test_lane_emulation_pause_resume_is_bit_identical():
+    s = O.default_settings(seed=9, num_tune=60, num_draws=30)
+    a = E.sample_lanes("funnel", 9, s, 2, threads_per_chain=32, smem_slots=5)
+    b = E.sample_lanes("funnel", 9, s, 2, threads_per_chain=32, smem_slots=5, max_per_launch=17)
+    assert np.array_equal(a["draws"], b["draws"]) and np.array_equal(a["stats"], b["stats"])
+    c = O.sample(O.Model("funnel", 9), s, 2)
+    np.testing.assert_allclose(a["draws"][:, :3], c["draws"][:, :3], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("tpc,slots", [(32, 3), (64, 0)])
+def test_lane_emulation_radon_production_geometry(radon_data, tpc, slots):
+    """The radon density exactly as the B200 runs it — observations cut into one contiguous range
+    per lane, prefix sums published at group ends, per-county gradients from the (county, floor)
+    piece lists, 6 unrolled dimensions per lane, momentum tier in 'shared memory' — against the
+    oracle's file-order evaluation: equal to rounding on the first draws."""
+    d = radon_data
+    J = d["n_county"]; D = 2 * J + 5
+    s = O.default_settings(seed=3, num_tune=40, num_draws=10, init_radius=1.0)
+    a = O.sample(O.Model("radon", D, y=d["y"], county=d["county"], floor=d["floor"], n_county=J), s, 2)
+    b = E.sample_lanes("radon", D, s, 2, threads_per_chain=tpc, smem_slots=slots, y=d["y"],
+                       county=d["county"], floor=d["floor"], n_county=J)
+    dd = np.abs(a["draws"] - b["draws"]).max(axis=(0, 2))
+    assert dd[0] < 1e-12 and dd[:5].max() < 1e-8, dd[:5]
+    assert np.array_equal(a["stats"][:, :5, STAT["n_steps"]], b["stats"][:, :5, STAT["n_steps"]])
+    assert abs(a["total_steps"] - b["total_steps"]) / a["total_steps"] < 0.25
+
+
+@pytest.mark.parametrize("kind,dim,tpc,slots", [("radon", 175, 32, 3), ("radon", 175, 64, 2), ("funnel", 9, 32, 4),
+                                                 ("normal", 100, 32, 3), ("normal", 40, 64, 3)])
+def test_lane_schedule_independence(radon_data, kind, dim, tpc, slots):
+    """Race check of the core.  Between two barriers the emulation runs the lanes of a chain one
+    after another; ascending, descending and freshly shuffled orders after every barrier are all
+    schedules independent thread scheduling allows, so a core with every needed barrier gives
+    bit-identical results under each.  (Negative control below: one barrier removed.)"""
+    kw = {}
+    if kind == "radon":
+        d = radon_data
+        kw = dict(y=d["y"], county=d["county"], floor=d["floor"], n_county=d["n_county"])
+    s = O.default_settings(seed=3, num_tune=40, num_draws=10, init_radius=1.0)
+    runs = [E.sample_lanes(kind, dim, s, 2, threads_per_chain=tpc, smem_slots=slots, lane_order=o,
+                           max_per_launch=23, **kw) for o in (0, 1, 2, 7)]
+    for r in runs[1:]:
+        assert np.array_equal(runs[0]["draws"], r["draws"]) and np.array_equal(runs[0]["stats"], r["stats"])
+
+
+def test_lane_schedule_check_detects_a_missing_barrier():
+    """The same check on a build of the core without the barrier that publishes a new leaf's
+    scalars (NB200_EMUL_DROP_BARRIER): the results now depend on the lane order."""
+    s = O.default_settings(seed=3, num_tune=40, num_draws=10)
+    a = E.sample_lanes("normal", 37, s, 2, threads_per_chain=32, smem_slots=3, lane_order=0, drop_barrier=True)
+    b = E.sample_lanes("normal", 37, s, 2, threads_per_chain=32, smem_slots=3, lane_order=1, drop_barrier=True)
+    assert not np.array_equal(a["draws"], b["draws"])
