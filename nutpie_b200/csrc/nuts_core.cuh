@@ -22,9 +22,13 @@
 // (index in trajectory, potential, kinetic energy) and the level stack live in
 // shared memory.
 //
-// Code-size discipline: leapfrog() is inlined at two call sites and
-// is_turning() at one (with every site inlined the kernel was 335 KB of SASS and
-// the profile showed instruction-fetch stalls).
+// Code-size discipline: with one warp per chain the kernel is bound by instruction
+// fetch (1-2 warps per scheduler walking ~3 K instructions per leapfrog), so the hot
+// loop keeps ONE inlined copy of leapfrog() and of is_turning() (a rolled loop walks
+// the pairs of a merge), one loop body per pass, rolled loops where unrolling buys
+// nothing; the only other copies of leapfrog() are the two cold ones inside the
+// step-size search.  The first version was 335 KB of SASS; every cut since measured
+// as a speed-up (profiles/r1_sweep_radon_codesize.txt).
 #pragma once
 #include "../../include/nutpie_b200.h"
 #include "group.cuh"
