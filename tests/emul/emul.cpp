@@ -314,6 +314,7 @@ extern "C" int emul_sample_lanes(const nb200_settings* st, const nb200_model_des
         RadonModel::Data d{L.J, L.N, L.n_steps, L.G, L.kmax, T, 0, L.obs.data(), L.group_base.data(),
                            L.group_list.data()};
         LANES_CASE(RadonModel, d, 32, 6) LANES_CASE(RadonModel, d, 64, 3) LANES_CASE(RadonModel, d, 128, 2)
+        LANES_CASE(RadonModel, d, 32, 1)
         break;
     }
     }

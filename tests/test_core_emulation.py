@@ -145,3 +145,39 @@ def test_lane_schedule_check_detects_a_missing_barrier():
     a = E.sample_lanes("normal", 37, s, 2, threads_per_chain=32, smem_slots=3, lane_order=0, drop_barrier=True)
     b = E.sample_lanes("normal", 37, s, 2, threads_per_chain=32, smem_slots=3, lane_order=1, drop_barrier=True)
     assert not np.array_equal(a["draws"], b["draws"])
+
+
+def _radon_edge_cases():
+    rng = np.random.default_rng(1)
+    J = 85
+    return [
+        ("few_observations", [0, 3, 3, 84, 84], [0, 1, 0, 0, 1], J),          # most lanes own nothing
+        ("one_observation", [42], [1], J),
+        ("one_county_holds_everything", [7] * 300, rng.integers(0, 2, 300), J),  # a pair cut into 32 pieces
+        ("all_floor_0", rng.integers(0, J, 200), [0] * 200, J),
+        ("all_floor_1", rng.integers(0, J, 200), [1] * 200, J),
+        ("empty_counties", rng.integers(0, J // 2, 500) * 2, rng.integers(0, 2, 500), J),
+        ("n_33", rng.integers(0, J, 33), rng.integers(0, 2, 33), J),            # one more than the lanes
+        ("n_1000_unsorted", rng.integers(0, J, 1000), rng.integers(0, 2, 1000), J),
+        ("three_counties", rng.integers(0, 3, 40), rng.integers(0, 2, 40), 3),   # D = 11: one dimension per lane
+    ]
+
+
+@pytest.mark.parametrize("name,county,floor,J", _radon_edge_cases(), ids=[c[0] for c in _radon_edge_cases()])
+def test_lane_emulation_radon_edge_layouts(name, county, floor, J):
+    """Ragged and degenerate inputs of the radon density's host 'compile' step (radon_layout.hpp)
+    at the GPU's lane geometry: lanes without observations, a (county, floor) pair cut into a piece
+    per lane, counties without observations, a single observation.  Same trees as the oracle,
+    positions equal to rounding."""
+    rng = np.random.default_rng(7)
+    county = np.asarray(county, dtype=np.int32)
+    floor = np.asarray(floor, dtype=np.uint8)
+    y = rng.normal(1.0, 0.8, size=len(county))
+    D = 2 * J + 5
+    s = O.default_settings(seed=2, num_tune=30, num_draws=10, init_radius=0.5)
+    kw = dict(y=y, county=county, floor=floor, n_county=J)
+    a = O.sample(O.Model("radon", D, **kw), s, 2)
+    b = E.sample_lanes("radon", D, s, 2, threads_per_chain=32, smem_slots=2, **kw)
+    dd = np.abs(a["draws"] - b["draws"]).max(axis=(0, 2))
+    assert dd[0] < 1e-11 and dd[:5].max() < 1e-7, dd[:5]  # rounding grows along the chain
+    assert np.array_equal(a["stats"][:, :5, STAT["n_steps"]], b["stats"][:, :5, STAT["n_steps"]])
