@@ -181,3 +181,27 @@ def test_lane_emulation_radon_edge_layouts(name, county, floor, J):
     dd = np.abs(a["draws"] - b["draws"]).max(axis=(0, 2))
     assert dd[0] < 1e-11 and dd[:5].max() < 1e-7, dd[:5]  # rounding grows along the chain
     assert np.array_equal(a["stats"][:, :5, STAT["n_steps"]], b["stats"][:, :5, STAT["n_steps"]])
+
+
+def test_core_is_clean_under_address_and_ub_sanitizers():
+    """Serial and lane emulation of the core from a library built with
+    -fsanitize=address,undefined: every index into the slot pool, the shared-memory tier, the
+    front buffer and the density scratch is in bounds for the geometries the GPU runs (radon at
+    32 / 64 lanes with 0, 3 and all slots on chip, maxdepth 12, chunked launches)."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    here = Path(E.__file__).resolve().parent
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not asan or not Path(asan).exists():
+        pytest.skip("libasan not available")
+    subprocess.run(["make", "-C", str(here), "libnuts_emul_asan.so"], check=True, stdout=subprocess.PIPE,
+                   stderr=subprocess.STDOUT)
+    env = dict(os.environ, LD_PRELOAD=asan,
+               ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:abort_on_error=1")
+    r = subprocess.run([sys.executable, str(here / "sanitize_run.py"), str(here / "libnuts_emul_asan.so")],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "SANITIZE-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+    assert "runtime error" not in r.stderr and "ERROR: AddressSanitizer" not in r.stderr, r.stderr[-4000:]
