@@ -237,7 +237,8 @@ struct LaneLaunch {
 template <class M, int T, int NIT>
 static int run_lanes_nit(const nb200_settings* st, const typename M::Data& md, uint64_t dim,
                          uint64_t n_chains, uint64_t chain_id_offset, double* draws, double* stats,
-                         uint64_t* total_steps, int max_per_launch, int smem_slots, int lane_order) {
+                         uint64_t* total_steps, int max_per_launch, int smem_slots, int lane_order,
+                         int expand) {
     KParams<M> P;
     std::memset(&P, 0, sizeof(P));
     P.st = *st;
@@ -250,7 +251,9 @@ static int run_lanes_nit(const nb200_settings* st, const typename M::Data& md, u
     P.chain_id_offset = chain_id_offset;
     P.n_total = st->num_tune + st->num_draws;
     P.n_rows = st->save_warmup ? P.n_total : st->num_draws;
-    P.sdim = dim; P.gdim = dim;
+    P.expand = expand;  // draws hold the expanded vector (Model::expand run by the lanes)
+    P.sdim = expand ? (uint64_t)M::expanded_dim((int)dim) : dim;
+    P.gdim = dim;
     P.max_draws_per_launch = max_per_launch;
     P.smem_slots = smem_slots < P.NS ? smem_slots : P.NS;
     P.var_in_smem = smem_slots > 0;
@@ -288,19 +291,19 @@ static int run_lanes_nit(const nb200_settings* st, const typename M::Data& md, u
 extern "C" int emul_sample_lanes(const nb200_settings* st, const nb200_model_desc* model, int T,
                                  uint64_t n_chains, uint64_t chain_id_offset, double* draws,
                                  double* stats, uint64_t* total_steps, int max_per_launch,
-                                 int smem_slots, int lane_order) {
+                                 int smem_slots, int lane_order, int expand) {
     const uint64_t dim = model->dim;
     const int nit = (int)((dim + T - 1) / T);
 #define LANES_CASE(MODEL, DATA, TT, NN)                                                          \
     if (T == TT && nit == NN)                                                                    \
         return run_lanes_nit<MODEL, TT, NN>(st, DATA, dim, n_chains, chain_id_offset, draws, stats, \
-                                            total_steps, max_per_launch, smem_slots, lane_order);
+                                            total_steps, max_per_launch, smem_slots, lane_order, expand);
     switch (model->kind) {
     case NB200_MODEL_NORMAL: {
         NormalModel::Data d{model->mu, 1.0 / (model->sigma * model->sigma)};
         LANES_CASE(NormalModel, d, 32, 1) LANES_CASE(NormalModel, d, 32, 2) LANES_CASE(NormalModel, d, 64, 1)
         if (T == 32) return run_lanes_nit<NormalModel, 32, 0>(st, d, dim, n_chains, chain_id_offset, draws, stats,
-                                                              total_steps, max_per_launch, smem_slots, lane_order);
+                                                              total_steps, max_per_launch, smem_slots, lane_order, expand);
         break;
     }
     case NB200_MODEL_FUNNEL: {
@@ -320,6 +323,15 @@ extern "C" int emul_sample_lanes(const nb200_settings* st, const nb200_model_des
     }
 #undef LANES_CASE
     return NB200_EINVAL;
+}
+
+extern "C" uint64_t emul_expanded_dim(const nb200_model_desc* model) {
+    switch (model->kind) {
+    case NB200_MODEL_NORMAL: return (uint64_t)NormalModel::expanded_dim((int)model->dim);
+    case NB200_MODEL_FUNNEL: return (uint64_t)FunnelModel::expanded_dim((int)model->dim);
+    case NB200_MODEL_RADON: return (uint64_t)RadonModel::expanded_dim((int)model->dim);
+    }
+    return 0;
 }
 
 extern "C" int emul_sample(const nb200_settings* st, const nb200_model_desc* model,

@@ -95,7 +95,7 @@ def sample(kind, dim, settings, n_chains, chain_id_offset=0, q0=None, init_mean=
 
 
 def sample_lanes(kind, dim, settings, n_chains, threads_per_chain=32, chain_id_offset=0, max_per_launch=0,
-                 smem_slots=0, lane_order=0, drop_barrier=False, **model_kw):
+                 smem_slots=0, lane_order=0, drop_barrier=False, expand=False, **model_kw):
     """The same core run by `threads_per_chain` cooperative lanes per chain (GroupLanes in
     emul.cpp): the geometry, per-thread loops, shared-memory tier and density layouts the GPU uses.
     lane_order: 0 lanes run in ascending order between barriers, 1 descending, >= 2 a fresh
@@ -105,12 +105,14 @@ def sample_lanes(kind, dim, settings, n_chains, threads_per_chain=32, chain_id_o
     desc, keep = make_desc(kind, dim, **model_kw)
     n_total = settings.num_tune + settings.num_draws
     n_rows = n_total if settings.save_warmup else settings.num_draws
-    draws = np.zeros((n_rows, n_chains, dim))
+    L.emul_expanded_dim.restype = C.c_uint64
+    width = int(L.emul_expanded_dim(C.byref(desc))) if expand else dim
+    draws = np.zeros((n_rows, n_chains, width))
     stats = np.zeros((n_rows, n_chains, 16))
     steps = C.c_uint64(0)
     rc = L.emul_sample_lanes(C.byref(settings), C.byref(desc), C.c_int(threads_per_chain), C.c_uint64(n_chains),
                              C.c_uint64(chain_id_offset), _ptr(draws), _ptr(stats), C.byref(steps),
-                             C.c_int(max_per_launch), C.c_int(smem_slots), C.c_int(lane_order))
+                             C.c_int(max_per_launch), C.c_int(smem_slots), C.c_int(lane_order), C.c_int(1 if expand else 0))
     if rc != 0:
         raise RuntimeError(f"emul_sample_lanes failed: {rc}")
     return dict(draws=draws.transpose(1, 0, 2), stats=stats.transpose(1, 0, 2), total_steps=int(steps.value))

@@ -205,3 +205,24 @@ def test_core_is_clean_under_address_and_ub_sanitizers():
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "SANITIZE-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
     assert "runtime error" not in r.stderr and "ERROR: AddressSanitizer" not in r.stderr, r.stderr[-4000:]
+
+
+def test_lane_emulation_device_expand_matches_host_expand(radon_data):
+    """expand_vector (src/pymc.rs:217-286) as the kernel runs it at draw write-out
+    (RadonModel::expand, every lane writing its share of the 4J + 5 values) against the host twin
+    CompiledDeviceModel._expand applied to the unconstrained draws of the same run."""
+    import nutpie_b200
+
+    d = radon_data
+    J = d["n_county"]; D = 2 * J + 5
+    kw = dict(y=d["y"], county=d["county"], floor=d["floor"], n_county=J)
+    s = O.default_settings(seed=6, num_tune=20, num_draws=10, init_radius=1.0)
+    raw = E.sample_lanes("radon", D, s, 2, threads_per_chain=32, smem_slots=3, **kw)
+    exp = E.sample_lanes("radon", D, s, 2, threads_per_chain=32, smem_slots=3, expand=True, **kw)
+    assert exp["draws"].shape[-1] == 4 * J + 5 and np.array_equal(raw["stats"], exp["stats"])
+    cm = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], J)
+    host = cm._expand(raw["draws"])
+    dev = cm._split_expanded(exp["draws"])
+    assert set(host) == set(dev)
+    for name in host:
+        np.testing.assert_allclose(dev[name], host[name], rtol=1e-15, atol=0, err_msg=name)
