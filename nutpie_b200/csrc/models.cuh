@@ -268,6 +268,7 @@ struct RadonModel {
                 step(rec[2], ss2);
                 step(rec[3], ss3);
             }
+#pragma unroll 1  // at most three steps: not worth 100 instructions of unrolled remainder
             for (; j0 < d.n_steps; ++j0) step(nb_ldg_obs(ob + (size_t)j0 * T, d.in_smem), ss0);
         }
         grp.sync();
