@@ -118,6 +118,40 @@ def lib() -> C.CDLL:
     return _LIB
 
 
+_LIB_FAST = None
+
+
+def _cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def lib_fast() -> C.CDLL:
+    """The same sources built for SPEED on the machine that runs them (-O3 -march=native, FMA
+    contraction allowed) — used only where the oracle is TIMED as the CPU baseline (bench.py), so
+    that the baseline is not handicapped by the literal, unfused arithmetic the parity tests want.
+    Rebuilt when the CPU model changes (the .so travels between machines)."""
+    global _LIB_FAST
+    if _LIB_FAST is None:
+        so, tag = _HERE / "liboracle_fast.so", _HERE / "liboracle_fast.cpu"
+        cpu = _cpu_model()
+        srcs = [_HERE / n for n in ("nuts_oracle.c", "models.c", "oracle.h", "philox.h")]
+        stale = (not so.exists() or not tag.exists() or tag.read_text() != cpu
+                 or any(x.stat().st_mtime > so.stat().st_mtime for x in srcs))
+        if stale:
+            subprocess.run(["make", "-B", "-C", str(_HERE), "liboracle_fast.so"], check=True,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+            tag.write_text(cpu)
+        _LIB_FAST = C.CDLL(str(so))
+        _LIB_FAST.oracle_sample.restype = C.c_int
+    return _LIB_FAST
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -125,8 +159,8 @@ def _ptr(a):
 class Model:
     """A host density in the reference plug-in ABI plus its user_data."""
 
-    def __init__(self, kind: str, dim: int, **kw):
-        L = lib()
+    def __init__(self, kind: str, dim: int, fast: bool = False, **kw):
+        L = lib_fast() if fast else lib()  # fast: density from the speed build (timing only)
         self.kind, self.dim = kind, int(dim)
         self._keep = []
         if kind == "normal":
@@ -176,10 +210,10 @@ class Model:
 
 
 def sample(model: Model, settings: Settings, n_chains: int, chain_id_offset: int = 0,
-           n_threads: int = 0, q0=None, init_mean=None, z_tape=None):
+           n_threads: int = 0, q0=None, init_mean=None, z_tape=None, fast: bool = False):
     """Run the oracle sampler.  Returns dict(draws, stats, gradients, mass_matrix_inv,
-    total_steps) with the nb200_trace_view layout."""
-    L = lib()
+    total_steps) with the nb200_trace_view layout.  fast: use the speed build (timing only)."""
+    L = lib_fast() if fast else lib()
     n_total = settings.num_tune + settings.num_draws
     n_rows = n_total if settings.save_warmup else settings.num_draws
     sdim = settings.store_dims if 0 < settings.store_dims < model.dim else model.dim
