@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NB200_ABI_VERSION 2
+#define NB200_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------- */
 #define NB200_OK 0
@@ -66,7 +66,8 @@ typedef struct nb200_settings {
     double da_k;               /* 0.75                                         */
     double da_t0;              /* 10                                           */
     double da_gamma;           /* 0.05                                         */
-    int32_t step_size_method;  /* 0 dual_average | 2 fixed (wrapper.rs:347)    */
+    int32_t step_size_method;  /* 0 dual_average | 1 adam | 2 fixed              */
+                               /* (wrapper.rs:347-392)                         */
     int32_t _pad0;
     double fixed_step_size;    /* used when step_size_method == 2              */
     /* mass-matrix schedule (nuts_rs EuclideanAdaptOptions) */
@@ -90,6 +91,15 @@ typedef struct nb200_settings {
                                /* CpuLogpFunc::expand_vector, src/pymc.rs:217-  */
                                /* 286; row width = nb200_model_expanded_dim().  */
                                /* Ignored when store_dims thins the draws.      */
+    int32_t store_divergences; /* wrapper.rs:438-442: divergence_start / _end /  */
+                               /* _momentum / _start_gradient rows (NaN unless   */
+                               /* the draw diverged)                             */
+    int32_t adaptation;        /* 0 diag (PyNutsSettings::Diag) | 1 low_rank     */
+                               /* (PyNutsSettings::LowRank, wrapper.rs:307-346)  */
+    double adam_learning_rate; /* wrapper.rs:376-392; default 0.05               */
+    double step_size_jitter;   /* wrapper.rs:393-407; 0 = off                    */
+    double mass_matrix_eigval_cutoff; /* wrapper.rs:307-326; default 2.0         */
+    double mass_matrix_gamma;  /* wrapper.rs:327-346; default 1e-5               */
 } nb200_settings;
 
 /* ---- model density plug-in ---------------------------------------------
@@ -129,6 +139,17 @@ typedef int (*nb200_expand_fn)(size_t dim, size_t expanded_dim, const double *x,
                              /* :57-88 hierarchical radon, plain-Normal raws,   */
                              /* dim = 2*n_county + 5                            */
 #define NB200_MODEL_CUSTOM 4 /* run-time compiled CUDA source (see above)       */
+#define NB200_MODEL_HOST 5   /* the reference's own HOST plug-in, honoured bit   */
+                             /* for bit: host_logp has the signature of          */
+                             /* RawLogpFunc (src/pymc.rs:23-29, produced by      */
+                             /* compile_pymc.py:970-1006), host_expand that of   */
+                             /* RawExpandFunc (src/pymc.rs:31-37).  The sampler  */
+                             /* kernel posts each position to a mailbox in       */
+                             /* mapped pinned memory and a pool of host threads  */
+                             /* calls the pointer (SURVEY.md §8f-3 fallback):    */
+                             /* rc > 0 => the trajectory diverges there, rc < 0  */
+                             /* => the sampler stops with NB200_ELOGP and keeps  */
+                             /* its partial trace (src/pymc.rs:166-181).         */
 
 typedef struct nb200_model_desc {
     int32_t kind;
@@ -144,6 +165,17 @@ typedef struct nb200_model_desc {
     uint64_t n_user_data;
     uint64_t n_user_scratch; /* NB200_MODEL_CUSTOM: doubles of per-chain shared    */
                              /* memory handed to the density as grp.scratch     */
+    nb200_logp_fn host_logp;     /* NB200_MODEL_HOST: LogpFunc.func               */
+    const void *host_user_data;  /* LogpFunc.user_data_ptr (read-only, shared by  */
+                                 /* all host threads: src/pymc.rs:47-48)          */
+    nb200_expand_fn host_expand; /* ExpandFunc.func or NULL (draws stay           */
+                                 /* unconstrained)                                */
+    const void *host_expand_user_data;
+    uint64_t host_expanded_dim;  /* ExpandFunc.expanded_dim                       */
+    int32_t host_threads;        /* threads calling host_logp; 0 = all cores the  */
+                                 /* process may use (the role of `cores`,         */
+                                 /* src/wrapper.rs:977)                           */
+    int32_t _pad2;
 } nb200_model_desc;
 
 /* ---- per-draw sampler statistics ---------------------------------------
@@ -255,7 +287,10 @@ int nb200_sampler_trace_into(nb200_sampler *s, double *draws, double *stats,
  * ideally pinned) BEFORE start: nb200_sampler_wait then streams finished rows into them
  * while the kernel is still sampling, so the D2H copy of the trace overlaps the run;
  * nb200_sampler_trace_into with the same pointers afterwards copies nothing twice. */
-int nb200_sampler_set_trace_target(nb200_sampler *s, double *draws, double *stats);
+int nb200_sampler_set_trace_target(nb200_sampler *s, double *draws, size_t draws_bytes,
+                                   double *stats, size_t stats_bytes);
+/* exact sizes in bytes the two buffers above must have */
+int nb200_sampler_trace_bytes(nb200_sampler *s, size_t *draws_bytes, size_t *stats_bytes);
 int nb200_sampler_destroy(nb200_sampler *s);
 
 /* ---- measurement hooks --------------------------------------------------
@@ -300,6 +335,18 @@ int nb200_sampler_set_z_tape(nb200_sampler *s, const double *z_tape);
 int nb200_custom_model_compile(const nb200_model_desc *model,
                                int threads_per_chain, int dims_per_thread,
                                char *log, size_t log_len);
+
+/* store_divergences: copy the divergence rows [n_rows][n_chains][4][width] (start location,
+ * end location, start momentum, start gradient — nuts-rs DivergenceInfo as surfaced by
+ * python/nutpie/sample.py:641-646; NaN for draws that did not diverge; width as `gradients`) */
+int nb200_sampler_divergence_trace_into(nb200_sampler *s, double *divergences);
+/* CpuLogpFunc::expand_vector (src/pymc.rs:217-286) over a finished trace of a
+ * NB200_MODEL_HOST model: out[i] = expand(q[i]) for n rows, on n_threads host threads
+ * (0 = all).  q rows are q_stride doubles apart, out rows expanded_dim.  Returns the first
+ * non-zero return code of `fn` as NB200_ELOGP. */
+int nb200_host_expand_rows(nb200_expand_fn fn, const void *user_data, size_t dim,
+                           size_t expanded_dim, uint64_t n, const double *q,
+                           size_t q_stride, double *out, int n_threads);
 
 void *nb200_host_alloc(size_t bytes);
 void nb200_host_free(void *p);

@@ -8,7 +8,8 @@ the C-ABI in include/nutpie_b200.h; models are device densities
 from . import models
 from ._lib import PyChainProgress as ChainProgress
 from ._lib import __version__
-from .compile import compile_pymc_model, compile_stan_model, from_cuda_source, from_pyfunc
+from .compile import (compile_pymc_model, compile_stan_model, from_cfuncs, from_cuda_source,
+                      from_pyfunc)
 from .datasets import make_radon_data
 from .models import custom_model, funnel_model, normal_model, radon_model
 from .sample import Trace, sample
@@ -16,5 +17,5 @@ from .sample import Trace, sample
 __all__ = [
     "__version__", "sample", "compile_pymc_model", "compile_stan_model", "from_pyfunc",
     "ChainProgress", "Trace", "models", "normal_model", "funnel_model", "radon_model",
-    "make_radon_data", "from_cuda_source", "custom_model",
+    "make_radon_data", "from_cuda_source", "custom_model", "from_cfuncs",
 ]

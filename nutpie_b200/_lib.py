@@ -40,6 +40,9 @@ _STAT_DTYPES = {
     "chain": np.uint64,
 }
 
+# python/nutpie/sample.py:641-646
+DIVERGENCE_COLUMNS = ["divergence_start", "divergence_end", "divergence_momentum",
+                      "divergence_start_gradient"]
 NB200_ETIMEOUT = 1
 _ERRORS = {-1: ValueError, -2: RuntimeError, -3: ValueError, -4: RuntimeError, -5: RuntimeError,
            -6: RuntimeError}
@@ -67,7 +70,17 @@ class Settings(C.Structure):
         ("init_radius", C.c_double),
         ("store_dims", C.c_uint64),
         ("save_warmup", C.c_int32), ("expand_draws", C.c_int32),
+        ("store_divergences", C.c_int32), ("adaptation", C.c_int32),
+        ("adam_learning_rate", C.c_double), ("step_size_jitter", C.c_double),
+        ("mass_matrix_eigval_cutoff", C.c_double), ("mass_matrix_gamma", C.c_double),
     ]
+
+
+# the reference's plug-in ABI (src/pymc.rs:23-37; numba side compile_pymc.py:975-981, 1018-1024)
+LOGP_FN = C.CFUNCTYPE(C.c_int, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                      C.POINTER(C.c_double), C.c_void_p)
+EXPAND_FN = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_size_t, C.POINTER(C.c_double),
+                        C.POINTER(C.c_double), C.c_void_p)
 
 
 class ModelDesc(C.Structure):
@@ -78,7 +91,11 @@ class ModelDesc(C.Structure):
                 ("n_obs", C.c_int32), ("n_county", C.c_int32),
                 ("y", C.c_void_p), ("county", C.c_void_p), ("floor", C.c_void_p),
                 ("cuda_source", C.c_char_p), ("user_data", C.c_void_p),
-                ("n_user_data", C.c_uint64), ("n_user_scratch", C.c_uint64)]
+                ("n_user_data", C.c_uint64), ("n_user_scratch", C.c_uint64),
+                ("host_logp", C.c_void_p), ("host_user_data", C.c_void_p),
+                ("host_expand", C.c_void_p), ("host_expand_user_data", C.c_void_p),
+                ("host_expanded_dim", C.c_uint64),
+                ("host_threads", C.c_int32), ("_pad2", C.c_int32)]
 
 
 class Progress(C.Structure):
@@ -90,7 +107,9 @@ class Progress(C.Structure):
                 ("tuning", C.c_int32), ("started", C.c_int32)]
 
 
-MODEL_KINDS = {"normal": 1, "funnel": 2, "radon": 3, "custom": 4}
+MODEL_KINDS = {"normal": 1, "funnel": 2, "radon": 3, "custom": 4, "host": 5}
+ABI_VERSION = 3
+LOW_RANK_SUPPORTED = False  # PyNutsSettings.LowRank exists; the kernel side does not yet
 
 
 def library_path() -> Path:
@@ -148,7 +167,16 @@ def load_library() -> C.CDLL:
         L.nb200_sampler_set_draws_per_launch.restype = C.c_int
         L.nb200_sampler_set_draws_per_launch.argtypes = [C.c_void_p, C.c_uint64]
         L.nb200_sampler_set_trace_target.restype = C.c_int
-        L.nb200_sampler_set_trace_target.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nb200_sampler_set_trace_target.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                     C.c_size_t]
+        L.nb200_sampler_trace_bytes.restype = C.c_int
+        L.nb200_sampler_trace_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t),
+                                                C.POINTER(C.c_size_t)]
+        L.nb200_sampler_divergence_trace_into.restype = C.c_int
+        L.nb200_sampler_divergence_trace_into.argtypes = [C.c_void_p, C.c_void_p]
+        L.nb200_host_expand_rows.restype = C.c_int
+        L.nb200_host_expand_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
+                                             C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         L.nb200_sampler_set_z_tape.restype = C.c_int
         L.nb200_sampler_set_z_tape.argtypes = [C.c_void_p, C.c_void_p]
         L.nb200_settings_default.restype = None
@@ -176,7 +204,7 @@ def load_library() -> C.CDLL:
         L.nb200_custom_model_compile.restype = C.c_int
         L.nb200_custom_model_compile.argtypes = [C.POINTER(ModelDesc), C.c_int, C.c_int,
                                                  C.c_char_p, C.c_size_t]
-        if L.nb200_abi_version() != 2:
+        if L.nb200_abi_version() != ABI_VERSION:
             raise RuntimeError("libnutpie_b200.so ABI version mismatch")
         _lib = L
         return L
@@ -231,6 +259,10 @@ _FLAT_DIRECT = {
     "store_gradient": ("store_gradient", bool),
     "num_tune": ("num_tune", int), "num_draws": ("num_draws", int),
     "max_energy_error": ("max_energy_error", float),
+    "store_divergences": ("store_divergences", bool),
+    "step_size_adam_learning_rate": ("adam_learning_rate", float),
+    "mass_matrix_eigval_cutoff": ("mass_matrix_eigval_cutoff", float),
+    "mass_matrix_gamma": ("mass_matrix_gamma", float),
     # ours (not in the reference): initial-point and trace controls
     "init_radius": ("init_radius", float), "num_try_init": ("num_try_init", int),
     "store_dims": ("store_dims", int),
@@ -238,12 +270,13 @@ _FLAT_DIRECT = {
 # options that exist in the reference but belong to samplers / adaptations that
 # are out of scope for the B200 engine
 _UNSUPPORTED = {
-    "target_integration_time": None, "extra_doublings": 0,
-    "mass_matrix_eigval_cutoff": None, "mass_matrix_gamma": None, "train_on_orbit": None,
-    "step_size_adam_learning_rate": None, "step_size_jitter": None,
-    "store_transformed": False, "store_divergences": False,
+    "target_integration_time": None, "extra_doublings": 0, "train_on_orbit": None,
+    "store_transformed": False,
     "microcanonical_trajectory": False, "exact_normal_trajectory": False,
 }
+# options that only exist for one adaptation (wrapper.rs:138-145: ValueError otherwise)
+_LOW_RANK_ONLY = ("mass_matrix_eigval_cutoff", "mass_matrix_gamma")
+_DIAG_ONLY = ("use_grad_based_mass_matrix",)
 
 
 class PyNutsSettings:
@@ -267,8 +300,9 @@ class PyNutsSettings:
 
     @staticmethod
     def LowRank(seed=None):
-        raise NotImplementedError(
-            "adaptation='low_rank' is not supported by the B200 engine (diag / draw_diag only)")
+        s = PyNutsSettings("low_rank", seed)
+        s._c.adaptation = 1
+        return s
 
     @staticmethod
     def Flow(seed=None):
@@ -291,7 +325,7 @@ class PyNutsSettings:
             if value == "dual_average":
                 c.step_size_method = 0
             elif value == "adam":
-                raise ValueError("step_size_adapt_method='adam' is not supported by the B200 engine")
+                c.step_size_method = 1
             else:
                 try:
                     c.fixed_step_size = float(value)
@@ -299,7 +333,12 @@ class PyNutsSettings:
                     raise ValueError("step_size_adapt_method must be a positive float when "
                                      "using fixed step size") from None
                 c.step_size_method = 2
+        elif name == "step_size_jitter":  # Option<f64>, wrapper.rs:393-407
+            c.step_size_jitter = 0.0 if value is None else float(value)
         elif name in _FLAT_DIRECT:
+            if (name in _LOW_RANK_ONLY and self._kind != "low_rank") or \
+                    (name in _DIAG_ONLY and self._kind != "diag"):
+                raise ValueError(f"Option {name} not available for {self._kind} adaptation")
             field, typ = _FLAT_DIRECT[name]
             setattr(c, field, typ(value))
         elif name in _UNSUPPORTED:
@@ -417,8 +456,11 @@ class PyTrace:
     which is what the end-to-end path uses to avoid a per-chain Arrow hop."""
 
     def __init__(self, draws, stats, rows_filled, gradients=None, mass_matrix_inv=None,
-                 variables=None, expand=None, keep=None, expanded=False):
+                 variables=None, expand=None, keep=None, expanded=False, divergences=None):
         self.draws, self.stats, self.rows_filled = draws, stats, rows_filled
+        # store_divergences: [chain, row, 4, dim] = start location, end location, start
+        # momentum, start gradient of the diverging leapfrog (NaN rows otherwise)
+        self.divergences = divergences
         self.expanded = expanded  # draws hold expanded vectors (constrained + deterministics)
         self.expand_fn = expand
         self.gradients, self.mass_matrix_inv = gradients, mass_matrix_inv
@@ -437,14 +479,15 @@ class PyTrace:
         return a.astype(dt) if dt is not None else a
 
     def get_arrow_trace(self):
-        """list[(posterior RecordBatch, sample_stats RecordBatch)] per chain
-        (src/wrapper.rs:1477-1494); single-take like the reference."""
+        """(posterior RecordBatches, sample_stats RecordBatches), one of each per chain —
+        `Vec<ArrowTrace>` unzipped exactly as src/wrapper.rs:1477-1494 returns it; single-take
+        like the reference."""
         import pyarrow as pa
 
         if self._taken:
-            raise ValueError("Trace was already taken")
+            raise ValueError("The trace was already taken")
         self._taken = True
-        out = []
+        out_draws, out_stats = [], []
         n_chains = self.draws.shape[0]
         for c in range(n_chains):
             n = int(self.rows_filled[c])
@@ -472,16 +515,25 @@ class PyTrace:
                 col = pa.array(a.astype(dt) if dt is not None else a)
                 scols.append(col)
                 sfields.append(pa.field(name, col.type, metadata={"dims": "", "shape": ""}))
-            for name, arr in (("gradient", self.gradients), ("mass_matrix_inv", self.mass_matrix_inv)):
+            vec_stats = [("gradient", self.gradients), ("mass_matrix_inv", self.mass_matrix_inv)]
+            if self.divergences is not None:
+                for k, name in enumerate(DIVERGENCE_COLUMNS):
+                    vec_stats.append((name, self.divergences[:, :, k]))
+            for name, arr in vec_stats:
                 if arr is not None:
                     a = np.ascontiguousarray(arr[c, :n])
                     col = pa.FixedSizeListArray.from_arrays(pa.array(a.reshape(-1)), a.shape[1])
+                    if name in DIVERGENCE_COLUMNS:  # null unless the draw diverged
+                        mask = np.isnan(a).all(axis=1)
+                        col = pa.FixedSizeListArray.from_arrays(pa.array(a.reshape(-1)), a.shape[1],
+                                                                mask=pa.array(mask))
                     scols.append(col)
                     sfields.append(pa.field(name, col.type, metadata={
                         "dims": "unconstrained_parameter", "shape": str(a.shape[1])}))
             stats = pa.RecordBatch.from_arrays(scols, schema=pa.schema(sfields))
-            out.append((posterior, stats))
-        return out
+            out_draws.append(posterior)
+            out_stats.append(stats)
+        return out_draws, out_stats
 
 
 class PySampler:
@@ -501,8 +553,13 @@ class PySampler:
         self.n_chains = int(n_chains if n_chains is not None else settings.num_chains)
         self._desc, self._keep = model._descriptor()
         self.dim = int(self._desc.dim)
+        self._host_model = int(self._desc.kind) == MODEL_KINDS["host"]
         if init_mean is not None:
             init_mean = np.ascontiguousarray(init_mean, dtype=np.float64).reshape(self.dim)
+        if q0 is None and self._host_model:
+            # Model::init_position (src/pymc.rs:505-534, src/pyfunc.rs:535-569): the model's
+            # own `init_func(seed)`; without one the engine draws U(-2, 2) on the device
+            q0 = model._initial_points(settings.seed, self.n_chains, int(chain_id_offset))
         if q0 is not None:
             q0 = np.ascontiguousarray(q0, dtype=np.float64).reshape(self.n_chains, self.dim)
         h = L.nb200_sampler_create(C.byref(self._c), C.byref(self._desc), self.n_chains,
@@ -511,26 +568,36 @@ class PySampler:
             msg = L.nb200_last_error().decode("utf-8", "replace")
             raise (ValueError if "must" in msg or "unknown" in msg else RuntimeError)(msg)
         self._h = C.c_void_p(h)
-        if z_tape is not None:
-            z_tape = np.ascontiguousarray(z_tape, dtype=np.float64)
-            _check(L.nb200_sampler_set_z_tape(self._h, _ptr(z_tape)))
-        if draws_per_launch:
-            _check(L.nb200_sampler_set_draws_per_launch(self._h, int(draws_per_launch)))
-        self._trace_buffers = trace_buffers
-        if trace_buffers is not None:  # rows are streamed into these while sampling runs
-            for k in ("draws", "stats"):
-                a = trace_buffers[k]
-                if not a.flags["C_CONTIGUOUS"] or a.dtype != np.float64:
-                    raise ValueError("trace buffers must be C-contiguous float64 arrays")
-            _check(L.nb200_sampler_set_trace_target(self._h, _ptr(trace_buffers["draws"]),
-                                                    _ptr(trace_buffers["stats"])))
+        self._lock = threading.RLock()  # guards _h against close() racing the progress thread
         self.n_total = int(self._c.num_tune + self._c.num_draws)
         self.n_rows = self.n_total if self._c.save_warmup else int(self._c.num_draws)
         sd = int(self._c.store_dims)
         self.grad_dim = sd if 0 < sd < self.dim else self.dim
-        self.expanded = bool(self._c.expand_draws) and not (0 < sd < self.dim)
+        self.expanded = bool(self._c.expand_draws) and not (0 < sd < self.dim) and not self._host_model
         self.sdim = int(L.nb200_model_expanded_dim(C.byref(self._desc))) if self.expanded else self.grad_dim
-        self._lock = threading.Lock()
+        try:
+            if z_tape is not None:
+                z_tape = np.ascontiguousarray(z_tape, dtype=np.float64)
+                _check(L.nb200_sampler_set_z_tape(self._h, _ptr(z_tape)))
+            if draws_per_launch:
+                _check(L.nb200_sampler_set_draws_per_launch(self._h, int(draws_per_launch)))
+            self._trace_buffers = trace_buffers
+            if trace_buffers is not None:  # rows are streamed into these while sampling runs
+                sh = self.trace_shapes()
+                for k in ("draws", "stats"):
+                    a = trace_buffers[k]
+                    if not a.flags["C_CONTIGUOUS"] or a.dtype != np.float64:
+                        raise ValueError("trace buffers must be C-contiguous float64 arrays")
+                    if tuple(a.shape) != sh[k]:  # checked BEFORE the engine may write into them
+                        raise ValueError(f"trace buffer '{k}' must be a row-major array of shape "
+                                         f"{sh[k]}, got {tuple(a.shape)}")
+                _check(L.nb200_sampler_set_trace_target(
+                    self._h, _ptr(trace_buffers["draws"]), trace_buffers["draws"].nbytes,
+                    _ptr(trace_buffers["stats"]), trace_buffers["stats"].nbytes))
+        except Exception:
+            L.nb200_sampler_destroy(self._h)
+            self._h = None
+            raise
         self._taken = False
         self._t_start = None
         self._progress_type = progress_type or ProgressType.none()
@@ -560,10 +627,40 @@ class PySampler:
             pt = ProgressType("callback", extra_callback_rate or 500, extra_callback)
         return PySampler(settings, model, progress_type=pt, **kw)
 
+    @staticmethod
+    def from_pymc(settings, cores, model, progress_type=None, extra_callback=None,
+                  extra_callback_rate=500, store=None, **kw):
+        """src/wrapper.rs:1190-1208 — `model` is a PyMcModel (LogpFunc + ExpandFunc pointers):
+        sampled through the host plug-in service, `cores` host threads calling the pointer."""
+        if not isinstance(model, PyMcModel):
+            raise TypeError("from_pymc needs a PyMcModel")
+        kw.pop("init_mean", None)  # passed down but unused by _make_model (compile_pymc.py:189)
+        model.host_threads = int(cores or 0)
+        return PySampler.from_device_model(settings, cores, model, progress_type, extra_callback,
+                                           extra_callback_rate, store, **kw)
+
+    @staticmethod
+    def from_pyfunc(settings, cores, model, progress_type=None, extra_callback=None,
+                    extra_callback_rate=500, store=None, **kw):
+        """src/wrapper.rs:1232-1250 — `model` is a PyModel (Python callables)."""
+        if not isinstance(model, PyModel):
+            raise TypeError("from_pyfunc needs a PyModel")
+        kw.pop("init_mean", None)
+        return PySampler.from_device_model(settings, cores, model, progress_type, extra_callback,
+                                           extra_callback_rate, store, **kw)
+
+    @staticmethod
+    def from_stan(*a, **k):
+        """src/wrapper.rs:1211-1229 — BridgeStan is out of scope."""
+        raise NotImplementedError("BridgeStan models are not supported by the B200 engine")
+
     # -- progress ---------------------------------------------------------
     def progress(self):
         arr = (Progress * self.n_chains)()
-        _check(self._L.nb200_sampler_progress(self._h, arr))
+        with self._lock:
+            if self._h is None:
+                raise ValueError("sampler is closed")
+            _check(self._L.nb200_sampler_progress(self._h, arr))
         rt = (time.perf_counter() - self._t_start) * 1e3 if self._t_start else 0.0
         return [PyChainProgress(arr[i], rt, ()) for i in range(self.n_chains)]
 
@@ -576,8 +673,9 @@ class PySampler:
                 import sys
 
                 print(f"progress callback failed: {exc}", file=sys.stderr)
-            if self._h is None or self._L.nb200_sampler_is_finished(self._h):
-                break
+            with self._lock:
+                if self._h is None or self._L.nb200_sampler_is_finished(self._h):
+                    break
 
     # -- control (src/wrapper.rs:1252-1365) -------------------------------
     def wait(self, timeout_seconds=None):
@@ -588,7 +686,13 @@ class PySampler:
             slice_s = 0.1
             if deadline is not None:
                 slice_s = min(slice_s, max(deadline - time.perf_counter(), 0.0))
-            rc = _check(self._L.nb200_sampler_wait(self._h, slice_s))
+            try:
+                rc = _check(self._L.nb200_sampler_wait(self._h, slice_s))
+            except RuntimeError as exc:
+                cause = getattr(self._model, "last_error", None)
+                if cause is not None:  # the Python density raised (src/pyfunc.rs:100-116)
+                    raise RuntimeError(str(exc)) from cause
+                raise
             if rc == 0:
                 return
             if deadline is not None and time.perf_counter() >= deadline:
@@ -634,6 +738,11 @@ class PySampler:
         rows = np.zeros(self.n_chains, dtype=np.uint64)
         _check(self._L.nb200_sampler_trace_into(self._h, _ptr(draws), _ptr(stats), _ptr(grads),
                                                 _ptr(mm), _ptr(rows)))
+        divs = None
+        if self._c.store_divergences:
+            divs = np.empty((self.n_rows, self.n_chains, 4, self.grad_dim))
+            _check(self._L.nb200_sampler_divergence_trace_into(self._h, _ptr(divs)))
+            divs = divs.transpose(1, 0, 2, 3)
         if self.expanded:  # rows already hold the expanded vector: slice it into variables
             expand = self._model._split_expanded
         elif self.sdim == self.dim:
@@ -644,14 +753,14 @@ class PySampler:
         tv = lambda a: None if a is None else a.transpose(1, 0, 2)
         return PyTrace(tv(draws), tv(stats), rows, tv(grads), tv(mm),
                        variables=self._model._variable_dims(), expand=expand,
-                       keep=[draws, stats, grads, mm], expanded=self.expanded)
+                       keep=[draws, stats, grads, mm], expanded=self.expanded, divergences=divs)
 
     def inspect(self, out=None):
         return self._trace(out)
 
     def take_results(self, out=None):
         if not self.is_finished():
-            raise ValueError("Sampler is still running")
+            raise ValueError("Sampler is still running")  # src/wrapper.rs:1431-1440
         if self._taken:
             raise ValueError("Sampler is empty")
         tr = self._trace(out)
@@ -680,11 +789,14 @@ class PySampler:
 
     def close(self):
         self._stop_progress.set()
-        if self._progress_thread is not None and self._progress_thread is not threading.current_thread():
-            self._progress_thread.join(timeout=2.0)
-        if self._h is not None:
-            self._L.nb200_sampler_destroy(self._h)
-            self._h = None
+        t = self._progress_thread
+        if t is not None and t is not threading.current_thread():
+            t.join()  # the loop wakes on the event; a slow user callback is waited for, never
+            #           raced: the native handle must outlive every call that uses it
+        with self._lock:
+            if self._h is not None:
+                self._L.nb200_sampler_destroy(self._h)
+                self._h = None
 
     def __del__(self):
         try:
@@ -767,3 +879,8 @@ def set_stage_loads(mode):
 
 def device_count() -> int:
     return int(load_library().nb200_device_count())
+
+
+# model-side classes of `nutpie._lib` (src/pymc.rs, src/pyfunc.rs, src/common.rs, src/stan.rs)
+from ._lib_models import (ExpandFunc, LogpFunc, PyMcModel, PyModel, PyVariable,  # noqa: E402
+                          StanLibrary, StanModel, chain_seed, store)

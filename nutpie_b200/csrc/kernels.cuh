@@ -57,6 +57,11 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, c
     ctx.lv_live = 0;
     ctx.n_parked = 0;
     ctx.defer_acc = false;
+    if constexpr (M::kNeedsChain) {  // host plug-in: mailbox index + request sequence number
+        ctx.md.chain = chain;
+        if (ctx.g.tid == 0) M::init_chain(ctx.md, ctx.msm);
+        ctx.g.sync();
+    }
 }
 
 // The sampler: W warps per chain, CPB chains per CTA (CPB > 1 only for W == 1).
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, kernel_min_blocks<M, W,
     if (chain >= P.n_chains) return;
     ChainCtx<M, GroupCuda<W>, NIT> ctx;
     setup_ctx<M, W, NIT>(ctx, P, chain, smem + block_data + (size_t)local * smem_per_chain);
-    ctx.md = md;
+    if constexpr (M::kHasBlockData) ctx.md = md;  // tables staged in shared memory
     ctx.run();
 }
 

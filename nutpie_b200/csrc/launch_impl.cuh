@@ -37,6 +37,7 @@ static cudaError_t launch_one(const KParams<M>& P, size_t smem_per_chain, size_t
 // (W, NIT) combinations with unrolled per-dimension loops; anything else runs NIT = 0
 template <class M>
 int supported_nit(int W, int nit) {
+    if constexpr (M::kRuntimeLoopsOnly) return 0;
     if (W == 1) return (nit == 1 || nit == 2 || nit == 3 || nit == 4 || nit == 6 || nit == 8) ? nit : 0;
     if (W == 2) return (nit == 1 || nit == 2 || nit == 3 || nit == 4) ? nit : 0;
     if (W == 4) return (nit == 1 || nit == 2) ? nit : 0;
@@ -49,10 +50,12 @@ cudaError_t launch_nuts(int W, int NIT, const KParams<M>& P, size_t smem_per_cha
 #define NB_CASE(WW, NN)                                                                       \
     if (W == WW && NIT == NN)                                                                 \
         return launch_one<M, WW, NN>(P, smem_per_chain, block_data, cpb, grid, block, stream);
-    NB_CASE(1, 1) NB_CASE(1, 2) NB_CASE(1, 3) NB_CASE(1, 4) NB_CASE(1, 6) NB_CASE(1, 8) NB_CASE(1, 0)
-    NB_CASE(2, 1) NB_CASE(2, 2) NB_CASE(2, 3) NB_CASE(2, 4) NB_CASE(2, 0)
-    NB_CASE(4, 1) NB_CASE(4, 2) NB_CASE(4, 0)
-    NB_CASE(8, 0) NB_CASE(16, 0) NB_CASE(32, 0)
+    NB_CASE(1, 0) NB_CASE(2, 0) NB_CASE(4, 0) NB_CASE(8, 0) NB_CASE(16, 0) NB_CASE(32, 0)
+    if constexpr (!M::kRuntimeLoopsOnly) {
+    NB_CASE(1, 1) NB_CASE(1, 2) NB_CASE(1, 3) NB_CASE(1, 4) NB_CASE(1, 6) NB_CASE(1, 8)
+    NB_CASE(2, 1) NB_CASE(2, 2) NB_CASE(2, 3) NB_CASE(2, 4)
+    NB_CASE(4, 1) NB_CASE(4, 2)
+    }
 #undef NB_CASE
     return cudaErrorInvalidValue;
 }

@@ -33,6 +33,8 @@ NB_HD T nb_ld_tab(const T* p, bool in_smem) {
 // tests/test_stan.py:16-24) and the D = 10 000 bandwidth-bound config 4.
 struct NormalModel {
     static constexpr bool kElementwise = true;
+    static constexpr bool kNeedsChain = false;
+    static constexpr bool kRuntimeLoopsOnly = false;
     static constexpr bool kHasBlockData = false;
     // g_i = -(q_i - mu) / var is non-finite only if q_i - mu is, and then so is the term
     // (q_i - mu)^2 of logp: the leapfrog needs no separate per-dimension gradient check
@@ -58,6 +60,8 @@ struct NormalModel {
 // Neal's funnel (docs/sample-stats.qmd:19-21; 9 parameters in BASELINE.json)
 struct FunnelModel {
     static constexpr bool kElementwise = false;
+    static constexpr bool kNeedsChain = false;
+    static constexpr bool kRuntimeLoopsOnly = false;
     static constexpr bool kHasBlockData = false;
     struct Data {
         int unused;
@@ -154,6 +158,8 @@ NB_HD void nb_exp3(const G&, double a, double b, double c, double& ea, double& e
 
 struct RadonModel {
     static constexpr bool kElementwise = false;
+    static constexpr bool kNeedsChain = false;
+    static constexpr bool kRuntimeLoopsOnly = false;
     // The observation records and group tables are the same for every chain: a CTA
     // that hosts several chains copies them into shared memory once (launch_impl.cuh).
     static constexpr bool kHasBlockData = true;
@@ -323,6 +329,99 @@ struct RadonModel {
     }
 };
 
+// ---- the reference's HOST plug-in (NB200_MODEL_HOST, include/nutpie_b200.h) ----
+// `int logp(size_t dim, const double* x, double* grad, double* logp, const void* user_data)`
+// (RawLogpFunc, src/pymc.rs:23-29) is a host function: the chain posts its position to a
+// per-chain mailbox in MAPPED PINNED host memory, rings a doorbell, and waits for the answer a
+// host thread writes back (nb200_api.cu: HostService).  Everything else — integrator, tree,
+// adaptation — stays in the persistent kernel, so any existing numba cfunc / LogpFunc samples
+// through the same engine.  Slow by construction (one PCIe round trip + a host call per
+// gradient): the fallback of SURVEY.md §8f-3, not the product path.
+struct HostModel {
+    static constexpr bool kElementwise = false;
+    static constexpr bool kHasBlockData = false;
+    static constexpr bool kRuntimeLoopsOnly = true;  // only the NIT = 0 kernels are instantiated
+    struct Data {
+        double* qbox;        // [n_chains][Dp]  device -> host
+        double* gbox;        // [n_chains][Dp]  host -> device
+        double* lpbox;       // [n_chains]
+        int* rcbox;          // [n_chains]      return code of the host function
+        unsigned* req;       // [n_chains]      doorbell: sequence number of the posted request
+        unsigned* resp;      // [n_chains]      sequence number of the last answered request
+        const volatile int* stop;  // the sampler's stop flag (abort must not hang on a dead host)
+        unsigned long long chain;  // set per chain by the kernel (kNeedsChain)
+        int Dp;
+    };
+    static constexpr bool kNeedsChain = true;
+    NB_HD static int smem_doubles(const Data&, int) { return 2; }  // [0] sequence number, [1] status
+    // Sequence numbers continue from the last doorbell this chain ever rang (a launch that was
+    // stopped while a request was in flight leaves req ahead of resp: the next request must
+    // still be a NEW number for the host thread to notice it).
+    NB_HD static void init_chain(const Data& d, double* sm) {
+#ifdef __CUDA_ARCH__
+        unsigned last;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(last) : "l"(d.req + d.chain) : "memory");
+        reinterpret_cast<unsigned*>(sm)[0] = last;
+#else
+        (void)d; (void)sm;
+#endif
+    }
+    template <class G>
+    NB_HD static double logp_grad(const G& grp, const Data& d, int D, const double* q, double* g,
+                                  double* sm) {
+#ifdef __CUDA_ARCH__
+        const size_t base = (size_t)d.chain * (size_t)d.Dp;
+        for (int i = grp.tid; i < D; i += grp.size()) d.qbox[base + i] = q[i];
+        __threadfence_system();
+        grp.sync();
+        unsigned* seqp = reinterpret_cast<unsigned*>(sm);
+        if (grp.tid == 0) {
+            const unsigned seq = seqp[0] + 1u;
+            seqp[0] = seq;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(d.req + d.chain), "r"(seq) : "memory");
+            unsigned got, ns = 2000u;
+            int status = 0;
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(d.resp + d.chain) : "memory");
+                if (got == seq) break;
+                if (d.stop && *d.stop) { status = 1; break; }  // aborted while waiting
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 60000000000ull) { status = 2; break; }  // 60 s: the host is gone
+                __nanosleep(ns);
+                if (ns < 32000u) ns *= 2u;
+            }
+            seqp[1] = (unsigned)status;
+        }
+        grp.sync();
+        const int status = (int)seqp[1];
+        double lp = __longlong_as_double(0x7ff8000000000000ll);
+        int rc = 1;
+        if (status == 0) {
+            for (int i = grp.tid; i < D; i += grp.size()) g[i] = __ldcv(d.gbox + base + i);
+            lp = __ldcv(d.lpbox + d.chain);
+            rc = __ldcv(d.rcbox + d.chain);
+        } else {
+            for (int i = grp.tid; i < D; i += grp.size()) g[i] = 0.0;
+        }
+        // rc > 0: recoverable (src/pymc.rs:178) -> the trajectory diverges here; rc < 0 is
+        // fatal: the host service has already raised the stop flag and recorded the code
+        return rc != 0 ? __longlong_as_double(0x7ff8000000000000ll) : lp;
+#else
+        (void)grp; (void)d; (void)D; (void)q; (void)g; (void)sm;
+        return 0.0;  // device only
+#endif
+    }
+    // expand_vector runs on the host as well (nb200_host_expand_rows): draws stay unconstrained
+    NB_HD static int expanded_dim(int D) { return D; }
+    template <class G>
+    NB_HD static void expand(const G& grp, const Data&, int D, const double* q, double* out) {
+        for (int i = grp.tid; i < D; i += grp.size()) out[i] = q[i];
+    }
+};
+
 }  // namespace nb200
 
 // ---- run-time compiled densities (NB200_MODEL_CUSTOM, include/nutpie_b200.h) ----
@@ -352,6 +451,8 @@ namespace nb200 {
 
 struct CustomModel {
     static constexpr bool kElementwise = false;
+    static constexpr bool kNeedsChain = false;
+    static constexpr bool kRuntimeLoopsOnly = false;
     static constexpr bool kHasBlockData = false;
     struct Data {
         const double* data;  // device copy of nb200_model_desc::user_data

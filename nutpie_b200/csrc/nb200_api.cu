@@ -7,11 +7,15 @@
 // start, poll progress, pause/resume/abort, hand out the trace.
 #include <cuda_runtime.h>
 
+#include <sched.h>
+
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -25,8 +29,8 @@
 using namespace nb200;
 
 // the Python/Rust bindings mirror these layouts field by field
-static_assert(sizeof(nb200_settings) == 192, "nb200_settings ABI layout changed");
-static_assert(sizeof(nb200_model_desc) == 96, "nb200_model_desc ABI layout changed");
+static_assert(sizeof(nb200_settings) == 232, "nb200_settings ABI layout changed");
+static_assert(sizeof(nb200_model_desc) == 144, "nb200_model_desc ABI layout changed");
 static_assert(sizeof(nb200_progress) == 56, "nb200_progress ABI layout changed");
 
 // ------------------------------------------------------------------ errors
@@ -80,6 +84,139 @@ static void pool_keep_memory(int device) {
     done.push_back(device);
 }
 
+
+// ------------------------------------------------------------------ host plug-in service
+// NB200_MODEL_HOST: the reference's RawLogpFunc (src/pymc.rs:23-29) is called by a pool of host
+// threads — the role nuts-rs gives its rayon workers (src/wrapper.rs:977) — on behalf of the
+// chains running in the persistent kernel.  Chain c posts q to qbox[c], rings req[c] (models.cuh,
+// HostModel::logp_grad); the thread that owns c calls the pointer, writes gbox[c] / lpbox[c] /
+// rcbox[c] and publishes resp[c] = req[c].  All six arrays and the stop flag live in MAPPED
+// pinned memory, so neither side issues a copy.
+static int usable_cores() {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+        const int n = CPU_COUNT(&set);
+        if (n > 0) return n;
+    }
+    const unsigned h = std::thread::hardware_concurrency();
+    return h ? (int)h : 1;
+}
+
+struct HostService {
+    nb200_logp_fn fn = nullptr;
+    const void* user_data = nullptr;
+    size_t D = 0, Dp = 0;
+    uint64_t n_chains = 0;
+    void* base = nullptr;  // one mapped pinned allocation
+    double *qbox = nullptr, *gbox = nullptr, *lpbox = nullptr;
+    int* rcbox = nullptr;
+    unsigned *req = nullptr, *resp = nullptr;
+    int* stop = nullptr;
+    // the same arrays as the device sees them
+    double *d_qbox = nullptr, *d_gbox = nullptr, *d_lpbox = nullptr;
+    int* d_rcbox = nullptr;
+    unsigned *d_req = nullptr, *d_resp = nullptr;
+    int* d_stop = nullptr;
+    std::vector<std::thread> threads;
+    std::atomic<bool> quit{false};
+    std::atomic<int> fatal_rc{0};
+    std::atomic<long long> fatal_chain{-1};
+    std::atomic<unsigned long long> calls{0};
+
+    int init(const nb200_model_desc& m, uint64_t chains, int dp) {
+        fn = m.host_logp;
+        user_data = m.host_user_data;
+        D = (size_t)m.dim;
+        Dp = (size_t)dp;
+        n_chains = chains;
+        const size_t vec = align16(sizeof(double) * Dp * n_chains);
+        const size_t sc = align16(sizeof(double) * n_chains);
+        const size_t wd = align16(sizeof(unsigned) * n_chains);
+        const size_t total = 2 * vec + sc + 3 * wd + 64;
+        if (cudaHostAlloc(&base, total, cudaHostAllocMapped) != cudaSuccess)
+            return fail(NB200_ECUDA, "cudaHostAlloc (mapped mailbox of the host plug-in) failed");
+        std::memset(base, 0, total);
+        char* b = static_cast<char*>(base);
+        qbox = reinterpret_cast<double*>(b);
+        gbox = reinterpret_cast<double*>(b + vec);
+        lpbox = reinterpret_cast<double*>(b + 2 * vec);
+        rcbox = reinterpret_cast<int*>(b + 2 * vec + sc);
+        req = reinterpret_cast<unsigned*>(b + 2 * vec + sc + wd);
+        resp = reinterpret_cast<unsigned*>(b + 2 * vec + sc + 2 * wd);
+        stop = reinterpret_cast<int*>(b + 2 * vec + sc + 3 * wd);
+        void* dbase = nullptr;
+        if (cudaHostGetDevicePointer(&dbase, base, 0) != cudaSuccess)
+            return fail(NB200_ECUDA, "cudaHostGetDevicePointer failed");
+        char* d = static_cast<char*>(dbase);
+        d_qbox = reinterpret_cast<double*>(d);
+        d_gbox = reinterpret_cast<double*>(d + vec);
+        d_lpbox = reinterpret_cast<double*>(d + 2 * vec);
+        d_rcbox = reinterpret_cast<int*>(d + 2 * vec + sc);
+        d_req = reinterpret_cast<unsigned*>(d + 2 * vec + sc + wd);
+        d_resp = reinterpret_cast<unsigned*>(d + 2 * vec + sc + 2 * wd);
+        d_stop = reinterpret_cast<int*>(d + 2 * vec + sc + 3 * wd);
+        int T = m.host_threads > 0 ? m.host_threads : usable_cores();
+        if ((uint64_t)T > n_chains) T = (int)n_chains;
+        if (T < 1) T = 1;
+        for (int t = 0; t < T; ++t) threads.emplace_back([this, t, T] { worker(t, T); });
+        return 0;
+    }
+
+    void worker(int t, int T) {
+        // a contiguous block of chains per thread: its doorbells share cache lines
+        const uint64_t lo = n_chains * (uint64_t)t / T, hi = n_chains * (uint64_t)(t + 1) / T;
+        std::vector<unsigned> last(hi - lo, 0u);
+        std::vector<double> grad(D);
+        unsigned idle = 0;
+        while (!quit.load(std::memory_order_relaxed)) {
+            bool any = false;
+            for (uint64_t c = lo; c < hi; ++c) {
+                const unsigned r = __atomic_load_n(req + c, __ATOMIC_ACQUIRE);
+                if (r == last[c - lo]) continue;
+                any = true;
+                double lp = 0.0;
+                int rc = fn(D, qbox + c * Dp, grad.data(), &lp, user_data);
+                // the reference's cfunc wrapper reports non-finite values itself
+                // (compile_pymc.py:996-999); do the same for pointers that do not
+                if (rc == 0) {
+                    if (!std::isfinite(lp)) rc = 4;
+                    else
+                        for (size_t i = 0; i < D; ++i)
+                            if (!std::isfinite(grad[i])) { rc = 3; break; }
+                }
+                std::memcpy(gbox + c * Dp, grad.data(), sizeof(double) * D);
+                lpbox[c] = lp;
+                rcbox[c] = rc;
+                if (rc < 0) {  // fatal (src/pymc.rs:178): stop the sampler, keep the partial trace
+                    int expect = 0;
+                    if (fatal_rc.compare_exchange_strong(expect, rc)) fatal_chain.store((long long)c);
+                    __atomic_store_n(stop, 1, __ATOMIC_RELEASE);
+                }
+                calls.fetch_add(1, std::memory_order_relaxed);
+                last[c - lo] = r;
+                __atomic_store_n(resp + c, r, __ATOMIC_RELEASE);
+            }
+            if (any) {
+                idle = 0;
+            } else if (++idle > 2000) {  // nothing posted for a while (paused / finished)
+                std::this_thread::sleep_for(std::chrono::microseconds(200));
+            } else if (idle > 50) {
+                std::this_thread::yield();
+            }
+        }
+    }
+
+    void shutdown() {
+        quit.store(true);
+        for (auto& th : threads)
+            if (th.joinable()) th.join();
+        threads.clear();
+        if (base) cudaFreeHost(base);
+        base = nullptr;
+    }
+};
+
 // ------------------------------------------------------------------ sampler
 enum class RunState { Created, Running, Paused, Finished, Aborted, Error };
 
@@ -105,6 +242,9 @@ struct nb200_sampler {
     std::vector<ChainScalars> h_sc_store;
     double *d_pool = nullptr, *d_var = nullptr, *d_wf = nullptr;
     double *d_draws = nullptr, *d_stats = nullptr, *d_grads = nullptr, *d_mm = nullptr;
+    double* d_div = nullptr;  // store_divergences: [n_rows][n_chains][4][grad_dim]
+    std::unique_ptr<HostService> host;  // NB200_MODEL_HOST only
+    std::string err;                    // message of the error that put the sampler in Error
     double *d_q0 = nullptr, *d_init_mean = nullptr, *d_tape = nullptr;
     // pinned host trace (lazy)
     double *h_draws = nullptr, *h_stats = nullptr, *h_grads = nullptr, *h_mm = nullptr;
@@ -166,8 +306,16 @@ static int validate(const nb200_settings* st, const nb200_model_desc* m) {
         return fail(NB200_EINVAL, "maxdepth must be in 1..19");
     if (m->dim < 1) return fail(NB200_EINVAL, "model dimension must be >= 1");
     if (m->dim > (1u << 22)) return fail(NB200_EINVAL, "model dimension must be <= 2^22");
-    if (st->step_size_method != 0 && st->step_size_method != 2)
-        return fail(NB200_EINVAL, "step_size_adapt_method: only dual_average and fixed are supported");
+    if (st->step_size_method < 0 || st->step_size_method > 2)
+        return fail(NB200_EINVAL, "step_size_adapt_method must be dual_average (0), adam (1) or fixed (2)");
+    if (st->step_size_method == 1 && !(st->adam_learning_rate > 0))
+        return fail(NB200_EINVAL, "step_size_adam_learning_rate must be > 0");
+    if (st->step_size_jitter < 0 || st->step_size_jitter >= 1)
+        return fail(NB200_EINVAL, "step_size_jitter must be in [0, 1)");
+    if (st->adaptation != 0 && st->adaptation != 1)
+        return fail(NB200_EINVAL, "adaptation must be diag (0) or low_rank (1)");
+    if (st->adaptation == 1)
+        return fail(NB200_EINVAL, "adaptation='low_rank' is not implemented by the B200 engine yet");
     if (m->kind == NB200_MODEL_RADON) {
         if (m->n_county < 1 || m->n_county > 32767)
             return fail(NB200_EINVAL, "radon: n_county must be in 1..32767");
@@ -189,6 +337,9 @@ static int validate(const nb200_settings* st, const nb200_model_desc* m) {
             return fail(NB200_EINVAL, "custom: user_data is null but n_user_data > 0");
         if (m->n_user_data > (1ull << 31)) return fail(NB200_EINVAL, "custom: user_data too large");
         if (m->n_user_scratch > 16384) return fail(NB200_EINVAL, "custom: at most 16384 doubles of scratch");
+    } else if (m->kind == NB200_MODEL_HOST) {
+        if (!m->host_logp) return fail(NB200_EINVAL, "host: host_logp is null");
+        if (m->host_threads < 0) return fail(NB200_EINVAL, "host: host_threads must be >= 0");
     } else {
         return fail(NB200_EINVAL, "unknown model kind");
     }
@@ -257,6 +408,11 @@ static int build_model_data(const nb200_model_desc& m, int, CustomModel::Data& d
     return 0;
 }
 
+static int build_model_data(const nb200_model_desc&, int, HostModel::Data& d, std::vector<void*>&) {
+    std::memset(&d, 0, sizeof(d));
+    return 0;
+}
+
 template <class M>
 static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_desc* m,
                                   uint64_t n_chains, uint64_t chain_id_offset, int device,
@@ -303,6 +459,14 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     g_upload_stream = nullptr;
     s->model_allocs_pooled = true;
     if (mrc != 0) return bail();
+    if constexpr (std::is_same<M, HostModel>::value) {
+        s->host.reset(new HostService());
+        if (s->host->init(*m, n_chains, s->Dp) != 0) return bail();
+        HostModel::Data& hd = P.mdata;
+        hd.qbox = s->host->d_qbox; hd.gbox = s->host->d_gbox; hd.lpbox = s->host->d_lpbox;
+        hd.rcbox = s->host->d_rcbox; hd.req = s->host->d_req; hd.resp = s->host->d_resp;
+        hd.stop = s->host->d_stop; hd.chain = 0; hd.Dp = s->Dp;
+    }
     const size_t fixed = smem_for<M>(s->W, P.mdata, s->Dp);
     size_t bdata = 0;
     if (s->W == 1) {
@@ -321,7 +485,9 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         }
         if (c > 8) c = 8;
         s->cpb = c;
-        if (bd > 0 && c >= 4) bdata = bd;
+        // stage the tables in shared memory only when they fit beside the chains' own state
+        // (a model with > ~10 k observations reads them through L2 instead)
+        if (bd > 0 && c >= 4 && bd + (size_t)c * fixed + 2048 <= 227 * 1024) bdata = bd;
     } else {
         s->cpb = 1;
     }
@@ -336,7 +502,8 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         if (per_sm > 32ull * s->cpb) per_sm = 32ull * s->cpb;     // CTA limit per SM
         if (per_sm < 1) per_sm = 1;
         const uint64_t ctas = (per_sm + s->cpb - 1) / s->cpb;
-        size_t budget = (kSmemSM - ctas * kSlack - ctas * bdata) / (ctas * s->cpb);
+        const size_t reserved = ctas * kSlack + ctas * bdata;
+        size_t budget = reserved < kSmemSM ? (kSmemSM - reserved) / (ctas * s->cpb) : 0;
         const size_t slot_b = align16(sizeof(double) * 4 * (size_t)s->Dp);
         const size_t var_b = align16(sizeof(double) * (size_t)s->Dp);
         int slots = 0, var_in = 0;
@@ -407,6 +574,11 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     ALLOC(s->d_stats, n_chains * s->n_rows * NB200_NSTAT * sizeof(double));
     if (st->store_gradient) ALLOC(s->d_grads, n_chains * s->n_rows * s->grad_dim * sizeof(double));
     if (st->store_mass_matrix) ALLOC(s->d_mm, n_chains * s->n_rows * s->grad_dim * sizeof(double));
+    if (st->store_divergences) {
+        const size_t nb = n_chains * s->n_rows * 4 * s->grad_dim * sizeof(double);
+        ALLOC(s->d_div, nb);
+        CHK(cudaMemsetAsync(s->d_div, 0xFF, nb, s->stream));  // all-ones = NaN: "did not diverge"
+    }
     ALLOC(s->d_stop, sizeof(int));
     CHK(cudaEventCreate(&s->ev0));
     CHK(cudaEventCreate(&s->ev1));
@@ -429,7 +601,10 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     P.pool = s->d_pool; P.var = s->d_var; P.welford = s->d_wf; P.sc = s->d_sc;
     P.draws = s->d_draws; P.stats = s->d_stats; P.grads = s->d_grads; P.mminv = s->d_mm;
     P.q0 = s->d_q0; P.init_mean = s->d_init_mean; P.z_tape = nullptr;
-    P.stop_flag = s->d_stop;
+    P.divs = s->d_div;
+    // host plug-in: the stop flag lives in mapped pinned memory so that the service thread that
+    // meets a fatal return code can raise it without a CUDA call
+    P.stop_flag = s->host ? s->host->d_stop : s->d_stop;
     s->rows_filled.assign(n_chains, 0);
     return s;
 }
@@ -446,6 +621,7 @@ uint64_t nb200_model_expanded_dim(const nb200_model_desc* model) {
     case NB200_MODEL_FUNNEL: return (uint64_t)FunnelModel::expanded_dim((int)model->dim);
     case NB200_MODEL_RADON: return (uint64_t)RadonModel::expanded_dim((int)model->dim);
     case NB200_MODEL_CUSTOM: return (uint64_t)CustomModel::expanded_dim((int)model->dim);
+    case NB200_MODEL_HOST: return (uint64_t)HostModel::expanded_dim((int)model->dim);
     }
     return 0;
 }
@@ -491,6 +667,12 @@ void nb200_settings_default(nb200_settings* s) {
     s->store_dims = 0;
     s->save_warmup = 1;
     s->expand_draws = 0;
+    s->store_divergences = 0;
+    s->adaptation = 0;
+    s->adam_learning_rate = 0.05;
+    s->step_size_jitter = 0.0;
+    s->mass_matrix_eigval_cutoff = 2.0;
+    s->mass_matrix_gamma = 1e-5;
 }
 
 void* nb200_host_alloc(size_t bytes) {
@@ -539,15 +721,31 @@ nb200_sampler* nb200_sampler_create(const nb200_settings* settings, const nb200_
         return create_impl<RadonModel>(settings, model, n_chains, chain_id_offset, device, q0, init_mean);
     case NB200_MODEL_CUSTOM:
         return create_impl<CustomModel>(settings, model, n_chains, chain_id_offset, device, q0, init_mean);
+    case NB200_MODEL_HOST:
+        return create_impl<HostModel>(settings, model, n_chains, chain_id_offset, device, q0, init_mean);
     }
     fail(NB200_EINVAL, "unknown model kind");
     return nullptr;
 }
 
-int nb200_sampler_set_trace_target(nb200_sampler* s, double* draws, double* stats) {
+int nb200_sampler_trace_bytes(nb200_sampler* s, size_t* draws_bytes, size_t* stats_bytes) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    if (draws_bytes) *draws_bytes = s->n_chains * s->n_rows * s->sdim * sizeof(double);
+    if (stats_bytes) *stats_bytes = s->n_chains * s->n_rows * NB200_NSTAT * sizeof(double);
+    return 0;
+}
+
+int nb200_sampler_set_trace_target(nb200_sampler* s, double* draws, size_t draws_bytes, double* stats,
+                                   size_t stats_bytes) {
     if (!s) return fail(NB200_EINVAL, "null sampler");
     std::lock_guard<std::mutex> lk(s->mu);
     if (s->state != RunState::Created) return fail(NB200_ESTATE, "trace target must be set before start");
+    // rows are streamed into these buffers while the kernel runs: a wrong size is a host
+    // memory overrun, so it is refused here and not discovered after sampling
+    if (draws && draws_bytes != s->n_chains * s->n_rows * s->sdim * sizeof(double))
+        return fail(NB200_EINVAL, "trace target: draws buffer must hold n_rows * n_chains * width doubles");
+    if (stats && stats_bytes != s->n_chains * s->n_rows * NB200_NSTAT * sizeof(double))
+        return fail(NB200_EINVAL, "trace target: stats buffer must hold n_rows * n_chains * 16 doubles");
     s->tgt_draws = draws;
     s->tgt_stats = stats;
     return 0;
@@ -581,6 +779,7 @@ int nb200_sampler_set_z_tape(nb200_sampler* s, const double* z_tape) {
     case NB200_MODEL_FUNNEL: set_tape<FunnelModel>(s); break;
     case NB200_MODEL_RADON: set_tape<RadonModel>(s); break;
     case NB200_MODEL_CUSTOM: set_tape<CustomModel>(s); break;
+    case NB200_MODEL_HOST: set_tape<HostModel>(s); break;
     }
     return 0;
 }
@@ -603,6 +802,7 @@ int nb200_sampler_start(nb200_sampler* s) {
     if (rc != 0) {
         s->state = RunState::Error;
         s->sampler_error = rc;
+        s->err = g_err;
         return rc;
     }
     s->state = RunState::Running;
@@ -666,12 +866,21 @@ static int on_launch_done(nb200_sampler* s) {
         if (s->h_sc[c].status < 0) {
             s->state = RunState::Error;
             s->sampler_error = s->h_sc[c].status;
-            return fail(s->h_sc[c].status,
-                        s->h_sc[c].status == NB200_EINIT
-                            ? "chain " + std::to_string(c) + ": no finite initial point found"
-                            : "chain " + std::to_string(c) + ": fatal logp error");
+            s->err = s->h_sc[c].status == NB200_EINIT
+                         ? "chain " + std::to_string(c) + ": no finite initial point found"
+                         : "chain " + std::to_string(c) + ": fatal logp error";
+            return fail(s->h_sc[c].status, s->err);
         }
         if (s->h_sc[c].status != 2) all_done = false;
+    }
+    if (s->host && s->host->fatal_rc.load() != 0) {
+        // src/pymc.rs:166-181: a negative return code is not recoverable — the sampler stops,
+        // wait() raises, the draws finished so far stay readable (trace / trace_into)
+        s->state = RunState::Error;
+        s->sampler_error = NB200_ELOGP;
+        s->err = "Logp function returned error code: " + std::to_string(s->host->fatal_rc.load()) +
+                 " (chain " + std::to_string(s->host->fatal_chain.load()) + ")";
+        return fail(NB200_ELOGP, s->err);
     }
     if (all_done) {
         if (s->tgt_draws || s->tgt_stats) {
@@ -694,7 +903,7 @@ int nb200_sampler_wait(nb200_sampler* s, double timeout_seconds) {
             case RunState::Created: return fail(NB200_ESTATE, "sampler not started");
             case RunState::Finished:
             case RunState::Aborted: return NB200_OK;
-            case RunState::Error: return fail(s->sampler_error, g_err.empty() ? "sampler error" : g_err);
+            case RunState::Error: return fail(s->sampler_error, s->err.empty() ? "sampler error" : s->err);
             case RunState::Paused: break;
             case RunState::Running: {
                 CU(cudaSetDevice(s->device));
@@ -707,6 +916,7 @@ int nb200_sampler_wait(nb200_sampler* s, double timeout_seconds) {
                     if (rc != 0) {
                         s->state = RunState::Error;
                         s->sampler_error = rc;
+                        s->err = g_err;
                         return rc;
                     }
                 } else if (q == cudaErrorNotReady) {
@@ -715,7 +925,8 @@ int nb200_sampler_wait(nb200_sampler* s, double timeout_seconds) {
                 } else {
                     s->state = RunState::Error;
                     s->sampler_error = NB200_ECUDA;
-                    return fail(NB200_ECUDA, std::string("kernel failed: ") + cudaGetErrorString(q));
+                    s->err = std::string("kernel failed: ") + cudaGetErrorString(q);
+                    return fail(NB200_ECUDA, s->err);
                 }
                 break;
             }
@@ -760,14 +971,19 @@ int nb200_sampler_progress(nb200_sampler* s, nb200_progress* out) {
 static int stop_and_drain(nb200_sampler* s) {
     CU(cudaSetDevice(s->device));
     int one = 1;
-    CU(cudaMemcpyAsync(s->d_stop, &one, sizeof(int), cudaMemcpyHostToDevice, s->side));
-    CU(cudaStreamSynchronize(s->side));
+    if (s->host) {  // mapped flag; the service threads keep answering until the kernel has left
+        __atomic_store_n(s->host->stop, 1, __ATOMIC_RELEASE);
+    } else {
+        CU(cudaMemcpyAsync(s->d_stop, &one, sizeof(int), cudaMemcpyHostToDevice, s->side));
+        CU(cudaStreamSynchronize(s->side));
+    }
     CU(cudaStreamSynchronize(s->stream));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->kernel_ms += ms;
     int zero = 0;
-    CU(cudaMemcpy(s->d_stop, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    if (s->host) __atomic_store_n(s->host->stop, 0, __ATOMIC_RELEASE);
+    else CU(cudaMemcpy(s->d_stop, &zero, sizeof(int), cudaMemcpyHostToDevice));
     return fetch_scalars(s);
 }
 
@@ -812,8 +1028,8 @@ static int copy_trace(nb200_sampler* s, double* draws, double* stats, double* gr
     if (rc != 0) return rc;
     const bool live = s->state == RunState::Running;
     for (uint64_t c = 0; c < s->n_chains; ++c) {
-        uint64_t d = s->h_sc[c].draw;
-        if (live && d > 0) d -= 1;  // the row being written may be incomplete
+        // while the kernel runs only the rows it has fenced and published are safe to read
+        uint64_t d = live ? s->h_sc[c].published : s->h_sc[c].draw;
         uint64_t r = s->st.save_warmup ? d : (d > s->st.num_tune ? d - s->st.num_tune : 0);
         s->rows_filled[c] = r < s->n_rows ? r : s->n_rows;
         if (rows) rows[c] = s->rows_filled[c];
@@ -866,6 +1082,43 @@ int nb200_sampler_trace(nb200_sampler* s, nb200_trace_view* out) {
     return 0;
 }
 
+int nb200_sampler_divergence_trace_into(nb200_sampler* s, double* divergences) {
+    if (!s || !divergences) return fail(NB200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state == RunState::Created) return fail(NB200_ESTATE, "sampler not started");
+    if (!s->d_div) return fail(NB200_EINVAL, "store_divergences was not set");
+    CU(cudaSetDevice(s->device));
+    const size_t nb = s->n_chains * s->n_rows * 4 * s->grad_dim * sizeof(double);
+    CU(cudaMemcpyAsync(divergences, s->d_div, nb, cudaMemcpyDeviceToHost, s->side));
+    CU(cudaStreamSynchronize(s->side));
+    return 0;
+}
+
+int nb200_host_expand_rows(nb200_expand_fn fn, const void* user_data, size_t dim, size_t expanded_dim,
+                           uint64_t n, const double* q, size_t q_stride, double* out, int n_threads) {
+    if (!fn || !q || !out) return fail(NB200_EINVAL, "null argument");
+    int T = n_threads > 0 ? n_threads : usable_cores();
+    if ((uint64_t)T > n) T = n ? (int)n : 1;
+    std::atomic<int> bad{0};
+    auto work = [&](int t) {
+        const uint64_t lo = n * (uint64_t)t / T, hi = n * (uint64_t)(t + 1) / T;
+        for (uint64_t i = lo; i < hi && bad.load(std::memory_order_relaxed) == 0; ++i) {
+            const int rc = fn(dim, expanded_dim, q + i * q_stride, out + i * expanded_dim, user_data);
+            if (rc != 0) {
+                int expect = 0;
+                bad.compare_exchange_strong(expect, rc);
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    if (bad.load() != 0)
+        return fail(NB200_ELOGP, "Expand function returned error code " + std::to_string(bad.load()));
+    return 0;
+}
+
 double nb200_sampler_kernel_ms(nb200_sampler* s) {
     if (!s) return 0.0;
     std::lock_guard<std::mutex> lk(s->mu);
@@ -902,14 +1155,17 @@ int nb200_sampler_destroy(nb200_sampler* s) {
     cudaSetDevice(s->device);
     if (s->state == RunState::Running) {
         int one = 1;
-        if (s->d_stop && s->side) {
+        if (s->host && s->host->stop) {
+            __atomic_store_n(s->host->stop, 1, __ATOMIC_RELEASE);
+        } else if (s->d_stop && s->side) {
             cudaMemcpyAsync(s->d_stop, &one, sizeof(int), cudaMemcpyHostToDevice, s->side);
             cudaStreamSynchronize(s->side);
         }
         if (s->stream) cudaStreamSynchronize(s->stream);
     }
+    if (s->host) s->host->shutdown();  // after the kernel: a waiting chain needs its answer
     void* dev[] = {s->d_pool, s->d_var, s->d_wf, s->d_sc, s->d_draws, s->d_stats, s->d_grads,
-                   s->d_mm, s->d_q0, s->d_init_mean, s->d_stop};
+                   s->d_mm, s->d_div, s->d_q0, s->d_init_mean, s->d_stop};
     for (void* p : dev) {
         if (!p) continue;
         if (s->stream) cudaFreeAsync(p, s->stream);  // back to the pool
@@ -1015,6 +1271,9 @@ extern "C" {
     case NB200_MODEL_FUNNEL: return CALL(FunnelModel);                         \
     case NB200_MODEL_RADON: return CALL(RadonModel);                           \
     case NB200_MODEL_CUSTOM: return CALL(CustomModel);                         \
+    case NB200_MODEL_HOST:                                                     \
+        return fail(NB200_EINVAL, "component entry points evaluate DEVICE densities; " \
+                                  "a host plug-in is called directly");                \
     }                                                                          \
     return fail(NB200_EINVAL, "unknown model kind");
 

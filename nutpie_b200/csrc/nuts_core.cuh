@@ -99,6 +99,7 @@ struct ChainShared {
     double lvLS[kMaxLevels];
     int idx[kMaxSlots];
     int lvL[kMaxLevels], lvR[kMaxLevels], lvD[kMaxLevels];
+    int stop;  // the host's stop flag as read by thread 0 (one decision for the whole group)
 };
 
 template <class M>
@@ -121,6 +122,8 @@ struct KParams {
     double* stats;     // [n_rows][n_chains][NB200_NSTAT]
     double* grads;     // optional, like draws
     double* mminv;     // optional, like draws
+    double* divs;      // optional [n_rows][n_chains][4][gdim]: divergence start / end location,
+                       // start momentum, start gradient (store_divergences); NaN-filled by the host
     const double* q0;        // optional [n_chains][D]
     const double* init_mean; // optional [D]
     const double* z_tape;    // optional [n_chains][n_total][D] (tests)
@@ -219,6 +222,7 @@ struct ChainCtx {
     int fg_sel, has_initial_mm;
     double last_mean, last_sym;
     uint32_t last_n_steps;
+    int div_src, div_dst;  // slots of the leapfrog that diverged in the running transition
 
     // f(i) for every dimension index owned by this thread
     template <class F>
@@ -725,6 +729,10 @@ struct ChainCtx {
         const double U = -lp;
         const double de = (kin + U) - E0;
         if (rc == 0 && (de > st().max_energy_error || !nb_isfinite(de))) rc = 1;
+        if (rc != 0) {
+            div_src = src;
+            div_dst = dst;
+        }
         if (g.tid == 0) {
             sh->idx[dst] = new_idx;
             sh->U[dst] = U;
@@ -1123,6 +1131,36 @@ struct ChainCtx {
         da_log_step_adapted = mk * da_log_step + (1.0 - mk) * da_log_step_adapted;
         da_count += 1;
     }
+    // Adam on the log step size (nuts-rs stepsize/adam.rs [recalled]: beta1 0.9, beta2 0.999,
+    // eps 1e-8, ascent on accept - target).  State reuses the dual-averaging slots:
+    // da_hbar = first moment, da_mu = second moment, da_count = step counter.
+    NB_HD void adam_new(double initial_step) {
+        da_log_step = log(initial_step);
+        da_log_step_adapted = da_log_step;
+        da_hbar = 0.0;
+        da_mu = 0.0;
+        da_count = 0;
+    }
+    NB_HD void adam_advance(double accept_stat) {
+        const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+        const double grad = accept_stat - st().target_accept;
+        da_count += 1;
+        da_hbar = b1 * da_hbar + (1.0 - b1) * grad;
+        da_mu = b2 * da_mu + (1.0 - b2) * grad * grad;
+        const double t = (double)da_count;
+        const double m_hat = da_hbar / (1.0 - pow(b1, t));
+        const double v_hat = da_mu / (1.0 - pow(b2, t));
+        da_log_step += st().adam_learning_rate * m_hat / (sqrt(v_hat) + eps);
+        da_log_step_adapted = da_log_step;
+    }
+    NB_HD void step_new(double initial_step) {
+        if (st().step_size_method == 1) adam_new(initial_step);
+        else da_new(initial_step);
+    }
+    NB_HD void step_advance(double accept_stat) {
+        if (st().step_size_method == 1) adam_advance(accept_stat);
+        else da_advance(accept_stat);
+    }
     NB_HD double clamp_step(double s) const {
         const double m = st().max_step_size;
         return (m > 0 && s > m) ? m : s;
@@ -1172,7 +1210,7 @@ struct ChainCtx {
             step_size = st().initial_step;
             found = 1;
         }
-        if (found == 1) da_new(step_size);
+        if (found == 1) step_new(step_size);
         acc_sum = keep_sum;
         acc_sym = keep_sym;
         acc_count = keep_count;
@@ -1289,7 +1327,7 @@ struct ChainCtx {
                 estimator_pass(dslot, is_good, n0, n1, update, fg_sel, fg_sel ? cnt1 : cnt0);
             did_change = update;
             if (did_change) last_update = t;
-            if (!fixed) da_advance(is_late ? last_sym : last_mean);
+            if (!fixed) step_advance(is_late ? last_sym : last_mean);
             if (did_change && has_initial_mm) {
                 has_initial_mm = 0;
                 step_size_search(dslot, (uint32_t)t);
@@ -1299,7 +1337,7 @@ struct ChainCtx {
             return;
         }
         if (fixed) return;
-        da_advance(last_sym);
+        step_advance(last_sym);
         if (t == num_tune - 1) step_size = clamp_step(exp(da_log_step_adapted));
         else step_size = clamp_step(exp(da_log_step));
     }
@@ -1368,7 +1406,7 @@ struct ChainCtx {
         last_update = 0;
         total_steps = 0;
         divergences = 0;
-        da_new(st().initial_step);
+        step_new(st().initial_step);
         step_size = st().initial_step;
         acc_sum = acc_sym = 0.0;
         acc_count = 0;
@@ -1433,8 +1471,31 @@ struct ChainCtx {
         const unsigned long long n_total = P->n_total, num_tune = st().num_tune;
         unsigned long long done_here = 0;
         while (t < n_total) {
-            if (P->stop_flag && *P->stop_flag) break;
+            if (P->stop_flag) {
+                // ONE read of the host's flag per chain and draw: with several warps per chain
+                // (a CTA per chain) each warp reading it on its own could see different values
+                // around the host's write and part of the chain would enter transition()'s
+                // barriers while the rest leaves the loop
+                bool stop_now;
+                if (G::kThreads <= 32) {
+                    stop_now = *P->stop_flag != 0;  // warp-uniform: one load instruction
+                } else {
+                    if (g.tid == 0) sh->stop = *P->stop_flag;
+                    g.sync();
+                    stop_now = sh->stop != 0;
+                    g.sync();  // everyone has read it before thread 0 may write the next one
+                }
+                if (stop_now) break;
+            }
             if (P->max_draws_per_launch && done_here >= P->max_draws_per_launch) break;
+            // step_size_jitter (src/wrapper.rs:393-407; nuts-rs [recalled]): the step used for a
+            // draw is the adapted one times a factor uniform in [1 - j, 1 + j]
+            const double step_base = step_size;
+            if (st().step_size_jitter > 0.0) {
+                uint64_t ja, jb;
+                rng_u64x2(st().seed, chain_gid, (uint32_t)t, RNG_JITTER, 0u, ja, jb);
+                step_size = step_base * (1.0 + st().step_size_jitter * (2.0 * rng_u01(ja) - 1.0));
+            }
             const double step_used = step_size;
             const bool keep = st().save_warmup || t >= num_tune;
             const unsigned long long row = st().save_warmup ? t : t - num_tune;
@@ -1446,9 +1507,30 @@ struct ChainCtx {
                 for (int i = g.tid; i < (int)P->gdim; i += g.size()) o[i] = var[i];
             }
             SampleInfo info;
+            div_src = div_dst = -1;
             const int sel = transition(cur, (uint32_t)t, info);
+            step_size = step_base;
             total_steps += acc_count;
             divergences += info.diverging;
+            if (keep && P->divs && info.diverging && div_src >= 0) {
+                // DivergenceInfo of the leapfrog that diverged: written before adapt() may reuse
+                // the two slots (rows of draws that did not diverge keep the host's NaN fill)
+                const int W4 = (int)P->gdim;
+                double* o = P->divs + row_off * 4 * (size_t)W4;
+                const double* qs_ = vec(div_src, VQ);
+                const double* qe_ = vec(div_dst, VQ);
+                const double* ps_ = vec(div_src, VP);
+                const double* gs_ = vec(div_src, VG);
+                for (int i = g.tid; i < W4; i += g.size()) {
+                    double gi;
+                    if constexpr (M::kElementwise) (void)M::term(md, i, qs_[i], gi);
+                    else gi = gs_[i];
+                    o[i] = qs_[i];
+                    o[W4 + i] = qe_[i];
+                    o[2 * W4 + i] = ps_[i];
+                    o[3 * W4 + i] = gi;
+                }
+            }
             // scalars of the selected state, captured before adapt() may reuse the slot
             const double selU = sh->U[sel], selK = sh->K[sel], E0t = E0;
             const int selIdx = sh->idx[sel];
@@ -1497,7 +1579,7 @@ struct ChainCtx {
             // every 16 draws (and at the end) fence the trace rows written so far and publish
             // the count: the host streams published rows to its buffers while sampling runs
             if ((t & 15ull) == 0 || t == n_total) {
-                nb_threadfence();
+                nb_threadfence_system();  // the reader is a copy engine on another stream
                 g.sync();
                 if (g.tid == 0) sc.published = t;
             }

@@ -17,7 +17,8 @@ enum : uint32_t {
     RNG_DIRECTION = 1,  // index = tree depth at the doubling
     RNG_MERGE = 2,      // index = merge sequence number inside the draw
     RNG_INIT_POS = 3,   // draw = attempt number, index = element pair
-    RNG_STEP_INIT = 4   // draw = draw index (0xFFFFFFFF before the first draw)
+    RNG_STEP_INIT = 4,  // draw = draw index (0xFFFFFFFF before the first draw)
+    RNG_JITTER = 5      // index 0: step-size jitter factor of the draw
 };
 
 NB_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,

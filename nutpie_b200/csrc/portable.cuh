@@ -57,6 +57,12 @@ NB_HD void nb_threadfence() {
 #endif
 }
 
+NB_HD void nb_threadfence_system() {
+#ifdef __CUDA_ARCH__
+    __threadfence_system();
+#endif
+}
+
 NB_HD bool nb_isfinite(double x) {
 #ifdef __CUDA_ARCH__
     return isfinite(x);

@@ -124,10 +124,12 @@ class CompiledDeviceModel:
     def reparameterized_names(self):
         return ["county_sd", "county_floor_sd", "sigma"] if self.kind == "radon" else []
 
-    def _make_sampler(self, settings, init_mean, cores, progress_type, store=None, **kw):
+    def _make_sampler(self, settings, init_mean, cores, progress_type, extra_callback=None,
+                      extra_callback_rate=500, store=None, **kw):
         """compile_pymc.py:168-187 — build the model object and start the sampler."""
         return _lib.PySampler.from_device_model(settings, cores, self, progress_type,
-                                                store=store, init_mean=init_mean, **kw)
+                                                extra_callback, extra_callback_rate, store,
+                                                init_mean=init_mean, **kw)
 
     def with_data(self, **updates):
         """compile_pymc.py:136-161 — replace data arrays, shapes must match."""

@@ -64,8 +64,10 @@ def _trace_to_groups(trace: _lib.PyTrace, compiled_model, settings, save_warmup,
         values = {"unconstrained_draw": draws}
     if var_names is not None:
         values = {k: v for k, v in values.items() if k in var_names}
-    out = Trace(dims={k: list(v) for k, v in compiled_model.dims.items()},
-                coords=dict(compiled_model.coords))
+    dims = dict(compiled_model.dims or {})
+    if hasattr(compiled_model, "_model_for_expand"):  # host plug-in: dims of the variable table
+        dims.update(compiled_model._model_for_expand()._variable_dims())
+    out = Trace(dims={k: list(v) for k, v in dims.items()}, coords=dict(compiled_model.coords or {}))
     for name, arr in values.items():
         out.warmup_posterior[name] = arr[:, :n_tune_rows]
         out.posterior[name] = arr[:, n_tune_rows:]
@@ -73,7 +75,10 @@ def _trace_to_groups(trace: _lib.PyTrace, compiled_model, settings, save_warmup,
         a = trace.stat(name)[:, :n_rows]
         out.warmup_sample_stats[name] = a[:, :n_tune_rows]
         out.sample_stats[name] = a[:, n_tune_rows:]
-    for name, arr in (("gradient", trace.gradients), ("mass_matrix_inv", trace.mass_matrix_inv)):
+    vec_stats = [("gradient", trace.gradients), ("mass_matrix_inv", trace.mass_matrix_inv)]
+    if trace.divergences is not None:  # sample.py:641-646
+        vec_stats += [(n, trace.divergences[:, :, k]) for k, n in enumerate(_lib.DIVERGENCE_COLUMNS)]
+    for name, arr in vec_stats:
         if arr is not None:
             out.warmup_sample_stats[name] = arr[:, :n_tune_rows]
             out.sample_stats[name] = arr[:, n_tune_rows:n_rows]
@@ -181,6 +186,8 @@ def _maybe_arviz(tr: Trace):
     if tr.warmup_posterior:
         groups["warmup_posterior"] = tr.warmup_posterior
         groups["warmup_sample_stats"] = tr.warmup_sample_stats
+    if tr.unconstrained_posterior:  # python/nutpie/sample.py:147-162
+        groups["unconstrained_posterior"] = tr.unconstrained_posterior
     try:
         return arviz.from_dict(groups, **kwargs)  # arviz >= 1.0
     except TypeError:
@@ -206,9 +213,11 @@ class _BackgroundSampler:
             progress_type = _lib.ProgressType("callback", progress_rate, progress_callback)
         else:
             progress_type = _lib.ProgressType.none()
+        # the reference's call (python/nutpie/sample.py:586-594) plus this engine's keywords
         self._sampler = compiled_model._make_sampler(
-            settings, init_mean, cores, progress_type, device=device,
-            chain_id_offset=chain_id_offset, trace_buffers=trace_buffers, **sampler_kw)
+            settings, init_mean, cores, progress_type, progress_callback, progress_rate,
+            _lib.PyStorage.arrow(), device=device, chain_id_offset=chain_id_offset,
+            trace_buffers=trace_buffers, **sampler_kw)
         self._html = None
 
     def wait(self, *, timeout=None):
@@ -319,6 +328,9 @@ def sample(
 
     if sampler == "nuts":
         if adaptation == "low_rank":
+            if not _lib.LOW_RANK_SUPPORTED:
+                raise NotImplementedError(
+                    "adaptation='low_rank' is not implemented by the B200 engine yet")
             settings = _lib.PyNutsSettings.LowRank(seed)
         elif adaptation == "flow":
             settings = _lib.PyNutsSettings.Flow(seed)

@@ -48,6 +48,21 @@ int oracle_logp_normal(size_t dim, const double *x, double *grad, double *logp_o
     return finish(dim, grad, -0.5 * acc * inv_var, logp_out);
 }
 
+/* pm.HalfNormal("a") (sigma = 1) on PyMC's log-transformed scale, x = log a — the model of the
+ * reference's seeded golden file tests/reference/test_deterministic_sampling_numba.txt
+ * (tests/test_pymc.py:533-541): logp(x) = log(2/sqrt(2 pi)) - exp(2x)/2 + x, per coordinate. */
+int oracle_logp_halfnormal(size_t dim, const double *x, double *grad, double *logp_out,
+                           const void *user_data) {
+    (void)user_data;
+    double logp = 0.0;
+    for (size_t i = 0; i < dim; ++i) {
+        double e2 = exp(2.0 * x[i]);
+        grad[i] = 1.0 - e2;
+        logp += HALF_LOG_2_OVER_PI - 0.5 * e2 + x[i];
+    }
+    return finish(dim, grad, logp, logp_out);
+}
+
 /* Neal's funnel (docs/sample-stats.qmd:19-21 with 9 parameters as in
  * BASELINE.json): x0 = log_sigma ~ N(0,1), x[k] ~ N(0, exp(x0)). */
 int oracle_logp_funnel(size_t dim, const double *x, double *grad, double *logp_out,

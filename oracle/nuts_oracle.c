@@ -122,6 +122,9 @@ typedef struct Chain {
     uint64_t last_update;
     uint64_t total_steps;
     int fatal;
+    /* DivergenceInfo of the running transition (store_divergences, python/nutpie/sample.py:641-646) */
+    int div_valid;
+    double *div; /* [4][dim]: start location, end location, start momentum, start gradient */
 } Chain;
 
 /* ------------------------------------------------- component: dual average */
@@ -141,6 +144,41 @@ static void da_advance(DualAverage *da, double accept_stat, double target, doubl
     double mk = pow(count, -k);
     da->log_step_adapted = mk * da->log_step + (1.0 - mk) * da->log_step_adapted;
     da->count += 1;
+}
+/* Adam on the log step size (nuts-rs stepsize/adam.rs [recalled]; src/wrapper.rs:347-392):
+ * state reuses the DualAverage slots — hbar = first moment, mu = second moment, count = t */
+static void adam_new(DualAverage *da, double initial_step) {
+    da->log_step = log(initial_step);
+    da->log_step_adapted = da->log_step;
+    da->hbar = 0.0;
+    da->mu = 0.0;
+    da->count = 0;
+}
+static void adam_advance(DualAverage *da, double accept_stat, double target, double lr) {
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    double grad = accept_stat - target;
+    da->count += 1;
+    da->hbar = b1 * da->hbar + (1.0 - b1) * grad;
+    da->mu = b2 * da->mu + (1.0 - b2) * grad * grad;
+    double t = (double)da->count;
+    double m_hat = da->hbar / (1.0 - pow(b1, t));
+    double v_hat = da->mu / (1.0 - pow(b2, t));
+    da->log_step += lr * m_hat / (sqrt(v_hat) + eps);
+    da->log_step_adapted = da->log_step;
+}
+static void step_new(const nb200_settings *st, DualAverage *da, double initial_step) {
+    if (st->step_size_method == 1) adam_new(da, initial_step);
+    else da_new(da, initial_step);
+}
+static void step_advance(const nb200_settings *st, DualAverage *da, double accept_stat) {
+    if (st->step_size_method == 1) adam_advance(da, accept_stat, st->target_accept, st->adam_learning_rate);
+    else da_advance(da, accept_stat, st->target_accept, st->da_k, st->da_t0, st->da_gamma);
+}
+void oracle_adam_advance(double state[5], double accept_stat, double target, double lr) {
+    DualAverage da = {state[0], state[1], state[2], state[3], (uint64_t)state[4]};
+    adam_advance(&da, accept_stat, target, lr);
+    state[0] = da.log_step; state[1] = da.log_step_adapted; state[2] = da.hbar;
+    state[3] = da.mu; state[4] = (double)da.count;
 }
 void oracle_dual_average_init(double state[5], double initial_step) {
     DualAverage da;
@@ -353,6 +391,13 @@ static int chain_leapfrog(Chain *c, const State *start, State *out, int dir) {
     if (rc < 0) return rc;
     c->acc_count += 1;
     c->total_steps += 1;
+    if (rc == 1 && c->div) {
+        c->div_valid = 1;
+        memcpy(c->div, start->q, c->dim * 8);
+        memcpy(c->div + c->dim, out->q, c->dim * 8);
+        memcpy(c->div + 2 * c->dim, start->p, c->dim * 8);
+        memcpy(c->div + 3 * c->dim, start->g, c->dim * 8);
+    }
     if (rc == 0) {
         double de = state_energy_error(out);
         double w = exp(-de);
@@ -531,7 +576,7 @@ static void step_size_init(Chain *c, const State *point, uint32_t rng_draw) {
             c->step_size = st->initial_step;
             found = 1;
         }
-        if (found == 1) da_new(&c->da, c->step_size);
+        if (found == 1) step_new(st, &c->da, c->step_size);
     }
     c->acc_count = keep_count; c->acc_sum = keep_sum; c->acc_sym_sum = keep_sym;
     c->total_steps = keep_total; /* search leapfrogs are not trajectory steps */
@@ -593,10 +638,7 @@ static void adapt(Chain *c, uint64_t t, const State *draw, const SampleInfo *inf
         if (force_update || (t - c->last_update >= st->mass_matrix_update_freq))
             did_change = update_mass_matrix(c);
         if (did_change) c->last_update = t;
-        if (!fixed) {
-            da_advance(&c->da, is_late ? c->last_sym : c->last_mean, st->target_accept,
-                       st->da_k, st->da_t0, st->da_gamma);
-        }
+        if (!fixed) step_advance(st, &c->da, is_late ? c->last_sym : c->last_mean);
         if (did_change && c->has_initial_mass_matrix) {
             c->has_initial_mass_matrix = 0;
             step_size_init(c, draw, (uint32_t)t);
@@ -606,7 +648,7 @@ static void adapt(Chain *c, uint64_t t, const State *draw, const SampleInfo *inf
         return;
     }
     if (fixed) return;
-    da_advance(&c->da, c->last_sym, st->target_accept, st->da_k, st->da_t0, st->da_gamma);
+    step_advance(st, &c->da, c->last_sym);
     if (t == num_tune - 1)
         c->step_size = clamp_step(c, exp(c->da.log_step_adapted));
     else
@@ -650,7 +692,8 @@ static int chain_init_position(Chain *c, State *s, const double *q0, const doubl
 static int run_chain(const nb200_settings *st, nb200_logp_fn logp, const void *ud, size_t dim,
                      uint32_t chain_id, const double *q0, const double *init_mean,
                      const double *z_tape, size_t n_rows, size_t sdim, double *draws,
-                     double *stats, double *grads, double *mminv, uint64_t *steps_out) {
+                     double *stats, double *grads, double *mminv, double *divs,
+                     uint64_t *steps_out) {
     Chain c;
     memset(&c, 0, sizeof(c));
     c.dim = dim; c.st = st; c.logp = logp; c.ud = ud; c.seed = st->seed;
@@ -658,6 +701,7 @@ static int run_chain(const nb200_settings *st, nb200_logp_fn logp, const void *u
     c.pool.dim = dim;
     c.var = (double *)calloc(dim + 1, 8);
     c.inv_std = (double *)calloc(dim + 1, 8);
+    c.div = divs ? (double *)calloc(4 * dim + 1, 8) : NULL;
     runvar_alloc(&c.fg_draw, dim); runvar_alloc(&c.fg_grad, dim);
     runvar_alloc(&c.bg_draw, dim); runvar_alloc(&c.bg_grad, dim);
 
@@ -673,19 +717,34 @@ static int run_chain(const nb200_settings *st, nb200_logp_fn logp, const void *u
         oracle_welford_add(dim, c.fg_grad.mean, c.fg_grad.m2, &c.fg_grad.count, cur->g);
         oracle_welford_add(dim, c.bg_grad.mean, c.bg_grad.m2, &c.bg_grad.count, cur->g);
         c.has_initial_mass_matrix = 1;
-        da_new(&c.da, st->initial_step);
+        step_new(st, &c.da, st->initial_step);
         c.step_size = st->initial_step;
         step_size_init(&c, cur, 0xFFFFFFFFu);
 
         uint64_t n_total = st->num_tune + st->num_draws;
         for (uint64_t t = 0; t < n_total && !c.fatal; ++t) {
             SampleInfo info;
+            /* step_size_jitter: factor uniform in [1 - j, 1 + j] on the step used for this draw */
+            double step_base = c.step_size;
+            if (st->step_size_jitter > 0.0) {
+                uint64_t ja, jb;
+                rng_u64x2(c.seed, c.chain_id, (uint32_t)t, RNG_JITTER, 0u, &ja, &jb);
+                c.step_size = step_base * (1.0 + st->step_size_jitter * (2.0 * rng_u01(ja) - 1.0));
+            }
             double step_used = c.step_size;
+            c.div_valid = 0;
             int store = st->save_warmup || t >= st->num_tune;
             size_t row = st->save_warmup ? t : t - st->num_tune;
             if (store && mminv) memcpy(mminv + row * sdim, c.var, sdim * 8);
             State *nxt = nuts_draw(&c, cur, (uint32_t)t, &info);
+            c.step_size = step_base;
             if (c.fatal) { state_release(&c.pool, nxt); break; }
+            if (store && row < n_rows && divs) {
+                double *o = divs + row * 4 * sdim;
+                for (size_t k = 0; k < 4; ++k)
+                    for (size_t i = 0; i < sdim; ++i)
+                        o[k * sdim + i] = c.div_valid && info.diverging ? c.div[k * dim + i] : NAN;
+            }
             adapt(&c, t, nxt, &info);
             if (store && row < n_rows) {
                 memcpy(draws + row * sdim, nxt->q, sdim * 8);
@@ -716,7 +775,7 @@ static int run_chain(const nb200_settings *st, nb200_logp_fn logp, const void *u
     *steps_out = c.total_steps;
     state_release(&c.pool, cur);
     pool_destroy(&c.pool);
-    free(c.var); free(c.inv_std);
+    free(c.var); free(c.inv_std); free(c.div);
     runvar_free(&c.fg_draw); runvar_free(&c.fg_grad);
     runvar_free(&c.bg_draw); runvar_free(&c.bg_grad);
     return rc;
@@ -728,7 +787,7 @@ typedef struct Job {
     const void *ud;
     uint64_t dim, n_chains, chain_id_offset;
     const double *q0, *init_mean, *z_tape;
-    double *draws, *stats, *gradients, *mminv;
+    double *draws, *stats, *gradients, *mminv, *divs;
     size_t n_total, n_rows, sdim;
     atomic_long next;  /* dynamic schedule over chains */
     atomic_ullong steps;
@@ -747,7 +806,8 @@ static void *worker(void *arg) {
                            j->n_rows, j->sdim, j->draws + (size_t)ci * j->n_rows * j->sdim,
                            j->stats + (size_t)ci * j->n_rows * NB200_NSTAT,
                            j->gradients ? j->gradients + (size_t)ci * j->n_rows * j->sdim : NULL,
-                           j->mminv ? j->mminv + (size_t)ci * j->n_rows * j->sdim : NULL, &s);
+                           j->mminv ? j->mminv + (size_t)ci * j->n_rows * j->sdim : NULL,
+                           j->divs ? j->divs + (size_t)ci * j->n_rows * 4 * j->sdim : NULL, &s);
         atomic_fetch_add(&j->steps, s);
         if (rc != 0) atomic_store(&j->err, rc);
     }
@@ -761,11 +821,22 @@ int oracle_sample(const nb200_settings *st, nb200_logp_fn logp, const void *user
                   const double *q0, const double *init_mean, const double *z_tape,
                   double *draws, double *stats, double *gradients, double *mass_matrix_inv,
                   uint64_t *total_steps) {
+    return oracle_sample_ex(st, logp, user_data, dim, n_chains, chain_id_offset, n_threads, q0,
+                            init_mean, z_tape, draws, stats, gradients, mass_matrix_inv, NULL,
+                            total_steps);
+}
+
+int oracle_sample_ex(const nb200_settings *st, nb200_logp_fn logp, const void *user_data,
+                     uint64_t dim, uint64_t n_chains, uint64_t chain_id_offset, int n_threads,
+                     const double *q0, const double *init_mean, const double *z_tape,
+                     double *draws, double *stats, double *gradients, double *mass_matrix_inv,
+                     double *divergences, uint64_t *total_steps) {
     Job j;
     memset(&j, 0, sizeof(j));
     j.st = st; j.logp = logp; j.ud = user_data; j.dim = dim; j.n_chains = n_chains;
     j.chain_id_offset = chain_id_offset; j.q0 = q0; j.init_mean = init_mean; j.z_tape = z_tape;
     j.draws = draws; j.stats = stats; j.gradients = gradients; j.mminv = mass_matrix_inv;
+    j.divs = divergences;
     j.n_total = st->num_tune + st->num_draws;
     j.n_rows = st->save_warmup ? j.n_total : st->num_draws;
     j.sdim = (st->store_dims && st->store_dims < dim) ? st->store_dims : dim;

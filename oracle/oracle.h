@@ -46,6 +46,7 @@ typedef struct oracle_radon_data {
 
 /* densities in the reference plug-in ABI (src/pymc.rs:23-29) */
 int oracle_logp_normal(size_t dim, const double *x, double *grad, double *logp, const void *ud);
+int oracle_logp_halfnormal(size_t dim, const double *x, double *grad, double *logp, const void *ud);
 int oracle_logp_funnel(size_t dim, const double *x, double *grad, double *logp, const void *ud);
 int oracle_logp_radon(size_t dim, const double *x, double *grad, double *logp, const void *ud);
 int oracle_logp_logreg(size_t dim, const double *x, double *grad, double *logp, const void *ud);
@@ -66,6 +67,14 @@ int oracle_sample(const nb200_settings *settings, nb200_logp_fn logp, const void
                   double *draws, double *stats, double *gradients, double *mass_matrix_inv,
                   uint64_t *total_steps);
 
+/* the same with the divergence rows of store_divergences:
+ * divergences [n_chains][n_rows][4][store_dims] (NaN unless the draw diverged) */
+int oracle_sample_ex(const nb200_settings *settings, nb200_logp_fn logp, const void *user_data,
+                     uint64_t dim, uint64_t n_chains, uint64_t chain_id_offset, int n_threads,
+                     const double *q0, const double *init_mean, const double *z_tape,
+                     double *draws, double *stats, double *gradients, double *mass_matrix_inv,
+                     double *divergences, uint64_t *total_steps);
+
 /* --- component entry points (known-answer tests at the nuts-rs Math seam) --- */
 /* one leapfrog, SURVEY Appendix A.2 */
 int oracle_leapfrog(nb200_logp_fn logp, const void *ud, size_t dim, const double *q,
@@ -79,6 +88,8 @@ int oracle_is_turning(size_t dim, int64_t idx1, const double *p1, const double *
 void oracle_dual_average_init(double state[5], double initial_step);
 void oracle_dual_average_advance(double state[5], double accept_stat, double target, double k,
                                  double t0, double gamma);
+/* Adam step-size rule on the same 5-slot state (hbar = m, mu = v, count = t) */
+void oracle_adam_advance(double state[5], double accept_stat, double target, double lr);
 /* running variance (Welford): mean[D], m2[D], *count */
 void oracle_welford_add(size_t dim, double *mean, double *m2, uint64_t *count, const double *x);
 /* mass-matrix refresh from the two estimators (grad-based) or draws only */

@@ -45,6 +45,9 @@ class Settings(C.Structure):
         ("init_radius", C.c_double),
         ("store_dims", C.c_uint64),
         ("save_warmup", C.c_int32), ("expand_draws", C.c_int32),
+        ("store_divergences", C.c_int32), ("adaptation", C.c_int32),
+        ("adam_learning_rate", C.c_double), ("step_size_jitter", C.c_double),
+        ("mass_matrix_eigval_cutoff", C.c_double), ("mass_matrix_gamma", C.c_double),
     ]
 
 
@@ -70,6 +73,9 @@ def default_settings(**kw) -> Settings:
     s.init_kind, s.num_try_init, s.init_radius = 0, 10, 2.0
     s.store_dims = 0
     s.save_warmup = 1
+    s.store_divergences, s.adaptation = 0, 0
+    s.adam_learning_rate, s.step_size_jitter = 0.05, 0.0
+    s.mass_matrix_eigval_cutoff, s.mass_matrix_gamma = 2.0, 1e-5
     for k, v in kw.items():
         if not hasattr(s, k):
             raise AttributeError(k)
@@ -113,12 +119,14 @@ def lib() -> C.CDLL:
                 pass  # GPU box without sources newer than the .so: use as is
         _LIB = C.CDLL(str(so))
         _LIB.oracle_sample.restype = C.c_int
+        _LIB.oracle_sample_ex.restype = C.c_int
         _LIB.oracle_leapfrog.restype = C.c_int
         _LIB.oracle_is_turning.restype = C.c_int
     return _LIB
 
 
 _LIB_FAST = None
+FAST_BUILD_KIND = None  # "fast" | "literal" (fallback): which build lib_fast() handed out
 
 
 def _cpu_model() -> str:
@@ -136,7 +144,7 @@ def lib_fast() -> C.CDLL:
     contraction allowed) — used only where the oracle is TIMED as the CPU baseline (bench.py), so
     that the baseline is not handicapped by the literal, unfused arithmetic the parity tests want.
     Rebuilt when the CPU model changes (the .so travels between machines)."""
-    global _LIB_FAST
+    global _LIB_FAST, FAST_BUILD_KIND
     if _LIB_FAST is None:
         so, tag = _HERE / "liboracle_fast.so", _HERE / "liboracle_fast.cpu"
         cpu = _cpu_model()
@@ -150,8 +158,16 @@ def lib_fast() -> C.CDLL:
                 tag.write_text(cpu)
             _LIB_FAST = C.CDLL(str(so))
             _LIB_FAST.oracle_sample.restype = C.c_int
-        except (OSError, subprocess.CalledProcessError):
+            _LIB_FAST.oracle_sample_ex.restype = C.c_int
+            FAST_BUILD_KIND = "fast"
+        except (OSError, subprocess.CalledProcessError) as exc:
+            import warnings
+
+            warnings.warn(f"speed build of the oracle failed ({exc}); timing the literal build "
+                          "(about 20% slower: the CPU baseline is understated)")
             _LIB_FAST = lib()  # no compiler on this machine: time the literal build
+            FAST_BUILD_KIND = "literal"
+
     return _LIB_FAST
 
 
@@ -171,6 +187,9 @@ class Model:
             self.ud = NormalData(float(kw.get("mu", 0.0)), float(kw.get("sigma", 1.0)))
         elif kind == "funnel":
             self.fn = L.oracle_logp_funnel
+            self.ud = NormalData(0.0, 1.0)
+        elif kind == "halfnormal":  # HalfNormal(1) on the log scale (the reference's golden model)
+            self.fn = L.oracle_logp_halfnormal
             self.ud = NormalData(0.0, 1.0)
         elif kind == "radon":
             y = np.ascontiguousarray(kw["y"], dtype=np.float64)
@@ -224,6 +243,7 @@ def sample(model: Model, settings: Settings, n_chains: int, chain_id_offset: int
     stats = np.zeros((n_chains, n_rows, NSTAT))
     grads = np.zeros((n_chains, n_rows, sdim)) if settings.store_gradient else None
     mm = np.zeros((n_chains, n_rows, sdim)) if settings.store_mass_matrix else None
+    divs = np.zeros((n_chains, n_rows, 4, sdim)) if settings.store_divergences else None
     if q0 is not None:
         q0 = np.ascontiguousarray(q0, dtype=np.float64).reshape(n_chains, model.dim)
     if init_mean is not None:
@@ -231,14 +251,14 @@ def sample(model: Model, settings: Settings, n_chains: int, chain_id_offset: int
     if z_tape is not None:
         z_tape = np.ascontiguousarray(z_tape, dtype=np.float64).reshape(n_chains, n_total, model.dim)
     steps = C.c_uint64(0)
-    rc = L.oracle_sample(C.byref(settings), model.fn_ptr, model.ud_ptr, C.c_uint64(model.dim),
-                         C.c_uint64(n_chains), C.c_uint64(chain_id_offset), C.c_int(n_threads),
-                         _ptr(q0), _ptr(init_mean), _ptr(z_tape), _ptr(draws), _ptr(stats),
-                         _ptr(grads), _ptr(mm), C.byref(steps))
+    rc = L.oracle_sample_ex(C.byref(settings), model.fn_ptr, model.ud_ptr, C.c_uint64(model.dim),
+                            C.c_uint64(n_chains), C.c_uint64(chain_id_offset), C.c_int(n_threads),
+                            _ptr(q0), _ptr(init_mean), _ptr(z_tape), _ptr(draws), _ptr(stats),
+                            _ptr(grads), _ptr(mm), _ptr(divs), C.byref(steps))
     if rc != 0:
         raise RuntimeError(f"oracle_sample failed with code {rc}")
     return dict(draws=draws, stats=stats, gradients=grads, mass_matrix_inv=mm,
-                total_steps=int(steps.value))
+                divergences=divs, total_steps=int(steps.value))
 
 
 def stat(stats: np.ndarray, name: str) -> np.ndarray:

@@ -87,3 +87,19 @@ def logreg_data(n_obs=200, dim=12, seed=3):
     beta = rng.normal(size=dim)
     y = (rng.random(n_obs) < 1.0 / (1.0 + np.exp(-X @ beta))).astype(np.float64)
     return np.concatenate([[float(n_obs), float(dim)], X.ravel(), y])
+
+# pm.HalfNormal("a") on the log scale (twin: oracle_logp_halfnormal) — the model of the
+# reference's golden file tests/reference/test_deterministic_sampling_numba.txt
+HALFNORMAL = r"""
+__device__ int nb200_user_logp(const nb200_group& grp, int dim, const double* q, double* grad,
+                               double* logp_partial, const double*) {
+    double acc = 0.0;
+    for (int i = grp.tid; i < dim; i += grp.nthreads) {
+        const double e2 = exp(2.0 * q[i]);
+        grad[i] = 1.0 - e2;
+        acc += -0.22579135264472743236 - 0.5 * e2 + q[i];
+    }
+    *logp_partial = acc;
+    return 0;
+}
+"""

@@ -24,4 +24,7 @@ summary = {
     "first5": x[:5].tolist(),
 }
 (OUT / "halfnormal_reference_summary.json").write_text(json.dumps(summary, indent=1))
+# the 200 values themselves (test OUTPUT data of the reference, chain-major 2 x 100): the
+# replicate-distribution test needs per-chain autocorrelations, not only the moments
+np.savetxt(OUT / "halfnormal_reference_values.txt", x, fmt="%.9g")
 print(summary)

@@ -24,14 +24,15 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for n in names:
         assert hasattr(L, n), f"missing export {n}"
-    assert L.nb200_abi_version() == 2
+    assert L.nb200_abi_version() == 3
 
 
 def test_settings_struct_layout_matches_header():
     from nutpie_b200 import _lib
     from oracle import pyoracle as O
 
-    assert C.sizeof(_lib.Settings) == C.sizeof(O.Settings) == 192
+    assert C.sizeof(_lib.Settings) == C.sizeof(O.Settings) == 232
+    assert C.sizeof(_lib.ModelDesc) == 144
     s = _lib.Settings()
     _lib.load_library().nb200_settings_default(C.byref(s))
     d = O.default_settings()
@@ -64,8 +65,19 @@ def test_settings_facade_follows_wrapper_rs():
     d = s.as_dict()
     assert d["sampler"] == "nuts" and d["adaptation"] == "diag" and d["settings"]["maxdepth"] == 6
     assert _lib.PyNutsSettings.Diag(None).seed != _lib.PyNutsSettings.Diag(None).seed
-    with pytest.raises(NotImplementedError):
-        _lib.PyNutsSettings.LowRank(1)
+    s.step_size_adapt_method = "adam"    # src/wrapper.rs:347-375
+    s.step_size_adam_learning_rate = 0.1
+    s.step_size_jitter = 0.2
+    s.store_divergences = True
+    assert (s._c.step_size_method, s._c.adam_learning_rate, s._c.step_size_jitter,
+            s._c.store_divergences) == (1, 0.1, 0.2, 1)
+    s.step_size_jitter = None
+    assert s._c.step_size_jitter == 0.0
+    lr = _lib.PyNutsSettings.LowRank(1)
+    lr.mass_matrix_gamma = 1e-4
+    assert lr.as_dict()["adaptation"] == "low_rank" and lr._c.mass_matrix_gamma == 1e-4
+    with pytest.raises(ValueError):      # diag-only option on the low-rank settings
+        lr.use_grad_based_mass_matrix = False
 
 
 def test_sampler_fails_loudly_without_gpu():
@@ -189,7 +201,7 @@ def test_expanded_layout_covers_every_variable(radon_data):
 def test_model_desc_layout():
     from nutpie_b200 import _lib
 
-    assert C.sizeof(_lib.ModelDesc) == 96
+    assert C.sizeof(_lib.ModelDesc) == 144
     assert _lib.ModelDesc.cuda_source.offset == 64 and _lib.ModelDesc.n_user_scratch.offset == 88
 
 
@@ -293,8 +305,8 @@ def test_arrow_batches_round_trip_through_the_reference_consumer():
 
     # complete run: identical to the dense path, variable by variable
     dense = S._trace_to_groups(trace([n_rows] * n_chains), cm, _S(), True)
-    pairs = trace([n_rows] * n_chains).get_arrow_trace()
-    post, st = [p for p, _ in pairs], [s for _, s in pairs]
+    post, st = trace([n_rows] * n_chains).get_arrow_trace()  # (draw batches, stat batches)
+    assert len(post) == len(st) == n_chains
     assert post[0].schema.field("county_effect").metadata == {b"dims": b"county", b"shape": str(J).encode()}
     via = S._arrow_to_groups(post, st, skip_vars=["tuning", "draw", "chain"], coords=cm.coords)
     assert set(via.posterior) == set(dense.posterior)
@@ -313,8 +325,7 @@ def test_arrow_batches_round_trip_through_the_reference_consumer():
     assert "sigma" not in uc.posterior and uc.unconstrained_posterior["sigma"].shape == (n_chains, draws)
     # ragged chains: chain 1 stopped inside warm-up, chain 2 after two posterior draws
     rows = [n_rows, 3, tune + 2]
-    pairs = trace(rows).get_arrow_trace()
-    rag = S._arrow_to_groups([p for p, _ in pairs], [s for _, s in pairs])
+    rag = S._arrow_to_groups(*trace(rows).get_arrow_trace())
     sig = rag.posterior["sigma"]
     assert sig.shape == (n_chains, draws) and rag.warmup_posterior["sigma"].shape == (n_chains, tune)
     assert np.isnan(sig[1]).all() and np.isnan(sig[2, 2:]).all() and not np.isnan(sig[2, :2]).any()

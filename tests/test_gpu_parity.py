@@ -344,9 +344,9 @@ def test_public_api_radon_shapes_and_save_warmup(radon_data):
                                tr.posterior["county_raw"] * tr.posterior["county_sd"][..., None])
     raw = nutpie_b200.sample(cm, chains=2, draws=10, tune=10, seed=1, return_raw_trace=True,
                              init_radius=1.0)
-    batches = raw.get_arrow_trace()
-    assert len(batches) == 2 and batches[0][0].num_rows == 20
-    assert batches[0][1].column("tuning").to_numpy(zero_copy_only=False).sum() == 10
+    draw_batches, stat_batches = raw.get_arrow_trace()  # src/wrapper.rs:1477-1494
+    assert len(draw_batches) == len(stat_batches) == 2 and draw_batches[0].num_rows == 20
+    assert stat_batches[0].column("tuning").to_numpy(zero_copy_only=False).sum() == 10
     with pytest.raises(ValueError):
         raw.get_arrow_trace()  # single-take, src/wrapper.rs:1477-1494
 

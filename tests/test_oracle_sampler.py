@@ -66,20 +66,62 @@ def test_repeated_values_are_stored():
     assert (idx[:, 1:][rep] == 0).all()
 
 
-def test_halfnormal_golden_is_plausible_under_our_sampler():
-    """tests/reference/test_deterministic_sampling_numba.txt: 200 |N(0,1)| draws from
-    HalfNormal('a').  Bit-level reproduction is out of reach (different RNG); the
-    committed copy of its summary statistics pins the distribution: our sampler on
-    the log-transformed half-normal must agree with them."""
-    import json
+def halfnormal_replicate_check(a, gold):
+    """`a`: [R, 2, 100] draws of HalfNormal(1) from R independent replicates of the reference's
+    golden run (2 chains x (100 tune + 100 draws)); `gold`: the reference's 200 values.
+    The reference's seeded stream (rand ChaCha8 + PyMC's jittered init) cannot be reproduced, so
+    its file is treated as ONE replicate: each of its summary statistics must be a plausible
+    draw from the replicate distribution of OUR sampler (two-sided, 1e-3 per tail), and our
+    pooled draws must have the exact half-normal law.  Returns the percentiles for reporting."""
+    from scipy import stats as ss
+
+    R = a.shape[0]
+    g = gold.reshape(2, 100)
+
+    def ac1(x):
+        x = np.log(x)
+        x = x - x.mean(-1, keepdims=True)
+        return (x[..., 1:] * x[..., :-1]).sum(-1) / (x * x).sum(-1)
+
+    flat = a.reshape(R, 200)
+    stat_fns = {
+        "mean": lambda v: v.reshape(-1, 200).mean(1),
+        "sd": lambda v: v.reshape(-1, 200).std(1),
+        "median": lambda v: np.median(v.reshape(-1, 200), axis=1),
+        "max": lambda v: v.reshape(-1, 200).max(1),
+        "n_repeated": lambda v: (v.reshape(-1, 2, 100)[..., 1:] == v.reshape(-1, 2, 100)[..., :-1]).sum((1, 2)),
+        "lag1_autocorr_log": lambda v: ac1(v.reshape(-1, 2, 100)).mean(1),
+    }
+    pct = {}
+    for name, f in stat_fns.items():
+        ours, ref = f(a), f(g[None])[0]
+        pct[name] = float(((ours < ref).mean() + (ours <= ref).mean()) / 2)
+        assert 1e-3 <= pct[name] <= 1 - 1e-3, (name, ref, pct[name], np.percentile(ours, [0.1, 50, 99.9]))
+    # exact law of the pooled draws: |N(0, 1)|; thinned to roughly independent draws
+    pooled = flat[:, ::10].ravel()
+    assert abs(pooled.mean() - np.sqrt(2 / np.pi)) < 4 * 0.603 / np.sqrt(pooled.size)
+    assert abs(pooled.std() - np.sqrt(1 - 2 / np.pi)) < 0.02
+    assert ss.kstest(pooled[:: max(1, pooled.size // 4000)], "halfnorm").pvalue > 1e-3
+    return pct
+
+
+def test_halfnormal_golden_is_a_plausible_replicate_of_our_sampler():
+    """tests/reference/test_deterministic_sampling_numba.txt (tests/test_pymc.py:533-541):
+    `pm.HalfNormal("a")`, seed=123, draws=100, tune=100, 2 chains -> 200 values.  Our sampler
+    runs the same model (log-transformed half-normal, PyMC's U(-1, 1) jitter) 1500 times with
+    the same run shape; see halfnormal_replicate_check for what is asserted.  (For the record:
+    the reference's file sits low — mean 0.56 at about the 0.2 percentile of replicate means,
+    one chain wandered to a = 3e-4 — but inside the bands.)"""
     from pathlib import Path
 
-    gold = json.loads((Path(__file__).parent / "golden" / "halfnormal_reference_summary.json").read_text())
-    assert gold["n"] == 200 and 0.5 < gold["mean"] < 1.1
-    # |N(0,1)| has mean sqrt(2/pi) ~ 0.798, sd ~ 0.603: the reference's 200 draws
-    # (100 per chain, autocorrelated) sit within wide bands of that
-    assert abs(gold["mean"] - 0.798) < 0.25
-    assert abs(gold["std"] - 0.603) < 0.25
+    gold = np.loadtxt(Path(__file__).parent / "golden" / "halfnormal_reference_values.txt")
+    assert gold.shape == (200,)
+    R = 1500
+    m = O.Model("halfnormal", 1)
+    s = O.default_settings(seed=123, num_tune=100, num_draws=100, init_radius=1.0)
+    r = O.sample(m, s, 2 * R)
+    a = np.exp(r["draws"][:, 100:, 0]).reshape(R, 2, 100)
+    halfnormal_replicate_check(a, gold)
 
 
 def test_window_schedule_mass_matrix_frozen_late():
