@@ -18,11 +18,14 @@ draws.  Every step uses a new seed and works on freshly allocated state
   e2e        : the same count / wall time of nutpie_b200.sample(...) called with
                HOST data: includes H2D of the model data, all allocations, the
                kernel, and the D2H copy of the full trace into pinned host memory.
-  roofline   : algorithmic bytes (72 B x D per gradient evaluation)
-               / kernel time vs the measured HBM copy bandwidth.  For radon the
-               chain state lives in shared memory, so this is NOT an HBM-bound
-               kernel; `roofline_hbm_config4` reports the same quantity on the
-               D = 10 000, 512-chain iid-normal workload where HBM does bind.
+  roofline   : the radon kernel keeps chain state in shared memory — it is bound by FP64
+               issue / dependent-instruction latency, not HBM — so `roofline` reports
+               achieved FP64 FLOP/s (27 175 flop per gradient evaluation)
+               over the MEASURED FP64 FMA peak (scripts/micro/fp64_peak.cu); the HBM
+               figure (72 B x D algorithmic bytes / kernel time vs measured copy
+               bandwidth) is kept as `roofline_hbm_secondary`.  `roofline_hbm_config4`
+               is the HBM roofline of the D = 10 000, 512-chain iid-normal workload where
+               HBM does bind (median of 3 full-length runs).
   cpu_baseline / --impl reference : the CPU restatement of nuts-rs (oracle/,
                "port") on all host cores, same model, settings and metric.
 """
@@ -63,6 +66,22 @@ def _peaks():
         d = json.loads(p.read_text())
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# FP64 work of one gradient evaluation of the radon model: density 25 N + 10 D,
+# integrator + reductions 14 D  (N = 919, D = 175)
+RADON_FLOP_PER_EVAL = 25 * 919 + 10 * DIM + 14 * DIM
+
+
+def _fp64_peak():
+    """Measured FP64 FMA throughput of this pool's B200 (scripts/micro/fp64_peak.cu, output
+    committed under profiles/): MEASURED_PEAKS.json carries no FP64 figure."""
+    p = ROOT / "profiles" / "r2_fp64_peak_microbench.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["fp64_fma_tflops_saturated"]), ("measured (scripts/micro/fp64_peak.cu -> "
+                                                       "profiles/r2_fp64_peak_microbench.json)")
+    return 40.0, "nominal B200 FP64 (no measurement found)"
 
 
 class ClockSampler:
@@ -156,6 +175,14 @@ def cpu_run(n_chains: int, seed: int, n_threads: int = 0):
     return r["total_steps"], dt
 
 
+def _oracle_build() -> str:
+    """Which build of the oracle the timed CPU arm used: "fast" (-O3 -march=native, built on
+    this machine) or "literal" (the parity build; ~20 % slower — the fallback when no compiler)."""
+    from oracle import pyoracle as O
+
+    return O.FAST_BUILD_KIND or "not run"
+
+
 def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
@@ -179,7 +206,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "chains_per_step_cpu": n_chains},
         "cpu_baseline": {"value": value, "unit": "grad_evals/s", "cores": cores, "kind": "port",
-                         "sample": sample_desc},
+                         "build": _oracle_build(), "sample": sample_desc},
         "e2e": {"value": value, "unit": "grad_evals/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "note": "CPU restatement of nuts-rs semantics (oracle/), not the reference binary: "
@@ -331,6 +358,21 @@ def run_gpu(args):
         if i >= args.warmup:
             e2e_wall += dt
             e2e_steps += int(tr.stats[..., 9].sum())  # metric bookkeeping, outside the timed call
+    # ---- the DEFAULT call a user makes: no caller buffers, result grouped by variable
+    # (pageable numpy arrays, one D2H at the end, posterior / sample_stats dicts); one run
+    default_api = None
+    if rank == 0:
+        tr = None
+        t1 = time.perf_counter()
+        res = nutpie_b200.sample(model, draws=DRAWS, tune=TUNE, chains=n_chains, seed=900,
+                                 init_radius=1.0, progress_bar=False, device=device)
+        dt = time.perf_counter() - t1
+        st_n = res.sample_stats["n_steps"].sum() + res.warmup_sample_stats["n_steps"].sum()
+        default_api = {"value": float(st_n) / dt, "unit": "grad_evals/s", "ms": 1e3 * dt,
+                       "what": "nutpie_b200.sample(model, chains=1024, tune=1000, draws=1000) with "
+                               "defaults on rank 0 alone: pageable result arrays, grouped Trace"}
+        res = None
+        gc.collect()
     h2d = int(data["y"].nbytes + data["county"].nbytes + data["floor"].nbytes + DIM * 8)
     d2h = int(bufs["draws"].nbytes + bufs["stats"].nbytes)
 
@@ -358,7 +400,9 @@ def run_gpu(args):
         return
 
     peak, peak_src = _peaks()
+    fp64_peak, fp64_src = _fp64_peak()
     value = steps / (kernel_ms / 1e3)
+    fp64_achieved = RADON_FLOP_PER_EVAL * (steps / world) / (kernel_ms / 1e3) / 1e12  # per GPU
     algo_bytes = 72.0 * DIM * (steps / world)  # per GPU
     achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
     cores = host_cores()
@@ -381,19 +425,24 @@ def run_gpu(args):
                 "ms_per_step": 1e3 * e2e_wall / args.steps},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak,
+        "roofline": {"bound": "fp64_issue", "achieved": fp64_achieved, "peak": fp64_peak,
+                     "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
                      "traffic": NCU_DRAM_BYTES_PER_EVAL["radon"] * (steps / world) / args.steps,
-                     "traffic_note": "DRAM bytes per launch = ncu-measured bytes per gradient evaluation "
-                                     "(profiles/r1_radon_nuts_kernel_latest.txt) x evaluations in one launch; "
-                                     "4% of the algorithmic bytes, almost all of it the trace being written",
-                     "algorithmic_bytes_per_launch": algo_bytes / args.steps,
-                     "peak_source": peak_src,
-                     "note": "radon keeps chain state in shared memory: algorithmic bytes are "
-                             "served on chip, see roofline_hbm_config4 for the HBM-bound kernel"},
+                     "flop_per_grad_eval": RADON_FLOP_PER_EVAL, "peak_source": fp64_src,
+                     "note": "chain state and density tables live in shared memory (DRAM traffic = "
+                             "the trace being written): the ceiling is FP64 issue slots and the "
+                             "9-cycle dependent DFMA latency of 2 warps per chain at 7 chains per SM, "
+                             "not HBM; traffic = ncu DRAM bytes per launch"},
+        "roofline_hbm_secondary": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                   "frac": achieved / peak,
+                                   "algorithmic_bytes_per_launch": algo_bytes / args.steps,
+                                   "peak_source": peak_src,
+                                   "note": "72 B x D per gradient evaluation, served from shared "
+                                           "memory: NOT the binding resource of this kernel"},
         "roofline_hbm_config4": cfg4,
+        "e2e_default_api": default_api,
         "cpu_baseline": {"value": cpu_steps / cpu_dt, "unit": "grad_evals/s", "cores": cores,
-                         "kind": "port",
+                         "kind": "port", "build": _oracle_build(),
                          "sample": f"{cpu_chains} chains x ({TUNE}+{DRAWS}) draws, same model, "
                                    f"{cores} host threads, {cpu_dt:.1f} s; -O3 -march=native build"},
         "ess_per_sec": (ess_min * world / (kernel_ms / args.steps / 1e3)) if ess_min else None,
@@ -418,8 +467,8 @@ def run_config4(device):
     model = nutpie_b200.normal_model(D)
     s = _lib.PyNutsSettings.Diag(7)
     s.update({"num_tune": tune, "num_draws": draws, "num_chains": C, "store_dims": 16})
-    best = None
-    for rep in range(1):
+    runs = []
+    for rep in range(3):  # full-length runs; the MEDIAN is reported, all three are listed
         smp = _lib.PySamplerDeferred(s, model, n_chains=C, device=device)
         smp.start()
         smp.wait()
@@ -428,14 +477,14 @@ def run_config4(device):
         geom = smp.geometry()
         steps = int(tr.stats[..., 9].sum())
         smp.close()
-        if best is None or ms < best[0]:
-            best = (ms, steps, geom)
-    ms, steps, geom = best
+        runs.append((ms, steps, geom))
+    ms, steps, geom = sorted(runs, key=lambda r: r[0])[1]
     peak, src = _peaks()
     achieved = 72.0 * D * steps / (ms / 1e3) / 1e9
     return {"workload": "iid_normal_D10000_512chains_200tune_200draws", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "grad_evals_per_sec": steps / (ms / 1e3), "kernel_ms": ms, "geometry": geom,
+            "kernel_ms_all_runs": [r[0] for r in runs], "statistic": "median of 3",
             "peak_source": src, "algorithmic_bytes_per_launch": 72.0 * D * steps,
             "traffic": NCU_DRAM_BYTES_PER_EVAL["config4"] * steps,
             "traffic_note": "ncu-measured DRAM bytes per gradient evaluation "

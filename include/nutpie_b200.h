@@ -317,6 +317,11 @@ void nb200_set_unroll(int32_t on);
  * staging, 2 = successive passes sweep the dimensions in alternating directions (the tail a
  * pass wrote is the first thing the next one reads), 4 = L2 eviction hints on the bulk copies */
 void nb200_set_stage_loads(int32_t mode);
+/* 1 (default) = densities that gather across dimensions run two warps per chain: an integrator
+ * warp producing leaves back to back and a tree warp consuming them (bit-identical traces);
+ * 0 = one warp does both.  nb200_sampler_is_pipelined reports what a sampler got. */
+void nb200_set_pipeline(int32_t on);
+int nb200_sampler_is_pipelined(nb200_sampler *s);
 /* limit the draws one kernel launch may advance each chain by (0 = run to the
  * end in one persistent launch); the host relaunches until done */
 int nb200_sampler_set_draws_per_launch(nb200_sampler *s, uint64_t n);

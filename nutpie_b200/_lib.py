@@ -191,6 +191,10 @@ def load_library() -> C.CDLL:
         L.nb200_set_stage_loads.argtypes = [C.c_int32]
         L.nb200_set_unroll.restype = None
         L.nb200_set_unroll.argtypes = [C.c_int32]
+        L.nb200_set_pipeline.restype = None
+        L.nb200_set_pipeline.argtypes = [C.c_int32]
+        L.nb200_sampler_is_pipelined.restype = C.c_int
+        L.nb200_sampler_is_pipelined.argtypes = [C.c_void_p]
         L.nb200_sampler_smem.restype = C.c_int
         L.nb200_sampler_smem.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.nb200_host_alloc.restype = C.c_void_p
@@ -625,6 +629,12 @@ class PySampler:
         pt = progress_type
         if extra_callback is not None and (pt is None or pt.callback is None):
             pt = ProgressType("callback", extra_callback_rate or 500, extra_callback)
+        devices = kw.pop("devices", None)
+        if devices is not None and not (isinstance(devices, (list, tuple)) and len(devices) == 1):
+            kw.pop("device", None)
+            return PyMultiSampler(settings, model, devices=devices, progress_type=pt, **kw)
+        if devices is not None:
+            kw["device"] = int(devices[0])
         return PySampler(settings, model, progress_type=pt, **kw)
 
     @staticmethod
@@ -780,7 +790,8 @@ class PySampler:
         sl, by = C.c_int32(), C.c_int32()
         _check(self._L.nb200_sampler_smem(self._h, C.byref(sl), C.byref(by)))
         return dict(threads_per_chain=a.value, block=b.value, grid=g.value,
-                    smem_slots=sl.value, smem_bytes_per_chain=by.value)
+                    smem_slots=sl.value, smem_bytes_per_chain=by.value,
+                    pipelined=bool(self._L.nb200_sampler_is_pipelined(self._h)))
 
     def device_buffers(self):
         d, s = C.c_void_p(), C.c_void_p()
@@ -797,6 +808,211 @@ class PySampler:
             if self._h is not None:
                 self._L.nb200_sampler_destroy(self._h)
                 self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+
+class MultiTrace:
+    """The traces of the device shards of one run, presented as one PyTrace: chains are in global
+    order (device 0's block first); `draws` / `stats` concatenate the per-device blocks on first
+    access (each block is a view of that device's own — pinned, if supplied — host buffer)."""
+
+    def __init__(self, parts):
+        self.parts = parts
+        self.expanded = parts[0].expanded
+        self.expand_fn = parts[0].expand_fn
+        self.variables = parts[0].variables
+        self._expand = parts[0]._expand
+        self._cache = {}
+        self._taken = False
+
+    def _cat(self, name):
+        if name not in self._cache:
+            vals = [getattr(p, name) for p in self.parts]
+            self._cache[name] = None if vals[0] is None else np.concatenate(vals, axis=0)
+        return self._cache[name]
+
+    draws = property(lambda self: self._cat("draws"))
+    stats = property(lambda self: self._cat("stats"))
+    rows_filled = property(lambda self: self._cat("rows_filled"))
+    gradients = property(lambda self: self._cat("gradients"))
+    mass_matrix_inv = property(lambda self: self._cat("mass_matrix_inv"))
+    divergences = property(lambda self: self._cat("divergences"))
+
+    def is_zarr(self):
+        return False
+
+    def is_arrow(self):
+        return True
+
+    def stat(self, name):
+        a = self.stats[..., STAT_NAMES.index(name)]
+        dt = _STAT_DTYPES.get(name)
+        return a.astype(dt) if dt is not None else a
+
+    def get_arrow_trace(self):
+        if self._taken:
+            raise ValueError("The trace was already taken")
+        self._taken = True
+        d, s = [], []
+        for p in self.parts:
+            a, b = p.get_arrow_trace()
+            d += a
+            s += b
+        return d, s
+
+
+class PyMultiSampler:
+    """One sampling job over several GPUs of ONE process — the analogue of `cores` in
+    nuts_rs::Sampler::new (src/wrapper.rs:977-1085; python/nutpie/sample.py:1061-1075 picks it):
+    chains are split into contiguous blocks of global chain ids, one PySampler (own stream,
+    own persistent kernel, own trace buffers) per device, one host thread per device while
+    waiting so that every device's finished rows stream to the host concurrently.  The random
+    streams are keyed by global chain id, so the result equals the single-device run chain for
+    chain (tests/test_gpu_parity.py::test_chain_sharding_reproduces_single_run)."""
+
+    def __init__(self, settings, model, *, n_chains=None, devices=None, chain_id_offset=0,
+                 progress_type=None, trace_buffers=None, q0=None, z_tape=None, **kw):
+        from .distributed import shard
+
+        n_chains = int(n_chains if n_chains is not None else settings.num_chains)
+        if devices is None:
+            devices = list(range(device_count()))
+        elif isinstance(devices, int):
+            devices = list(range(devices))
+        devices = [int(d) for d in devices][:max(1, n_chains)]
+        if not devices:
+            raise RuntimeError("no CUDA device available: the B200 engine has no CPU fallback")
+        self.devices = devices
+        self.n_chains = n_chains
+        self.parts = []
+        self._progress_type = progress_type or ProgressType.none()
+        self._model = model
+        self._stop_progress = threading.Event()
+        self._progress_thread = None
+        try:
+            for i, dev in enumerate(devices):
+                n_local, off = shard(n_chains, i, len(devices))
+                if n_local == 0:
+                    continue
+                sl = slice(off, off + n_local)
+                bufs = None
+                if trace_buffers is not None:  # per-device list of dict(draws=, stats=)
+                    bufs = trace_buffers[i]
+                self.parts.append(PySampler(
+                    settings, model, n_chains=n_local, chain_id_offset=int(chain_id_offset) + off,
+                    device=dev, trace_buffers=bufs, autostart=False,
+                    q0=None if q0 is None else np.asarray(q0)[sl],
+                    z_tape=None if z_tape is None else np.asarray(z_tape)[sl], **kw))
+            for p in self.parts:  # all devices start before anyone waits
+                p.start()
+        except Exception:
+            self.close()
+            raise
+        self._t_start = time.perf_counter()
+        if self._progress_type.callback is not None:
+            self._progress_thread = threading.Thread(target=self._progress_loop, daemon=True)
+            self._progress_thread.start()
+
+    def _progress_loop(self):
+        rate = max(self._progress_type.rate_ms, 10) / 1e3
+        while not self._stop_progress.wait(rate):
+            try:
+                self._progress_type.callback(self.progress())
+            except Exception as exc:
+                import sys
+
+                print(f"progress callback failed: {exc}", file=sys.stderr)
+            if self.is_finished():
+                break
+
+    def progress(self):
+        return [c for p in self.parts for c in p.progress()]
+
+    def _each(self, fn):
+        """fn(part) on one host thread per device; re-raises the first failure."""
+        errs = [None] * len(self.parts)
+
+        def run(i, p):
+            try:
+                fn(p)
+            except BaseException as exc:  # noqa: BLE001 - re-raised below
+                errs[i] = exc
+
+        ths = [threading.Thread(target=run, args=(i, p)) for i, p in enumerate(self.parts)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+
+    def wait(self, timeout_seconds=None):
+        self._each(lambda p: p.wait(timeout_seconds))
+
+    def pause(self):
+        self._each(lambda p: p.pause())
+
+    def resume(self):
+        self._each(lambda p: p.resume())
+
+    def abort(self):
+        self._each(lambda p: p.abort())
+
+    def is_finished(self):
+        return all(p.is_finished() for p in self.parts)
+
+    def is_empty(self, ignore_error=False):
+        return all(p.is_empty(ignore_error) for p in self.parts)
+
+    def flush(self):
+        return None
+
+    def inspect(self, out=None):
+        return MultiTrace([p.inspect() for p in self.parts])
+
+    def take_results(self, out=None):
+        if not self.is_finished():
+            raise ValueError("Sampler is still running")
+        res = [None] * len(self.parts)
+
+        def take(i, p):
+            res[i] = p.take_results()
+
+        ths = [threading.Thread(target=take, args=(i, p)) for i, p in enumerate(self.parts)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if any(r is None for r in res):
+            raise ValueError("Sampler is empty")
+        return MultiTrace(res)
+
+    def kernel_ms(self):
+        """device time of the slowest device (the job's time)"""
+        return max(p.kernel_ms() for p in self.parts)
+
+    def launch_count(self):
+        return sum(p.launch_count() for p in self.parts)
+
+    def geometry(self):
+        g = self.parts[0].geometry()
+        g["devices"] = list(self.devices)
+        return g
+
+    def close(self):
+        self._stop_progress.set()
+        t = self._progress_thread
+        if t is not None and t is not threading.current_thread():
+            t.join()
+        for p in self.parts:
+            p.close()
 
     def __del__(self):
         try:
@@ -869,6 +1085,11 @@ def set_smem_slots(n: int):
 
 def set_unroll(on: bool):
     load_library().nb200_set_unroll(1 if on else 0)
+
+
+def set_pipeline(on: bool):
+    """Two warps per chain (integrator + tree) for gathering densities: True = auto, False = off."""
+    load_library().nb200_set_pipeline(1 if on else 0)
 
 
 def set_stage_loads(mode):

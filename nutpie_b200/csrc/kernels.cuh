@@ -94,7 +94,62 @@ __global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, kernel_min_blocks<M, W,
     ChainCtx<M, GroupCuda<W>, NIT> ctx;
     setup_ctx<M, W, NIT>(ctx, P, chain, smem + block_data + (size_t)local * smem_per_chain);
     if constexpr (M::kHasBlockData) ctx.md = md;  // tables staged in shared memory
+#ifdef NB200_PIPE_PROFILE
+    const long long t_begin = clock64();
+#endif
     ctx.run();
+#ifdef NB200_PIPE_PROFILE
+    if (ctx.g.tid == 0 && (chain % 257) == 0)
+        printf("chain %llu one-warp total %lld | leapfrog %lld (n %lld)\n", chain, clock64() - t_begin,
+               ctx.prof[7], ctx.prof[8]);
+#endif
+}
+
+// Two warps per chain (W = 1 density geometry, see ChainCtx::producer_main).  Warps are dealt to
+// the SM's four schedulers round-robin (warp % 4): warps 4g, 4g+1 are the PRODUCERS of chains 2g,
+// 2g+1 and warps 4g+2, 4g+3 their CONSUMERS, so two schedulers run nothing but the integrator
+// loop and two nothing but the tree loop — each scheduler's instruction cache sees one loop
+// (mixing the roles on a scheduler made instruction fetch the bottleneck:
+// profiles/r2_pipeline_notes.txt).  512 threads = up to 8 chains per CTA, 128 registers.
+template <class M, int NIT>
+__global__ void __launch_bounds__(512, 1)
+    nuts_kernel_piped(const __grid_constant__ KParams<M> P, size_t smem_per_chain, size_t block_data,
+                      int cpb) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    typename M::Data md = P.mdata;
+    if constexpr (M::kHasBlockData) {
+        if (block_data > 0) {
+            M::load_block_data(md, smem, threadIdx.x, blockDim.x);
+            __syncthreads();
+        }
+    }
+    const int warp = threadIdx.x >> 5;
+    const int local = ((warp >> 2) << 1) | (warp & 1);
+    const int role = ((warp >> 1) & 1) ^ 1;  // 1 = producer (integrator), 0 = consumer (tree)
+    const unsigned long long chain = (unsigned long long)blockIdx.x * cpb + local;
+    if (local >= cpb || chain >= P.n_chains) return;
+    ChainCtx<M, GroupCuda<1>, NIT> ctx;
+    setup_ctx<M, 1, NIT>(ctx, P, chain, smem + block_data + (size_t)local * smem_per_chain);
+    if constexpr (M::kHasBlockData) ctx.md = md;
+    ctx.piped = true;
+    if (role == 0 && ctx.g.tid == 0) ctx.pipe_init_barriers();
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + local) : "memory");  // the chain's two warps
+#ifdef NB200_PIPE_PROFILE
+    const long long t_begin = clock64();
+#endif
+    if (role == 0) {
+        ctx.run();
+        ctx.pipe_quit();
+    } else {
+        ctx.producer_main();
+    }
+#ifdef NB200_PIPE_PROFILE
+    if (ctx.g.tid == 0 && (chain % 257) == 0)
+        printf("chain %llu role %d total %lld | C: wait_full %lld (n %lld) end_draw %lld (n %lld) | "
+               "P: wait_cmd %lld momentum %lld wait_empty %lld leapfrog %lld (n %lld)\n",
+               chain, role, clock64() - t_begin, ctx.prof[0], ctx.prof[1], ctx.prof[2], ctx.prof[3],
+               ctx.prof[4], ctx.prof[5], ctx.prof[6], ctx.prof[7], ctx.prof[8]);
+#endif
 }
 
 // Component kernel: mode 0 = density at q (slot 0); mode 1 = one leapfrog

@@ -34,6 +34,39 @@ static cudaError_t launch_one(const KParams<M>& P, size_t smem_per_chain, size_t
     return cudaGetLastError();
 }
 
+template <class M, int NIT>
+static cudaError_t launch_one_piped(const KParams<M>& P, size_t smem_per_chain, size_t block_data,
+                                    int cpb, int grid, cudaStream_t stream) {
+    const size_t smem = block_data + smem_per_chain * cpb;
+    cudaError_t e = cudaFuncSetAttribute(nuts_kernel_piped<M, NIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(nuts_kernel_piped<M, NIT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    // warps come in groups of four (two producers, two consumers): see nuts_kernel_piped
+    nuts_kernel_piped<M, NIT><<<grid, 128 * ((cpb + 1) / 2), smem, stream>>>(P, smem_per_chain, block_data, cpb);
+    return cudaGetLastError();
+}
+
+// two-warp pipeline kernels exist for these unrolled trip counts (densities with kPipelined)
+template <class M>
+bool supports_pipeline(int NIT) {
+    if constexpr (M::kPipelined) return NIT == 2 || NIT == 3 || NIT == 4 || NIT == 6 || NIT == 8;
+    else return false;
+}
+
+template <class M>
+cudaError_t launch_nuts_piped(int NIT, const KParams<M>& P, size_t smem_per_chain, size_t block_data,
+                              int cpb, int grid, cudaStream_t stream) {
+    if constexpr (M::kPipelined) {
+#define NB_CASE(NN) \
+    if (NIT == NN) return launch_one_piped<M, NN>(P, smem_per_chain, block_data, cpb, grid, stream);
+        NB_CASE(2) NB_CASE(3) NB_CASE(4) NB_CASE(6) NB_CASE(8)
+#undef NB_CASE
+    }
+    return cudaErrorInvalidValue;
+}
+
 // (W, NIT) combinations with unrolled per-dimension loops; anything else runs NIT = 0
 template <class M>
 int supported_nit(int W, int nit) {
@@ -103,6 +136,9 @@ size_t model_block_data_bytes(const typename M::Data& md) {
     template cudaError_t launch_component<M>(int, const KParams<M>&, int, const double*,        \
                                              double*, size_t, unsigned);                        \
     template size_t smem_fixed<M>(int, const M::Data&, int);                                    \
+    template bool supports_pipeline<M>(int);                                                    \
+    template cudaError_t launch_nuts_piped<M>(int, const KParams<M>&, size_t, size_t, int, int, \
+                                              cudaStream_t);                                    \
     template size_t model_block_data_bytes<M>(const M::Data&);
 
 }  // namespace nb200

@@ -35,6 +35,7 @@ struct NormalModel {
     static constexpr bool kElementwise = true;
     static constexpr bool kNeedsChain = false;
     static constexpr bool kRuntimeLoopsOnly = false;
+    static constexpr bool kPipelined = false;  // two-warp producer / consumer kernels exist
     static constexpr bool kHasBlockData = false;
     // g_i = -(q_i - mu) / var is non-finite only if q_i - mu is, and then so is the term
     // (q_i - mu)^2 of logp: the leapfrog needs no separate per-dimension gradient check
@@ -62,6 +63,7 @@ struct FunnelModel {
     static constexpr bool kElementwise = false;
     static constexpr bool kNeedsChain = false;
     static constexpr bool kRuntimeLoopsOnly = false;
+    static constexpr bool kPipelined = false;  // two-warp producer / consumer kernels exist
     static constexpr bool kHasBlockData = false;
     struct Data {
         int unused;
@@ -160,6 +162,7 @@ struct RadonModel {
     static constexpr bool kElementwise = false;
     static constexpr bool kNeedsChain = false;
     static constexpr bool kRuntimeLoopsOnly = false;
+    static constexpr bool kPipelined = true;   // two-warp producer / consumer kernels exist
     // The observation records and group tables are the same for every chain: a CTA
     // that hosts several chains copies them into shared memory once (launch_impl.cuh).
     static constexpr bool kHasBlockData = true;
@@ -341,6 +344,7 @@ struct HostModel {
     static constexpr bool kElementwise = false;
     static constexpr bool kHasBlockData = false;
     static constexpr bool kRuntimeLoopsOnly = true;  // only the NIT = 0 kernels are instantiated
+    static constexpr bool kPipelined = false;
     struct Data {
         double* qbox;        // [n_chains][Dp]  device -> host
         double* gbox;        // [n_chains][Dp]  host -> device
@@ -453,6 +457,7 @@ struct CustomModel {
     static constexpr bool kElementwise = false;
     static constexpr bool kNeedsChain = false;
     static constexpr bool kRuntimeLoopsOnly = false;
+    static constexpr bool kPipelined = false;  // two-warp producer / consumer kernels exist
     static constexpr bool kHasBlockData = false;
     struct Data {
         const double* data;  // device copy of nb200_model_desc::user_data

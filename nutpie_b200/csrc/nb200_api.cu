@@ -58,6 +58,7 @@ static std::atomic<int> g_threads_per_chain{0};
 static std::atomic<int> g_chains_per_block{0};
 static std::atomic<int> g_smem_slots{-1};
 static std::atomic<int> g_force_nit{-1};
+static std::atomic<int> g_pipeline{1};     // two-warp producer / consumer kernels (nb200_set_pipeline)
 static std::atomic<int> g_stage_loads{3};  // staging + alternating sweep (nb200_set_stage_loads)
 static inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 // + working mass matrix + hot tier of the pool
@@ -227,6 +228,7 @@ struct nb200_sampler {
     nb200_model_desc model{};
     uint64_t n_chains = 0, chain_id_offset = 0;
     int W = 1, NIT = 0, cpb = 1, grid = 0, block = 0;
+    bool piped = false;  // two warps per chain: integrator + tree (nuts_kernel_piped)
     size_t smem_per_chain = 0, block_data = 0;
     cudaStream_t stream = nullptr, side = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -267,7 +269,8 @@ struct SamplerImpl : nb200_sampler {
     KParams<M> P;
     int launch() override {
         P.max_draws_per_launch = draws_per_launch;
-        cudaError_t e = launch_nuts<M>(W, NIT, P, smem_per_chain, block_data, cpb, grid, block, stream);
+        cudaError_t e = piped ? launch_nuts_piped<M>(NIT, P, smem_per_chain, block_data, cpb, grid, stream)
+                              : launch_nuts<M>(W, NIT, P, smem_per_chain, block_data, cpb, grid, block, stream);
         if (e != cudaSuccess) return fail(NB200_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
         return 0;
     }
@@ -439,6 +442,17 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     const int D = (int)m->dim;
     s->Dp = (D + 3) / 4 * 4;
     s->NS = 3 * ((int)st->maxdepth + 1) + 3;
+    {
+        const int T = 32 * s->W;
+        s->NIT = supported_nit<M>(s->W, (D + T - 1) / T);
+        if (g_force_nit.load() == 0) s->NIT = 0;
+        // Two warps per chain (integrator + tree) when the density does enough work per leaf to
+        // hide the tree bookkeeping behind it; needs kPipeDepth extra pool slots.
+        s->piped = s->W == 1 && s->NIT > 0 && g_pipeline.load() != 0 && D >= 64 &&
+                   g_threads_per_chain.load() == 0 && supports_pipeline<M>(s->NIT) &&
+                   s->NS + kPipeDepth <= kMaxSlots;
+        if (s->piped) s->NS += kPipeDepth;
+    }
     s->n_total = st->num_tune + st->num_draws;
     s->n_rows = st->save_warmup ? s->n_total : st->num_draws;
     const bool thinned = st->store_dims && st->store_dims < m->dim;
@@ -484,6 +498,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
             }
         }
         if (c > 8) c = 8;
+        // (piped: 8 chains = 16 warps = 512 threads, 128 registers per thread)
         s->cpb = c;
         // stage the tables in shared memory only when they fit beside the chains' own state
         // (a model with > ~10 k observations reads them through L2 instead)
@@ -497,7 +512,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     {
         const size_t kSmemSM = 227 * 1024, kSlack = 1024;  // 1 KB/CTA reserved by the driver
         uint64_t per_sm = (n_chains + 147) / 148;
-        const uint64_t max_res = (uint64_t)(2048 / (32 * s->W));  // thread limit per SM
+        const uint64_t max_res = (uint64_t)(2048 / (32 * s->W * (s->piped ? 2 : 1)));  // thread limit per SM
         if (per_sm > max_res) per_sm = max_res;
         if (per_sm > 32ull * s->cpb) per_sm = 32ull * s->cpb;     // CTA limit per SM
         if (per_sm < 1) per_sm = 1;
@@ -522,14 +537,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         P.var_in_smem = var_in;
         s->smem_per_chain = chain_smem_total(fixed, s->Dp, var_in, slots);
     }
-    {
-        const int T = 32 * s->W;
-        int nit = (D + T - 1) / T;
-        s->NIT = supported_nit<M>(s->W, nit);
-        const int f = g_force_nit.load();
-        if (f == 0) s->NIT = 0;
-    }
-    s->block = 32 * s->W * s->cpb;
+    s->block = s->piped ? 128 * ((s->cpb + 1) / 2) : 32 * s->W * s->cpb;
     s->grid = (int)((n_chains + s->cpb - 1) / s->cpb);
     if (bdata + s->smem_per_chain * s->cpb > 227 * 1024) {
         fail(NB200_EINVAL, "model dimension too large: a density that gathers across dimensions "
@@ -635,6 +643,7 @@ void nb200_set_chains_per_block(int32_t c) { g_chains_per_block.store(c); }
 void nb200_set_smem_slots(int32_t n) { g_smem_slots.store(n); }
 void nb200_set_unroll(int32_t on) { g_force_nit.store(on ? -1 : 0); }
 void nb200_set_stage_loads(int32_t mode) { g_stage_loads.store(mode & 7); }
+void nb200_set_pipeline(int32_t on) { g_pipeline.store(on ? 1 : 0); }
 
 void nb200_settings_default(nb200_settings* s) {
     std::memset(s, 0, sizeof(*s));
@@ -1142,6 +1151,8 @@ int nb200_sampler_geometry(nb200_sampler* s, int32_t* tpc, int32_t* block, int32
     if (grid) *grid = s->grid;
     return 0;
 }
+
+int nb200_sampler_is_pipelined(nb200_sampler* s) { return s && s->piped ? 1 : 0; }
 
 int nb200_sampler_smem(nb200_sampler* s, int32_t* smem_slots, int32_t* bytes_per_chain) {
     if (!s) return fail(NB200_EINVAL, "null sampler");

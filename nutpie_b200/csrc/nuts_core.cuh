@@ -90,6 +90,25 @@ struct ChainScalars {
     int has_initial_mm;
     int cur_slot;
     int status;                  // 0 not started, 1 running, 2 finished, <0 NB200_E*
+    int sweep_rev;               // direction of the last streaming pass (a relaunch must continue
+                                 // the alternation: the sweep order fixes the order of the sums)
+};
+
+// Producer / consumer pipeline of one chain (two warps, see ChainCtx::producer_main): a ring of
+// kPipeDepth leaves in flight.  The CONSUMER (tree warp) grants entry e a destination slot and
+// arrives on empty[e]; the PRODUCER (integrator warp) runs the leapfrog into that slot, writes
+// the leaf's scalars and arrives on full[e].  dst = -1 is the end-of-draw marker.
+constexpr int kPipeDepth = 4;
+struct PipeShared {
+    unsigned long long full[kPipeDepth], empty[kPipeDepth];  // mbarriers (count 1)
+    unsigned long long cmd;                                   // mbarrier: next command posted
+    double de[kPipeDepth];   // energy error of the leaf
+    double step_size, E0;    // command: step size of the draw; reply: energy of its first point
+    int dst[kPipeDepth], rc[kPipeDepth], l0[kPipeDepth];
+    int cur;                 // command: slot of the current point
+    unsigned draw;           // command: draw index
+    int quit;                // command: the chain is done for this launch
+    int stop;                // consumer -> producer: skip the leaves still granted
 };
 
 // per-chain shared-memory scalars
@@ -100,6 +119,7 @@ struct ChainShared {
     int idx[kMaxSlots];
     int lvL[kMaxLevels], lvR[kMaxLevels], lvD[kMaxLevels];
     int stop;  // the host's stop flag as read by thread 0 (one decision for the whole group)
+    PipeShared pipe;
 };
 
 template <class M>
@@ -223,6 +243,26 @@ struct ChainCtx {
     double last_mean, last_sym;
     uint32_t last_n_steps;
     int div_src, div_dst;  // slots of the leapfrog that diverged in the running transition
+    // two-warp pipeline (device only): this warp's running leaf / grant / command counters,
+    // the slots granted to the producer but not yet received back, collector switch
+    bool piped = false, skip_acc = false;
+#ifdef NB200_PIPE_PROFILE
+    long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#ifdef __CUDA_ARCH__
+#define NB_PROF_CLK() clock64()
+#else
+#define NB_PROF_CLK() 0ll
+#endif
+#define NB_PROF_T0() const long long prof_t0_ = NB_PROF_CLK()
+#define NB_PROF_ADD(i) prof[i] += NB_PROF_CLK() - prof_t0_
+#define NB_PROF_INC(i) prof[i] += 1
+#else
+#define NB_PROF_T0()
+#define NB_PROF_ADD(i)
+#define NB_PROF_INC(i)
+#endif
+    unsigned kcons = 0, kgrant = 0, ncmd = 0;
+    unsigned long long reserved = 0;
 
     // f(i) for every dimension index owned by this thread
     template <class F>
@@ -263,7 +303,7 @@ struct ChainCtx {
         if (tL >= 0) live |= 1ull << tL;
         if (tR >= 0) live |= 1ull << tR;
         if (tD >= 0) live |= 1ull << tD;
-        live |= lv_live;
+        live |= lv_live | reserved;
         const unsigned long long all = NS >= 64 ? ~0ull : ((1ull << NS) - 1ull);
         return nb_ffsll(~live & all) - 1;  // lowest free slot: keeps the hot set small
     }
@@ -741,6 +781,8 @@ struct ChainCtx {
 #ifndef NB200_EMUL_DROP_BARRIER  // (tests/emul builds one library without this barrier: the
         g.sync();                // negative control of the lane-schedule race check)
 #endif
+        last_de = de;
+        if (skip_acc) return rc;  // pipeline producer: the consumer keeps the collectors
         acc_count += 1;
         if (rc == 0) {
 #ifdef __CUDA_ARCH__
@@ -935,7 +977,198 @@ struct ChainCtx {
         g.sync();
     }
 
+
+    // ------------------------------------------------- two-warp pipeline of one chain
+    // The tree bookkeeping of leaf k (U-turn checks against older states, log-sum-exp weights,
+    // multinomial draws, acceptance statistics: ~1/3 of a leaf's instructions) does not feed the
+    // integration of leaf k + 1, only the decision to STOP.  So a chain is owned by two warps: the
+    // PRODUCER integrates leaves back to back (it knows the doubling directions — Philox keyed by
+    // draw and depth — and tracks the two trajectory ends itself), the CONSUMER builds the tree
+    // from them and ends the draw when it turns / diverges / reaches maxdepth; leaves produced
+    // past that point are dropped.  Same arithmetic in the same order as the one-warp kernel:
+    // traces are bit-identical.  The critical path per leaf becomes max(integrate, bookkeep)
+    // instead of their sum.
+#ifdef __CUDA_ARCH__
+    NB_D PipeShared* pp() const { return &sh->pipe; }
+    NB_D void pipe_init_barriers() {  // one lane, before the chain's warps meet
+        PipeShared* ps = pp();
+        for (int e = 0; e < kPipeDepth; ++e) {
+            nb_mbar_init(&ps->full[e], 1);
+            nb_mbar_init(&ps->empty[e], 1);
+        }
+        nb_mbar_init(&ps->cmd, 1);
+        ps->quit = 0;
+        ps->stop = 0;
+        nb_mbar_init_fence();
+    }
+    // consumer: hand entry (kgrant % depth) a fresh destination slot
+    NB_D void pipe_grant(int slot) {
+        PipeShared* ps = pp();
+        const unsigned e = kgrant % kPipeDepth;
+        if (slot >= 0) reserved |= 1ull << slot;
+        if (g.tid == 0) ps->dst[e] = slot;
+        __syncwarp();
+        if (g.tid == 0) nb_mbar_arrive(nb_smem_u32(&ps->empty[e]));
+        kgrant += 1;
+    }
+    NB_D void pipe_begin_draw(int cur, uint32_t t) {
+        PipeShared* ps = pp();
+        front_slot = -1;  // the front buffer belongs to the producer during the draw
+        reserved = 0;
+        if (g.tid == 0) {
+            ps->cur = cur;
+            ps->draw = t;
+            ps->step_size = step_size;
+        }
+        for (int e = 0; e < kPipeDepth; ++e) pipe_grant(alloc());
+        __syncwarp();
+        if (g.tid == 0) nb_mbar_arrive(nb_smem_u32(&ps->cmd));
+    }
+    // consumer: next leaf (blocks until the producer has filled it)
+    NB_D int pipe_recv(int& dst) {
+        PipeShared* ps = pp();
+        const unsigned e = kcons % kPipeDepth;
+        {
+            NB_PROF_T0();
+            nb_mbar_wait(nb_smem_u32(&ps->full[e]), (kcons / kPipeDepth) & 1u);
+            NB_PROF_ADD(0);
+            NB_PROF_INC(1);
+        }
+        kcons += 1;
+        dst = ps->dst[e];
+        const int rc = ps->rc[e];
+        const double de = ps->de[e];
+        l0_turn = ps->l0[e] != 0;
+        reserved &= ~(1ull << dst);
+        acc_count += 1;
+        if (rc == 0) {
+            if (defer_acc) {
+                if ((unsigned)g.tid == n_parked) de_parked = de;
+                if (++n_parked == 32u) flush_acc();
+            } else {
+                const double w = exp(-de);
+                const double a = w < 1.0 ? w : 1.0;
+                acc_sum += a;
+                acc_sym += 2.0 * a / (1.0 + w);
+            }
+        }
+        last_de = de;
+        return rc;
+    }
+    // consumer: the draw is over — have the producer skip what is still granted, collect those
+    // entries, then post the end-of-draw marker and wait for its acknowledgement
+    NB_D void pipe_end_draw() {
+        PipeShared* ps = pp();
+        NB_PROF_T0();
+        if (g.tid == 0) *(volatile int*)&ps->stop = 1;
+        while (kcons < kgrant) {
+            const unsigned e = kcons % kPipeDepth;
+            nb_mbar_wait(nb_smem_u32(&ps->full[e]), (kcons / kPipeDepth) & 1u);
+            kcons += 1;
+        }
+        pipe_grant(-1);
+        {
+            const unsigned e = kcons % kPipeDepth;
+            nb_mbar_wait(nb_smem_u32(&ps->full[e]), (kcons / kPipeDepth) & 1u);
+            kcons += 1;
+        }
+        E0 = ps->E0;
+        reserved = 0;
+        __syncwarp();
+        if (g.tid == 0) *(volatile int*)&ps->stop = 0;
+        __syncwarp();
+        NB_PROF_ADD(2);
+        NB_PROF_INC(3);
+    }
+    NB_D void pipe_quit() {
+        PipeShared* ps = pp();
+        if (g.tid == 0) ps->quit = 1;
+        __syncwarp();
+        if (g.tid == 0) nb_mbar_arrive(nb_smem_u32(&ps->cmd));
+    }
+    // producer: the whole life of the integrator warp
+    NB_D void producer_main() {
+        PipeShared* ps = pp();
+        skip_acc = true;
+        defer_acc = false;
+        unsigned k = 0;
+        const int maxdepth = (int)st().maxdepth;
+        for (;;) {
+            {
+                NB_PROF_T0();
+                nb_mbar_wait(nb_smem_u32(&ps->cmd), ncmd & 1u);
+                NB_PROF_ADD(4);
+            }
+            ncmd += 1;
+            if (ps->quit) return;
+            const int cur = ps->cur;
+            const uint32_t t = ps->draw;
+            step_size = ps->step_size;
+            front_slot = -1;
+            {
+                NB_PROF_T0();
+                init_momentum(cur, RNG_MOMENTUM, t);
+                NB_PROF_ADD(5);
+            }
+            if (g.tid == 0) ps->E0 = E0;
+            int end_f = cur, end_b = cur;
+            bool over = false;
+            for (int depth = 0; depth < maxdepth && !over; ++depth) {
+                uint64_t ra, rb;
+                rng_u64x2(st().seed, chain_gid, t, RNG_DIRECTION, (uint32_t)depth, ra, rb);
+                const int dir = (ra & 1) ? 1 : -1;
+                const bool check = st().check_turning && depth >= (int)st().mindepth;
+                int src = dir > 0 ? end_f : end_b;
+                const unsigned n_leaf = 1u << depth;
+                for (unsigned j = 0; j < n_leaf; ++j) {
+                    const unsigned e = k % kPipeDepth;
+                    {
+                        NB_PROF_T0();
+                        nb_mbar_wait(nb_smem_u32(&ps->empty[e]), (k / kPipeDepth) & 1u);
+                        NB_PROF_ADD(6);
+                    }
+                    k += 1;
+                    const int dst = ps->dst[e];
+                    if (dst >= 0 && !*(volatile int*)&ps->stop) {
+                        const bool fuse_l0 = kFuseL0 && check && ((j & 1u) || depth == 0);
+                        NB_PROF_T0();
+                        const int rc = leapfrog(src, dst, dir, fuse_l0);
+                        NB_PROF_ADD(7);
+                        NB_PROF_INC(8);
+                        if (g.tid == 0) {
+                            ps->de[e] = last_de;
+                            ps->rc[e] = rc;
+                            ps->l0[e] = l0_turn ? 1 : 0;
+                        }
+                        src = dst;
+                    }
+                    __syncwarp();
+                    if (g.tid == 0) nb_mbar_arrive(nb_smem_u32(&ps->full[e]));
+                    if (dst < 0) {
+                        over = true;
+                        break;
+                    }
+                }
+                if (dir > 0) end_f = src;
+                else end_b = src;
+            }
+            if (!over) {  // every leaf up to maxdepth is out: the end-of-draw marker follows
+                for (;;) {
+                    const unsigned e = k % kPipeDepth;
+                    nb_mbar_wait(nb_smem_u32(&ps->empty[e]), (k / kPipeDepth) & 1u);
+                    k += 1;
+                    const int dst = ps->dst[e];
+                    __syncwarp();
+                    if (g.tid == 0) nb_mbar_arrive(nb_smem_u32(&ps->full[e]));
+                    if (dst < 0) break;
+                }
+            }
+        }
+    }
+#endif
+
     // ------------------------------------------------------------- transition
+    template <bool PIPED = false>
     NB_HD int transition(int cur, uint32_t t, SampleInfo& info) {
         draw = t;
         n_merge = 0;
@@ -943,10 +1176,14 @@ struct ChainCtx {
         acc_count = 0;
         n_parked = 0;
         defer_acc = true;
-        init_momentum(cur, RNG_MOMENTUM, t);
         mL = mR = mD = cur;
         tL = tR = tD = -1;
         lv_live = 0;
+#ifdef __CUDA_ARCH__
+        if constexpr (PIPED) pipe_begin_draw(cur, t);
+        else
+#endif
+            init_momentum(cur, RNG_MOMENTUM, t);
         double m_ls = 0.0;
         int depth = 0;
         unsigned spec_bits = 0;  // speculative C verdicts per level (bit 31: main tree)
@@ -965,7 +1202,7 @@ struct ChainCtx {
             tL = tR = tD = -1;
             bool stop = false;  // the new sub-tree is discarded and the transition ends
             for (unsigned j = 0; j < n_leaf && !stop && !done; ++j) {
-                const int dst = alloc();
+                int dst = PIPED ? -1 : alloc();
                 // ---- plan the U-turn checks that pair the new leaf N with older states.
                 // Merging sub-tree s (earlier) with t (later, ending in N) needs three pairs:
                 //   A = (far end of s, N),  B = (near end of s, N)  [depth > 0],
@@ -998,7 +1235,22 @@ struct ChainCtx {
                         if (np < kMaxFused) plist[np++] = dir > 0 ? mR : mL;
                     }
                 }
-                const int rc = leapfrog(prev, dst, dir, fuse_l0, plist, np);
+                int rc;
+#ifdef __CUDA_ARCH__
+                if constexpr (PIPED) {
+                    rc = pipe_recv(dst);
+                    if (rc != 0) {
+                        div_src = prev;
+                        div_dst = dst;
+                    }
+                } else
+#endif
+                {
+                    NB_PROF_T0();
+                    rc = leapfrog(prev, dst, dir, fuse_l0, plist, np);
+                    NB_PROF_ADD(7);
+                    NB_PROF_INC(8);
+                }
                 if (rc != 0) {
                     info.diverging = 1;
                     stop = true;
@@ -1016,6 +1268,9 @@ struct ChainCtx {
                     return is_turning(x, n_slot);
                 };
                 tL = tR = tD = dst;
+#ifdef __CUDA_ARCH__
+                if constexpr (PIPED) pipe_grant(alloc());  // keep the producer kPipeDepth leaves ahead
+#endif
                 double t_ls = -last_de;
                 int k = 0;
                 // Merge the new leaf with the parked siblings of equal depth (binary
@@ -1105,6 +1360,9 @@ struct ChainCtx {
             }
             if (stop) done = true;
         }
+#ifdef __CUDA_ARCH__
+        if constexpr (PIPED) pipe_end_draw();
+#endif
         flush_acc();
         defer_acc = false;
         if (!done) info.maxdepth_reached = 1;
@@ -1422,6 +1680,7 @@ struct ChainCtx {
         cnt0 = s.cnt[0]; cnt1 = s.cnt[1]; last_update = s.last_update;
         total_steps = s.total_steps; divergences = s.divergences;
         fg_sel = s.fg_sel; has_initial_mm = s.has_initial_mm;
+        sweep_rev = s.sweep_rev != 0;
     }
     NB_HD void store(ChainScalars& s, unsigned long long next_draw, int cur, int status) const {
         s.step_size = step_size;
@@ -1435,6 +1694,7 @@ struct ChainCtx {
         s.cur_slot = cur;
         s.draw = next_draw;
         s.status = status;
+        s.sweep_rev = sweep_rev ? 1 : 0;
     }
 
     // Runs the chain from its persisted state until finished, stopped or the
@@ -1508,7 +1768,12 @@ struct ChainCtx {
             }
             SampleInfo info;
             div_src = div_dst = -1;
-            const int sel = transition(cur, (uint32_t)t, info);
+            int sel;
+#ifdef __CUDA_ARCH__
+            if (piped) sel = transition<true>(cur, (uint32_t)t, info);
+            else
+#endif
+                sel = transition<false>(cur, (uint32_t)t, info);
             step_size = step_base;
             total_steps += acc_count;
             divergences += info.diverging;

@@ -84,6 +84,9 @@ NB_D void nb_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.clust
 NB_D void nb_mbar_expect_tx(uint32_t bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+NB_D void nb_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 NB_D void nb_mbar_wait(uint32_t bar, unsigned parity) {
     unsigned ok;
     do {

@@ -295,6 +295,7 @@ def sample(
     store_unconstrained: bool = False,
     var_names=None,
     device: int = 0,
+    devices=None,
     chain_id_offset: int = 0,
     trace_buffers=None,
     expand_on_device: bool | None = None,
@@ -304,7 +305,10 @@ def sample(
 
     Same keyword surface as `nutpie.sample` (python/nutpie/sample.py:823-1102);
     `cores` is accepted and ignored (chains map to warps/CTAs, not host threads).
-    Extra keywords: `device` (CUDA device index), `chain_id_offset` (global id
+    Extra keywords: `device` (CUDA device index), `devices` (an int n = the first n GPUs, a
+    list of device indices, or "all": ONE call samples over several GPUs of this process —
+    chains are split into contiguous blocks, one persistent kernel and one host thread per
+    device, the role `cores` plays in the reference), `chain_id_offset` (global id
     of this process's first chain when a run is sharded over GPUs),
     `trace_buffers` (dict(draws=, stats=) of preallocated — ideally pinned —
     host arrays to receive the trace)."""
@@ -347,6 +351,8 @@ def sample(
         raise ValueError(f"Unknown sampler '{sampler}'. Expected one of: 'nuts', 'mclmc'.")
 
     sampler_kw = {}
+    if devices is not None:
+        sampler_kw["devices"] = list(range(_lib.device_count())) if devices == "all" else devices
     for k in ("q0", "z_tape", "draws_per_launch"):
         if k in kwargs:
             sampler_kw[k] = kwargs.pop(k)

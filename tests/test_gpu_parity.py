@@ -542,3 +542,28 @@ def test_custom_public_api_variables():
     post = tr.posterior
     assert np.asarray(post["intercept"]).shape == (8, 50)
     assert np.asarray(post["beta"]).shape == (8, 50, 11)
+
+
+def test_single_process_multi_device_equals_one_device(radon_data):
+    """ONE `sample(chains=...)` call over several devices of the process
+    (one persistent kernel + one host thread per device, the analogue of `cores`,
+    src/wrapper.rs:977-1085) equals the one-device run chain for chain.  With a single GPU on
+    the box the two shards run as two concurrent samplers of device 0."""
+    d = radon_data
+    J = d["n_county"]
+    cm = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], J)
+    kw = dict(chains=20, draws=60, tune=90, seed=5, init_radius=1.0, progress_bar=False)
+    one = nutpie_b200.sample(cm, **kw)
+    devs = [0, 0, 0] if _lib.device_count() < 3 else [0, 1, 2]
+    seen = []
+    multi = nutpie_b200.sample(cm, devices=devs, progress_callback=lambda ps: seen.append(len(ps)),
+                               progress_rate=10, **kw)
+    for name in ("intercept", "county_effect", "sigma"):
+        assert np.array_equal(one.posterior[name], multi.posterior[name]), name
+        assert np.array_equal(one.warmup_posterior[name], multi.warmup_posterior[name]), name
+    for name in ("n_steps", "step_size", "diverging"):
+        assert np.array_equal(one.sample_stats[name], multi.sample_stats[name]), name
+    assert not seen or set(seen) == {20}
+    raw = nutpie_b200.sample(cm, devices=devs, return_raw_trace=True, **kw)
+    assert isinstance(raw, _lib.MultiTrace) and [p.draws.shape[0] for p in raw.parts] == [7, 7, 6]
+    assert raw.draws.shape[0] == 20 and list(raw.stats[:, 0, STAT["chain"]]) == list(range(20))

@@ -316,12 +316,16 @@ def test_fatal_return_code_stops_the_sampler_and_keeps_the_partial_trace(radon_d
     sig = types.int64(types.uint64, types.CPointer(types.double), types.CPointer(types.double),
                       types.CPointer(types.double), types.voidptr)
 
+    calls = np.zeros(1, dtype=np.int64)  # user_data: evaluation counter (fails after 4000)
+
     @cfunc(sig, nopython=True)
     def logp(dim, x_, out_, logp_, ud_):
         x = carray(x_, (2,))
         out = carray(out_, (2,))
         lp = carray(logp_, ())
-        if x[0] > 2.5:
+        n = carray(ud_, (1,), np.int64)
+        n[0] += 1
+        if n[0] > 4000:
             return -7
         out[0] = -x[0]
         out[1] = -x[1]
@@ -330,7 +334,7 @@ def test_fatal_return_code_stops_the_sampler_and_keeps_the_partial_trace(radon_d
 
     s = _lib.PyNutsSettings.Diag(4)
     s.update({"num_tune": 200, "num_draws": 2000})
-    model = _lib.PyMcModel(_lib.LogpFunc(logp.address, 0, logp),
+    model = _lib.PyMcModel(_lib.LogpFunc(logp.address, calls.ctypes.data, (logp, calls)),
                            _lib.ExpandFunc(2, 2, 0, 0, None),
                            _lib.PyVariable.new_variables(["x"], ["float64"], [[2]], {}, {}),
                            2, {}, {}, lambda seed: np.zeros(2), None)
