@@ -82,6 +82,30 @@ struct GroupCuda {
         }
     }
 
+    // exclusive prefix sum over the group in thread order: thread t gets x_0 + ... + x_{t-1}
+    // (Hillis-Steele inside a warp, then the earlier warps' totals added in warp order)
+    NB_D double exclusive_scan(double x) const {
+        const int lane = tid & 31;
+        double v = x;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off) v += y;
+        }
+        double excl = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) excl = 0.0;
+        if (W > 1) {
+            const int warp = tid >> 5;
+            __syncthreads();  // previous users of `red` are done
+            if (lane == 31) red[warp] = v;
+            __syncthreads();
+            double base = 0.0;
+            for (int w = 0; w < warp; ++w) base += red[w];
+            excl = base + excl;
+        }
+        return excl;
+    }
+
     // sum N values over the group; result identical on all threads
     template <int N>
     NB_D void reduce(double (&v)[N]) const {
@@ -106,6 +130,46 @@ struct GroupCuda {
 };
 #endif
 
+#ifdef __CUDACC__
+// L lanes of a warp own one chain (L = 4, 8, 16): a warp hosts 32 / L chains.  For densities with
+// a handful of dimensions (BASELINE configs 1 and 5: D = 1, 9) a full warp per chain leaves most
+// lanes idle on every instruction; here the chains of a warp run the same code side by side and
+// only part ways where their trees differ (independent thread scheduling serialises the
+// divergent stretches and reconverges them).  Reductions are xor butterflies inside the aligned
+// L-lane group, so every lane of a chain holds bit-identical sums.
+template <int L>
+struct GroupSub {
+    static_assert(L == 4 || L == 8 || L == 16, "sub-warp groups are 4, 8 or 16 lanes");
+    static constexpr int kThreads = L;
+    int tid;        // lane inside the chain's group
+    unsigned mask;  // the group's lanes inside the warp
+    double* red;    // unused (interface parity with GroupCuda)
+    static constexpr int kMaxRed = 12;
+
+    NB_D int size() const { return L; }
+    NB_D void sync() const { __syncwarp(mask); }
+    template <int N>
+    NB_D void reduce(double (&v)[N]) const {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int off = L / 2; off > 0; off >>= 1) v[i] += __shfl_xor_sync(mask, v[i], off);
+        }
+    }
+    NB_D double exclusive_scan(double x) const {
+        double v = x;
+#pragma unroll
+        for (int off = 1; off < L; off <<= 1) {
+            const double y = __shfl_up_sync(mask, v, off, L);
+            if (tid >= off) v += y;
+        }
+        double excl = __shfl_up_sync(mask, v, 1, L);
+        if (tid == 0) excl = 0.0;
+        return excl;
+    }
+};
+#endif
+
 // one host thread plays the whole group (tests/emul only)
 struct GroupSerial {
     static constexpr int kThreads = 1;
@@ -114,6 +178,7 @@ struct GroupSerial {
     NB_HD void sync() const {}
     template <int N>
     NB_HD void reduce(double (&)[N]) const {}
+    NB_HD double exclusive_scan(double) const { return 0.0; }
 };
 
 }  // namespace nb200

@@ -13,18 +13,24 @@ __host__ __device__ inline size_t stage_bytes(int Dp) {
     return M::kElementwise ? 0 : ((4 * sizeof(double) * (size_t)Dp + 15) & ~size_t(15));
 }
 
-template <class M, int W, int NIT>
-__device__ __forceinline__ void setup_ctx(ChainCtx<M, GroupCuda<W>, NIT>& ctx, const KParams<M>& P,
+template <class M, int W, int NIT, class G = GroupCuda<W>>
+__device__ __forceinline__ void setup_ctx(ChainCtx<M, G, NIT>& ctx, const KParams<M>& P,
                                           unsigned long long chain, unsigned char* smem_chain) {
-    ctx.g.tid = (W == 1) ? (threadIdx.x & 31) : threadIdx.x;
+    if constexpr (G::kThreads < 32) {  // sub-warp group: L aligned lanes of the warp
+        const int lane = threadIdx.x & 31;
+        ctx.g.tid = lane % G::kThreads;
+        ctx.g.mask = ((1u << G::kThreads) - 1u) << (lane - ctx.g.tid);
+    } else {
+        ctx.g.tid = (W == 1) ? (threadIdx.x & 31) : threadIdx.x;
+    }
     ctx.P = &P;
     ctx.md = P.mdata;
     ctx.sh = reinterpret_cast<ChainShared*>(smem_chain);
     size_t off = (sizeof(ChainShared) + 15) & ~size_t(15);
     ctx.msm = reinterpret_cast<double*>(smem_chain + off);
-    off += (sizeof(double) * (size_t)M::smem_doubles(P.mdata, 32 * W) + 15) & ~size_t(15);
+    off += (sizeof(double) * (size_t)M::smem_doubles(P.mdata, G::kThreads) + 15) & ~size_t(15);
     ctx.g.red = reinterpret_cast<double*>(smem_chain + off);
-    if (W > 1) off += (sizeof(double) * W * GroupCuda<W>::kMaxRed + 15) & ~size_t(15);
+    if (W > 1) off += (sizeof(double) * W * G::kMaxRed + 15) & ~size_t(15);
     ctx.stage = smem_chain + off;
     ctx.stage_phase = 0;
     ctx.sweep_rev = false;
@@ -103,6 +109,21 @@ __global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, kernel_min_blocks<M, W,
         printf("chain %llu one-warp total %lld | leapfrog %lld (n %lld)\n", chain, clock64() - t_begin,
                ctx.prof[7], ctx.prof[8]);
 #endif
+}
+
+// Sub-warp geometry: L lanes per chain, 32 / L chains per warp, `wpb` warps per CTA (GroupSub).
+template <class M, int L, int NIT>
+__global__ void __launch_bounds__(256, 1)
+    nuts_kernel_sub(const __grid_constant__ KParams<M> P, size_t smem_per_chain) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int CPW = 32 / L;  // chains per warp
+    const int local = (threadIdx.x >> 5) * CPW + (threadIdx.x & 31) / L;
+    const int cpb = (blockDim.x >> 5) * CPW;
+    const unsigned long long chain = (unsigned long long)blockIdx.x * cpb + local;
+    if (chain >= P.n_chains) return;
+    ChainCtx<M, GroupSub<L>, NIT> ctx;
+    setup_ctx<M, 1, NIT, GroupSub<L>>(ctx, P, chain, smem + (size_t)local * smem_per_chain);
+    ctx.run();
 }
 
 // Two warps per chain (W = 1 density geometry, see ChainCtx::producer_main).  Warps are dealt to

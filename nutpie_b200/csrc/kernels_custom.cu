@@ -235,6 +235,9 @@ template int supported_nit<CustomModel>(int, int);
 template size_t smem_fixed<CustomModel>(int, const CustomModel::Data&, int);
 template size_t model_block_data_bytes<CustomModel>(const CustomModel::Data&);
 template bool supports_pipeline<CustomModel>(int);
+template int sub_warp_lanes<CustomModel>(int, int);
+template cudaError_t launch_nuts_sub<CustomModel>(int, int, const KParams<CustomModel>&, size_t, int, int,
+                                                  cudaStream_t);
 template cudaError_t launch_nuts_piped<CustomModel>(int, const KParams<CustomModel>&, size_t, size_t,
                                                     int, int, cudaStream_t);
 

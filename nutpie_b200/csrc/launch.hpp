@@ -13,6 +13,11 @@ template <class M>
 cudaError_t launch_nuts(int W, int NIT, const KParams<M>& P, size_t smem_per_chain,
                         size_t block_data, int cpb, int grid, int block, cudaStream_t stream);
 template <class M>
+int sub_warp_lanes(int D, int forced_lanes);
+template <class M>
+cudaError_t launch_nuts_sub(int L, int NIT, const KParams<M>& P, size_t smem_per_chain, int wpb,
+                            int grid, cudaStream_t stream);
+template <class M>
 bool supports_pipeline(int NIT);
 template <class M>
 cudaError_t launch_nuts_piped(int NIT, const KParams<M>& P, size_t smem_per_chain, size_t block_data,

@@ -48,6 +48,46 @@ static cudaError_t launch_one_piped(const KParams<M>& P, size_t smem_per_chain, 
     return cudaGetLastError();
 }
 
+// ---- sub-warp geometry (GroupSub<L>): L lanes per chain, densities with kSubWarp
+template <class M, int L, int NIT>
+static cudaError_t launch_one_sub(const KParams<M>& P, size_t smem_per_chain, int wpb, int grid,
+                                  cudaStream_t stream) {
+    const size_t smem = smem_per_chain * (size_t)wpb * (32 / L);
+    cudaError_t e = cudaFuncSetAttribute(nuts_kernel_sub<M, L, NIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    nuts_kernel_sub<M, L, NIT><<<grid, 32 * wpb, smem, stream>>>(P, smem_per_chain);
+    return cudaGetLastError();
+}
+
+// (lanes per chain, unrolled dimensions per lane) pairs that exist; 0 = none
+template <class M>
+int sub_warp_lanes(int D, int forced_lanes) {
+    if constexpr (M::kSubWarp) {
+        if (forced_lanes == 4) return D <= 12 ? 4 : 0;  // up to three dimensions per lane
+        if (forced_lanes == 8 || forced_lanes == 16) return D <= 2 * forced_lanes ? forced_lanes : 0;
+        if (forced_lanes != 0) return 0;
+        if (D <= 4) return 4;
+        if (D <= 16) return 8;
+        return 0;
+    } else {
+        (void)D; (void)forced_lanes;
+        return 0;
+    }
+}
+
+template <class M>
+cudaError_t launch_nuts_sub(int L, int NIT, const KParams<M>& P, size_t smem_per_chain, int wpb,
+                            int grid, cudaStream_t stream) {
+    if constexpr (M::kSubWarp) {
+#define NB_CASE(LL, NN) \
+    if (L == LL && NIT == NN) return launch_one_sub<M, LL, NN>(P, smem_per_chain, wpb, grid, stream);
+        NB_CASE(4, 1) NB_CASE(4, 2) NB_CASE(4, 3) NB_CASE(8, 1) NB_CASE(8, 2) NB_CASE(16, 1) NB_CASE(16, 2)
+#undef NB_CASE
+    }
+    return cudaErrorInvalidValue;
+}
+
 // two-warp pipeline kernels exist for these unrolled trip counts (densities with kPipelined)
 template <class M>
 bool supports_pipeline(int NIT) {
@@ -137,6 +177,9 @@ size_t model_block_data_bytes(const typename M::Data& md) {
                                              double*, size_t, unsigned);                        \
     template size_t smem_fixed<M>(int, const M::Data&, int);                                    \
     template bool supports_pipeline<M>(int);                                                    \
+    template int sub_warp_lanes<M>(int, int);                                                   \
+    template cudaError_t launch_nuts_sub<M>(int, int, const KParams<M>&, size_t, int, int,      \
+                                            cudaStream_t);                                      \
     template cudaError_t launch_nuts_piped<M>(int, const KParams<M>&, size_t, size_t, int, int, \
                                               cudaStream_t);                                    \
     template size_t model_block_data_bytes<M>(const M::Data&);

@@ -36,6 +36,7 @@ struct NormalModel {
     static constexpr bool kNeedsChain = false;
     static constexpr bool kRuntimeLoopsOnly = false;
     static constexpr bool kPipelined = false;  // two-warp producer / consumer kernels exist
+    static constexpr bool kSubWarp = true;     // sub-warp (4/8/16 lanes per chain) kernels exist
     static constexpr bool kHasBlockData = false;
     // g_i = -(q_i - mu) / var is non-finite only if q_i - mu is, and then so is the term
     // (q_i - mu)^2 of logp: the leapfrog needs no separate per-dimension gradient check
@@ -64,6 +65,7 @@ struct FunnelModel {
     static constexpr bool kNeedsChain = false;
     static constexpr bool kRuntimeLoopsOnly = false;
     static constexpr bool kPipelined = false;  // two-warp producer / consumer kernels exist
+    static constexpr bool kSubWarp = true;     // sub-warp (4/8/16 lanes per chain) kernels exist
     static constexpr bool kHasBlockData = false;
     struct Data {
         int unused;
@@ -105,14 +107,16 @@ struct FunnelModel {
 // {y, meta} so a warp's loads coalesce into one LDG.128 per observation.  Inside
 // a range, a GROUP is a maximal run of equal (county, floor): all its
 // observations share the linear predictor mu[2*county + floor], which every
-// thread reads from a shared table (meta carries its byte offset).  The walk is
-// a running PREFIX sum of residuals over the thread's range is stored to the group's
-// private slot when the end-of-group bit is set (a group's sum is the difference of two
-// consecutive prefixes of the same thread).  Because ranges are
-// contiguous, a (county, floor) pair owns at most `kmax` groups; the host lists
-// them (padded with a slot that always holds 0), so the per-county gradient is a
-// fixed-order sum of kmax terms — no atomics, no data-dependent branches,
-// bitwise reproducible (determinism contract, tests/test_stan.py:67-101).
+// thread reads from a shared table (meta carries its byte offset).  The walk keeps a
+// running PREFIX sum of residuals over the thread's range and stores it to the group's
+// private slot when the end-of-group bit is set.  An exclusive scan of the threads' range
+// totals (warp shuffles) turns those into GLOBAL prefixes over the sorted observations, and
+// the sum of a (county, floor) pair is the difference of two of them: the prefix where its
+// last piece ends minus the prefix where the previous non-empty pair ends — one 16-byte
+// table record and eight shared-memory loads per county, however the ranges cut the pairs
+// (the first version summed up to kmax piece differences per pair in a rolled loop: 10 % of
+// a leapfrog's instructions).  No atomics, no data-dependent branches, bitwise reproducible
+// (determinism contract, tests/test_stan.py:67-101).
 struct RadonObs {
     double y;
     int32_t meta;  // byte offset of mu[2*county+floor] | 1 if last observation of its group
@@ -163,6 +167,7 @@ struct RadonModel {
     static constexpr bool kNeedsChain = false;
     static constexpr bool kRuntimeLoopsOnly = false;
     static constexpr bool kPipelined = true;   // two-warp producer / consumer kernels exist
+    static constexpr bool kSubWarp = false;
     // The observation records and group tables are the same for every chain: a CTA
     // that hosts several chains copies them into shared memory once (launch_impl.cuh).
     static constexpr bool kHasBlockData = true;
@@ -171,8 +176,9 @@ struct RadonModel {
         int T, in_smem;              // group size the layout was built for; tables live in shared memory
         const RadonObs* obs;         // [n_steps][T]; padding: y = 0, meta -> mu[2J] (= 0), no end bit
         const int32_t* group_base;   // [T]   first group slot of each thread (one spare slot each)
-        const uint32_t* group_list;  // [2J][kmax] (slot | prev_slot << 16) of each (county, floor) piece;
-                                     // prev = previous group of the same thread, or G; padding = (G, G)
+        const uint32_t* group_list;  // [J][4]: per county {slot | prev_slot << 16, thread |
+                                     // prev_thread << 16} for floor 0, then floor 1: where the
+                                     // pair's last piece ends / where the previous pair's does
     };
     // expand_vector for the radon model (src/pymc.rs:217-286; producer
     // python/nutpie/compile_pymc.py:816-861): value variables on the constrained scale
@@ -198,7 +204,7 @@ struct RadonModel {
     }
     NB_HD static size_t block_data_bytes(const Data& d) {
         size_t b = sizeof(RadonObs) * (size_t)d.n_steps * d.T;
-        b += (sizeof(uint32_t) * (size_t)2 * d.J * d.kmax + 15) & ~size_t(15);
+        b += (sizeof(uint32_t) * (size_t)4 * d.J + 15) & ~size_t(15);
         b += (sizeof(int32_t) * (size_t)d.T + 15) & ~size_t(15);
         return b;
     }
@@ -211,8 +217,8 @@ struct RadonModel {
         for (int i = tid; i < n16; i += nthreads) o[i] = __ldg(src + i);
         size_t off = sizeof(RadonObs) * (size_t)n16;
         uint32_t* gl = reinterpret_cast<uint32_t*>(dst + off);
-        for (int i = tid; i < 2 * d.J * d.kmax; i += nthreads) gl[i] = __ldg(d.group_list + i);
-        off += (sizeof(uint32_t) * (size_t)2 * d.J * d.kmax + 15) & ~size_t(15);
+        for (int i = tid; i < 4 * d.J; i += nthreads) gl[i] = __ldg(d.group_list + i);
+        off += (sizeof(uint32_t) * (size_t)4 * d.J + 15) & ~size_t(15);
         int32_t* gb = reinterpret_cast<int32_t*>(dst + off);
         for (int i = tid; i < d.T; i += nthreads) gb[i] = __ldg(d.group_base + i);
         d.obs = reinterpret_cast<const RadonObs*>(dst);
@@ -221,8 +227,8 @@ struct RadonModel {
         d.in_smem = 1;
     }
 #endif
-    // mu[2J+1] (last = 0 for padding) + gsum[G+1] (last = 0 for padding)
-    NB_HD static int smem_doubles(const Data& d, int) { return 2 * d.J + 1 + d.G + 1; }
+    // mu[2J+1] (last = 0 for padding) + gsum[G+1] (last = 0) + thread offsets[T+1] (last = 0)
+    NB_HD static int smem_doubles(const Data& d, int T) { return 2 * d.J + 1 + d.G + 1 + T + 1; }
 
     template <class G>
     NB_HD static double logp_grad(const G& grp, const Data& d, int, const double* q, double* g,
@@ -238,7 +244,8 @@ struct RadonModel {
         const double inv_sigma = 1.0 / sigma;
         const double inv_s2 = inv_sigma * inv_sigma;
         double* mu = sm;                // [2J+1] linear predictor per (county, floor)
-        double* gsum = sm + 2 * J + 1;  // [G+1]  per-group sum of residuals
+        double* gsum = sm + 2 * J + 1;  // [G+1]  running prefix of residuals at each group end
+        double* toff = gsum + d.G + 1;  // [T+1]  sum of the residuals of all earlier threads
 #pragma unroll 1
         for (int c = grp.tid; c < J; c += T) {
             const double a = intercept + q[1 + c] * sd_a;
@@ -248,9 +255,11 @@ struct RadonModel {
         if (grp.tid == 0) {
             mu[2 * J] = 0.0;
             gsum[d.G] = 0.0;
+            toff[T] = 0.0;
         }
         grp.sync();
         double ss0 = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
+        double range_sum;
         {
             char* kp = reinterpret_cast<char*>(gsum + nb_ld_tab(d.group_base + grp.tid, d.in_smem));
             const char* mub = reinterpret_cast<const char*>(mu);
@@ -279,24 +288,29 @@ struct RadonModel {
             }
 #pragma unroll 1  // at most three steps: not worth 100 instructions of unrolled remainder
             for (; j0 < d.n_steps; ++j0) step(nb_ldg_obs(ob + (size_t)j0 * T, d.in_smem), ss0);
+            range_sum = pre;
         }
+        // global prefix = thread-local prefix + what all earlier threads summed
+        toff[grp.tid] = grp.exclusive_scan(range_sum);
         grp.sync();
         double acc[7] = {(ss0 + ss1) + (ss2 + ss3), 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         // kept rolled (as is the piece loop inside): the kernel is bound by instruction fetch, and
         // unrolling these two cost 660 SASS instructions for nothing (+3 % rolled, measured)
 #pragma unroll 1
         for (int c = grp.tid; c < J; c += T) {
-            const uint32_t* gl = d.group_list + (size_t)(2 * c) * d.kmax;
-            double S0 = 0.0, S1 = 0.0;
-            // a group's sum = prefix at its end - prefix at the end of the previous group of
-            // the same thread (slot G, always 0, for a thread's first group and for padding)
-#pragma unroll 1
-            for (int k = 0; k < d.kmax; ++k) {
-                const uint32_t e0 = nb_ld_tab(gl + k, d.in_smem);
-                const uint32_t e1 = nb_ld_tab(gl + d.kmax + k, d.in_smem);
-                S0 += gsum[e0 & 0xFFFFu] - gsum[e0 >> 16];
-                S1 += gsum[e1 & 0xFFFFu] - gsum[e1 >> 16];
-            }
+            // one 16-byte record per county: the sum of a (county, floor) pair is the difference
+            // of two global prefixes (end of its last piece, end of the previous pair's)
+            uint32_t e0, t0, e1, t1;
+#ifdef __CUDA_ARCH__
+            const uint4 rec4 = d.in_smem ? *reinterpret_cast<const uint4*>(d.group_list + 4 * c)
+                                         : __ldg(reinterpret_cast<const uint4*>(d.group_list + 4 * c));
+            e0 = rec4.x; t0 = rec4.y; e1 = rec4.z; t1 = rec4.w;
+#else
+            e0 = d.group_list[4 * c]; t0 = d.group_list[4 * c + 1];
+            e1 = d.group_list[4 * c + 2]; t1 = d.group_list[4 * c + 3];
+#endif
+            const double S0 = (gsum[e0 & 0xFFFFu] + toff[t0 & 0xFFFFu]) - (gsum[e0 >> 16] + toff[t0 >> 16]);
+            const double S1 = (gsum[e1 & 0xFFFFu] + toff[t1 & 0xFFFFu]) - (gsum[e1 >> 16] + toff[t1 >> 16]);
             const double E = (S0 + S1) * inv_s2;  // sum over the county of d logp / d mu_i
             const double F = S1 * inv_s2;         // same, floor = 1 observations only
             const double ra = q[1 + c], rb = q[J + 3 + c];
@@ -345,6 +359,7 @@ struct HostModel {
     static constexpr bool kHasBlockData = false;
     static constexpr bool kRuntimeLoopsOnly = true;  // only the NIT = 0 kernels are instantiated
     static constexpr bool kPipelined = false;
+    static constexpr bool kSubWarp = false;
     struct Data {
         double* qbox;        // [n_chains][Dp]  device -> host
         double* gbox;        // [n_chains][Dp]  host -> device
@@ -458,6 +473,7 @@ struct CustomModel {
     static constexpr bool kNeedsChain = false;
     static constexpr bool kRuntimeLoopsOnly = false;
     static constexpr bool kPipelined = false;  // two-warp producer / consumer kernels exist
+    static constexpr bool kSubWarp = false;    // sub-warp (4/8/16 lanes per chain) kernels exist
     static constexpr bool kHasBlockData = false;
     struct Data {
         const double* data;  // device copy of nb200_model_desc::user_data

@@ -58,7 +58,7 @@ static std::atomic<int> g_threads_per_chain{0};
 static std::atomic<int> g_chains_per_block{0};
 static std::atomic<int> g_smem_slots{-1};
 static std::atomic<int> g_force_nit{-1};
-static std::atomic<int> g_pipeline{1};     // two-warp producer / consumer kernels (nb200_set_pipeline)
+static std::atomic<int> g_pipeline{0};     // two-warp producer / consumer kernels: opt-in (nb200_set_pipeline)
 static std::atomic<int> g_stage_loads{3};  // staging + alternating sweep (nb200_set_stage_loads)
 static inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 // + working mass matrix + hot tier of the pool
@@ -229,6 +229,7 @@ struct nb200_sampler {
     uint64_t n_chains = 0, chain_id_offset = 0;
     int W = 1, NIT = 0, cpb = 1, grid = 0, block = 0;
     bool piped = false;  // two warps per chain: integrator + tree (nuts_kernel_piped)
+    int sub = 0;         // lanes per chain of the sub-warp geometry (nuts_kernel_sub); 0 = none
     size_t smem_per_chain = 0, block_data = 0;
     cudaStream_t stream = nullptr, side = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -269,8 +270,10 @@ struct SamplerImpl : nb200_sampler {
     KParams<M> P;
     int launch() override {
         P.max_draws_per_launch = draws_per_launch;
-        cudaError_t e = piped ? launch_nuts_piped<M>(NIT, P, smem_per_chain, block_data, cpb, grid, stream)
-                              : launch_nuts<M>(W, NIT, P, smem_per_chain, block_data, cpb, grid, block, stream);
+        cudaError_t e =
+            sub ? launch_nuts_sub<M>(sub, NIT, P, smem_per_chain, block / 32, grid, stream)
+            : piped ? launch_nuts_piped<M>(NIT, P, smem_per_chain, block_data, cpb, grid, stream)
+                    : launch_nuts<M>(W, NIT, P, smem_per_chain, block_data, cpb, grid, block, stream);
         if (e != cudaSuccess) return fail(NB200_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
         return 0;
     }
@@ -283,6 +286,7 @@ static size_t smem_for(int W, const typename M::Data& md, int Dp) {
 
 static int pick_W(const nb200_model_desc& m, uint64_t n_chains) {
     int t = g_threads_per_chain.load();
+    if (t == 4 || t == 8 || t == 16) return 1;  // sub-warp groups (create_impl picks the lanes)
     if (t > 0) return t / 32;
     if (m.dim >= 2048) {  // streaming regime (config 4): a CTA per chain; prefer CTAs small
         // enough that every chain is resident at once.  With bulk-copy staging the bytes in
@@ -443,6 +447,18 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     s->Dp = (D + 3) / 4 * 4;
     s->NS = 3 * ((int)st->maxdepth + 1) + 3;
     {
+        const int forced_t = g_threads_per_chain.load();
+        if (s->W == 1 && forced_t < 32 && g_force_nit.load() != 0)
+            s->sub = sub_warp_lanes<M>(D, forced_t);
+        if (forced_t > 0 && forced_t < 32 && s->sub == 0) {
+            fail(NB200_EINVAL, "threads per chain must be 4 (dim <= 12), 8 or 16 (dim <= 2 x threads) for "
+                               "this density, or 32..1024 (power of two)");
+            return bail();
+        }
+    }
+    if (s->sub) {
+        s->NIT = (D + s->sub - 1) / s->sub;
+    } else {
         const int T = 32 * s->W;
         s->NIT = supported_nit<M>(s->W, (D + T - 1) / T);
         if (g_force_nit.load() == 0) s->NIT = 0;
@@ -499,6 +515,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         }
         if (c > 8) c = 8;
         // (piped: 8 chains = 16 warps = 512 threads, 128 registers per thread)
+        if (s->sub) c = 4 * (32 / s->sub);  // four warps per CTA, 32 / lanes chains per warp
         s->cpb = c;
         // stage the tables in shared memory only when they fit beside the chains' own state
         // (a model with > ~10 k observations reads them through L2 instead)
@@ -512,7 +529,8 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     {
         const size_t kSmemSM = 227 * 1024, kSlack = 1024;  // 1 KB/CTA reserved by the driver
         uint64_t per_sm = (n_chains + 147) / 148;
-        const uint64_t max_res = (uint64_t)(2048 / (32 * s->W * (s->piped ? 2 : 1)));  // thread limit per SM
+        const int tpc = s->sub ? s->sub : 32 * s->W * (s->piped ? 2 : 1);
+        const uint64_t max_res = (uint64_t)(2048 / tpc);  // thread limit per SM
         if (per_sm > max_res) per_sm = max_res;
         if (per_sm > 32ull * s->cpb) per_sm = 32ull * s->cpb;     // CTA limit per SM
         if (per_sm < 1) per_sm = 1;
@@ -537,7 +555,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         P.var_in_smem = var_in;
         s->smem_per_chain = chain_smem_total(fixed, s->Dp, var_in, slots);
     }
-    s->block = s->piped ? 128 * ((s->cpb + 1) / 2) : 32 * s->W * s->cpb;
+    s->block = s->sub ? 128 : (s->piped ? 128 * ((s->cpb + 1) / 2) : 32 * s->W * s->cpb);
     s->grid = (int)((n_chains + s->cpb - 1) / s->cpb);
     if (bdata + s->smem_per_chain * s->cpb > 227 * 1024) {
         fail(NB200_EINVAL, "model dimension too large: a density that gathers across dimensions "
@@ -1146,7 +1164,7 @@ int nb200_sampler_device_buffers(nb200_sampler* s, void** draws, void** stats) {
 }
 int nb200_sampler_geometry(nb200_sampler* s, int32_t* tpc, int32_t* block, int32_t* grid) {
     if (!s) return fail(NB200_EINVAL, "null sampler");
-    if (tpc) *tpc = 32 * s->W;
+    if (tpc) *tpc = s->sub ? s->sub : 32 * s->W;
     if (block) *block = s->block;
     if (grid) *grid = s->grid;
     return 0;

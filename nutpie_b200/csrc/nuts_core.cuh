@@ -466,6 +466,9 @@ struct ChainCtx {
             stage_phase ^= 1u << sidx;
             if (k < D2) body(k, reinterpret_cast<const double2*>(stage + (size_t)sidx * BUF) + g.tid);
             if (c + kStages < nchunk) {
+                // (a consumer-release mbarrier per stage — each warp arrives, thread 0 waits and
+                // refills — measured 6 % SLOWER than this CTA barrier: the waiting thread spins
+                // inside warp 0 and stalls it; profiles/r2_config4_notes.txt)
                 g.sync();  // every thread is done reading this stage
                 if (g.tid == 0) issue(c + kStages);
             }

@@ -19,7 +19,10 @@ struct RadonLayout {
     int J = 0, N = 0, T = 0, n_steps = 0, G = 0, kmax = 1;
     std::vector<RadonObs> obs;           // [n_steps][T]
     std::vector<int32_t> group_base;     // [T]
-    std::vector<uint32_t> group_list;    // [2J][kmax]  slot | prev_slot << 16
+    // [J][4]: for the county's (floor 0, floor 1) pairs, where the pair's LAST piece ends and
+    // where the previous non-empty pair's last piece ends — {slot | prev_slot << 16,
+    // thread | prev_thread << 16} each; an empty pair has slot = prev_slot (sum 0)
+    std::vector<uint32_t> group_list;
 };
 
 inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
@@ -56,16 +59,35 @@ inline RadonLayout build_radon_layout(int n_obs, int n_county, const double* y,
             }
         }
     }
-    L.G = slot;  // slot G itself (one past) always holds 0 and pads the lists
+    L.G = slot;  // slot G itself (one past) always holds 0: "before the first observation"
     L.kmax = 1;
     for (auto& p : pieces) L.kmax = std::max<int>(L.kmax, (int)p.size());
-    const uint32_t pad = (uint32_t)L.G | ((uint32_t)L.G << 16);
-    L.group_list.assign((size_t)2 * n_county * L.kmax, pad);
-    for (int k = 0; k < 2 * n_county; ++k)
-        for (size_t i = 0; i < pieces[k].size(); ++i) {
-            const int pv = pieces[k][i].second < 0 ? L.G : pieces[k][i].second;
-            L.group_list[(size_t)k * L.kmax + i] = (uint32_t)pieces[k][i].first | ((uint32_t)pv << 16);
+    // A pair's sum of residuals = global prefix at its end - global prefix at the end of the
+    // previous non-empty pair, where the global prefix at a group end = the owning thread's
+    // running prefix (stored in the group's slot) + the sum of all earlier threads' ranges
+    // (exclusive scan over the threads, slot T of that table = 0).
+    std::vector<int> owner(slot + 1, T);  // thread that owns each group slot (slot G -> T)
+    for (int t = 0; t < T; ++t) {
+        const int hi = t + 1 < T ? L.group_base[t + 1] : slot;
+        for (int g2 = L.group_base[t]; g2 < hi; ++g2) owner[g2] = t;
+    }
+    L.group_list.assign((size_t)4 * n_county, 0u);
+    int prev_slot = L.G, prev_thread = T;
+    for (int k = 0; k < 2 * n_county; ++k) {
+        uint32_t a, b;
+        if (pieces[k].empty()) {  // no observations: both ends coincide
+            a = (uint32_t)L.G | ((uint32_t)L.G << 16);
+            b = (uint32_t)T | ((uint32_t)T << 16);
+        } else {
+            const int last = pieces[k].back().first;
+            a = (uint32_t)last | ((uint32_t)prev_slot << 16);
+            b = (uint32_t)owner[last] | ((uint32_t)prev_thread << 16);
+            prev_slot = last;
+            prev_thread = owner[last];
         }
+        L.group_list[(size_t)2 * k] = a;
+        L.group_list[(size_t)2 * k + 1] = b;
+    }
     return L;
 }
 

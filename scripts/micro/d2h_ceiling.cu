@@ -1,0 +1,63 @@
+// d2h_ceiling.cu — what device-to-host bandwidth does this BOX sustain when n GPUs copy into
+// pinned host memory at the same time?  The end-to-end arm of bench.py lands 5.9 GB of trace per
+// GPU and step in host memory; at 8 GPUs its scaling is bounded by this number, not by the
+// sampler (e2e efficiency 0.43 at N = 8).  One host thread + stream per device,
+// 256 MB chunks, cudaMemcpyAsync from device memory to cudaHostAlloc'ed buffers, 2 s per point.
+// Build: nvcc -O2 -o d2h_ceiling d2h_ceiling.cu -lpthread      Usage: ./d2h_ceiling [max_gpus]
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1);} } while (0)
+
+int main(int argc, char** argv) {
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (argc > 1 && atoi(argv[1]) < ndev) ndev = atoi(argv[1]);
+    const size_t chunk = 256ull << 20, ring = 4;  // 1 GB of pinned memory per device
+    std::vector<void*> dsrc(ndev), hdst(ndev);
+    std::vector<cudaStream_t> st(ndev);
+    for (int d = 0; d < ndev; ++d) {
+        CK(cudaSetDevice(d));
+        CK(cudaMalloc(&dsrc[d], chunk));
+        CK(cudaMemset(dsrc[d], 1, chunk));
+        CK(cudaHostAlloc(&hdst[d], chunk * ring, cudaHostAllocDefault));
+        CK(cudaStreamCreateWithFlags(&st[d], cudaStreamNonBlocking));
+    }
+    printf("{\"how\": \"n devices copy 256 MB chunks device->pinned host concurrently for 2 s each\", \"points\": [");
+    for (int n = 1; n <= ndev; n *= 2) {
+        std::atomic<bool> go{false}, stop{false};
+        std::vector<double> bytes(n, 0.0);
+        std::vector<std::thread> th;
+        for (int d = 0; d < n; ++d)
+            th.emplace_back([&, d] {
+                cudaSetDevice(d);
+                while (!go.load()) std::this_thread::yield();
+                size_t i = 0;
+                while (!stop.load()) {
+                    cudaMemcpyAsync((char*)hdst[d] + (i % ring) * chunk, dsrc[d], chunk, cudaMemcpyDeviceToHost, st[d]);
+                    cudaStreamSynchronize(st[d]);
+                    bytes[d] += (double)chunk;
+                    ++i;
+                }
+            });
+        auto t0 = std::chrono::steady_clock::now();
+        go.store(true);
+        std::this_thread::sleep_for(std::chrono::seconds(2));
+        stop.store(true);
+        for (auto& t : th) t.join();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        double tot = 0.0, mn = 1e30;
+        for (double b : bytes) { tot += b; if (b < mn) mn = b; }
+        printf("%s{\"gpus\": %d, \"aggregate_gbs\": %.1f, \"slowest_gpu_gbs\": %.1f}", n > 1 ? ", " : "", n,
+               tot / dt / 1e9, mn / dt / 1e9);
+        fflush(stdout);
+    }
+    printf("]}\n");
+    return 0;
+}

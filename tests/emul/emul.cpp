@@ -205,6 +205,37 @@ struct GroupLanes {
         }
         s->yield();  // every lane has read: the scratch may be reused
     }
+    // GroupCuda::exclusive_scan in the same association order: Hillis-Steele inside each warp,
+    // then the totals of the earlier warps added in warp order
+    double exclusive_scan(double x) const {
+        double* red = s->red.data();
+        red[(size_t)tid * LaneSched::kMaxRed] = x;
+        s->yield();
+        const int w = tid / 32, lane = tid % 32;
+        auto warp_incl = [&](int ww, double* out) {
+            double v[32], y[32];
+            for (int l = 0; l < 32; ++l) v[l] = red[(size_t)(ww * 32 + l) * LaneSched::kMaxRed];
+            for (int off = 1; off < 32; off <<= 1) {
+                for (int l = 0; l < 32; ++l) y[l] = l >= off ? v[l] + v[l - off] : v[l];
+                for (int l = 0; l < 32; ++l) v[l] = y[l];
+            }
+            for (int l = 0; l < 32; ++l) out[l] = v[l];
+        };
+        double mine[32];
+        warp_incl(w, mine);
+        double excl = lane == 0 ? 0.0 : mine[lane - 1];
+        if (T > 32) {
+            double base = 0.0;
+            for (int ww = 0; ww < w; ++ww) {
+                double o[32];
+                warp_incl(ww, o);
+                base += o[31];
+            }
+            excl = base + excl;
+        }
+        s->yield();
+        return excl;
+    }
 };
 
 template <class M, int T, int NIT>

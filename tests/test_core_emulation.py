@@ -115,7 +115,9 @@ def test_lane_emulation_radon_production_geometry(radon_data, tpc, slots):
     b = E.sample_lanes("radon", D, s, 2, threads_per_chain=tpc, smem_slots=slots, y=d["y"],
                        county=d["county"], floor=d["floor"], n_county=J)
     dd = np.abs(a["draws"] - b["draws"]).max(axis=(0, 2))
-    assert dd[0] < 1e-12 and dd[:5].max() < 1e-8, dd[:5]
+    # (global-prefix differences: sums of ~900 residuals cancel down to one pair's sum, which costs
+    # a few more ulps than adding the pair's own residuals as the oracle does)
+    assert dd[0] < 1e-11 and dd[:5].max() < 1e-8, dd[:5]
     assert np.array_equal(a["stats"][:, :5, STAT["n_steps"]], b["stats"][:, :5, STAT["n_steps"]])
     assert abs(a["total_steps"] - b["total_steps"]) / a["total_steps"] < 0.25
 

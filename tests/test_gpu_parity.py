@@ -567,3 +567,49 @@ def test_single_process_multi_device_equals_one_device(radon_data):
     raw = nutpie_b200.sample(cm, devices=devs, return_raw_trace=True, **kw)
     assert isinstance(raw, _lib.MultiTrace) and [p.draws.shape[0] for p in raw.parts] == [7, 7, 6]
     assert raw.draws.shape[0] == 20 and list(raw.stats[:, 0, STAT["chain"]]) == list(range(20))
+
+
+@pytest.mark.parametrize("dim,tpc", [(1, 4), (1, 8), (3, 4), (9, 4), (9, 8), (12, 16), (30, 16)])
+def test_sub_warp_geometry_matches_oracle_draw_for_draw(dim, tpc):
+    """Sub-warp groups (4 / 8 / 16 lanes per chain, 32 / lanes chains per warp: the geometry of
+    BASELINE configs 1 and 5): chains that share a warp part ways wherever their trees differ,
+    yet every chain reproduces the oracle's trees exactly on an order-independent density —
+    and 70 chains (not a multiple of the chains per warp or per CTA) all finish."""
+    gm, om = nutpie_b200.normal_model(dim, 1.5, 0.7), O.Model("normal", dim, mu=1.5, sigma=0.7)
+    _lib.set_threads_per_chain(tpc)
+    s, so = settings_pair(seed=8, num_tune=200, num_draws=100, store_mass_matrix=1)
+    smp = _lib.PySampler(s, gm, n_chains=70)
+    try:
+        smp.wait()
+        tr, geom = smp.take_results(), smp.geometry()
+    finally:
+        smp.close()
+    assert geom["threads_per_chain"] == tpc
+    ref = O.sample(om, so, 70)
+    for k in ("depth", "n_steps", "index_in_trajectory", "diverging", "maxdepth_reached"):
+        assert np.array_equal(tr.stats[..., STAT[k]], ref["stats"][..., STAT[k]]), k
+    np.testing.assert_allclose(tr.draws[:, :3], ref["draws"][:, :3], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(tr.draws, ref["draws"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(tr.mass_matrix_inv, ref["mass_matrix_inv"], rtol=1e-2)
+
+
+def test_sub_warp_funnel_equals_warp_per_chain_at_first_then_statistically():
+    """The gathering density path (shared-memory front, group reductions) on 8-lane groups: the
+    first draws equal the warp-per-chain run to rounding; pause / resume and chunked launches
+    stay bit-identical; auto geometry picks the sub-warp kernel for D = 9."""
+    m = nutpie_b200.funnel_model(9)
+    mk = lambda: settings_pair(seed=21, num_tune=150, num_draws=100, maxdepth=12)[0]
+    _lib.set_threads_per_chain(32)
+    warp = run_gpu(mk(), m, 40)
+    _lib.set_threads_per_chain(0)
+    smp = _lib.PySampler(mk(), m, n_chains=40)
+    try:
+        smp.wait()
+        sub, geom = smp.take_results(), smp.geometry()
+    finally:
+        smp.close()
+    assert geom["threads_per_chain"] == 8
+    np.testing.assert_allclose(sub.draws[:, :3], warp.draws[:, :3], rtol=1e-9, atol=1e-11)
+    assert np.mean(sub.stats[:, :30, STAT["n_steps"]] == warp.stats[:, :30, STAT["n_steps"]]) > 0.9
+    chunked = run_gpu(mk(), m, 40, draws_per_launch=23)
+    assert np.array_equal(chunked.draws, sub.draws) and np.array_equal(chunked.stats, sub.stats)
