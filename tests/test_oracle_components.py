@@ -199,3 +199,28 @@ def test_nonfinite_logp_return_codes():
     assert rc in (3, 4)
     lp, g, rc = m.logp_grad(np.array([0.1, 1.0, 1.0]))
     assert rc == 0
+
+
+def test_adam_step_size_rule_known_answer():
+    """Adam on the log step size (nuts-rs stepsize/adam.rs as recalled; settings surfaced at
+    src/wrapper.rs:347-392): 20-line numpy transcription vs oracle_adam_advance."""
+    import ctypes as C
+
+    L = O.lib()
+    L.oracle_adam_advance.restype = None
+    state = (C.c_double * 5)(np.log(0.1), np.log(0.1), 0.0, 0.0, 0.0)
+    log_step, m, v, b1, b2, eps, lr, target = np.log(0.1), 0.0, 0.0, 0.9, 0.999, 1e-8, 0.05, 0.8
+    rng = np.random.default_rng(0)
+    for t in range(1, 40):
+        acc = float(rng.uniform(0.3, 1.0))
+        L.oracle_adam_advance(state, C.c_double(acc), C.c_double(target), C.c_double(lr))
+        g = acc - target
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g * g
+        log_step += lr * (m / (1 - b1**t)) / (np.sqrt(v / (1 - b2**t)) + eps)
+        assert abs(state[0] - log_step) < 1e-13 and state[1] == state[0] and state[4] == t
+    # too-high acceptance -> larger steps
+    s2 = (C.c_double * 5)(0.0, 0.0, 0.0, 0.0, 0.0)
+    for _ in range(10):
+        L.oracle_adam_advance(s2, C.c_double(0.99), C.c_double(0.8), C.c_double(0.05))
+    assert s2[0] > 0.3
