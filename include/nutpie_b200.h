@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NB200_ABI_VERSION 3
+#define NB200_ABI_VERSION 4
 
 /* ---- error codes ------------------------------------------------------- */
 #define NB200_OK 0
@@ -100,6 +100,9 @@ typedef struct nb200_settings {
     double step_size_jitter;   /* wrapper.rs:393-407; 0 = off                    */
     double mass_matrix_eigval_cutoff; /* wrapper.rs:307-326; default 2.0         */
     double mass_matrix_gamma;  /* wrapper.rs:327-346; default 1e-5               */
+    uint64_t mass_matrix_max_rank; /* ours: at most this many eigenpairs are kept */
+                               /* (largest |log eigenvalue| first; nuts-rs keeps   */
+                               /* all beyond the cutoff); default 32, <= dim       */
 } nb200_settings;
 
 /* ---- model density plug-in ---------------------------------------------
@@ -345,6 +348,11 @@ int nb200_custom_model_compile(const nb200_model_desc *model,
  * end location, start momentum, start gradient — nuts-rs DivergenceInfo as surfaced by
  * python/nutpie/sample.py:641-646; NaN for draws that did not diverge; width as `gradients`) */
 int nb200_sampler_divergence_trace_into(nb200_sampler *s, double *divergences);
+/* adaptation = low_rank with store_mass_matrix (the reference's mass_matrix_eigvals column,
+ * tests/test_pymc.py:116-131; mass_matrix_stds arrives in the mass_matrix_inv rows): copy the
+ * eigenvalue rows [n_rows][n_chains][max_rank], NaN beyond the rank in use.  *max_rank
+ * receives the row width; eigvals may be NULL to query it. */
+int nb200_sampler_eigvals_trace_into(nb200_sampler *s, double *eigvals, uint64_t *max_rank);
 /* CpuLogpFunc::expand_vector (src/pymc.rs:217-286) over a finished trace of a
  * NB200_MODEL_HOST model: out[i] = expand(q[i]) for n rows, on n_threads host threads
  * (0 = all).  q rows are q_stride doubles apart, out rows expanded_dim.  Returns the first
@@ -372,6 +380,15 @@ int nb200_leapfrog(const nb200_model_desc *model, int device, uint64_t n,
                    const int32_t *dir, const int64_t *idx, double *q_out,
                    double *p_out, double *g_out, double *p_sum_out,
                    double *logp_out, double *kinetic_out, int32_t *rc);
+/* low-rank metric at the component seam (oracle twin: oracle_lowrank_update / _velocity /
+ * _momentum): refresh the metric from a window of n draws and gradients [n][dim] on the device,
+ * then v_out[v] = M^-1 p[v] and momentum_out[v] = M^1/2 z[v] for n_vec vectors [n_vec][dim].
+ * stds_out [dim], vals_out [max_rank], vecs_out [max_rank][dim], *rank_out may be NULL. */
+int nb200_lowrank_component(int device, uint64_t dim, uint64_t n, const double *draws,
+                            const double *grads, double gamma, double cutoff,
+                            uint64_t max_rank, uint64_t n_vec, const double *p, double *v_out,
+                            const double *z, double *momentum_out, double *stds_out,
+                            double *vals_out, double *vecs_out, uint64_t *rank_out);
 
 #ifdef __cplusplus
 }

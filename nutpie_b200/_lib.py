@@ -73,6 +73,7 @@ class Settings(C.Structure):
         ("store_divergences", C.c_int32), ("adaptation", C.c_int32),
         ("adam_learning_rate", C.c_double), ("step_size_jitter", C.c_double),
         ("mass_matrix_eigval_cutoff", C.c_double), ("mass_matrix_gamma", C.c_double),
+        ("mass_matrix_max_rank", C.c_uint64),
     ]
 
 
@@ -108,8 +109,8 @@ class Progress(C.Structure):
 
 
 MODEL_KINDS = {"normal": 1, "funnel": 2, "radon": 3, "custom": 4, "host": 5}
-ABI_VERSION = 3
-LOW_RANK_SUPPORTED = False  # PyNutsSettings.LowRank exists; the kernel side does not yet
+ABI_VERSION = 4
+LOW_RANK_SUPPORTED = True  # csrc/lowrank.cuh (built-in and host plug-in densities)
 
 
 def library_path() -> Path:
@@ -174,6 +175,12 @@ def load_library() -> C.CDLL:
                                                 C.POINTER(C.c_size_t)]
         L.nb200_sampler_divergence_trace_into.restype = C.c_int
         L.nb200_sampler_divergence_trace_into.argtypes = [C.c_void_p, C.c_void_p]
+        L.nb200_sampler_eigvals_trace_into.restype = C.c_int
+        L.nb200_sampler_eigvals_trace_into.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.nb200_lowrank_component.restype = C.c_int
+        L.nb200_lowrank_component.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                              C.c_double, C.c_double, C.c_uint64, C.c_uint64] + \
+            [C.c_void_p] * 7 + [C.POINTER(C.c_uint64)]
         L.nb200_host_expand_rows.restype = C.c_int
         L.nb200_host_expand_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                              C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
@@ -267,6 +274,7 @@ _FLAT_DIRECT = {
     "step_size_adam_learning_rate": ("adam_learning_rate", float),
     "mass_matrix_eigval_cutoff": ("mass_matrix_eigval_cutoff", float),
     "mass_matrix_gamma": ("mass_matrix_gamma", float),
+    "mass_matrix_max_rank": ("mass_matrix_max_rank", int),
     # ours (not in the reference): initial-point and trace controls
     "init_radius": ("init_radius", float), "num_try_init": ("num_try_init", int),
     "store_dims": ("store_dims", int),
@@ -279,7 +287,7 @@ _UNSUPPORTED = {
     "microcanonical_trajectory": False, "exact_normal_trajectory": False,
 }
 # options that only exist for one adaptation (wrapper.rs:138-145: ValueError otherwise)
-_LOW_RANK_ONLY = ("mass_matrix_eigval_cutoff", "mass_matrix_gamma")
+_LOW_RANK_ONLY = ("mass_matrix_eigval_cutoff", "mass_matrix_gamma", "mass_matrix_max_rank")
 _DIAG_ONLY = ("use_grad_based_mass_matrix",)
 
 
@@ -304,8 +312,12 @@ class PyNutsSettings:
 
     @staticmethod
     def LowRank(seed=None):
+        # nuts-rs LowRankNutsSettings::default() [recalled]: the metric is refreshed every 10
+        # draws (a refresh is an eigen-decomposition, not a vector pass), 800 tuning draws
         s = PyNutsSettings("low_rank", seed)
         s._c.adaptation = 1
+        s._c.mass_matrix_update_freq = 10
+        s._c.num_tune = 800
         return s
 
     @staticmethod
@@ -460,8 +472,12 @@ class PyTrace:
     which is what the end-to-end path uses to avoid a per-chain Arrow hop."""
 
     def __init__(self, draws, stats, rows_filled, gradients=None, mass_matrix_inv=None,
-                 variables=None, expand=None, keep=None, expanded=False, divergences=None):
+                 variables=None, expand=None, keep=None, expanded=False, divergences=None,
+                 mass_matrix_eigvals=None, low_rank=False):
         self.draws, self.stats, self.rows_filled = draws, stats, rows_filled
+        # adaptation="low_rank" + store_mass_matrix: the mass-matrix rows are mass_matrix_stds and
+        # mass_matrix_eigvals [chain, row, max_rank] holds the eigenvalues in use (NaN-padded)
+        self.mass_matrix_eigvals, self.low_rank = mass_matrix_eigvals, low_rank
         # store_divergences: [chain, row, 4, dim] = start location, end location, start
         # momentum, start gradient of the diverging leapfrog (NaN rows otherwise)
         self.divergences = divergences
@@ -470,6 +486,14 @@ class PyTrace:
         self.gradients, self.mass_matrix_inv = gradients, mass_matrix_inv
         self.variables, self._expand, self._keep = variables, expand, keep
         self._taken = False
+
+    def mass_matrix_columns(self):
+        """The store_mass_matrix columns under the reference's names (python/nutpie/sample.py:
+        631-650): mass_matrix_inv (diag) | mass_matrix_stds + mass_matrix_eigvals (low rank)."""
+        if self.low_rank:
+            return [("mass_matrix_stds", self.mass_matrix_inv),
+                    ("mass_matrix_eigvals", self.mass_matrix_eigvals)]
+        return [("mass_matrix_inv", self.mass_matrix_inv)]
 
     def is_zarr(self):
         return False
@@ -519,7 +543,7 @@ class PyTrace:
                 col = pa.array(a.astype(dt) if dt is not None else a)
                 scols.append(col)
                 sfields.append(pa.field(name, col.type, metadata={"dims": "", "shape": ""}))
-            vec_stats = [("gradient", self.gradients), ("mass_matrix_inv", self.mass_matrix_inv)]
+            vec_stats = [("gradient", self.gradients)] + self.mass_matrix_columns()
             if self.divergences is not None:
                 for k, name in enumerate(DIVERGENCE_COLUMNS):
                     vec_stats.append((name, self.divergences[:, :, k]))
@@ -532,8 +556,10 @@ class PyTrace:
                         col = pa.FixedSizeListArray.from_arrays(pa.array(a.reshape(-1)), a.shape[1],
                                                                 mask=pa.array(mask))
                     scols.append(col)
+                    dim_name = "mass_matrix_eigvals_dim" if name == "mass_matrix_eigvals" \
+                        else "unconstrained_parameter"
                     sfields.append(pa.field(name, col.type, metadata={
-                        "dims": "unconstrained_parameter", "shape": str(a.shape[1])}))
+                        "dims": dim_name, "shape": str(a.shape[1])}))
             stats = pa.RecordBatch.from_arrays(scols, schema=pa.schema(sfields))
             out_draws.append(posterior)
             out_stats.append(stats)
@@ -753,6 +779,14 @@ class PySampler:
             divs = np.empty((self.n_rows, self.n_chains, 4, self.grad_dim))
             _check(self._L.nb200_sampler_divergence_trace_into(self._h, _ptr(divs)))
             divs = divs.transpose(1, 0, 2, 3)
+        eig = None
+        low_rank = self._c.adaptation == 1
+        if low_rank and self._c.store_mass_matrix:
+            width = C.c_uint64(0)
+            _check(self._L.nb200_sampler_eigvals_trace_into(self._h, None, C.byref(width)))
+            eig = np.empty((self.n_rows, self.n_chains, int(width.value)))
+            _check(self._L.nb200_sampler_eigvals_trace_into(self._h, _ptr(eig), None))
+            eig = eig.transpose(1, 0, 2)
         if self.expanded:  # rows already hold the expanded vector: slice it into variables
             expand = self._model._split_expanded
         elif self.sdim == self.dim:
@@ -763,7 +797,8 @@ class PySampler:
         tv = lambda a: None if a is None else a.transpose(1, 0, 2)
         return PyTrace(tv(draws), tv(stats), rows, tv(grads), tv(mm),
                        variables=self._model._variable_dims(), expand=expand,
-                       keep=[draws, stats, grads, mm], expanded=self.expanded, divergences=divs)
+                       keep=[draws, stats, grads, mm], expanded=self.expanded, divergences=divs,
+                       mass_matrix_eigvals=eig, low_rank=low_rank)
 
     def inspect(self, out=None):
         return self._trace(out)
@@ -843,6 +878,9 @@ class MultiTrace:
     gradients = property(lambda self: self._cat("gradients"))
     mass_matrix_inv = property(lambda self: self._cat("mass_matrix_inv"))
     divergences = property(lambda self: self._cat("divergences"))
+    mass_matrix_eigvals = property(lambda self: self._cat("mass_matrix_eigvals"))
+    low_rank = property(lambda self: self.parts[0].low_rank)
+    mass_matrix_columns = PyTrace.mass_matrix_columns
 
     def is_zarr(self):
         return False
@@ -1069,6 +1107,31 @@ def leapfrog(model, q, p, g, var, p_sum, eps, direction, idx, device=0):
                             _ptr(p_sum), _ptr(eps), _ptr(direction), _ptr(idx), _ptr(qo),
                             _ptr(po), _ptr(go), _ptr(so), _ptr(lp), _ptr(kin), _ptr(rc)))
     return dict(q=qo, p=po, g=go, p_sum=so, logp=lp, kinetic=kin, rc=rc)
+
+
+def lowrank_component(draws, grads, gamma=1e-5, cutoff=2.0, max_rank=32, p=None, z=None, device=0):
+    """Refresh the low-rank metric on the device from a window [n][dim] of draws / gradients and
+    apply it: returns dict(stds, vals [k], vecs [k][dim], velocity = M^-1 p, momentum = M^1/2 z)."""
+    L = load_library()
+    draws = np.ascontiguousarray(draws, dtype=np.float64)
+    grads = np.ascontiguousarray(grads, dtype=np.float64)
+    n, dim = draws.shape
+    max_rank = min(int(max_rank), dim)
+    f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(-1, dim)
+    p, z = f(p), f(z)
+    n_vec = max(len(p) if p is not None else 0, len(z) if z is not None else 0)
+    if p is None and n_vec:
+        p = np.zeros((n_vec, dim))
+    if z is None and n_vec:
+        z = np.zeros((n_vec, dim))
+    v, pm = np.zeros((n_vec, dim)), np.zeros((n_vec, dim))
+    stds, vals, vecs = np.zeros(dim), np.zeros(max_rank), np.zeros((max_rank, dim))
+    k = C.c_uint64(0)
+    _check(L.nb200_lowrank_component(device, dim, n, _ptr(draws), _ptr(grads), gamma, cutoff, max_rank,
+                                     n_vec, _ptr(p), _ptr(v), _ptr(z), _ptr(pm), _ptr(stds), _ptr(vals),
+                                     _ptr(vecs), C.byref(k)))
+    kk = int(k.value)
+    return dict(stds=stds, vals=vals[:kk].copy(), vecs=vecs[:kk].copy(), velocity=v, momentum=pm)
 
 
 def set_threads_per_chain(t: int):

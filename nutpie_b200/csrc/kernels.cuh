@@ -13,8 +13,8 @@ __host__ __device__ inline size_t stage_bytes(int Dp) {
     return M::kElementwise ? 0 : ((4 * sizeof(double) * (size_t)Dp + 15) & ~size_t(15));
 }
 
-template <class M, int W, int NIT, class G = GroupCuda<W>>
-__device__ __forceinline__ void setup_ctx(ChainCtx<M, G, NIT>& ctx, const KParams<M>& P,
+template <class M, int W, int NIT, class G = GroupCuda<W>, bool LR = false>
+__device__ __forceinline__ void setup_ctx(ChainCtx<M, G, NIT, LR>& ctx, const KParams<M>& P,
                                           unsigned long long chain, unsigned char* smem_chain) {
     if constexpr (G::kThreads < 32) {  // sub-warp group: L aligned lanes of the warp
         const int lane = threadIdx.x & 31;
@@ -55,7 +55,21 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, G, NIT>& ctx, const KParam
     ctx.NS = P.NS;
     ctx.chain_local = chain;
     ctx.chain_gid = (uint32_t)(P.chain_id_offset + chain);
-    ctx.pool = P.pool + (size_t)chain * P.NS * 4 * (size_t)P.Dp;
+    ctx.pool = P.pool + (size_t)chain * P.NS * (LR ? 5 : 4) * (size_t)P.Dp;
+    if constexpr (LR) {
+        const size_t Dp = (size_t)P.Dp, R = (size_t)P.lr_max_rank;
+        ctx.lr.stds = P.lr_stds + chain * Dp;
+        ctx.lr.vals = P.lr_vals + chain * R;
+        ctx.lr.vecs = P.lr_vecs + chain * R * Dp;
+        ctx.lr.coef = P.lr_coef + chain * R;
+        ctx.lr.win = P.lr_win + chain * (size_t)P.lr_cap * 2 * Dp;
+        ctx.lr.matL = P.lr_mat + chain * 2 * (size_t)P.D * Dp;
+        ctx.lr.matW = ctx.lr.matL + (size_t)P.D * Dp;
+        ctx.lr.cols = P.lr_cols + chain * 6 * Dp;
+        ctx.lr.cap = P.lr_cap;
+        ctx.lr.max_rank = P.lr_max_rank;
+        ctx.lr.k = ctx.lr.len = ctx.lr.split = ctx.lr.head = 0;
+    }
     ctx.varg = P.var + (size_t)chain * P.Dp;
     ctx.var = P.var_in_smem ? svar : ctx.varg;
     ctx.wf = P.welford + (size_t)chain * 8 * (size_t)P.Dp;
@@ -82,7 +96,7 @@ constexpr int kernel_min_blocks() {
     if (W == 4 && M::kElementwise && NIT == 0) return 4;
     return 1;
 }
-template <class M, int W, int NIT>
+template <class M, int W, int NIT, bool LR = false>
 __global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, kernel_min_blocks<M, W, NIT>())
     nuts_kernel(const __grid_constant__ KParams<M> P, size_t smem_per_chain, size_t block_data) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -97,8 +111,8 @@ __global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, kernel_min_blocks<M, W,
     const int cpb = (W == 1) ? (blockDim.x >> 5) : 1;
     const unsigned long long chain = (unsigned long long)blockIdx.x * cpb + local;
     if (chain >= P.n_chains) return;
-    ChainCtx<M, GroupCuda<W>, NIT> ctx;
-    setup_ctx<M, W, NIT>(ctx, P, chain, smem + block_data + (size_t)local * smem_per_chain);
+    ChainCtx<M, GroupCuda<W>, NIT, LR> ctx;
+    setup_ctx<M, W, NIT, GroupCuda<W>, LR>(ctx, P, chain, smem + block_data + (size_t)local * smem_per_chain);
     if constexpr (M::kHasBlockData) ctx.md = md;  // tables staged in shared memory
 #ifdef NB200_PIPE_PROFILE
     const long long t_begin = clock64();

@@ -126,8 +126,9 @@ int compile_locked(Program& prog, int W, int NIT, Built** out) {
         t_log = std::string("nvrtcCreateProgram: ") + n.getErrorString(r);
         return -1;
     }
-    const std::string nuts_expr = "nb200::nuts_kernel<nb200::CustomModel, " + std::to_string(W) +
-                                  ", " + std::to_string(NIT) + ">";
+    // NIT = -1 selects the low-rank engine (nuts_kernel<M, W, 0, true>, lowrank.cuh)
+    const std::string nuts_expr = "nb200::nuts_kernel<nb200::CustomModel, " + std::to_string(W) + ", " +
+                                  (NIT < 0 ? std::string("0, true") : std::to_string(NIT)) + ">";
     const std::string comp_expr = "nb200::component_kernel<nb200::CustomModel, " + std::to_string(W) + ">";
     n.addNameExpression(p, nuts_expr.c_str());
     n.addNameExpression(p, comp_expr.c_str());
@@ -215,6 +216,13 @@ cudaError_t launch_nuts<CustomModel>(int W, int NIT, const KParams<CustomModel>&
     KParams<CustomModel> Pc = P;
     void* args[] = {&Pc, &smem_per_chain, &block_data};
     return cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream);
+}
+
+template <>
+cudaError_t launch_nuts_lr<CustomModel>(int W, const KParams<CustomModel>& P, size_t smem_per_chain,
+                                        size_t block_data, int cpb, int grid, int block,
+                                        cudaStream_t stream) {
+    return launch_nuts<CustomModel>(W, -1, P, smem_per_chain, block_data, cpb, grid, block, stream);
 }
 
 template <>

@@ -23,6 +23,9 @@ template <class M>
 cudaError_t launch_nuts_piped(int NIT, const KParams<M>& P, size_t smem_per_chain, size_t block_data,
                               int cpb, int grid, cudaStream_t stream);
 template <class M>
+cudaError_t launch_nuts_lr(int W, const KParams<M>& P, size_t smem_per_chain, size_t block_data,
+                           int cpb, int grid, int block, cudaStream_t stream);
+template <class M>
 size_t model_block_data_bytes(const typename M::Data& md);
 template <class M>
 cudaError_t launch_component(int W, const KParams<M>& P, int mode, const double* scal, double* out,

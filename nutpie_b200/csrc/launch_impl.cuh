@@ -34,6 +34,25 @@ static cudaError_t launch_one(const KParams<M>& P, size_t smem_per_chain, size_t
     return cudaGetLastError();
 }
 
+// low-rank adaptation (lowrank.cuh): the run-time-loop engine with five vectors per slot
+template <class M, int W>
+static cudaError_t launch_one_lr(const KParams<M>& P, size_t smem_per_chain, size_t block_data, int cpb,
+                                 int grid, int block, cudaStream_t stream) {
+    const size_t smem = block_data + smem_per_chain * cpb;
+    cudaError_t e = cudaFuncSetAttribute(nuts_kernel<M, W, 0, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    nuts_kernel<M, W, 0, true><<<grid, block, smem, stream>>>(P, smem_per_chain, block_data);
+    return cudaGetLastError();
+}
+template <class M>
+cudaError_t launch_nuts_lr(int W, const KParams<M>& P, size_t smem_per_chain, size_t block_data,
+                           int cpb, int grid, int block, cudaStream_t stream) {
+    if (W == 1) return launch_one_lr<M, 1>(P, smem_per_chain, block_data, cpb, grid, block, stream);
+    if (W == 4) return launch_one_lr<M, 4>(P, smem_per_chain, block_data, cpb, grid, block, stream);
+    return cudaErrorInvalidValue;
+}
+
 template <class M, int NIT>
 static cudaError_t launch_one_piped(const KParams<M>& P, size_t smem_per_chain, size_t block_data,
                                     int cpb, int grid, cudaStream_t stream) {
@@ -182,6 +201,8 @@ size_t model_block_data_bytes(const typename M::Data& md) {
                                             cudaStream_t);                                      \
     template cudaError_t launch_nuts_piped<M>(int, const KParams<M>&, size_t, size_t, int, int, \
                                               cudaStream_t);                                    \
+    template cudaError_t launch_nuts_lr<M>(int, const KParams<M>&, size_t, size_t, int, int, int,  \
+                                           cudaStream_t);                                          \
     template size_t model_block_data_bytes<M>(const M::Data&);
 
 }  // namespace nb200

@@ -1,0 +1,349 @@
+// lowrank.cuh — the low-rank modified mass matrix (adaptation = "low_rank",
+// PyNutsSettings::LowRank, src/wrapper.rs:307-346; python/nutpie/sample.py:921-933; the
+// arithmetic is nuts-rs' mass_matrix/low_rank.rs, restated in oracle/lowrank.c), executed by the
+// thread group that owns a chain, INSIDE the persistent sampler kernel.
+//
+//   M^-1 = S (I + V (L - I) V^T) S        S = diag(stds) [D], V [k][Dp] orthonormal rows,
+//                                          L = diag(vals) [k]
+//
+// Per leapfrog the metric costs two contractions with V (k x D each way, V streamed from L2).
+// The refresh — every mass_matrix_update_freq draws while the windows are open — estimates
+//   Sigma = (X~X~^T + gamma I) # (G~G~^T + gamma I)^-1      (matrix geometric mean)
+// from the chain's window of draws and gradients and keeps its eigenpairs beyond the cutoff.
+// nuts-rs takes three symmetric eigen-decompositions and four matrix square roots through faer;
+// here the geometric mean is taken through Cholesky factors, which needs only two matrices of
+// scratch per chain and two one-sided (Hestenes) Jacobi runs whose inner loops are contiguous
+// column sweeps — coalesced for a warp, and no eigenvector accumulation:
+//   B = G~G~^T + gamma I = L L^T                      (Cholesky, in place)
+//   M = L^T (X~X~^T + gamma I) L = C C^T              (two triangular products + Cholesky, in place)
+//   C J1 = U Theta^1/2                                (one-sided Jacobi: M = U Theta U^T)
+//   H = L^-T U Theta^1/4   =>   H H^T = L^-T M^1/2 L^-1 = Sigma      (back substitution)
+//   H J2 = W Lambda^1/2                               (one-sided Jacobi: Sigma = W Lambda W^T)
+// Written against the group policy G (tid / size / sync / reduce) like the rest of the core, so
+// tests/emul runs the very same code on the CPU against the oracle's dense evaluation.
+#pragma once
+#include "portable.cuh"
+
+namespace nb200 {
+
+// per-chain low-rank state: pointers into the sampler's global buffers + the window counters
+struct LrState {
+    double* stds;   // [Dp]
+    double* vals;   // [max_rank]
+    double* vecs;   // [max_rank][Dp]
+    double* coef;   // [max_rank] contraction coefficients (scratch)
+    double* win;    // [cap][2][Dp] ring of (draw, gradient); logical entry j = slot (head + j) % cap
+    double* matL;   // [D][Dp] column-major scratch (ld = Dp)
+    double* matW;   // [D][Dp]
+    double* cols;   // [6][Dp] scratch: mean x, mean g, scale x, scale g, key, lambda
+    int k;          // eigenpairs in use
+    int len, split, head, cap;  // window: [foreground-only part | background part] split at `split`
+    int max_rank;
+};
+
+// coef_j = f_j * sum_i V_ji (sc_i x_i)   for all j < k   (sc = stds or nullptr for 1)
+// mode 0: f_j = vals_j - 1 (velocity);  mode 1: f_j = 1 / sqrt(vals_j) - 1 (momentum)
+template <class G>
+NB_HD void lr_coefficients(const G& g, const LrState& L, int D, int Dp, const double* x,
+                           const double* sc, int mode) {
+    for (int j0 = 0; j0 < L.k; j0 += 8) {
+        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int i = g.tid; i < D; i += g.size()) {
+            const double t = sc ? sc[i] * x[i] : x[i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j0 + j < L.k) acc[j] += L.vecs[(size_t)(j0 + j) * Dp + i] * t;
+        }
+        g.reduce(acc);
+        if (g.tid == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j0 + j < L.k) {
+                    const double lam = L.vals[j0 + j];
+                    L.coef[j0 + j] = (mode == 0 ? lam - 1.0 : 1.0 / sqrt(lam) - 1.0) * acc[j];
+                }
+        }
+    }
+    g.sync();
+}
+
+// v = M^-1 p   (p, v: [D]; may not alias)
+template <class G>
+NB_HD void lr_velocity(const G& g, const LrState& L, int D, int Dp, const double* p, double* v) {
+    lr_coefficients(g, L, D, Dp, p, L.stds, 0);
+    for (int i = g.tid; i < D; i += g.size()) {
+        const double s = L.stds[i];
+        double a = s * p[i];
+        for (int j = 0; j < L.k; ++j) a += L.vecs[(size_t)j * Dp + i] * L.coef[j];
+        v[i] = a * s;
+    }
+    g.sync();  // coef may be overwritten by the next contraction
+}
+
+// p <- M^1/2 z in place (z standard normal on entry), with the square root S^-1 (I + V (L^-1/2 - I) V^T)
+template <class G>
+NB_HD void lr_momentum(const G& g, const LrState& L, int D, int Dp, double* p) {
+    lr_coefficients(g, L, D, Dp, p, (const double*)nullptr, 1);
+    for (int i = g.tid; i < D; i += g.size()) {
+        double a = p[i];
+        for (int j = 0; j < L.k; ++j) a += L.vecs[(size_t)j * Dp + i] * L.coef[j];
+        p[i] = a / L.stds[i];
+    }
+    g.sync();
+}
+
+// window deque -----------------------------------------------------------------------------
+NB_HD double* lr_win_entry(const LrState& L, int Dp, int j, int which) {
+    int slot = L.head + j;
+    if (slot >= L.cap) slot -= L.cap;
+    return L.win + ((size_t)slot * 2 + which) * Dp;
+}
+// append (q, grad) — grad_of(i) yields the gradient (stored or recomputed by the caller)
+template <class G, class F>
+NB_HD void lr_push(const G& g, LrState& L, int D, int Dp, const double* q, F&& grad_of) {
+    if (L.len == L.cap) {  // cannot happen with cap = 3 * max switch_freq + 2; drop the oldest
+        L.head = L.head + 1 == L.cap ? 0 : L.head + 1;
+        L.len -= 1;
+        if (L.split > 0) L.split -= 1;
+    }
+    double* wq = lr_win_entry(L, Dp, L.len, 0);
+    double* wg = lr_win_entry(L, Dp, L.len, 1);
+    for (int i = g.tid; i < D; i += g.size()) {
+        wq[i] = q[i];
+        wg[i] = grad_of(i);
+    }
+    L.len += 1;
+    g.sync();
+}
+// the foreground-only part is dropped, what was the background becomes the foreground
+NB_HD void lr_switch(LrState& L) {
+    L.head = (L.head + L.split) % L.cap;
+    L.len -= L.split;
+    L.split = L.len;
+}
+
+// one-sided Jacobi on the columns of A [r][ld] (column-major): on return the columns are
+// mutually orthogonal, A_out = A_in J with J orthogonal.  Cyclic sweeps until no pair rotates.
+template <class G>
+NB_HD void lr_jacobi_columns(const G& g, double* A, int r, int ld) {
+    const double tol = 1e-13;  // |cos| between two columns below which they count as orthogonal
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        int rotated = 0;
+        for (int p = 0; p < r - 1; ++p) {
+            double* ap = A + (size_t)p * ld;
+            for (int q = p + 1; q < r; ++q) {
+                double* aq = A + (size_t)q * ld;
+                double acc[3] = {0.0, 0.0, 0.0};
+                for (int i = g.tid; i < r; i += g.size()) {
+                    const double x = ap[i], y = aq[i];
+                    acc[0] += x * x;
+                    acc[1] += y * y;
+                    acc[2] += x * y;
+                }
+                g.reduce(acc);
+                const double gam = acc[2];
+                if (!(fabs(gam) > tol * sqrt(acc[0] * acc[1]))) continue;  // uniform: identical sums
+                rotated = 1;
+                const double zeta = (acc[1] - acc[0]) / (2.0 * gam);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int i = g.tid; i < r; i += g.size()) {
+                    const double x = ap[i], y = aq[i];
+                    ap[i] = c * x - s * y;
+                    aq[i] = s * x + c * y;
+                }
+                g.sync();
+            }
+        }
+        if (!rotated) break;
+    }
+}
+
+// in-place Cholesky of the lower triangle of A [r][ld] (column-major): A = C C^T, the strict
+// upper triangle is zeroed.  Returns false on a non-positive pivot.
+template <class G>
+NB_HD bool lr_cholesky(const G& g, double* A, int r, int ld) {
+    for (int j = 0; j < r; ++j) {
+        double* aj = A + (size_t)j * ld;
+        for (int i = j + g.tid; i < r; i += g.size()) {
+            double t = aj[i];
+            for (int k = 0; k < j; ++k) t -= A[(size_t)k * ld + i] * A[(size_t)k * ld + j];
+            aj[i] = t;
+        }
+        g.sync();
+        const double piv = aj[j];
+        g.sync();
+        if (!(piv > 0.0) || !nb_isfinite(piv)) return false;
+        const double d = sqrt(piv);
+        for (int i = g.tid; i < r; i += g.size()) {
+            if (i < j) aj[i] = 0.0;
+            else if (i == j) aj[i] = d;
+            else aj[i] = aj[i] / d;
+        }
+        g.sync();
+    }
+    return true;
+}
+
+// Refresh the metric from the window.  Returns false (metric unchanged) when the window is too
+// short or a factorisation breaks down.
+template <class G>
+NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double cutoff) {
+    const int n = L.len, r = D, ld = Dp;
+    if (n < 3) return false;
+    double* mx = L.cols;
+    double* mg = L.cols + Dp;
+    double* xs = L.cols + 2 * (size_t)Dp;
+    double* gs = L.cols + 3 * (size_t)Dp;
+    double* key = L.cols + 4 * (size_t)Dp;
+    double* lam = L.cols + 5 * (size_t)Dp;
+    const double dn = (double)n;
+    // ---- 1. per-dimension means, scales: stds_i = sqrt(sd(x_i) / sd(g_i))
+    for (int i = g.tid; i < D; i += g.size()) {
+        double sx = 0.0, sg = 0.0;
+        for (int j = 0; j < n; ++j) {
+            sx += lr_win_entry(L, Dp, j, 0)[i];
+            sg += lr_win_entry(L, Dp, j, 1)[i];
+        }
+        sx /= dn;
+        sg /= dn;
+        double vx = 0.0, vg = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double a = lr_win_entry(L, Dp, j, 0)[i] - sx, b = lr_win_entry(L, Dp, j, 1)[i] - sg;
+            vx += a * a;
+            vg += b * b;
+        }
+        double s = sqrt(sqrt(vx / dn) / sqrt(vg / dn));
+        if (!nb_isfinite(s) || s <= 0.0) s = L.stds[i];
+        if (s < 1e-10) s = 1e-10;
+        if (s > 1e10) s = 1e10;
+        L.stds[i] = s;
+        mx[i] = sx;
+        mg[i] = sg;
+        xs[i] = 1.0 / (s * sqrt(dn));
+        gs[i] = s / sqrt(dn);
+    }
+    g.sync();
+    // ---- 2. W = X~X~^T + gamma I,  Lm = G~G~^T + gamma I   (full symmetric storage)
+    double* Lm = L.matL;
+    double* W = L.matW;
+    for (int a0 = 0; a0 < r; a0 += g.size()) {
+        const int a = a0 + g.tid;
+        const bool live = a < r;
+        const double mxa = live ? mx[a] : 0.0, mga = live ? mg[a] : 0.0;
+        const double xsa = live ? xs[a] : 0.0, gsa = live ? gs[a] : 0.0;
+        const int bmax = a0 + g.size() < r ? a0 + g.size() : r;  // columns b <= the chunk's last row
+        for (int b = 0; b < bmax; ++b) {
+            const double mxb = mx[b], mgb = mg[b], xsb = xs[b], gsb = gs[b];
+            double ax = 0.0, ag = 0.0;
+            if (live && b <= a) {
+                for (int j = 0; j < n; ++j) {
+                    const double* wq = lr_win_entry(L, Dp, j, 0);
+                    const double* wg = lr_win_entry(L, Dp, j, 1);
+                    ax += ((wq[a] - mxa) * xsa) * ((wq[b] - mxb) * xsb);
+                    ag += ((wg[a] - mga) * gsa) * ((wg[b] - mgb) * gsb);
+                }
+                if (a == b) {
+                    ax += gamma;
+                    ag += gamma;
+                }
+                W[(size_t)b * ld + a] = ax;
+                W[(size_t)a * ld + b] = ax;
+                Lm[(size_t)b * ld + a] = ag;
+                Lm[(size_t)a * ld + b] = ag;
+            }
+        }
+    }
+    g.sync();
+    // ---- 3. Lm = chol(B)
+    if (!lr_cholesky(g, Lm, r, ld)) return false;
+    // ---- 4. W <- A Lm (ascending columns, in place), then W <- Lm^T W (lower triangle, in place)
+    for (int c = 0; c < r; ++c) {
+        for (int i = g.tid; i < r; i += g.size()) {
+            double t = 0.0;
+            for (int k = c; k < r; ++k) t += W[(size_t)k * ld + i] * Lm[(size_t)c * ld + k];
+            W[(size_t)c * ld + i] = t;
+        }
+    }
+    g.sync();
+    for (int j = 0; j < r; ++j) {
+        double* wj = W + (size_t)j * ld;
+        for (int i0 = j; i0 < r; i0 += 8) {
+            double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int k = i0 + g.tid; k < r; k += g.size()) {
+                const double t = wj[k];
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    if (i0 + m < r && k >= i0 + m) acc[m] += Lm[(size_t)(i0 + m) * ld + k] * t;
+            }
+            g.reduce(acc);  // (its barriers order the reads above before the writes below)
+            g.sync();
+            if (g.tid == 0) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    if (i0 + m < r) wj[i0 + m] = acc[m];
+            }
+            g.sync();
+        }
+    }
+    // ---- 5. W = chol(M)
+    if (!lr_cholesky(g, W, r, ld)) return false;
+    // ---- 6. columns of W -> U Theta^1/2
+    lr_jacobi_columns(g, W, r, ld);
+    // ---- 7. W <- Lm^-T (W Theta^-1/4): every thread back-substitutes whole columns
+    for (int j = g.tid; j < r; j += g.size()) {
+        double* wj = W + (size_t)j * ld;
+        double th = 0.0;
+        for (int i = 0; i < r; ++i) th += wj[i] * wj[i];
+        const double sc = th > 0.0 ? 1.0 / sqrt(sqrt(th)) : 0.0;
+        for (int i = r - 1; i >= 0; --i) {
+            double t = wj[i] * sc;
+            const double* li = Lm + (size_t)i * ld;
+            for (int k = i + 1; k < r; ++k) t -= li[k] * wj[k];
+            wj[i] = t / li[i];
+        }
+    }
+    g.sync();
+    // ---- 8. columns of W -> W_sigma Lambda^1/2
+    lr_jacobi_columns(g, W, r, ld);
+    // ---- 9. keep the eigenpairs beyond the cutoff, largest |log lambda| first
+    for (int j = g.tid; j < r; j += g.size()) {
+        const double* wj = W + (size_t)j * ld;
+        double l2 = 0.0;
+        for (int i = 0; i < r; ++i) l2 += wj[i] * wj[i];
+        lam[j] = l2;
+        const bool keep = nb_isfinite(l2) && l2 > 0.0 && (l2 > cutoff || l2 < 1.0 / cutoff);
+        key[j] = keep ? fabs(log(l2)) : -1.0;
+    }
+    g.sync();
+    int k = 0;
+    const int kmax = L.max_rank < r ? L.max_rank : r;
+    while (k < kmax) {
+        int best = -1;
+        double bk = -1.0;  // keepers have key > 0, everything else -1
+        for (int j = 0; j < r; ++j) {  // every thread scans the same keys: uniform result
+            const double kj = key[j];
+            if (kj > bk) {
+                best = j;
+                bk = kj;
+            }
+        }
+        if (best < 0) break;
+        const double l2 = lam[best];
+        const double inv = 1.0 / sqrt(l2);
+        const double* wb = W + (size_t)best * ld;
+        double* vk = L.vecs + (size_t)k * Dp;
+        for (int i = g.tid; i < D; i += g.size()) vk[i] = wb[i] * inv;
+        g.sync();  // everyone has read key[] before it changes
+        if (g.tid == 0) {
+            L.vals[k] = l2;
+            key[best] = -1.0;
+        }
+        g.sync();
+        ++k;
+    }
+    L.k = k;
+    return true;
+}
+
+}  // namespace nb200

@@ -29,7 +29,7 @@
 using namespace nb200;
 
 // the Python/Rust bindings mirror these layouts field by field
-static_assert(sizeof(nb200_settings) == 232, "nb200_settings ABI layout changed");
+static_assert(sizeof(nb200_settings) == 240, "nb200_settings ABI layout changed");
 static_assert(sizeof(nb200_model_desc) == 144, "nb200_model_desc ABI layout changed");
 static_assert(sizeof(nb200_progress) == 56, "nb200_progress ABI layout changed");
 
@@ -246,6 +246,11 @@ struct nb200_sampler {
     double *d_pool = nullptr, *d_var = nullptr, *d_wf = nullptr;
     double *d_draws = nullptr, *d_stats = nullptr, *d_grads = nullptr, *d_mm = nullptr;
     double* d_div = nullptr;  // store_divergences: [n_rows][n_chains][4][grad_dim]
+    // adaptation = low_rank (lowrank.cuh): per-chain metric, window, scratch; eigenvalue trace
+    bool lr = false;
+    int lr_cap = 0, lr_max_rank = 0;
+    double *d_lr_stds = nullptr, *d_lr_vals = nullptr, *d_lr_vecs = nullptr, *d_lr_coef = nullptr;
+    double *d_lr_win = nullptr, *d_lr_mat = nullptr, *d_lr_cols = nullptr, *d_eig = nullptr;
     std::unique_ptr<HostService> host;  // NB200_MODEL_HOST only
     std::string err;                    // message of the error that put the sampler in Error
     double *d_q0 = nullptr, *d_init_mean = nullptr, *d_tape = nullptr;
@@ -271,7 +276,8 @@ struct SamplerImpl : nb200_sampler {
     int launch() override {
         P.max_draws_per_launch = draws_per_launch;
         cudaError_t e =
-            sub ? launch_nuts_sub<M>(sub, NIT, P, smem_per_chain, block / 32, grid, stream)
+            lr  ? launch_nuts_lr<M>(W, P, smem_per_chain, block_data, cpb, grid, block, stream)
+            : sub ? launch_nuts_sub<M>(sub, NIT, P, smem_per_chain, block / 32, grid, stream)
             : piped ? launch_nuts_piped<M>(NIT, P, smem_per_chain, block_data, cpb, grid, stream)
                     : launch_nuts<M>(W, NIT, P, smem_per_chain, block_data, cpb, grid, block, stream);
         if (e != cudaSuccess) return fail(NB200_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -321,8 +327,15 @@ static int validate(const nb200_settings* st, const nb200_model_desc* m) {
         return fail(NB200_EINVAL, "step_size_jitter must be in [0, 1)");
     if (st->adaptation != 0 && st->adaptation != 1)
         return fail(NB200_EINVAL, "adaptation must be diag (0) or low_rank (1)");
-    if (st->adaptation == 1)
-        return fail(NB200_EINVAL, "adaptation='low_rank' is not implemented by the B200 engine yet");
+    if (st->adaptation == 1) {
+        // the refresh factorises two dim x dim matrices per chain (lowrank.cuh)
+        if (m->dim > 1024)
+            return fail(NB200_EINVAL, "adaptation='low_rank' supports models of up to 1024 dimensions");
+        if (!(st->mass_matrix_eigval_cutoff > 1.0))
+            return fail(NB200_EINVAL, "mass_matrix_eigval_cutoff must be > 1");
+        if (!(st->mass_matrix_gamma > 0.0)) return fail(NB200_EINVAL, "mass_matrix_gamma must be > 0");
+        if (st->mass_matrix_max_rank < 1) return fail(NB200_EINVAL, "mass_matrix_max_rank must be >= 1");
+    }
     if (m->kind == NB200_MODEL_RADON) {
         if (m->n_county < 1 || m->n_county > 32767)
             return fail(NB200_EINVAL, "radon: n_county must be in 1..32767");
@@ -438,7 +451,8 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         fail(NB200_ECUDA, "cudaSetDevice failed");
         return bail();
     }
-    s->W = pick_W(*m, n_chains);
+    s->lr = st->adaptation == 1;
+    s->W = s->lr ? 1 : pick_W(*m, n_chains);  // low rank: a warp per chain, run-time loops
     if (s->W < 1 || s->W > 32 || (s->W & (s->W - 1))) {
         fail(NB200_EINVAL, "threads per chain must be 32..1024, power of two");
         return bail();
@@ -446,7 +460,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     const int D = (int)m->dim;
     s->Dp = (D + 3) / 4 * 4;
     s->NS = 3 * ((int)st->maxdepth + 1) + 3;
-    {
+    if (!s->lr) {
         const int forced_t = g_threads_per_chain.load();
         if (s->W == 1 && forced_t < 32 && g_force_nit.load() != 0)
             s->sub = sub_warp_lanes<M>(D, forced_t);
@@ -461,10 +475,10 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     } else {
         const int T = 32 * s->W;
         s->NIT = supported_nit<M>(s->W, (D + T - 1) / T);
-        if (g_force_nit.load() == 0) s->NIT = 0;
+        if (g_force_nit.load() == 0 || s->lr) s->NIT = 0;
         // Two warps per chain (integrator + tree) when the density does enough work per leaf to
         // hide the tree bookkeeping behind it; needs kPipeDepth extra pool slots.
-        s->piped = s->W == 1 && s->NIT > 0 && g_pipeline.load() != 0 && D >= 64 &&
+        s->piped = !s->lr && s->W == 1 && s->NIT > 0 && g_pipeline.load() != 0 && D >= 64 &&
                    g_threads_per_chain.load() == 0 && supports_pipeline<M>(s->NIT) &&
                    s->NS + kPipeDepth <= kMaxSlots;
         if (s->piped) s->NS += kPipeDepth;
@@ -545,8 +559,9 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
             slots = (int)((budget - fixed - var_b) / slot_b);
             if (slots > s->NS) slots = s->NS;
         }
+        if (s->lr) slots = var_in = 0;  // low rank: the state pool and the metric stay in HBM / L2
         const int forced = g_smem_slots.load();
-        if (forced >= 0) {
+        if (forced >= 0 && !s->lr) {
             slots = forced > s->NS ? s->NS : forced;
             var_in = (fixed + var_b + slots * slot_b) <= kSmemSM - kSlack;
         }
@@ -564,7 +579,7 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     }
     if constexpr (std::is_same<M, CustomModel>::value) {
         // compile now so that errors in the user's source surface here, with the NVRTC log
-        if (custom_compile(P.mdata.program, s->W, s->NIT) != 0) {
+        if (custom_compile(P.mdata.program, s->W, s->lr ? -1 : s->NIT) != 0) {
             fail(NB200_ECOMPILE, custom_last_log());
             return bail();
         }
@@ -592,7 +607,23 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         }                                                                               \
     } while (0)
     const size_t vecb = sizeof(double) * (size_t)s->Dp;
-    ALLOC(s->d_pool, n_chains * (size_t)s->NS * 4 * vecb);
+    ALLOC(s->d_pool, n_chains * (size_t)s->NS * (s->lr ? 5 : 4) * vecb);
+    if (s->lr) {
+        // window capacity: foreground-only + background + the stretch after the last switch
+        const uint64_t f = st->mass_matrix_switch_freq > st->early_mass_matrix_switch_freq
+                               ? st->mass_matrix_switch_freq : st->early_mass_matrix_switch_freq;
+        s->lr_cap = (int)(3 * f + 2 < s->n_total + 2 ? 3 * f + 2 : s->n_total + 2);
+        s->lr_max_rank = (int)(st->mass_matrix_max_rank < m->dim ? st->mass_matrix_max_rank : m->dim);
+        const size_t R = (size_t)s->lr_max_rank;
+        ALLOC(s->d_lr_stds, n_chains * vecb);
+        ALLOC(s->d_lr_vals, n_chains * R * sizeof(double));
+        ALLOC(s->d_lr_vecs, n_chains * R * vecb);
+        ALLOC(s->d_lr_coef, n_chains * R * sizeof(double));
+        ALLOC(s->d_lr_win, n_chains * (size_t)s->lr_cap * 2 * vecb);
+        ALLOC(s->d_lr_mat, n_chains * 2 * (size_t)D * vecb);
+        ALLOC(s->d_lr_cols, n_chains * 6 * vecb);
+        if (st->store_mass_matrix) ALLOC(s->d_eig, n_chains * s->n_rows * R * sizeof(double));
+    }
     ALLOC(s->d_var, n_chains * vecb);
     ALLOC(s->d_wf, n_chains * 8 * vecb);
     ALLOC(s->d_sc, n_chains * sizeof(ChainScalars));
@@ -628,6 +659,10 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     P.draws = s->d_draws; P.stats = s->d_stats; P.grads = s->d_grads; P.mminv = s->d_mm;
     P.q0 = s->d_q0; P.init_mean = s->d_init_mean; P.z_tape = nullptr;
     P.divs = s->d_div;
+    P.lr_stds = s->d_lr_stds; P.lr_vals = s->d_lr_vals; P.lr_vecs = s->d_lr_vecs;
+    P.lr_coef = s->d_lr_coef; P.lr_win = s->d_lr_win; P.lr_mat = s->d_lr_mat;
+    P.lr_cols = s->d_lr_cols; P.eigvals = s->d_eig;
+    P.lr_cap = s->lr_cap; P.lr_max_rank = s->lr_max_rank;
     // host plug-in: the stop flag lives in mapped pinned memory so that the service thread that
     // meets a fatal return code can raise it without a CUDA call
     P.stop_flag = s->host ? s->host->d_stop : s->d_stop;
@@ -700,6 +735,7 @@ void nb200_settings_default(nb200_settings* s) {
     s->step_size_jitter = 0.0;
     s->mass_matrix_eigval_cutoff = 2.0;
     s->mass_matrix_gamma = 1e-5;
+    s->mass_matrix_max_rank = 32;
 }
 
 void* nb200_host_alloc(size_t bytes) {
@@ -1121,6 +1157,20 @@ int nb200_sampler_divergence_trace_into(nb200_sampler* s, double* divergences) {
     return 0;
 }
 
+int nb200_sampler_eigvals_trace_into(nb200_sampler* s, double* eigvals, uint64_t* max_rank) {
+    if (!s) return fail(NB200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (max_rank) *max_rank = (uint64_t)s->lr_max_rank;
+    if (!eigvals) return 0;  // size query
+    if (s->state == RunState::Created) return fail(NB200_ESTATE, "sampler not started");
+    if (!s->d_eig) return fail(NB200_EINVAL, "needs adaptation = low_rank and store_mass_matrix");
+    CU(cudaSetDevice(s->device));
+    const size_t nb = s->n_chains * s->n_rows * (size_t)s->lr_max_rank * sizeof(double);
+    CU(cudaMemcpyAsync(eigvals, s->d_eig, nb, cudaMemcpyDeviceToHost, s->side));
+    CU(cudaStreamSynchronize(s->side));
+    return 0;
+}
+
 int nb200_host_expand_rows(nb200_expand_fn fn, const void* user_data, size_t dim, size_t expanded_dim,
                            uint64_t n, const double* q, size_t q_stride, double* out, int n_threads) {
     if (!fn || !q || !out) return fail(NB200_EINVAL, "null argument");
@@ -1194,7 +1244,8 @@ int nb200_sampler_destroy(nb200_sampler* s) {
     }
     if (s->host) s->host->shutdown();  // after the kernel: a waiting chain needs its answer
     void* dev[] = {s->d_pool, s->d_var, s->d_wf, s->d_sc, s->d_draws, s->d_stats, s->d_grads,
-                   s->d_mm, s->d_div, s->d_q0, s->d_init_mean, s->d_stop};
+                   s->d_mm, s->d_div, s->d_q0, s->d_init_mean, s->d_stop, s->d_lr_stds, s->d_lr_vals,
+                   s->d_lr_vecs, s->d_lr_coef, s->d_lr_win, s->d_lr_mat, s->d_lr_cols, s->d_eig};
     for (void* p : dev) {
         if (!p) continue;
         if (s->stream) cudaFreeAsync(p, s->stream);  // back to the pool
@@ -1358,3 +1409,94 @@ int nb200_leapfrog(const nb200_model_desc* model, int device, uint64_t n, const 
 }
 
 }  // extern "C"
+
+// ---- low-rank metric at the component seam (tests): one warp refreshes the metric from a
+// window of draws / gradients, then applies M^-1 and M^1/2 to the caller's vectors
+__global__ void __launch_bounds__(32)
+    lr_component_kernel(LrState L, int D, int Dp, double gamma, double cutoff, int n_vec,
+                        const double* p_in, double* v_out, double* z_io, int* out) {
+    GroupCuda<1> g;
+    g.tid = threadIdx.x;
+    g.red = nullptr;
+    const bool ok = lr_update(g, L, D, Dp, gamma, cutoff);
+    for (int v = 0; v < n_vec; ++v) {
+        lr_velocity(g, L, D, Dp, p_in + (size_t)v * Dp, v_out + (size_t)v * Dp);
+        lr_momentum(g, L, D, Dp, z_io + (size_t)v * Dp);
+    }
+    if (g.tid == 0) {
+        out[0] = ok ? 1 : 0;
+        out[1] = L.k;
+    }
+}
+
+extern "C" int nb200_lowrank_component(int device, uint64_t dim, uint64_t n, const double* draws,
+                                       const double* grads, double gamma, double cutoff,
+                                       uint64_t max_rank, uint64_t n_vec, const double* p,
+                                       double* v_out, const double* z, double* momentum_out,
+                                       double* stds_out, double* vals_out, double* vecs_out,
+                                       uint64_t* rank_out) {
+    if (!draws || !grads || dim < 1 || dim > 1024 || n < 1 || max_rank < 1)
+        return fail(NB200_EINVAL, "bad low-rank component input");
+    if (nb200_device_count() < 1) return fail(NB200_ECUDA, "no CUDA device available");
+    CU(cudaSetDevice(device));
+    const int D = (int)dim, Dp = (D + 3) / 4 * 4;
+    const int R = (int)(max_rank < dim ? max_rank : dim);
+    const size_t vecb = sizeof(double) * (size_t)Dp;
+    std::vector<void*> keep;
+    auto dalloc = [&](size_t bytes) -> double* {
+        void* ptr = nullptr;
+        if (cudaMalloc(&ptr, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+        cudaMemset(ptr, 0, bytes ? bytes : 8);
+        keep.push_back(ptr);
+        return (double*)ptr;
+    };
+    auto cleanup = [&]() {
+        for (void* ptr : keep) cudaFree(ptr);
+    };
+    LrState L;
+    std::memset(&L, 0, sizeof(L));
+    L.stds = dalloc(vecb); L.vals = dalloc(sizeof(double) * R); L.vecs = dalloc(vecb * R);
+    L.coef = dalloc(sizeof(double) * R); L.win = dalloc(vecb * 2 * n);
+    L.matL = dalloc(vecb * D); L.matW = dalloc(vecb * D); L.cols = dalloc(vecb * 6);
+    double* d_p = dalloc(vecb * (n_vec ? n_vec : 1));
+    double* d_v = dalloc(vecb * (n_vec ? n_vec : 1));
+    double* d_z = dalloc(vecb * (n_vec ? n_vec : 1));
+    int* d_out = (int*)dalloc(2 * sizeof(int));
+    if (!d_out || !L.win || !L.matW) {
+        cleanup();
+        return fail(NB200_ECUDA, "cudaMalloc failed");
+    }
+    L.cap = (int)n; L.len = (int)n; L.split = 0; L.head = 0; L.k = 0; L.max_rank = R;
+    std::vector<double> h((size_t)n * 2 * Dp, 0.0), ones(Dp, 1.0);
+    for (uint64_t j = 0; j < n; ++j)
+        for (int i = 0; i < D; ++i) {
+            h[(j * 2 + 0) * Dp + i] = draws[j * dim + i];
+            h[(j * 2 + 1) * Dp + i] = grads[j * dim + i];
+        }
+    cudaMemcpy(L.win, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(L.stds, ones.data(), vecb, cudaMemcpyHostToDevice);
+    for (uint64_t v = 0; v < n_vec; ++v) {
+        if (p) cudaMemcpy(d_p + v * Dp, p + v * dim, sizeof(double) * D, cudaMemcpyHostToDevice);
+        if (z) cudaMemcpy(d_z + v * Dp, z + v * dim, sizeof(double) * D, cudaMemcpyHostToDevice);
+    }
+    lr_component_kernel<<<1, 32>>>(L, D, Dp, gamma, cutoff, (int)n_vec, d_p, d_v, d_z, d_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(NB200_ECUDA, std::string("lr_component_kernel: ") + cudaGetErrorString(e));
+    }
+    int out[2] = {0, 0};
+    cudaMemcpy(out, d_out, sizeof(out), cudaMemcpyDeviceToHost);
+    for (uint64_t v = 0; v < n_vec; ++v) {
+        if (v_out) cudaMemcpy(v_out + v * dim, d_v + v * Dp, sizeof(double) * D, cudaMemcpyDeviceToHost);
+        if (momentum_out) cudaMemcpy(momentum_out + v * dim, d_z + v * Dp, sizeof(double) * D, cudaMemcpyDeviceToHost);
+    }
+    if (stds_out) cudaMemcpy(stds_out, L.stds, sizeof(double) * D, cudaMemcpyDeviceToHost);
+    if (vals_out) cudaMemcpy(vals_out, L.vals, sizeof(double) * out[1], cudaMemcpyDeviceToHost);
+    if (vecs_out)
+        for (int k = 0; k < out[1]; ++k)
+            cudaMemcpy(vecs_out + (size_t)k * dim, L.vecs + (size_t)k * Dp, sizeof(double) * D, cudaMemcpyDeviceToHost);
+    if (rank_out) *rank_out = (uint64_t)out[1];
+    cleanup();
+    return out[0] ? 0 : fail(NB200_EINVAL, "low-rank refresh broke down (window too short or not positive definite)");
+}

@@ -32,6 +32,7 @@
 #pragma once
 #include "../../include/nutpie_b200.h"
 #include "group.cuh"
+#include "lowrank.cuh"
 #include "models.cuh"
 #include "philox.cuh"
 #include "portable.cuh"
@@ -71,7 +72,8 @@ constexpr int kMaxSlots = 64;
 constexpr int kMaxLevels = 20;
 constexpr double kVarLower = 1e-20, kVarUpper = 1e20;
 
-enum { VQ = 0, VP = 1, VG = 2, VS = 3 };  // q, p, grad, p_sum inside a slot
+enum { VQ = 0, VP = 1, VG = 2, VS = 3, VV = 4 };  // q, p, grad, p_sum inside a slot; low-rank
+                                                   // adaptation adds the velocity M^-1 p
 
 // persistent per-chain scalar state (global memory; also the progress record)
 struct ChainScalars {
@@ -92,6 +94,7 @@ struct ChainScalars {
     int status;                  // 0 not started, 1 running, 2 finished, <0 NB200_E*
     int sweep_rev;               // direction of the last streaming pass (a relaunch must continue
                                  // the alternation: the sweep order fixes the order of the sums)
+    int lr_k, lr_len, lr_split, lr_head;  // low-rank adaptation: rank in use, window deque
 };
 
 // Producer / consumer pipeline of one chain (two warps, see ChainCtx::producer_main): a ring of
@@ -148,6 +151,16 @@ struct KParams {
     const double* init_mean; // optional [D]
     const double* z_tape;    // optional [n_chains][n_total][D] (tests)
     const volatile int* stop_flag;
+    // low-rank adaptation (st.adaptation == 1; lowrank.cuh): per-chain metric, window and scratch
+    double* lr_stds;   // [n_chains][Dp]
+    double* lr_vals;   // [n_chains][lr_max_rank]
+    double* lr_vecs;   // [n_chains][lr_max_rank][Dp]
+    double* lr_coef;   // [n_chains][lr_max_rank]
+    double* lr_win;    // [n_chains][lr_cap][2][Dp]
+    double* lr_mat;    // [n_chains][2][D][Dp]
+    double* lr_cols;   // [n_chains][6][Dp]
+    double* eigvals;   // optional trace [n_rows][n_chains][lr_max_rank] (store_mass_matrix), NaN-padded
+    int lr_cap, lr_max_rank;
     // streaming leapfrog (bit mask): 1 = inputs come through bulk-copy staging; 2 = successive
     // passes sweep the dimensions in alternating directions, so the tail a pass has just written
     // is the first thing the next pass reads (still in L2); 4 = the bulk copies carry L2
@@ -193,8 +206,11 @@ static __device__ __noinline__ double2 nb_flush_parked(double de, unsigned n, do
 // NIT > 0: every per-dimension loop runs exactly NIT predicated iterations
 // (NIT * group size >= D), fully unrolled so independent loads overlap;
 // NIT == 0: run-time trip count (any D).
-template <class M, class G, int NIT = 0>
+template <class M, class G, int NIT = 0, bool LR = false>
 struct ChainCtx {
+    static_assert(!LR || NIT == 0, "the low-rank engine runs the run-time loops");
+    static constexpr int kVecs = LR ? 5 : 4;  // vectors per pool slot
+    LrState lr;  // low-rank adaptation only
     G g;
     const KParams<M>* P;
     typename M::Data md;  // density data (a per-CTA copy may point into shared memory)
@@ -289,9 +305,9 @@ struct ChainCtx {
     NB_HD double* vec(int slot, int comp) const {
         if ((comp & 1) && slot < 2 * smem_slots)  // VP = 1, VS = 3
             return spool + (unsigned)((slot * 2 + (comp >> 1)) * Dp);
-        return pool + (unsigned)((slot * 4 + comp) * Dp);
+        return pool + (unsigned)((slot * kVecs + comp) * Dp);
     }
-    NB_HD double* gvec(int slot, int comp) const { return pool + (unsigned)((slot * 4 + comp) * Dp); }
+    NB_HD double* gvec(int slot, int comp) const { return pool + (unsigned)((slot * kVecs + comp) * Dp); }
     NB_HD const nb200_settings& st() const { return P->st; }
 
     // ------------------------------------------------------------ slot pool
@@ -351,11 +367,11 @@ struct ChainCtx {
     //   * up to kMaxFused further partners cost two vector reads each instead of a
     //     separate five-vector pass plus its own reduction.
     // All verdicts share one reduction with logp / kinetic energy.
-    static constexpr bool kFuseL0 = M::kElementwise || NIT > 0;  // not the run-time-loop front path
+    static constexpr bool kFuseL0 = (M::kElementwise || NIT > 0) && !LR;  // not the run-time-loop front path
     // Measured (profiles/r1_sweep_*): planning + extra partner loads pay off only in the
     // streaming regime (large D, run-time loops), where each separate check is a pass over
     // HBM; for small D they cost more than the on-chip is_turning() they replace.
-    static constexpr int kMaxFused = (M::kElementwise && NIT == 0) ? NB200_MAX_FUSED : 0;
+    static constexpr int kMaxFused = (M::kElementwise && NIT == 0 && !LR) ? NB200_MAX_FUSED : 0;
     static constexpr int kFusedDim = kMaxFused > 0 ? kMaxFused : 1;
 
     // The pair (x, new leaf N) in is_turning()'s terms: with (s, e) = the earlier / later of
@@ -484,6 +500,7 @@ struct ChainCtx {
     // plist[0..np): older states to pair with the new leaf; verdicts in fused_bits.
     NB_HD int leapfrog(int src, int dst, int dir, bool want_l0 = false, const int* plist = nullptr,
                        int np = 0) {
+        if constexpr (LR) return leapfrog_lr(src, dst, dir);
         const double eps = (double)dir * step_size;
         const double heps = 0.5 * eps;
         const double* qs = vec(src, VQ);
@@ -818,8 +835,143 @@ struct ChainCtx {
 #endif
     }
 
+    // ------------------------------------------------ low-rank metric (lowrank.cuh)
+    // One leapfrog under M^-1 = S (I + V (L - I) V^T) S.  The velocity needs a contraction over
+    // ALL dimensions between the momentum half step and the position step, so the pass cannot be
+    // fused like the diagonal one: five short passes over the slot's vectors in global memory /
+    // L2 (the state pool has no shared-memory tier here) and two k x D contractions with V.  The
+    // velocity of every state is kept in the slot (VV): the U-turn criterion projects on it.
+    NB_HD int leapfrog_lr(int src, int dst, int dir) {
+        const double eps = (double)dir * step_size;
+        const double heps = 0.5 * eps;
+        const double* qs = gvec(src, VQ);
+        const double* ps = gvec(src, VP);
+        const double* gs = gvec(src, VG);
+        const double* ss = gvec(src, VS);
+        double* qd = gvec(dst, VQ);
+        double* pd = gvec(dst, VP);
+        double* gd = gvec(dst, VG);
+        double* sd = gvec(dst, VS);
+        double* vd = gvec(dst, VV);
+        const int new_idx = sh->idx[src] + dir;
+        const bool restart_sum = new_idx == -1;
+        for (int i = g.tid; i < D; i += g.size()) pd[i] = ps[i] + heps * gs[i];
+        g.sync();
+        lr_velocity(g, lr, D, Dp, pd, vd);
+        for (int i = g.tid; i < D; i += g.size()) qd[i] = qs[i] + eps * vd[i];
+        g.sync();
+        bool bad;
+        const double lp = eval_logp(dst, bad);
+        g.sync();
+        for (int i = g.tid; i < D; i += g.size()) pd[i] = pd[i] + heps * gd[i];
+        g.sync();
+        lr_velocity(g, lr, D, Dp, pd, vd);
+        double acc[1] = {0.0};
+        for (int i = g.tid; i < D; i += g.size()) {
+            const double pn = pd[i];
+            acc[0] += pn * vd[i];
+            sd[i] = restart_sum ? pn : ss[i] + pn;
+        }
+        g.reduce(acc);
+        const double kin = 0.5 * acc[0];
+        int rc = (bad || !nb_isfinite(lp)) ? 1 : 0;
+        const double U = -lp;
+        const double de = (kin + U) - E0;
+        if (rc == 0 && (de > st().max_energy_error || !nb_isfinite(de))) rc = 1;
+        if (rc != 0) {
+            div_src = src;
+            div_dst = dst;
+        }
+        if (g.tid == 0) {
+            sh->idx[dst] = new_idx;
+            sh->U[dst] = U;
+            sh->K[dst] = kin;
+        }
+        g.sync();
+        last_de = de;
+        acc_count += 1;
+        if (rc == 0) {
+            const double w = exp(-de);
+            const double a = w < 1.0 ? w : 1.0;
+            acc_sum += a;
+            acc_sym += 2.0 * a / (1.0 + w);
+        }
+        l0_turn = false;
+        fused_bits = 0;
+        return rc;
+    }
+    // U-turn criterion on the stored velocities (oracle: is_turning_v)
+    NB_HD bool is_turning_lr(int s1, int s2) const {
+        int a = sh->idx[s1], b = sh->idx[s2];
+        int ss_ = s1, se_ = s2;
+        if (!(a < b)) {
+            int t = a; a = b; b = t;
+            ss_ = s2; se_ = s1;
+        }
+        const int mode = (a >= 0 && b >= 0) ? 0 : ((b >= 0 && a < 0) ? 1 : 2);
+        const double* p_s = gvec(ss_, VP);
+        const double* s_s = gvec(ss_, VS);
+        const double* v_s = gvec(ss_, VV);
+        const double* p_e = gvec(se_, VP);
+        const double* s_e = gvec(se_, VS);
+        const double* v_e = gvec(se_, VV);
+        double acc[2] = {0.0, 0.0};
+        for (int i = g.tid; i < D; i += g.size()) {
+            double rho;
+            if (mode == 0) rho = s_e[i] - s_s[i] + p_s[i];
+            else if (mode == 1) rho = s_e[i] + s_s[i];
+            else rho = s_s[i] - s_e[i] + p_e[i];
+            acc[0] += rho * v_e[i];
+            acc[1] += rho * v_s[i];
+        }
+        g.reduce(acc);
+        return (acc[0] < 0.0) | (acc[1] < 0.0);
+    }
+    // fresh momentum p = M^1/2 z, v = M^-1 p, p_sum = p, K, idx = 0, E0
+    NB_HD void init_momentum_lr(int slot, uint32_t purpose, uint32_t rng_draw) {
+        double* pd = gvec(slot, VP);
+        double* sd = gvec(slot, VS);
+        double* vd = gvec(slot, VV);
+        const double* tape = nullptr;
+        if (purpose == RNG_MOMENTUM && P->z_tape)
+            tape = P->z_tape + ((size_t)chain_local * P->n_total + rng_draw) * (size_t)D;
+        for (int j = g.tid; 2 * j < D; j += g.size()) {
+            double z0, z1;
+            const int i0 = 2 * j, i1 = 2 * j + 1;
+            if (tape) {
+                z0 = tape[i0];
+                z1 = i1 < D ? tape[i1] : 0.0;
+            } else {
+                uint64_t a, b;
+                rng_u64x2(st().seed, chain_gid, rng_draw, purpose, (uint32_t)j, a, b);
+                rng_normal_pair(a, b, z0, z1);
+            }
+            pd[i0] = z0;
+            if (i1 < D) pd[i1] = z1;
+        }
+        g.sync();
+        lr_momentum(g, lr, D, Dp, pd);
+        lr_velocity(g, lr, D, Dp, pd, vd);
+        double acc[1] = {0.0};
+        for (int i = g.tid; i < D; i += g.size()) {
+            const double p = pd[i];
+            sd[i] = p;
+            acc[0] += p * vd[i];
+        }
+        g.reduce(acc);
+        const double kin = 0.5 * acc[0];
+        if (g.tid == 0) {
+            sh->idx[slot] = 0;
+            sh->K[slot] = kin;
+        }
+        E0 = kin + sh->U[slot];
+        front_slot = -1;
+        g.sync();
+    }
+
     // ------------------------------------------------------------------ U-turn
     NB_HD bool is_turning(int s1, int s2) const {
+        if constexpr (LR) return is_turning_lr(s1, s2);
         int a = sh->idx[s1], b = sh->idx[s2];
         int ss_ = s1, se_ = s2;
         if (!(a < b)) {
@@ -914,6 +1066,10 @@ struct ChainCtx {
     // ------------------------------------------------------- fresh momentum
     // p = z / sqrt(var), p_sum = p, K, idx = 0, E0 = K + U   (initialize_trajectory)
     NB_HD void init_momentum(int slot, uint32_t purpose, uint32_t rng_draw) {
+        if constexpr (LR) {
+            init_momentum_lr(slot, purpose, rng_draw);
+            return;
+        }
         double* pd = vec(slot, VP);
         double* sd = vec(slot, VS);
         if constexpr (!M::kElementwise) {
@@ -1565,6 +1721,34 @@ struct ChainCtx {
                 is_early ? st().early_mass_matrix_switch_freq : st().mass_matrix_switch_freq;
             const int didx = sh->idx[dslot];
             const bool is_good = info.diverging ? ((didx < 0 ? -didx : didx) > 4) : (didx != 0);
+            if constexpr (LR) {
+                // low-rank strategy: the estimators are a window (deque) of draws and gradients;
+                // the schedule (switch / refresh / first-change step-size search) is the diagonal one
+                if (is_good) {
+                    const double* q = gvec(dslot, VQ);
+                    const double* gr = gvec(dslot, VG);
+                    lr_push(g, lr, D, Dp, q, [&](int i) { return gr[i]; });
+                }
+                const bool could_switch = (unsigned long long)(lr.len - lr.split) >= switch_freq;
+                const bool is_late = switch_freq + t > final_window;
+                bool force_update = false;
+                if (could_switch && !is_late) {
+                    lr_switch(lr);
+                    force_update = true;
+                }
+                bool did_change = false;
+                if (force_update || (t - last_update >= st().mass_matrix_update_freq))
+                    did_change = lr_update(g, lr, D, Dp, st().mass_matrix_gamma, st().mass_matrix_eigval_cutoff);
+                if (did_change) last_update = t;
+                if (!fixed) step_advance(is_late ? last_sym : last_mean);
+                if (did_change && has_initial_mm) {
+                    has_initial_mm = 0;
+                    step_size_search(dslot, (uint32_t)t);
+                } else if (!fixed) {
+                    step_size = clamp_step(exp(da_log_step));
+                }
+                return;
+            }
             if (is_good) {
                 cnt0 += 1;
                 cnt1 += 1;
@@ -1661,6 +1845,14 @@ struct ChainCtx {
             w1[i] = x; w1[Dp + i] = 0.0; w1[2 * Dp + i] = y; w1[3 * Dp + i] = 0.0;
         }
         g.sync();
+        if constexpr (LR) {
+            // low rank [nuts-rs, recalled]: identity metric, the window seeded with the initial point
+            for (int i = g.tid; i < D; i += g.size()) lr.stds[i] = 1.0;
+            lr.k = 0;
+            lr.len = lr.split = lr.head = 0;
+            g.sync();
+            lr_push(g, lr, D, Dp, q, [&](int i) { return gr[i]; });
+        }
         cnt0 = cnt1 = 1;
         fg_sel = 0;
         has_initial_mm = 1;
@@ -1684,6 +1876,9 @@ struct ChainCtx {
         total_steps = s.total_steps; divergences = s.divergences;
         fg_sel = s.fg_sel; has_initial_mm = s.has_initial_mm;
         sweep_rev = s.sweep_rev != 0;
+        if constexpr (LR) {
+            lr.k = s.lr_k; lr.len = s.lr_len; lr.split = s.lr_split; lr.head = s.lr_head;
+        }
     }
     NB_HD void store(ChainScalars& s, unsigned long long next_draw, int cur, int status) const {
         s.step_size = step_size;
@@ -1698,6 +1893,9 @@ struct ChainCtx {
         s.draw = next_draw;
         s.status = status;
         s.sweep_rev = sweep_rev ? 1 : 0;
+        if constexpr (LR) {
+            s.lr_k = lr.k; s.lr_len = lr.len; s.lr_split = lr.split; s.lr_head = lr.head;
+        }
     }
 
     // Runs the chain from its persisted state until finished, stopped or the
@@ -1766,8 +1964,17 @@ struct ChainCtx {
             // contiguous block, so the host streams them out with linear copies
             const size_t row_off = ((size_t)row * P->n_chains + chain_local);
             if (keep && P->mminv) {
+                // store_mass_matrix: mass_matrix_inv (diag) | mass_matrix_stds (low rank)
                 double* o = P->mminv + row_off * P->gdim;
-                for (int i = g.tid; i < (int)P->gdim; i += g.size()) o[i] = var[i];
+                const double* src_ = LR ? lr.stds : var;
+                for (int i = g.tid; i < (int)P->gdim; i += g.size()) o[i] = src_[i];
+            }
+            if constexpr (LR) {
+                if (keep && P->eigvals) {  // mass_matrix_eigvals, NaN-padded to the maximal rank
+                    double* o = P->eigvals + row_off * (size_t)lr.max_rank;
+                    for (int j = g.tid; j < lr.max_rank; j += g.size())
+                        o[j] = j < lr.k ? lr.vals[j] : nan("");
+                }
             }
             SampleInfo info;
             div_src = div_dst = -1;

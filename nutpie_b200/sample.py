@@ -75,14 +75,15 @@ def _trace_to_groups(trace: _lib.PyTrace, compiled_model, settings, save_warmup,
         a = trace.stat(name)[:, :n_rows]
         out.warmup_sample_stats[name] = a[:, :n_tune_rows]
         out.sample_stats[name] = a[:, n_tune_rows:]
-    vec_stats = [("gradient", trace.gradients), ("mass_matrix_inv", trace.mass_matrix_inv)]
+    vec_stats = [("gradient", trace.gradients)] + trace.mass_matrix_columns()
     if trace.divergences is not None:  # sample.py:641-646
         vec_stats += [(n, trace.divergences[:, :, k]) for k, n in enumerate(_lib.DIVERGENCE_COLUMNS)]
     for name, arr in vec_stats:
         if arr is not None:
             out.warmup_sample_stats[name] = arr[:, :n_tune_rows]
             out.sample_stats[name] = arr[:, n_tune_rows:n_rows]
-            out.dims[name] = ["unconstrained_parameter"]
+            out.dims[name] = ["mass_matrix_eigvals_dim" if name == "mass_matrix_eigvals"
+                              else "unconstrained_parameter"]
     if store_unconstrained and full and not trace.expanded:
         out.sample_stats["unconstrained_draw"] = draws[:, n_tune_rows:]
         out.warmup_sample_stats["unconstrained_draw"] = draws[:, :n_tune_rows]

@@ -125,7 +125,26 @@ typedef struct Chain {
     /* DivergenceInfo of the running transition (store_divergences, python/nutpie/sample.py:641-646) */
     int div_valid;
     double *div; /* [4][dim]: start location, end location, start momentum, start gradient */
+    /* low-rank strategy (st->adaptation == 1; oracle/lowrank.c): metric + the window of draws
+     * and gradients, a deque [foreground-only part | background part] split at lr_split */
+    int lr;
+    double *lr_stds, *lr_vals, *lr_vecs;
+    size_t lr_k, lr_max_rank;
+    double *lr_win_q, *lr_win_g;
+    size_t lr_len, lr_split, lr_cap;
 } Chain;
+
+/* the metric a leapfrog / U-turn check runs under: diagonal (var) or low rank */
+typedef struct Metric {
+    const double *var;
+    int lr;
+    const double *stds, *vals, *vecs;
+    size_t k;
+} Metric;
+static Metric chain_metric(const Chain *c) {
+    Metric m = {c->var, c->lr, c->lr_stds, c->lr_vals, c->lr_vecs, c->lr_k};
+    return m;
+}
 
 /* ------------------------------------------------- component: dual average */
 static void da_new(DualAverage *da, double initial_step) {
@@ -272,11 +291,17 @@ void oracle_rng_normals(uint64_t seed, uint32_t chain, uint32_t draw, uint32_t p
 
 /* -------------------------------------------------- component: leapfrog */
 /* returns 0 ok, 1 divergence (recoverable logp error or energy error), <0 fatal */
-static int leapfrog_raw(nb200_logp_fn logp, const void *ud, size_t dim, const double *var,
+static int leapfrog_raw(nb200_logp_fn logp, const void *ud, size_t dim, const Metric *mt,
                         const State *start, State *out, double step_size, int dir,
                         double max_energy_error) {
+    const double *var = mt->var;
     double eps = (double)dir * step_size;
     out->E0 = start->E0;
+    if (mt->lr) {
+        for (size_t i = 0; i < dim; ++i) out->p[i] = start->p[i] + 0.5 * eps * start->g[i];
+        oracle_lowrank_velocity(dim, mt->stds, mt->k, mt->vals, mt->vecs, out->p, out->v);
+        for (size_t i = 0; i < dim; ++i) out->q[i] = start->q[i] + eps * out->v[i];
+    } else
     for (size_t i = 0; i < dim; ++i) {
         double ph = start->p[i] + 0.5 * eps * start->g[i]; /* first momentum half step */
         out->p[i] = ph;
@@ -294,6 +319,11 @@ static int leapfrog_raw(nb200_logp_fn logp, const void *ud, size_t dim, const do
     }
     out->U = -lp;
     double kin = 0.0;
+    if (mt->lr) {
+        for (size_t i = 0; i < dim; ++i) out->p[i] = out->p[i] + 0.5 * eps * out->g[i];
+        oracle_lowrank_velocity(dim, mt->stds, mt->k, mt->vals, mt->vecs, out->p, out->v);
+        for (size_t i = 0; i < dim; ++i) kin += out->p[i] * out->v[i];
+    } else
     for (size_t i = 0; i < dim; ++i) {
         double pn = out->p[i] + 0.5 * eps * out->g[i]; /* second momentum half step */
         out->p[i] = pn;
@@ -321,7 +351,8 @@ int oracle_leapfrog(nb200_logp_fn logp, const void *ud, size_t dim, const double
     memcpy(a->q, q, dim * 8); memcpy(a->p, p, dim * 8); memcpy(a->g, g, dim * 8);
     memcpy(a->p_sum, p_sum, dim * 8);
     a->idx = idx; a->E0 = 0.0; a->U = 0.0; a->K = 0.0;
-    int rc = leapfrog_raw(logp, ud, dim, var, a, b, eps, dir, INFINITY);
+    Metric mt = {var, 0, NULL, NULL, NULL, 0};
+    int rc = leapfrog_raw(logp, ud, dim, &mt, a, b, eps, dir, INFINITY);
     memcpy(q_out, b->q, dim * 8); memcpy(p_out, b->p, dim * 8); memcpy(g_out, b->g, dim * 8);
     memcpy(p_sum_out, b->p_sum, dim * 8);
     *logp_out = -b->U; *kinetic_out = b->K;
@@ -354,7 +385,23 @@ int oracle_is_turning(size_t dim, int64_t idx1, const double *p1, const double *
                       int64_t idx2, const double *p2, const double *psum2, const double *var) {
     return is_turning_raw(dim, idx1, p1, psum1, idx2, p2, psum2, var);
 }
+/* the same criterion on stored velocities v = M^-1 p (any metric) */
+static int is_turning_v(size_t dim, const State *s1, const State *s2) {
+    const State *s = s1->idx < s2->idx ? s1 : s2, *e = s1->idx < s2->idx ? s2 : s1;
+    int64_t a = s->idx, b = e->idx;
+    double t_end = 0.0, t_start = 0.0;
+    for (size_t i = 0; i < dim; ++i) {
+        double rho;
+        if (a >= 0 && b >= 0)      rho = e->p_sum[i] - s->p_sum[i] + s->p[i];
+        else if (b >= 0 && a < 0)  rho = e->p_sum[i] + s->p_sum[i];
+        else                       rho = s->p_sum[i] - e->p_sum[i] + e->p[i];
+        t_end += rho * e->v[i];
+        t_start += rho * s->v[i];
+    }
+    return (t_end < 0.0) | (t_start < 0.0);
+}
 static int is_turning(const Chain *c, const State *s1, const State *s2) {
+    if (c->lr) return is_turning_v(c->dim, s1, s2);
     return is_turning_raw(c->dim, s1->idx, s1->p, s1->p_sum, s2->idx, s2->p, s2->p_sum, c->var);
 }
 
@@ -371,6 +418,11 @@ static void initialize_trajectory(Chain *c, State *s, uint32_t purpose, uint32_t
     double *z = s->p_sum; /* scratch, overwritten below */
     fill_momentum_normals(c, purpose, draw, z);
     double kin = 0.0;
+    if (c->lr) {
+        oracle_lowrank_momentum(c->dim, c->lr_stds, c->lr_k, c->lr_vals, c->lr_vecs, z, s->p);
+        oracle_lowrank_velocity(c->dim, c->lr_stds, c->lr_k, c->lr_vals, c->lr_vecs, s->p, s->v);
+        for (size_t i = 0; i < c->dim; ++i) kin += s->p[i] * s->v[i];
+    } else
     for (size_t i = 0; i < c->dim; ++i) {
         double p = c->inv_std[i] * z[i];
         s->p[i] = p;
@@ -386,7 +438,8 @@ static void initialize_trajectory(Chain *c, State *s, uint32_t purpose, uint32_t
 
 /* leapfrog + acceptance-rate collector (nuts-rs AcceptanceRateCollector) */
 static int chain_leapfrog(Chain *c, const State *start, State *out, int dir) {
-    int rc = leapfrog_raw(c->logp, c->ud, c->dim, c->var, start, out, c->step_size, dir,
+    Metric mt = chain_metric(c);
+    int rc = leapfrog_raw(c->logp, c->ud, c->dim, &mt, start, out, c->step_size, dir,
                           c->st->max_energy_error);
     if (rc < 0) return rc;
     c->acc_count += 1;
@@ -598,6 +651,35 @@ static int update_mass_matrix(Chain *c) {
     return 1;
 }
 
+/* low-rank strategy: window deque + refresh of the metric (oracle/lowrank.c) */
+static void lr_push(Chain *c, const double *q, const double *g) {
+    if (c->lr_len == c->lr_cap) {
+        c->lr_cap = c->lr_cap ? 2 * c->lr_cap : 64;
+        c->lr_win_q = (double *)realloc(c->lr_win_q, c->lr_cap * c->dim * 8);
+        c->lr_win_g = (double *)realloc(c->lr_win_g, c->lr_cap * c->dim * 8);
+    }
+    memcpy(c->lr_win_q + c->lr_len * c->dim, q, c->dim * 8);
+    memcpy(c->lr_win_g + c->lr_len * c->dim, g, c->dim * 8);
+    c->lr_len += 1;
+}
+static void lr_switch(Chain *c) { /* drop the foreground-only part; the rest becomes it */
+    size_t keep = c->lr_len - c->lr_split;
+    memmove(c->lr_win_q, c->lr_win_q + c->lr_split * c->dim, keep * c->dim * 8);
+    memmove(c->lr_win_g, c->lr_win_g + c->lr_split * c->dim, keep * c->dim * 8);
+    c->lr_len = keep;
+    c->lr_split = keep;
+}
+static int lr_update(Chain *c) {
+    if (c->lr_len < 3) return 0;
+    size_t k = 0;
+    if (oracle_lowrank_update(c->dim, c->lr_len, c->lr_win_q, c->lr_win_g, c->st->mass_matrix_gamma,
+                              c->st->mass_matrix_eigval_cutoff, c->lr_max_rank, c->lr_stds,
+                              c->lr_vals, c->lr_vecs, &k) != 0)
+        return 0;
+    c->lr_k = k;
+    return 1;
+}
+
 /* nuts-rs GlobalStrategy::adapt, called after every draw (Appendix A.5) */
 static void adapt(Chain *c, uint64_t t, const State *draw, const SampleInfo *info) {
     const nb200_settings *st = c->st;
@@ -617,16 +699,21 @@ static void adapt(Chain *c, uint64_t t, const State *draw, const SampleInfo *inf
             is_early ? st->early_mass_matrix_switch_freq : st->mass_matrix_switch_freq;
         /* DrawGradCollector: which draws feed the estimators */
         int is_good = info->diverging ? (llabs(draw->idx) > 4) : (draw->idx != 0);
-        if (is_good) {
+        if (is_good && c->lr) {
+            lr_push(c, draw->q, draw->g);
+        } else if (is_good) {
             oracle_welford_add(c->dim, c->fg_draw.mean, c->fg_draw.m2, &c->fg_draw.count, draw->q);
             oracle_welford_add(c->dim, c->fg_grad.mean, c->fg_grad.m2, &c->fg_grad.count, draw->g);
             oracle_welford_add(c->dim, c->bg_draw.mean, c->bg_draw.m2, &c->bg_draw.count, draw->q);
             oracle_welford_add(c->dim, c->bg_grad.mean, c->bg_grad.m2, &c->bg_grad.count, draw->g);
         }
-        int could_switch = c->bg_draw.count >= switch_freq;
+        int could_switch = (c->lr ? c->lr_len - c->lr_split : c->bg_draw.count) >= switch_freq;
         int is_late = switch_freq + t > final_window;
         int force_update = 0;
-        if (could_switch && !is_late) {
+        if (could_switch && !is_late && c->lr) {
+            lr_switch(c);
+            force_update = 1;
+        } else if (could_switch && !is_late) {
             RunVar td = c->fg_draw, tg = c->fg_grad;
             c->fg_draw = c->bg_draw; c->fg_grad = c->bg_grad;
             c->bg_draw = td; c->bg_grad = tg;
@@ -636,7 +723,7 @@ static void adapt(Chain *c, uint64_t t, const State *draw, const SampleInfo *inf
         }
         int did_change = 0;
         if (force_update || (t - c->last_update >= st->mass_matrix_update_freq))
-            did_change = update_mass_matrix(c);
+            did_change = c->lr ? lr_update(c) : update_mass_matrix(c);
         if (did_change) c->last_update = t;
         if (!fixed) step_advance(st, &c->da, is_late ? c->last_sym : c->last_mean);
         if (did_change && c->has_initial_mass_matrix) {
@@ -692,7 +779,7 @@ static int chain_init_position(Chain *c, State *s, const double *q0, const doubl
 static int run_chain(const nb200_settings *st, nb200_logp_fn logp, const void *ud, size_t dim,
                      uint32_t chain_id, const double *q0, const double *init_mean,
                      const double *z_tape, size_t n_rows, size_t sdim, double *draws,
-                     double *stats, double *grads, double *mminv, double *divs,
+                     double *stats, double *grads, double *mminv, double *divs, double *eigvals,
                      uint64_t *steps_out) {
     Chain c;
     memset(&c, 0, sizeof(c));
@@ -704,6 +791,13 @@ static int run_chain(const nb200_settings *st, nb200_logp_fn logp, const void *u
     c.div = divs ? (double *)calloc(4 * dim + 1, 8) : NULL;
     runvar_alloc(&c.fg_draw, dim); runvar_alloc(&c.fg_grad, dim);
     runvar_alloc(&c.bg_draw, dim); runvar_alloc(&c.bg_grad, dim);
+    c.lr = st->adaptation == 1;
+    c.lr_max_rank = st->mass_matrix_max_rank < dim ? st->mass_matrix_max_rank : dim;
+    if (c.lr) {
+        c.lr_stds = (double *)calloc(dim + 1, 8);
+        c.lr_vals = (double *)calloc(c.lr_max_rank + 1, 8);
+        c.lr_vecs = (double *)calloc(c.lr_max_rank * dim + 1, 8);
+    }
 
     State *cur = state_new(&c.pool);
     int rc = chain_init_position(&c, cur, q0, init_mean);
@@ -716,6 +810,11 @@ static int run_chain(const nb200_settings *st, nb200_logp_fn logp, const void *u
         oracle_welford_add(dim, c.bg_draw.mean, c.bg_draw.m2, &c.bg_draw.count, cur->q);
         oracle_welford_add(dim, c.fg_grad.mean, c.fg_grad.m2, &c.fg_grad.count, cur->g);
         oracle_welford_add(dim, c.bg_grad.mean, c.bg_grad.m2, &c.bg_grad.count, cur->g);
+        if (c.lr) { /* low rank [recalled]: identity metric, the window seeded with the initial point */
+            for (size_t i = 0; i < dim; ++i) c.lr_stds[i] = 1.0;
+            c.lr_k = 0;
+            lr_push(&c, cur->q, cur->g);
+        }
         c.has_initial_mass_matrix = 1;
         step_new(st, &c.da, st->initial_step);
         c.step_size = st->initial_step;
@@ -735,7 +834,12 @@ static int run_chain(const nb200_settings *st, nb200_logp_fn logp, const void *u
             c.div_valid = 0;
             int store = st->save_warmup || t >= st->num_tune;
             size_t row = st->save_warmup ? t : t - st->num_tune;
-            if (store && mminv) memcpy(mminv + row * sdim, c.var, sdim * 8);
+            /* store_mass_matrix: mass_matrix_inv (diag) | mass_matrix_stds + mass_matrix_eigvals
+             * (low rank; eigvals NaN-padded to mass_matrix_max_rank) */
+            if (store && mminv) memcpy(mminv + row * sdim, c.lr ? c.lr_stds : c.var, sdim * 8);
+            if (store && eigvals && c.lr)
+                for (size_t k = 0; k < st->mass_matrix_max_rank; ++k)
+                    eigvals[row * st->mass_matrix_max_rank + k] = k < c.lr_k ? c.lr_vals[k] : NAN;
             State *nxt = nuts_draw(&c, cur, (uint32_t)t, &info);
             c.step_size = step_base;
             if (c.fatal) { state_release(&c.pool, nxt); break; }
@@ -776,6 +880,7 @@ static int run_chain(const nb200_settings *st, nb200_logp_fn logp, const void *u
     state_release(&c.pool, cur);
     pool_destroy(&c.pool);
     free(c.var); free(c.inv_std); free(c.div);
+    free(c.lr_stds); free(c.lr_vals); free(c.lr_vecs); free(c.lr_win_q); free(c.lr_win_g);
     runvar_free(&c.fg_draw); runvar_free(&c.fg_grad);
     runvar_free(&c.bg_draw); runvar_free(&c.bg_grad);
     return rc;
@@ -787,7 +892,7 @@ typedef struct Job {
     const void *ud;
     uint64_t dim, n_chains, chain_id_offset;
     const double *q0, *init_mean, *z_tape;
-    double *draws, *stats, *gradients, *mminv, *divs;
+    double *draws, *stats, *gradients, *mminv, *divs, *eigvals;
     size_t n_total, n_rows, sdim;
     atomic_long next;  /* dynamic schedule over chains */
     atomic_ullong steps;
@@ -807,7 +912,9 @@ static void *worker(void *arg) {
                            j->stats + (size_t)ci * j->n_rows * NB200_NSTAT,
                            j->gradients ? j->gradients + (size_t)ci * j->n_rows * j->sdim : NULL,
                            j->mminv ? j->mminv + (size_t)ci * j->n_rows * j->sdim : NULL,
-                           j->divs ? j->divs + (size_t)ci * j->n_rows * 4 * j->sdim : NULL, &s);
+                           j->divs ? j->divs + (size_t)ci * j->n_rows * 4 * j->sdim : NULL,
+                           j->eigvals ? j->eigvals + (size_t)ci * j->n_rows * j->st->mass_matrix_max_rank
+                                      : NULL, &s);
         atomic_fetch_add(&j->steps, s);
         if (rc != 0) atomic_store(&j->err, rc);
     }
@@ -831,12 +938,23 @@ int oracle_sample_ex(const nb200_settings *st, nb200_logp_fn logp, const void *u
                      const double *q0, const double *init_mean, const double *z_tape,
                      double *draws, double *stats, double *gradients, double *mass_matrix_inv,
                      double *divergences, uint64_t *total_steps) {
+    return oracle_sample_lr(st, logp, user_data, dim, n_chains, chain_id_offset, n_threads, q0,
+                            init_mean, z_tape, draws, stats, gradients, mass_matrix_inv,
+                            divergences, NULL, total_steps);
+}
+
+int oracle_sample_lr(const nb200_settings *st, nb200_logp_fn logp, const void *user_data,
+                     uint64_t dim, uint64_t n_chains, uint64_t chain_id_offset, int n_threads,
+                     const double *q0, const double *init_mean, const double *z_tape,
+                     double *draws, double *stats, double *gradients, double *mass_matrix_inv,
+                     double *divergences, double *eigvals, uint64_t *total_steps) {
     Job j;
     memset(&j, 0, sizeof(j));
     j.st = st; j.logp = logp; j.ud = user_data; j.dim = dim; j.n_chains = n_chains;
     j.chain_id_offset = chain_id_offset; j.q0 = q0; j.init_mean = init_mean; j.z_tape = z_tape;
     j.draws = draws; j.stats = stats; j.gradients = gradients; j.mminv = mass_matrix_inv;
     j.divs = divergences;
+    j.eigvals = eigvals;
     j.n_total = st->num_tune + st->num_draws;
     j.n_rows = st->save_warmup ? j.n_total : st->num_draws;
     j.sdim = (st->store_dims && st->store_dims < dim) ? st->store_dims : dim;

@@ -75,6 +75,25 @@ int oracle_sample_ex(const nb200_settings *settings, nb200_logp_fn logp, const v
                      double *draws, double *stats, double *gradients, double *mass_matrix_inv,
                      double *divergences, uint64_t *total_steps);
 
+/* the same with adaptation = low_rank traces: with store_mass_matrix the mass_matrix_inv rows
+ * hold mass_matrix_stds, and eigvals [n_chains][n_rows][mass_matrix_max_rank] the kept
+ * eigenvalues (NaN-padded) — the reference's mass_matrix_stds / mass_matrix_eigvals columns */
+int oracle_sample_lr(const nb200_settings *settings, nb200_logp_fn logp, const void *user_data,
+                     uint64_t dim, uint64_t n_chains, uint64_t chain_id_offset, int n_threads,
+                     const double *q0, const double *init_mean, const double *z_tape,
+                     double *draws, double *stats, double *gradients, double *mass_matrix_inv,
+                     double *divergences, double *eigvals, uint64_t *total_steps);
+
+/* low-rank metric components (oracle/lowrank.c): estimate from a window of n draws / gradients
+ * [n][dim]; v = M^-1 p; p = M^1/2 z */
+int oracle_lowrank_update(size_t dim, size_t n, const double *draws, const double *grads,
+                          double gamma, double cutoff, size_t max_rank, double *stds,
+                          double *vals, double *vecs, size_t *rank_out);
+void oracle_lowrank_velocity(size_t dim, const double *stds, size_t k, const double *vals,
+                             const double *vecs, const double *p, double *v);
+void oracle_lowrank_momentum(size_t dim, const double *stds, size_t k, const double *vals,
+                             const double *vecs, const double *z, double *p);
+
 /* --- component entry points (known-answer tests at the nuts-rs Math seam) --- */
 /* one leapfrog, SURVEY Appendix A.2 */
 int oracle_leapfrog(nb200_logp_fn logp, const void *ud, size_t dim, const double *q,

@@ -48,6 +48,7 @@ class Settings(C.Structure):
         ("store_divergences", C.c_int32), ("adaptation", C.c_int32),
         ("adam_learning_rate", C.c_double), ("step_size_jitter", C.c_double),
         ("mass_matrix_eigval_cutoff", C.c_double), ("mass_matrix_gamma", C.c_double),
+        ("mass_matrix_max_rank", C.c_uint64),
     ]
 
 
@@ -76,6 +77,7 @@ def default_settings(**kw) -> Settings:
     s.store_divergences, s.adaptation = 0, 0
     s.adam_learning_rate, s.step_size_jitter = 0.05, 0.0
     s.mass_matrix_eigval_cutoff, s.mass_matrix_gamma = 2.0, 1e-5
+    s.mass_matrix_max_rank = 32
     for k, v in kw.items():
         if not hasattr(s, k):
             raise AttributeError(k)
@@ -98,7 +100,7 @@ LOGP_FN = C.CFUNCTYPE(C.c_int, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_
 
 def build(force: bool = False) -> Path:
     so = _HERE / "liboracle.so"
-    srcs = [_HERE / n for n in ("nuts_oracle.c", "models.c", "oracle.h", "philox.h")]
+    srcs = [_HERE / n for n in ("nuts_oracle.c", "models.c", "lowrank.c", "oracle.h", "philox.h")]
     srcs.append(_HERE.parent / "include" / "nutpie_b200.h")
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(_HERE), "liboracle.so"], check=True,
@@ -148,7 +150,7 @@ def lib_fast() -> C.CDLL:
     if _LIB_FAST is None:
         so, tag = _HERE / "liboracle_fast.so", _HERE / "liboracle_fast.cpu"
         cpu = _cpu_model()
-        srcs = [_HERE / n for n in ("nuts_oracle.c", "models.c", "oracle.h", "philox.h")]
+        srcs = [_HERE / n for n in ("nuts_oracle.c", "models.c", "lowrank.c", "oracle.h", "philox.h")]
         stale = (not so.exists() or not tag.exists() or tag.read_text() != cpu
                  or any(x.stat().st_mtime > so.stat().st_mtime for x in srcs))
         try:
@@ -251,14 +253,60 @@ def sample(model: Model, settings: Settings, n_chains: int, chain_id_offset: int
     if z_tape is not None:
         z_tape = np.ascontiguousarray(z_tape, dtype=np.float64).reshape(n_chains, n_total, model.dim)
     steps = C.c_uint64(0)
-    rc = L.oracle_sample_ex(C.byref(settings), model.fn_ptr, model.ud_ptr, C.c_uint64(model.dim),
+    low_rank = settings.adaptation == 1
+    eig = (np.full((n_chains, n_rows, settings.mass_matrix_max_rank), np.nan)
+           if settings.store_mass_matrix and low_rank else None)
+    L.oracle_sample_lr.restype = C.c_int
+    rc = L.oracle_sample_lr(C.byref(settings), model.fn_ptr, model.ud_ptr, C.c_uint64(model.dim),
                             C.c_uint64(n_chains), C.c_uint64(chain_id_offset), C.c_int(n_threads),
                             _ptr(q0), _ptr(init_mean), _ptr(z_tape), _ptr(draws), _ptr(stats),
-                            _ptr(grads), _ptr(mm), _ptr(divs), C.byref(steps))
+                            _ptr(grads), _ptr(mm), _ptr(divs), _ptr(eig), C.byref(steps))
     if rc != 0:
         raise RuntimeError(f"oracle_sample failed with code {rc}")
+    # low rank: the mass-matrix rows are mass_matrix_stds, eigvals the kept eigenvalues
     return dict(draws=draws, stats=stats, gradients=grads, mass_matrix_inv=mm,
-                divergences=divs, total_steps=int(steps.value))
+                mass_matrix_eigvals=eig, divergences=divs, total_steps=int(steps.value))
+
+
+def lowrank_update(draws, grads, gamma=1e-5, cutoff=2.0, max_rank=32, stds0=None):
+    """oracle_lowrank_update on a window [n][dim]: returns (stds, vals [k], vecs [k][dim])."""
+    L = lib()
+    draws = np.ascontiguousarray(draws, dtype=np.float64)
+    grads = np.ascontiguousarray(grads, dtype=np.float64)
+    n, dim = draws.shape
+    max_rank = min(max_rank, dim)
+    stds = np.ones(dim) if stds0 is None else np.array(stds0, dtype=np.float64)
+    vals, vecs = np.zeros(max_rank + 1), np.zeros((max_rank + 1, dim))
+    k = C.c_size_t(0)
+    L.oracle_lowrank_update.restype = C.c_int
+    rc = L.oracle_lowrank_update(C.c_size_t(dim), C.c_size_t(n), _ptr(draws), _ptr(grads),
+                                 C.c_double(gamma), C.c_double(cutoff), C.c_size_t(max_rank),
+                                 _ptr(stds), _ptr(vals), _ptr(vecs), C.byref(k))
+    if rc != 0:
+        raise RuntimeError(f"oracle_lowrank_update failed with code {rc}")
+    return stds, vals[:k.value].copy(), vecs[:k.value].copy()
+
+
+def lowrank_velocity(stds, vals, vecs, p):
+    L = lib()
+    L.oracle_lowrank_velocity.restype = None
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    v = np.empty_like(p)
+    vecs = np.ascontiguousarray(vecs, dtype=np.float64)
+    L.oracle_lowrank_velocity(C.c_size_t(len(p)), _ptr(np.ascontiguousarray(stds)), C.c_size_t(len(vals)),
+                              _ptr(np.ascontiguousarray(vals)), _ptr(vecs), _ptr(p), _ptr(v))
+    return v
+
+
+def lowrank_momentum(stds, vals, vecs, z):
+    L = lib()
+    L.oracle_lowrank_momentum.restype = None
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    p = np.empty_like(z)
+    vecs = np.ascontiguousarray(vecs, dtype=np.float64)
+    L.oracle_lowrank_momentum(C.c_size_t(len(z)), _ptr(np.ascontiguousarray(stds)), C.c_size_t(len(vals)),
+                              _ptr(np.ascontiguousarray(vals)), _ptr(vecs), _ptr(z), _ptr(p))
+    return p
 
 
 def stat(stats: np.ndarray, name: str) -> np.ndarray:

@@ -14,7 +14,7 @@
 
 using namespace nb200;
 
-template <class M, int NIT>
+template <class M, int NIT, bool LR = false>
 static int run_all_nit(const nb200_settings* st, const typename M::Data& md, uint64_t dim,
                    uint64_t n_chains, uint64_t chain_id_offset, const double* q0,
                    const double* init_mean, const double* z_tape, double* draws, double* stats,
@@ -37,9 +37,17 @@ static int run_all_nit(const nb200_settings* st, const typename M::Data& md, uin
     P.max_draws_per_launch = max_per_launch;
     P.smem_slots = smem_slots < P.NS ? smem_slots : P.NS;
     P.var_in_smem = smem_slots > 0;
-    std::vector<double> pool((size_t)P.NS * 4 * P.Dp), var(P.Dp), wf(8 * (size_t)P.Dp);
+    std::vector<double> pool((size_t)P.NS * (LR ? 5 : 4) * P.Dp), var(P.Dp), wf(8 * (size_t)P.Dp);
     std::vector<ChainScalars> sc(n_chains);
     std::memset(sc.data(), 0, sizeof(ChainScalars) * n_chains);
+    // low-rank adaptation: one chain's metric / window / scratch (chains run one after another)
+    const uint64_t lr_f = st->mass_matrix_switch_freq > st->early_mass_matrix_switch_freq
+                              ? st->mass_matrix_switch_freq : st->early_mass_matrix_switch_freq;
+    const int lr_cap = LR ? (int)(3 * lr_f + 2) : 1;
+    const int lr_rank = LR ? (int)(st->mass_matrix_max_rank < dim ? st->mass_matrix_max_rank : dim) : 1;
+    std::vector<double> lr_stds(P.Dp), lr_vals(lr_rank), lr_vecs((size_t)lr_rank * P.Dp), lr_coef(lr_rank);
+    std::vector<double> lr_win(LR ? (size_t)lr_cap * 2 * P.Dp : 1), lr_mat(LR ? 2 * (size_t)P.D * P.Dp : 1);
+    std::vector<double> lr_cols(6 * (size_t)P.Dp);
     P.sc = sc.data();
     P.draws = draws; P.stats = stats; P.grads = grads; P.mminv = mminv;
     P.q0 = q0; P.init_mean = init_mean; P.z_tape = z_tape;
@@ -57,11 +65,17 @@ static int run_all_nit(const nb200_settings* st, const typename M::Data& md, uin
             // the shared-memory tier does not survive a launch: scramble it
             std::fill(spool.begin(), spool.end(), -777.0);
             std::fill(svar.begin(), svar.end(), -777.0);
-            ChainCtx<M, GroupSerial, NIT> ctx;
+            ChainCtx<M, GroupSerial, NIT, LR> ctx;
             std::memset((void*)&ctx, 0, sizeof(ctx));
             ctx.P = &P; ctx.md = P.mdata; ctx.sh = &sh; ctx.msm = msm.data();
             ctx.front = stage.data(); ctx.front_slot = -1; ctx.sweep_rev = false; ctx.n_parked = 0; ctx.defer_acc = false;
             std::fill(stage.begin(), stage.end(), -555.0);
+            if (LR) {
+                ctx.lr.stds = lr_stds.data(); ctx.lr.vals = lr_vals.data(); ctx.lr.vecs = lr_vecs.data();
+                ctx.lr.coef = lr_coef.data(); ctx.lr.win = lr_win.data(); ctx.lr.matL = lr_mat.data();
+                ctx.lr.matW = lr_mat.data() + (size_t)P.D * P.Dp; ctx.lr.cols = lr_cols.data();
+                ctx.lr.cap = lr_cap; ctx.lr.max_rank = lr_rank;
+            }
             ctx.D = P.D; ctx.Dp = P.Dp; ctx.NS = P.NS;
             ctx.chain_local = c;
             ctx.chain_gid = (uint32_t)(chain_id_offset + c);
@@ -81,6 +95,7 @@ static int run_all_nit(const nb200_settings* st, const typename M::Data& md, uin
 // the unrolled (NIT > 0) code paths are exercised when one thread's trip count is small
 template <class M, class... A>
 static int run_all(const nb200_settings* st, const typename M::Data& md, uint64_t dim, A... rest) {
+    if (st->adaptation == 1) return run_all_nit<M, 0, true>(st, md, dim, rest...);
     switch (dim) {
     case 1: return run_all_nit<M, 1>(st, md, dim, rest...);
     case 2: return run_all_nit<M, 2>(st, md, dim, rest...);
@@ -391,4 +406,48 @@ extern "C" int emul_sample(const nb200_settings* st, const nb200_model_desc* mod
     }
     }
     return NB200_EINVAL;
+}
+
+// the low-rank refresh + metric application of lowrank.cuh on one host thread (the twin of
+// nb200_lowrank_component): window [n][dim] -> stds, vals, vecs; v = M^-1 p, pm = M^1/2 z
+extern "C" int emul_lowrank_component(uint64_t dim, uint64_t n, const double* draws, const double* grads,
+                                      double gamma, double cutoff, uint64_t max_rank, uint64_t n_vec,
+                                      const double* p, double* v_out, const double* z, double* pm_out,
+                                      double* stds_out, double* vals_out, double* vecs_out,
+                                      uint64_t* rank_out) {
+    const int D = (int)dim, Dp = (D + 3) / 4 * 4;
+    const int R = (int)(max_rank < dim ? max_rank : dim);
+    std::vector<double> stds(Dp, 1.0), vals(R), vecs((size_t)R * Dp), coef(R), win((size_t)n * 2 * Dp),
+        mat(2 * (size_t)D * Dp), cols(6 * (size_t)Dp), pv(Dp), vv(Dp);
+    for (uint64_t j = 0; j < n; ++j)
+        for (int i = 0; i < D; ++i) {
+            win[(j * 2 + 0) * Dp + i] = draws[j * dim + i];
+            win[(j * 2 + 1) * Dp + i] = grads[j * dim + i];
+        }
+    LrState L;
+    L.stds = stds.data(); L.vals = vals.data(); L.vecs = vecs.data(); L.coef = coef.data();
+    L.win = win.data(); L.matL = mat.data(); L.matW = mat.data() + (size_t)D * Dp; L.cols = cols.data();
+    L.k = 0; L.len = (int)n; L.split = 0; L.head = 0; L.cap = (int)n; L.max_rank = R;
+    GroupSerial g;
+    g.tid = 0;
+    const bool ok = lr_update(g, L, D, Dp, gamma, cutoff);
+    for (uint64_t v = 0; v < n_vec; ++v) {
+        if (p && v_out) {
+            for (int i = 0; i < D; ++i) pv[i] = p[v * dim + i];
+            lr_velocity(g, L, D, Dp, pv.data(), vv.data());
+            for (int i = 0; i < D; ++i) v_out[v * dim + i] = vv[i];
+        }
+        if (z && pm_out) {
+            for (int i = 0; i < D; ++i) pv[i] = z[v * dim + i];
+            lr_momentum(g, L, D, Dp, pv.data());
+            for (int i = 0; i < D; ++i) pm_out[v * dim + i] = pv[i];
+        }
+    }
+    if (stds_out) for (int i = 0; i < D; ++i) stds_out[i] = stds[i];
+    if (vals_out) for (int k = 0; k < L.k; ++k) vals_out[k] = vals[k];
+    if (vecs_out)
+        for (int k = 0; k < L.k; ++k)
+            for (int i = 0; i < D; ++i) vecs_out[(size_t)k * dim + i] = vecs[(size_t)k * Dp + i];
+    if (rank_out) *rank_out = (uint64_t)L.k;
+    return ok ? 0 : 1;
 }

@@ -24,14 +24,14 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for n in names:
         assert hasattr(L, n), f"missing export {n}"
-    assert L.nb200_abi_version() == 3
+    assert L.nb200_abi_version() == 4
 
 
 def test_settings_struct_layout_matches_header():
     from nutpie_b200 import _lib
     from oracle import pyoracle as O
 
-    assert C.sizeof(_lib.Settings) == C.sizeof(O.Settings) == 232
+    assert C.sizeof(_lib.Settings) == C.sizeof(O.Settings) == 240
     assert C.sizeof(_lib.ModelDesc) == 144
     s = _lib.Settings()
     _lib.load_library().nb200_settings_default(C.byref(s))
@@ -175,7 +175,7 @@ def test_unsupported_samplers_and_adaptations_are_explicit():
     import nutpie_b200
 
     m = nutpie_b200.normal_model(2)
-    for kw in (dict(adaptation="low_rank"), dict(adaptation="flow"), dict(sampler="mclmc")):
+    for kw in (dict(adaptation="flow"), dict(sampler="mclmc")):
         with pytest.raises(NotImplementedError):
             nutpie_b200.sample(m, chains=1, draws=1, tune=1, **kw)
     with pytest.raises(ValueError):
