@@ -22,6 +22,7 @@
 // Written against the group policy G (tid / size / sync / reduce) like the rest of the core, so
 // tests/emul runs the very same code on the CPU against the oracle's dense evaluation.
 #pragma once
+#include "group.cuh"
 #include "portable.cuh"
 
 namespace nb200 {
@@ -123,39 +124,192 @@ NB_HD void lr_switch(LrState& L) {
 }
 
 // one-sided Jacobi on the columns of A [r][ld] (column-major): on return the columns are
-// mutually orthogonal, A_out = A_in J with J orthogonal.  Cyclic sweeps until no pair rotates.
-template <class G>
-NB_HD void lr_jacobi_columns(const G& g, double* A, int r, int ld) {
-    const double tol = 1e-13;  // |cos| between two columns below which they count as orthogonal
+// mutually orthogonal, A_out = A_in J with J orthogonal.  Round-robin (tournament) sweeps: a round
+// pairs every column with exactly one other, so its pairs are independent — kJacobiPairs of them
+// are rotated together (their column loads are in flight at the same time and their dot products
+// share one reduction), which is what hides the L2 / HBM latency of a single warp walking a
+// matrix that lives in global memory.  Sweeps until a whole sweep rotates nothing.
+constexpr int kJacobiPairs = 4;
+// Jacobi rotation that makes two columns with squared norms alpha, beta and inner product gam
+// orthogonal: (c, s).  Returns false when they already are (|cos| <= 1e-13); cos2 receives the
+// squared cosine.  t = tan(theta) is the smaller root of t^2 + 2 zeta t - 1 = 0 with
+// zeta = (beta - alpha) / (2 gam), written with one square root and one division.
+NB_HD bool lr_rotation(double alpha, double beta, double gam, double& c, double& s, double& cos2) {
+    const double ab = alpha * beta, g2 = gam * gam;
+    cos2 = ab > 0.0 ? g2 / ab : 0.0;
+    if (!(g2 > 1e-26 * ab)) return false;
+    const double a = beta - alpha, b = 2.0 * gam;
+    const double h = sqrt(a * a + b * b);
+    const double t = (a >= 0.0 ? b : -b) / (fabs(a) + h);
+    c = 1.0 / sqrt(1.0 + t * t);
+    s = c * t;
+    return true;
+}
+NB_HD void lr_round_robin_pair(int t, int k, int m, int& a, int& b) {
+    a = k == 0 ? m - 1 : (t + k) % (m - 1);
+    b = k == 0 ? t : (t + (m - 1) - k) % (m - 1);
+}
+#ifdef __CUDACC__
+// A warp per chain and r <= 32 NR: the columns of the kJacobiPairs pairs of a step live in
+// REGISTERS (NR rows per lane) between the dot products and the rotation — one round trip to
+// L2 / HBM per step with all its loads in flight together, instead of one per 32 rows and pass.
+// Same arithmetic in the same order as the generic loop below (bit-identical results).
+template <int NR>
+__device__ __noinline__ void lr_jacobi_warp(double* A, int r, int ld) {
+    constexpr int NP = kJacobiPairs;
+    const int lane = threadIdx.x & 31;
+    const int m = (r + 1) & ~1;
     for (int sweep = 0; sweep < 40; ++sweep) {
         int rotated = 0;
-        for (int p = 0; p < r - 1; ++p) {
-            double* ap = A + (size_t)p * ld;
-            for (int q = p + 1; q < r; ++q) {
-                double* aq = A + (size_t)q * ld;
-                double acc[3] = {0.0, 0.0, 0.0};
+        double worst = 0.0;  // largest squared cosine rotated away in this sweep
+        for (int t = 0; t < m - 1; ++t) {
+            for (int k0 = 0; k0 < m / 2; k0 += NP) {
+                double* ap[NP];
+                double* aq[NP];
+                bool on[NP];
+                double x[NP][NR], y[NP][NR];
+                double acc[3 * NP];
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    int a, b;
+                    lr_round_robin_pair(t, k0 + u, m, a, b);
+                    on[u] = k0 + u < m / 2 && a < r && b < r;
+                    if (!on[u]) a = b = 0;
+                    ap[u] = A + (size_t)a * ld;
+                    aq[u] = A + (size_t)b * ld;
+#pragma unroll
+                    for (int it = 0; it < NR; ++it) {
+                        const int i = lane + 32 * it;
+                        x[u][it] = i < r ? ap[u][i] : 0.0;
+                        y[u][it] = i < r ? aq[u][i] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                    for (int it = 0; it < NR; ++it) {
+                        s0 += x[u][it] * x[u][it];
+                        s1 += y[u][it] * y[u][it];
+                        s2 += x[u][it] * y[u][it];
+                    }
+                    acc[3 * u] = s0;
+                    acc[3 * u + 1] = s1;
+                    acc[3 * u + 2] = s2;
+                }
+                GroupCuda<1>::warp_reduce(acc);
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    double c, sn, cos2;
+                    if (on[u] && lr_rotation(acc[3 * u], acc[3 * u + 1], acc[3 * u + 2], c, sn, cos2)) {
+                        worst = cos2 > worst ? cos2 : worst;
+#pragma unroll
+                        for (int it = 0; it < NR; ++it) {
+                            const int i = lane + 32 * it;
+                            if (i < r) {
+                                ap[u][i] = c * x[u][it] - sn * y[u][it];
+                                aq[u][i] = sn * x[u][it] + c * y[u][it];
+                            }
+                        }
+                        any = true;
+                    }
+                }
+                if (any) {
+                    rotated = 1;
+                    __syncwarp();
+                }
+            }
+        }
+        // quadratic convergence: a sweep whose worst cosine was below 1e-7 leaves them below ~1e-13
+#ifdef NB200_LR_PROFILE
+        if (blockIdx.x == 0 && threadIdx.x == 0) printf("  jacobi sweep %d: worst cos^2 %.3e\n", sweep, worst);
+#endif
+        if (!rotated || worst < 1e-14) break;
+    }
+}
+#endif
+template <class G>
+NB_HD void lr_jacobi_columns(const G& g, double* A, int r, int ld) {
+    constexpr int NP = kJacobiPairs;
+    if (r < 2) return;
+#ifdef __CUDA_ARCH__
+    if constexpr (G::kThreads == 32) {
+        switch ((r + 31) / 32) {
+        case 1: lr_jacobi_warp<1>(A, r, ld); return;
+        case 2: lr_jacobi_warp<2>(A, r, ld); return;
+        case 3: lr_jacobi_warp<3>(A, r, ld); return;
+        case 4: lr_jacobi_warp<4>(A, r, ld); return;
+        case 5: case 6: lr_jacobi_warp<6>(A, r, ld); return;
+        case 7: case 8: lr_jacobi_warp<8>(A, r, ld); return;
+        default: break;  // wider matrices: the two-pass loop below
+        }
+    }
+#endif
+    const int m = (r + 1) & ~1;  // players of the tournament (an odd r gets a bye: index r)
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        int rotated = 0;
+        double worst = 0.0;  // largest squared cosine rotated away in this sweep
+        for (int t = 0; t < m - 1; ++t) {
+            for (int k0 = 0; k0 < m / 2; k0 += NP) {
+                double* ap[NP];
+                double* aq[NP];
+                bool on[NP];
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    const int k = k0 + u;
+                    int a, b;
+                    lr_round_robin_pair(t, k, m, a, b);
+                    on[u] = k < m / 2 && a < r && b < r;
+                    if (!on[u]) a = b = 0;
+                    ap[u] = A + (size_t)a * ld;
+                    aq[u] = A + (size_t)b * ld;
+                }
+                double acc[3 * NP];
+#pragma unroll
+                for (int u = 0; u < 3 * NP; ++u) acc[u] = 0.0;
                 for (int i = g.tid; i < r; i += g.size()) {
-                    const double x = ap[i], y = aq[i];
-                    acc[0] += x * x;
-                    acc[1] += y * y;
-                    acc[2] += x * y;
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        const double x = ap[u][i], y = aq[u][i];
+                        acc[3 * u] += x * x;
+                        acc[3 * u + 1] += y * y;
+                        acc[3 * u + 2] += x * y;
+                    }
                 }
                 g.reduce(acc);
-                const double gam = acc[2];
-                if (!(fabs(gam) > tol * sqrt(acc[0] * acc[1]))) continue;  // uniform: identical sums
+                double c[NP], s[NP];
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    double cos2;
+                    // (uniform over the group: the reduced sums are bit-identical on every thread)
+                    if (on[u] && lr_rotation(acc[3 * u], acc[3 * u + 1], acc[3 * u + 2], c[u], s[u], cos2)) {
+                        worst = cos2 > worst ? cos2 : worst;
+                        any = true;
+                    } else {
+                        on[u] = false;
+                        c[u] = 1.0;
+                        s[u] = 0.0;
+                    }
+                }
+                if (!any) continue;
                 rotated = 1;
-                const double zeta = (acc[1] - acc[0]) / (2.0 * gam);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
                 for (int i = g.tid; i < r; i += g.size()) {
-                    const double x = ap[i], y = aq[i];
-                    ap[i] = c * x - s * y;
-                    aq[i] = s * x + c * y;
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        if (on[u]) {
+                            const double x = ap[u][i], y = aq[u][i];
+                            ap[u][i] = c[u] * x - s[u] * y;
+                            aq[u][i] = s[u] * x + c[u] * y;
+                        }
+                    }
                 }
                 g.sync();
             }
         }
-        if (!rotated) break;
+        // quadratic convergence: a sweep whose worst cosine was below 1e-7 leaves them below ~1e-13
+        if (!rotated || worst < 1e-14) break;
     }
 }
 
@@ -187,10 +341,24 @@ NB_HD bool lr_cholesky(const G& g, double* A, int r, int ld) {
 
 // Refresh the metric from the window.  Returns false (metric unchanged) when the window is too
 // short or a factorisation breaks down.
+#if defined(NB200_LR_PROFILE) && defined(__CUDA_ARCH__)
+#define NB_LR_MARK(name)                                                                       \
+    do {                                                                                       \
+        const long long now_ = clock64();                                                      \
+        if (g.tid == 0 && blockIdx.x == 0 && threadIdx.x == 0)                                 \
+            printf("lr_update n=%d r=%d %-12s %10.3f Mcycles\n", n, r, name, (now_ - mark_) * 1e-6); \
+        mark_ = clock64();                                                                     \
+    } while (0)
+#define NB_LR_MARK_INIT() long long mark_ = clock64()
+#else
+#define NB_LR_MARK(name)
+#define NB_LR_MARK_INIT()
+#endif
 template <class G>
 NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double cutoff) {
     const int n = L.len, r = D, ld = Dp;
     if (n < 3) return false;
+    NB_LR_MARK_INIT();
     double* mx = L.cols;
     double* mg = L.cols + Dp;
     double* xs = L.cols + 2 * (size_t)Dp;
@@ -224,6 +392,7 @@ NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double
         gs[i] = s / sqrt(dn);
     }
     g.sync();
+    NB_LR_MARK("stats");
     // ---- 2. W = X~X~^T + gamma I,  Lm = G~G~^T + gamma I   (full symmetric storage)
     double* Lm = L.matL;
     double* W = L.matW;
@@ -255,8 +424,10 @@ NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double
         }
     }
     g.sync();
+    NB_LR_MARK("gram");
     // ---- 3. Lm = chol(B)
     if (!lr_cholesky(g, Lm, r, ld)) return false;
+    NB_LR_MARK("chol B");
     // ---- 4. W <- A Lm (ascending columns, in place), then W <- Lm^T W (lower triangle, in place)
     for (int c = 0; c < r; ++c) {
         for (int i = g.tid; i < r; i += g.size()) {
@@ -286,10 +457,13 @@ NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double
             g.sync();
         }
     }
+    NB_LR_MARK("L^T A L");
     // ---- 5. W = chol(M)
     if (!lr_cholesky(g, W, r, ld)) return false;
+    NB_LR_MARK("chol M");
     // ---- 6. columns of W -> U Theta^1/2
     lr_jacobi_columns(g, W, r, ld);
+    NB_LR_MARK("jacobi 1");
     // ---- 7. W <- Lm^-T (W Theta^-1/4): every thread back-substitutes whole columns
     for (int j = g.tid; j < r; j += g.size()) {
         double* wj = W + (size_t)j * ld;
@@ -304,8 +478,10 @@ NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double
         }
     }
     g.sync();
+    NB_LR_MARK("back subst");
     // ---- 8. columns of W -> W_sigma Lambda^1/2
     lr_jacobi_columns(g, W, r, ld);
+    NB_LR_MARK("jacobi 2");
     // ---- 9. keep the eigenpairs beyond the cutoff, largest |log lambda| first
     for (int j = g.tid; j < r; j += g.size()) {
         const double* wj = W + (size_t)j * ld;
@@ -343,6 +519,7 @@ NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double
         ++k;
     }
     L.k = k;
+    NB_LR_MARK("select");
     return true;
 }
 
