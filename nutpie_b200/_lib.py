@@ -611,6 +611,13 @@ class PySampler:
                 _check(L.nb200_sampler_set_z_tape(self._h, _ptr(z_tape)))
             if draws_per_launch:
                 _check(L.nb200_sampler_set_draws_per_launch(self._h, int(draws_per_launch)))
+            if trace_buffers is None:
+                # the default call: plain (pageable) result arrays, registered as the streaming
+                # target all the same — finished rows land in them while the kernel runs (through
+                # the engine's pinned staging ring, nb200_api.cu d2h_block), so that the trace is
+                # on the host when sampling ends instead of one serial copy afterwards
+                sh = self.trace_shapes()
+                trace_buffers = {"draws": np.empty(sh["draws"]), "stats": np.empty(sh["stats"])}
             self._trace_buffers = trace_buffers
             if trace_buffers is not None:  # rows are streamed into these while sampling runs
                 sh = self.trace_shapes()

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <thread>
 #include <vector>
 
@@ -30,7 +31,7 @@ int main(int argc, char** argv) {
         CK(cudaStreamCreateWithFlags(&st[d], cudaStreamNonBlocking));
     }
     printf("{\"how\": \"n devices copy 256 MB chunks device->pinned host concurrently for 2 s each\", \"points\": [");
-    for (int n = 1; n <= ndev; n *= 2) {
+    for (int n = 1; n <= ndev; n = n < 4 ? n * 2 : n + 2) {
         std::atomic<bool> go{false}, stop{false};
         std::vector<double> bytes(n, 0.0);
         std::vector<std::thread> th;
@@ -57,6 +58,46 @@ int main(int argc, char** argv) {
         printf("%s{\"gpus\": %d, \"aggregate_gbs\": %.1f, \"slowest_gpu_gbs\": %.1f}", n > 1 ? ", " : "", n,
                tot / dt / 1e9, mn / dt / 1e9);
         fflush(stdout);
+    }
+    printf("], \"host_copy\": [");
+    // what the host cores themselves sustain: T threads, each streaming 64 MB blocks src -> dst
+    // (the cost of expanding / regrouping a trace on the host instead of on the device)
+    {
+        const size_t blk = 64ull << 20;
+        const int maxT = (int)std::thread::hardware_concurrency();
+        bool first = true;
+        for (int T = 1; T <= maxT; T *= 2) {
+            std::vector<char*> src(T), dst(T);
+            for (int t = 0; t < T; ++t) {
+                src[t] = (char*)malloc(blk);
+                dst[t] = (char*)malloc(blk);
+                memset(src[t], 1, blk);
+                memset(dst[t], 2, blk);
+            }
+            std::atomic<bool> go{false}, stop{false};
+            std::vector<double> bytes(T, 0.0);
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; ++t)
+                th.emplace_back([&, t] {
+                    while (!go.load()) std::this_thread::yield();
+                    while (!stop.load()) {
+                        memcpy(dst[t], src[t], blk);
+                        bytes[t] += (double)blk;
+                    }
+                });
+            auto t0 = std::chrono::steady_clock::now();
+            go.store(true);
+            std::this_thread::sleep_for(std::chrono::milliseconds(700));
+            stop.store(true);
+            for (auto& t : th) t.join();
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            double tot = 0.0;
+            for (double b : bytes) tot += b;
+            printf("%s{\"threads\": %d, \"copied_gbs\": %.1f}", first ? "" : ", ", T, tot / dt / 1e9);
+            first = false;
+            fflush(stdout);
+            for (int t = 0; t < T; ++t) { free(src[t]); free(dst[t]); }
+        }
     }
     printf("]}\n");
     return 0;
