@@ -56,8 +56,10 @@ WORKLOAD = "radon_hierarchical_D175_1024chains_per_gpu_1000tune_1000draws"
 # DRAM bytes per gradient evaluation of nuts_kernel, from the committed `ncu --set full`
 # captures (dram__bytes_read.sum + dram__bytes_write.sum over the capture's leapfrog count):
 #   profiles/r1_radon_nuts_kernel_latest.txt   : 729.7 MB / 1 323 933 evaluations
-#   profiles/r1_config4_nuts_kernel_latest.txt : 1055.9 GB / 1 383 687 evaluations
-NCU_DRAM_BYTES_PER_EVAL = {"radon": 729.67e6 / 1323933, "config4": 1055.889e9 / 1383687}
+#   profiles/r2_config4_full_length_ncu.txt    : 6294.5 GB / 7 043 325 evaluations (the full-length
+#       launch; the 50-draw warm-up capture of round 1 gave 763 KB per evaluation — early trees
+#       are short and do fewer separate U-turn passes per leaf)
+NCU_DRAM_BYTES_PER_EVAL = {"radon": 729.67e6 / 1323933, "config4": 6294.4818e9 / 7043325}
 
 
 def _peaks():
@@ -488,7 +490,7 @@ def run_config4(device):
             "peak_source": src, "algorithmic_bytes_per_launch": 72.0 * D * steps,
             "traffic": NCU_DRAM_BYTES_PER_EVAL["config4"] * steps,
             "traffic_note": "ncu-measured DRAM bytes per gradient evaluation "
-                            "(profiles/r1_config4_nuts_kernel_latest.txt) x evaluations in this launch"}
+                            "(profiles/r2_config4_full_length_ncu.txt) x evaluations in this launch"}
 
 
 def main():
