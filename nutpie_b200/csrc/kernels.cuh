@@ -2,6 +2,9 @@
 // into kernels_<model>.cu for the built-in densities and by NVRTC at run time for
 // NB200_MODEL_CUSTOM (kernels_custom.cu amalgamates this header with the user's source).
 #pragma once
+#ifdef NB200_PIPE_PROFILE
+#include <cstdio>
+#endif
 #include "nuts_core.cuh"
 
 namespace nb200 {
@@ -120,8 +123,15 @@ __global__ void __launch_bounds__(W == 1 ? 256 : 32 * W, kernel_min_blocks<M, W,
     ctx.run();
 #ifdef NB200_PIPE_PROFILE
     if (ctx.g.tid == 0 && (chain % 257) == 0)
-        printf("chain %llu one-warp total %lld | leapfrog %lld (n %lld)\n", chain, clock64() - t_begin,
-               ctx.prof[7], ctx.prof[8]);
+        printf("chain %llu one-warp total %lld | leapfrog %lld (n %lld) = pre %lld + density %lld + post %lld | "
+               "is_turning passes %lld (n %lld)\n", chain, clock64() - t_begin, ctx.prof[7], ctx.prof[8],
+               ctx.prof[0], ctx.prof[1], ctx.prof[2], ctx.prof[4], ctx.prof[5]);
+    if constexpr (M::kHasBlockData) {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            printf("  density phases (chain 0, cumulative over launches): setup %lld walk %lld scan %lld counties %lld "
+                   "reduce %lld tail %lld\n", g_density_prof[0], g_density_prof[1], g_density_prof[2],
+                   g_density_prof[3], g_density_prof[4], g_density_prof[5]);
+    }
 #endif
 }
 

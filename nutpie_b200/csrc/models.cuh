@@ -162,6 +162,22 @@ NB_HD void nb_exp3(const G&, double a, double b, double c, double& ea, double& e
 #endif
 }
 
+#if defined(NB200_PIPE_PROFILE) && defined(__CUDACC__)
+// cycle profile of the density's phases (chain 0 of the launch only; printed by nuts_kernel)
+__device__ long long g_density_prof[8];
+#endif
+#if defined(NB200_PIPE_PROFILE) && defined(__CUDA_ARCH__)
+#define NB_DP_INIT() long long dp_mark_ = clock64(); const bool dp_on_ = blockIdx.x == 0 && threadIdx.x == 0
+#define NB_DP_MARK(i)                                             \
+    do {                                                          \
+        const long long now_ = clock64();                         \
+        if (dp_on_) g_density_prof[i] += now_ - dp_mark_;         \
+        dp_mark_ = now_;                                          \
+    } while (0)
+#else
+#define NB_DP_INIT()
+#define NB_DP_MARK(i)
+#endif
 struct RadonModel {
     static constexpr bool kElementwise = false;
     static constexpr bool kNeedsChain = false;
@@ -240,6 +256,7 @@ struct RadonModel {
         const double log_sd_b = q[2 * J + 3];
         const double log_sigma = q[2 * J + 4];
         double sd_a, sd_b, sigma;
+        NB_DP_INIT();
         nb_exp3(grp, log_sd_a, log_sd_b, log_sigma, sd_a, sd_b, sigma);
         const double inv_sigma = 1.0 / sigma;
         const double inv_s2 = inv_sigma * inv_sigma;
@@ -258,6 +275,7 @@ struct RadonModel {
             toff[T] = 0.0;
         }
         grp.sync();
+        NB_DP_MARK(0);  // exp, 1 / sigma, linear predictors
         double ss0 = 0.0, ss1 = 0.0, ss2 = 0.0, ss3 = 0.0;
         double range_sum;
         {
@@ -277,22 +295,47 @@ struct RadonModel {
             };
             // four records are loaded before they are consumed; the 0..3 left over go one by one
             int j0 = 0;
+            // `mu` is read-only during the walk, but it shares the scratch with the prefix slots the
+            // walk writes: the four predictors of a group are loaded BEFORE its first (conditional)
+            // store, or each load would wait behind the store in front of it
+            auto step_m = [&](const RadonObs& rc, double m, double& ss) {
+                const double r = rc.y - m;
+                ss += r * r;
+                pre += r;
+                if (rc.meta & 1) {  // last observation of its group: publish the prefix sum
+                    *reinterpret_cast<double*>(kp) = pre;
+                    kp += 8;
+                }
+            };
+            // (a depth-one software pipeline across groups — next group's records and predictors
+            // requested before this group's stores — measured 7 % SLOWER: more code in a loop that
+            // is bound by instruction fetch, and the first register spills; gpurun_out/r2_s29)
             for (; j0 + 4 <= d.n_steps; j0 += 4) {
                 RadonObs rec[4];
+                double m[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) rec[u] = nb_ldg_obs(ob + (size_t)(j0 + u) * T, d.in_smem);
-                step(rec[0], ss0);
-                step(rec[1], ss1);
-                step(rec[2], ss2);
-                step(rec[3], ss3);
+#ifdef NB200_OLD_OBS_WALK  // A/B baseline: predictor loads interleaved with the stores
+                step(rec[0], ss0); step(rec[1], ss1); step(rec[2], ss2); step(rec[3], ss3);
+                (void)m;
+#else
+#pragma unroll
+                for (int u = 0; u < 4; ++u) m[u] = *reinterpret_cast<const double*>(mub + (rec[u].meta & ~7));
+                step_m(rec[0], m[0], ss0);
+                step_m(rec[1], m[1], ss1);
+                step_m(rec[2], m[2], ss2);
+                step_m(rec[3], m[3], ss3);
+#endif
             }
 #pragma unroll 1  // at most three steps: not worth 100 instructions of unrolled remainder
             for (; j0 < d.n_steps; ++j0) step(nb_ldg_obs(ob + (size_t)j0 * T, d.in_smem), ss0);
             range_sum = pre;
         }
+        NB_DP_MARK(1);  // observation walk
         // global prefix = thread-local prefix + what all earlier threads summed
         toff[grp.tid] = grp.exclusive_scan(range_sum);
         grp.sync();
+        NB_DP_MARK(2);  // scan
         double acc[7] = {(ss0 + ss1) + (ss2 + ss3), 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         // kept rolled (as is the piece loop inside): the kernel is bound by instruction fetch, and
         // unrolling these two cost 660 SASS instructions for nothing (+3 % rolled, measured)
@@ -323,7 +366,9 @@ struct RadonModel {
             g[1 + c] = sd_a * E - ra;
             g[J + 3 + c] = sd_b * F - rb;
         }
+        NB_DP_MARK(3);  // county loop
         grp.reduce(acc);
+        NB_DP_MARK(4);  // reduction
         const double ssn = acc[0] * inv_s2;
         // constants: -1/2 (N + 2J + 2) log 2pi - log 10 - log 2 + 3/2 log(2/pi) - log 1.5
         const double kConst = -0.5 * NB_LOG_2PI * (double)(d.N + 2 * J + 2) - 2.3025850929940456840 -
@@ -342,6 +387,7 @@ struct RadonModel {
             g[2 * J + 3] = acc[2] - sd_b * sd_b + 1.0;
             g[2 * J + 4] = ssn - d.N - sigma * sigma * (1.0 / 2.25) + 1.0;
         }
+        NB_DP_MARK(5);  // scalar tail
         return logp;
     }
 };

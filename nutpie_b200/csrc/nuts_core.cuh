@@ -272,7 +272,19 @@ struct ChainCtx {
 #define NB_PROF_T0() const long long prof_t0_ = NB_PROF_CLK()
 #define NB_PROF_ADD(i) prof[i] += NB_PROF_CLK() - prof_t0_
 #define NB_PROF_INC(i) prof[i] += 1
+// consecutive regions of one function: MARK(i) charges the time since the previous mark to slot i
+#define NB_PROF_MARK_INIT() long long prof_mark_ = piped ? 0 : NB_PROF_CLK()
+#define NB_PROF_MARK(i)                                  \
+    do {                                                 \
+        if (!piped) {                                    \
+            const long long now_ = NB_PROF_CLK();        \
+            prof[i] += now_ - prof_mark_;                \
+            prof_mark_ = now_;                           \
+        }                                                \
+    } while (0)
 #else
+#define NB_PROF_MARK_INIT()
+#define NB_PROF_MARK(i)
 #define NB_PROF_T0()
 #define NB_PROF_ADD(i)
 #define NB_PROF_INC(i)
@@ -700,6 +712,33 @@ struct ChainCtx {
                 // half-step momenta and the mass matrix stay in registers across the
                 // density evaluation
                 double ph[NIT], vr[NIT];
+                NB_PROF_MARK_INIT();
+#ifndef NB200_OLD_LEAPFROG_LOADS
+                // every load of the pass before its first store: the front, the mass matrix and the
+                // pool slot are reached through pointers the compiler cannot tell apart, so a load
+                // placed after a store waits for it (six serialised shared-memory round trips)
+                {
+                    double q0[NIT];
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) {
+                        const int i = g.tid + it * G::kThreads;
+                        if (it + 1 < NIT || i < D) {
+                            vr[it] = var[i];
+                            ph[it] = fp[i] + heps * fg[i];
+                            q0[it] = fq[i];
+                        }
+                    }
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) {
+                        const int i = g.tid + it * G::kThreads;
+                        if (it + 1 < NIT || i < D) {
+                            const double qn = q0[it] + eps * (vr[it] * ph[it]);
+                            fq[i] = qn;
+                            qd[i] = qn;
+                        }
+                    }
+                }
+#else
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
                     const int i = g.tid + it * G::kThreads;
@@ -711,21 +750,44 @@ struct ChainCtx {
                         qd[i] = qn;
                     }
                 }
+#endif
                 g.sync();
+                NB_PROF_MARK(0);
                 lp = M::logp_grad(g, md, D, fq, fg, msm);
                 g.sync();
+                NB_PROF_MARK(1);
                 double tacc[2 + 2 * kMaxFused];
 #pragma unroll
                 for (int c = 0; c < 2 + 2 * kMaxFused; ++c) tacc[c] = 0.0;
+#ifndef NB200_OLD_LEAPFROG_LOADS
+                double gnv[NIT], pov[NIT], sov[NIT];
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
                     const int i = g.tid + it * G::kThreads;
                     if (it + 1 < NIT || i < D) {
+                        gnv[it] = fg[i];
+                        pov[it] = fp[i];
+                        sov[it] = fs[i];
+                    }
+                }
+#endif
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int i = g.tid + it * G::kThreads;
+                    if (it + 1 < NIT || i < D) {
+#ifndef NB200_OLD_LEAPFROG_LOADS
+                        const double gn = gnv[it];
+#else
                         const double gn = fg[i];
+#endif
                         const double pn = ph[it] + heps * gn;
                         const double vpn = vr[it] * pn;
                         acc[0] += pn * vpn;
+#ifndef NB200_OLD_LEAPFROG_LOADS
+                        const double p_old = pov[it], s_old = sov[it];
+#else
                         const double p_old = fp[i], s_old = fs[i];
+#endif
                         const double sn = restart_sum ? pn : s_old + pn;
                         if (want_l0) turn_terms(m_src, p_old, s_old, pn, sn, vr[it], vpn, tacc[0], tacc[1]);
 #pragma unroll
@@ -757,6 +819,7 @@ struct ChainCtx {
                 } else {
                     g.reduce(acc);
                 }
+                NB_PROF_MARK(2);
             } else {
                 for (int i = g.tid; i < D; i += g.size()) {
                     const double ph = fp[i] + heps * fg[i];
@@ -1469,8 +1532,12 @@ struct ChainCtx {
                             }
                             const int t_first = dir > 0 ? tL : tR;
 #pragma unroll 1
-                            for (int w = 0; w < n_pairs && !turn; ++w)
+                            for (int w = 0; w < n_pairs && !turn; ++w) {
+                                NB_PROF_MARK_INIT();
                                 turn = is_turning(w == 1 ? near_s : far_s, w == 2 ? t_first : dst);
+                                NB_PROF_MARK(4);
+                                if (!piped) NB_PROF_INC(5);
+                            }
                         }
                     }
                     const double new_ls = nb_logaddexp(s_ls, t_ls);
