@@ -372,7 +372,8 @@ def run_gpu(args):
         st_n = res.sample_stats["n_steps"].sum() + res.warmup_sample_stats["n_steps"].sum()
         default_api = {"value": float(st_n) / dt, "unit": "grad_evals/s", "ms": 1e3 * dt,
                        "what": "nutpie_b200.sample(model, chains=1024, tune=1000, draws=1000) with "
-                               "defaults on rank 0 alone: pageable result arrays, grouped Trace"}
+                               "defaults on rank 0 alone: pageable result arrays (rows streamed through the engine's pinned "
+                               "staging ring while sampling runs), grouped Trace"}
         res = None
         gc.collect()
     h2d = int(data["y"].nbytes + data["county"].nbytes + data["floor"].nbytes + DIM * 8)

@@ -123,8 +123,8 @@ NB_HD void lr_switch(LrState& L) {
     L.split = L.len;
 }
 
-// one-sided Jacobi on the columns of A [r][ld] (column-major): on return the columns are
-// mutually orthogonal, A_out = A_in J with J orthogonal.  Round-robin (tournament) sweeps: a round
+// one-sided Jacobi on the nc columns (r rows each) of A (column-major, leading dimension ld): on
+// return the columns are mutually orthogonal, A_out = A_in J with J orthogonal.  Round-robin (tournament) sweeps: a round
 // pairs every column with exactly one other, so its pairs are independent — kJacobiPairs of them
 // are rotated together (their column loads are in flight at the same time and their dot products
 // share one reduction), which is what hides the L2 / HBM latency of a single warp walking a
@@ -155,10 +155,10 @@ NB_HD void lr_round_robin_pair(int t, int k, int m, int& a, int& b) {
 // L2 / HBM per step with all its loads in flight together, instead of one per 32 rows and pass.
 // Same arithmetic in the same order as the generic loop below (bit-identical results).
 template <int NR>
-__device__ __noinline__ void lr_jacobi_warp(double* A, int r, int ld) {
+__device__ __noinline__ void lr_jacobi_warp(double* A, int r, int nc, int ld) {
     constexpr int NP = kJacobiPairs;
     const int lane = threadIdx.x & 31;
-    const int m = (r + 1) & ~1;
+    const int m = (nc + 1) & ~1;
     for (int sweep = 0; sweep < 40; ++sweep) {
         int rotated = 0;
         double worst = 0.0;  // largest squared cosine rotated away in this sweep
@@ -173,7 +173,7 @@ __device__ __noinline__ void lr_jacobi_warp(double* A, int r, int ld) {
                 for (int u = 0; u < NP; ++u) {
                     int a, b;
                     lr_round_robin_pair(t, k0 + u, m, a, b);
-                    on[u] = k0 + u < m / 2 && a < r && b < r;
+                    on[u] = k0 + u < m / 2 && a < nc && b < nc;
                     if (!on[u]) a = b = 0;
                     ap[u] = A + (size_t)a * ld;
                     aq[u] = A + (size_t)b * ld;
@@ -230,23 +230,23 @@ __device__ __noinline__ void lr_jacobi_warp(double* A, int r, int ld) {
 }
 #endif
 template <class G>
-NB_HD void lr_jacobi_columns(const G& g, double* A, int r, int ld) {
+NB_HD void lr_jacobi_columns(const G& g, double* A, int r, int nc, int ld) {
     constexpr int NP = kJacobiPairs;
-    if (r < 2) return;
+    if (nc < 2) return;
 #ifdef __CUDA_ARCH__
     if constexpr (G::kThreads == 32) {
         switch ((r + 31) / 32) {
-        case 1: lr_jacobi_warp<1>(A, r, ld); return;
-        case 2: lr_jacobi_warp<2>(A, r, ld); return;
-        case 3: lr_jacobi_warp<3>(A, r, ld); return;
-        case 4: lr_jacobi_warp<4>(A, r, ld); return;
-        case 5: case 6: lr_jacobi_warp<6>(A, r, ld); return;
-        case 7: case 8: lr_jacobi_warp<8>(A, r, ld); return;
+        case 1: lr_jacobi_warp<1>(A, r, nc, ld); return;
+        case 2: lr_jacobi_warp<2>(A, r, nc, ld); return;
+        case 3: lr_jacobi_warp<3>(A, r, nc, ld); return;
+        case 4: lr_jacobi_warp<4>(A, r, nc, ld); return;
+        case 5: case 6: lr_jacobi_warp<6>(A, r, nc, ld); return;
+        case 7: case 8: lr_jacobi_warp<8>(A, r, nc, ld); return;
         default: break;  // wider matrices: the two-pass loop below
         }
     }
 #endif
-    const int m = (r + 1) & ~1;  // players of the tournament (an odd r gets a bye: index r)
+    const int m = (nc + 1) & ~1;  // players of the tournament (an odd count gets a bye: index nc)
     for (int sweep = 0; sweep < 40; ++sweep) {
         int rotated = 0;
         double worst = 0.0;  // largest squared cosine rotated away in this sweep
@@ -260,7 +260,7 @@ NB_HD void lr_jacobi_columns(const G& g, double* A, int r, int ld) {
                     const int k = k0 + u;
                     int a, b;
                     lr_round_robin_pair(t, k, m, a, b);
-                    on[u] = k < m / 2 && a < r && b < r;
+                    on[u] = k < m / 2 && a < nc && b < nc;
                     if (!on[u]) a = b = 0;
                     ap[u] = A + (size_t)a * ld;
                     aq[u] = A + (size_t)b * ld;
@@ -354,10 +354,79 @@ NB_HD bool lr_cholesky(const G& g, double* A, int r, int ld) {
 #define NB_LR_MARK(name)
 #define NB_LR_MARK_INIT()
 #endif
+// Sigma = A # B^-1 for SPD A (in W) and B (in Lm), both [r][ld] column-major, through Cholesky
+// factors; on return the columns of W are the eigenvectors of Sigma scaled by the square roots of
+// their eigenvalues (so lambda_j = |column j|^2).  Lm and W are destroyed.  False on breakdown.
+template <class G>
+NB_HD bool lr_geometric_mean_eig(const G& g, double* Lm, double* W, int r, int ld) {
+    // Lm = chol(B)
+    if (!lr_cholesky(g, Lm, r, ld)) return false;
+    // W <- A Lm (ascending columns, in place), then W <- Lm^T W (lower triangle, in place)
+    for (int c = 0; c < r; ++c) {
+        for (int i = g.tid; i < r; i += g.size()) {
+            double t = 0.0;
+            for (int k = c; k < r; ++k) t += W[(size_t)k * ld + i] * Lm[(size_t)c * ld + k];
+            W[(size_t)c * ld + i] = t;
+        }
+    }
+    g.sync();
+    for (int j = 0; j < r; ++j) {
+        double* wj = W + (size_t)j * ld;
+        for (int i0 = j; i0 < r; i0 += 8) {
+            double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int k = i0 + g.tid; k < r; k += g.size()) {
+                const double t = wj[k];
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    if (i0 + m < r && k >= i0 + m) acc[m] += Lm[(size_t)(i0 + m) * ld + k] * t;
+            }
+            g.reduce(acc);
+            g.sync();  // every thread has read column j before its head is overwritten
+            if (g.tid == 0) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    if (i0 + m < r) wj[i0 + m] = acc[m];
+            }
+            g.sync();
+        }
+    }
+    // W = chol(M), M = Lm^T A Lm
+    if (!lr_cholesky(g, W, r, ld)) return false;
+    // columns of W -> U Theta^1/2
+    lr_jacobi_columns(g, W, r, r, ld);
+    // W <- Lm^-T (W Theta^-1/4): every thread back-substitutes whole columns
+    for (int j = g.tid; j < r; j += g.size()) {
+        double* wj = W + (size_t)j * ld;
+        double th = 0.0;
+        for (int i = 0; i < r; ++i) th += wj[i] * wj[i];
+        const double sc = th > 0.0 ? 1.0 / sqrt(sqrt(th)) : 0.0;
+        for (int i = r - 1; i >= 0; --i) {
+            double t = wj[i] * sc;
+            const double* li = Lm + (size_t)i * ld;
+            for (int k = i + 1; k < r; ++k) t -= li[k] * wj[k];
+            wj[i] = t / li[i];
+        }
+    }
+    g.sync();
+    // columns of W -> W_sigma Lambda^1/2
+    lr_jacobi_columns(g, W, r, r, ld);
+    return true;
+}
+
+// Refresh the metric from the window.  Returns false (metric unchanged) when the window is too
+// short or a factorisation breaks down.
+//   * D <= 10 n / 3: the matrices are formed in the full space (r = D).
+//   * fewer draws: both covariances are gamma I outside the span of the 2 n window vectors and
+//     Sigma is the identity there (eigenvalue 1, never kept), so the estimate is taken in that
+//     span — an orthonormal basis Q [D x r], r <= 2 n, from a one-sided Jacobi run on the window
+//     vectors themselves, the r x r problem in Q's coordinates, eigenvectors mapped back through
+//     Q (what nuts-rs does with thin SVDs and a pivoted QR).  The early windows hold 10-20 draws:
+//     the refresh is then a 40 x 40 problem instead of a D x D one.
 template <class G>
 NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double cutoff) {
-    const int n = L.len, r = D, ld = Dp;
+    const int n = L.len;
     if (n < 3) return false;
+    int r = D, ld = Dp;          // size / leading dimension of the eigenproblem
     NB_LR_MARK_INIT();
     double* mx = L.cols;
     double* mg = L.cols + Dp;
@@ -366,7 +435,7 @@ NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double
     double* key = L.cols + 4 * (size_t)Dp;
     double* lam = L.cols + 5 * (size_t)Dp;
     const double dn = (double)n;
-    // ---- 1. per-dimension means, scales: stds_i = sqrt(sd(x_i) / sd(g_i))
+    // ---- per-dimension means, scales: stds_i = sqrt(sd(x_i) / sd(g_i))
     for (int i = g.tid; i < D; i += g.size()) {
         double sx = 0.0, sg = 0.0;
         for (int j = 0; j < n; ++j) {
@@ -393,96 +462,152 @@ NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double
     }
     g.sync();
     NB_LR_MARK("stats");
-    // ---- 2. W = X~X~^T + gamma I,  Lm = G~G~^T + gamma I   (full symmetric storage)
-    double* Lm = L.matL;
-    double* W = L.matW;
-    for (int a0 = 0; a0 < r; a0 += g.size()) {
-        const int a = a0 + g.tid;
-        const bool live = a < r;
-        const double mxa = live ? mx[a] : 0.0, mga = live ? mg[a] : 0.0;
-        const double xsa = live ? xs[a] : 0.0, gsa = live ? gs[a] : 0.0;
-        const int bmax = a0 + g.size() < r ? a0 + g.size() : r;  // columns b <= the chunk's last row
-        for (int b = 0; b < bmax; ++b) {
-            const double mxb = mx[b], mgb = mg[b], xsb = xs[b], gsb = gs[b];
-            double ax = 0.0, ag = 0.0;
-            if (live && b <= a) {
+    // (the subspace form must fit the two D x Dp scratch matrices: Q and the projections in one,
+    // the two small matrices in the other)
+    const bool subspace = 10 * n <= 3 * D &&
+                          (size_t)2 * n * Dp + (size_t)2 * (2 * n + 3) * n <= (size_t)D * Dp &&
+                          (size_t)2 * (2 * n + 3) * 2 * n <= (size_t)D * Dp;
+    double* Lm = L.matL;         // full space: B, then its Cholesky factor
+    double* W = L.matW;          // full space: A, ..., eigenvectors of Sigma
+    const double* Q = nullptr;   // subspace: orthonormal basis [D][Dp] (first r columns of matL)
+    if (!subspace) {
+        // ---- W = X~X~^T + gamma I,  Lm = G~G~^T + gamma I   (full symmetric storage)
+        for (int a0 = 0; a0 < r; a0 += g.size()) {
+            const int a = a0 + g.tid;
+            const bool live = a < r;
+            const double mxa = live ? mx[a] : 0.0, mga = live ? mg[a] : 0.0;
+            const double xsa = live ? xs[a] : 0.0, gsa = live ? gs[a] : 0.0;
+            const int bmax = a0 + g.size() < r ? a0 + g.size() : r;  // columns b <= the chunk's last row
+            for (int b = 0; b < bmax; ++b) {
+                const double mxb = mx[b], mgb = mg[b], xsb = xs[b], gsb = gs[b];
+                double ax = 0.0, ag = 0.0;
+                if (live && b <= a) {
+                    for (int j = 0; j < n; ++j) {
+                        const double* wq = lr_win_entry(L, Dp, j, 0);
+                        const double* wg = lr_win_entry(L, Dp, j, 1);
+                        ax += ((wq[a] - mxa) * xsa) * ((wq[b] - mxb) * xsb);
+                        ag += ((wg[a] - mga) * gsa) * ((wg[b] - mgb) * gsb);
+                    }
+                    if (a == b) {
+                        ax += gamma;
+                        ag += gamma;
+                    }
+                    W[(size_t)b * ld + a] = ax;
+                    W[(size_t)a * ld + b] = ax;
+                    Lm[(size_t)b * ld + a] = ag;
+                    Lm[(size_t)a * ld + b] = ag;
+                }
+            }
+        }
+        g.sync();
+        NB_LR_MARK("gram");
+    } else {
+        // ---- Z = [X~ G~] in matL (2 n columns of D rows); its columns orthogonalised in place
+        double* Z = L.matL;
+        const int nz = 2 * n;
+        for (int c = 0; c < nz; ++c) {
+            const double* w = lr_win_entry(L, Dp, c < n ? c : c - n, c < n ? 0 : 1);
+            const double* mean = c < n ? mx : mg;
+            const double* scale = c < n ? xs : gs;
+            double* zc = Z + (size_t)c * Dp;
+            for (int i = g.tid; i < D; i += g.size()) zc[i] = (w[i] - mean[i]) * scale[i];
+        }
+        g.sync();
+        lr_jacobi_columns(g, Z, D, nz, Dp);
+        // squared norms of the orthogonal columns; the ones above the noise floor are kept,
+        // normalised and packed to the front: Q
+        double smax = 0.0;
+        for (int c0 = 0; c0 < nz; c0 += 8) {
+            double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int i = g.tid; i < D; i += g.size()) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (c0 + u < nz) {
+                        const double z = Z[(size_t)(c0 + u) * Dp + i];
+                        acc[u] += z * z;
+                    }
+            }
+            g.reduce(acc);
+            g.sync();
+            if (g.tid == 0) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (c0 + u < nz) key[c0 + u] = acc[u];  // (key / lam are free until the selection)
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u < nz && acc[u] > smax) smax = acc[u];
+            g.sync();
+        }
+        if (!(smax > 0.0) || !nb_isfinite(smax)) return false;
+        r = 0;
+        for (int c = 0; c < nz; ++c) {
+            const double s2 = key[c];
+            if (!(s2 > 1e-12 * smax)) continue;  // uniform: every thread reads the same value
+            const double inv = 1.0 / sqrt(s2);
+            const double* src = Z + (size_t)c * Dp;
+            double* dst = Z + (size_t)r * Dp;  // r <= c: an earlier or the same column
+            for (int i = g.tid; i < D; i += g.size()) dst[i] = src[i] * inv;
+            ++r;
+        }
+        g.sync();
+        if (r < 1) return false;
+        Q = Z;
+        ld = (r + 3) & ~3;
+        // small matrices in matW: B_p, A_p [r][ld]; projections X_p, G_p [n][ld] behind Q in matL
+        Lm = L.matW;
+        W = L.matW + (size_t)ld * r;
+        double* Xp = L.matL + (size_t)r * Dp;
+        double* Gp = Xp + (size_t)ld * n;
+        for (int j = 0; j < n; ++j) {
+            const double* wq = lr_win_entry(L, Dp, j, 0);
+            const double* wg = lr_win_entry(L, Dp, j, 1);
+            for (int a0 = 0; a0 < r; a0 += 4) {
+                double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                for (int i = g.tid; i < D; i += g.size()) {
+                    const double x = (wq[i] - mx[i]) * xs[i], y = (wg[i] - mg[i]) * gs[i];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (a0 + u < r) {
+                            const double q = Q[(size_t)(a0 + u) * Dp + i];
+                            acc[u] += q * x;
+                            acc[4 + u] += q * y;
+                        }
+                }
+                g.reduce(acc);
+                if (g.tid == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (a0 + u < r) {
+                            Xp[(size_t)j * ld + a0 + u] = acc[u];
+                            Gp[(size_t)j * ld + a0 + u] = acc[4 + u];
+                        }
+                }
+            }
+        }
+        g.sync();
+        // A_p = X_p X_p^T + gamma I -> W,  B_p = G_p G_p^T + gamma I -> Lm
+        for (int a = g.tid; a < r; a += g.size()) {
+            for (int b = 0; b < r; ++b) {
+                double ax = 0.0, ag = 0.0;
                 for (int j = 0; j < n; ++j) {
-                    const double* wq = lr_win_entry(L, Dp, j, 0);
-                    const double* wg = lr_win_entry(L, Dp, j, 1);
-                    ax += ((wq[a] - mxa) * xsa) * ((wq[b] - mxb) * xsb);
-                    ag += ((wg[a] - mga) * gsa) * ((wg[b] - mgb) * gsb);
+                    ax += Xp[(size_t)j * ld + a] * Xp[(size_t)j * ld + b];
+                    ag += Gp[(size_t)j * ld + a] * Gp[(size_t)j * ld + b];
                 }
                 if (a == b) {
                     ax += gamma;
                     ag += gamma;
                 }
                 W[(size_t)b * ld + a] = ax;
-                W[(size_t)a * ld + b] = ax;
                 Lm[(size_t)b * ld + a] = ag;
-                Lm[(size_t)a * ld + b] = ag;
             }
         }
+        g.sync();
+        NB_LR_MARK("subspace");
     }
-    g.sync();
-    NB_LR_MARK("gram");
-    // ---- 3. Lm = chol(B)
-    if (!lr_cholesky(g, Lm, r, ld)) return false;
-    NB_LR_MARK("chol B");
-    // ---- 4. W <- A Lm (ascending columns, in place), then W <- Lm^T W (lower triangle, in place)
-    for (int c = 0; c < r; ++c) {
-        for (int i = g.tid; i < r; i += g.size()) {
-            double t = 0.0;
-            for (int k = c; k < r; ++k) t += W[(size_t)k * ld + i] * Lm[(size_t)c * ld + k];
-            W[(size_t)c * ld + i] = t;
-        }
-    }
-    g.sync();
-    for (int j = 0; j < r; ++j) {
-        double* wj = W + (size_t)j * ld;
-        for (int i0 = j; i0 < r; i0 += 8) {
-            double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            for (int k = i0 + g.tid; k < r; k += g.size()) {
-                const double t = wj[k];
-#pragma unroll
-                for (int m = 0; m < 8; ++m)
-                    if (i0 + m < r && k >= i0 + m) acc[m] += Lm[(size_t)(i0 + m) * ld + k] * t;
-            }
-            g.reduce(acc);  // (its barriers order the reads above before the writes below)
-            g.sync();
-            if (g.tid == 0) {
-#pragma unroll
-                for (int m = 0; m < 8; ++m)
-                    if (i0 + m < r) wj[i0 + m] = acc[m];
-            }
-            g.sync();
-        }
-    }
-    NB_LR_MARK("L^T A L");
-    // ---- 5. W = chol(M)
-    if (!lr_cholesky(g, W, r, ld)) return false;
-    NB_LR_MARK("chol M");
-    // ---- 6. columns of W -> U Theta^1/2
-    lr_jacobi_columns(g, W, r, ld);
-    NB_LR_MARK("jacobi 1");
-    // ---- 7. W <- Lm^-T (W Theta^-1/4): every thread back-substitutes whole columns
-    for (int j = g.tid; j < r; j += g.size()) {
-        double* wj = W + (size_t)j * ld;
-        double th = 0.0;
-        for (int i = 0; i < r; ++i) th += wj[i] * wj[i];
-        const double sc = th > 0.0 ? 1.0 / sqrt(sqrt(th)) : 0.0;
-        for (int i = r - 1; i >= 0; --i) {
-            double t = wj[i] * sc;
-            const double* li = Lm + (size_t)i * ld;
-            for (int k = i + 1; k < r; ++k) t -= li[k] * wj[k];
-            wj[i] = t / li[i];
-        }
-    }
-    g.sync();
-    NB_LR_MARK("back subst");
-    // ---- 8. columns of W -> W_sigma Lambda^1/2
-    lr_jacobi_columns(g, W, r, ld);
-    NB_LR_MARK("jacobi 2");
-    // ---- 9. keep the eigenpairs beyond the cutoff, largest |log lambda| first
+    if (!lr_geometric_mean_eig(g, Lm, W, r, ld)) return false;
+    NB_LR_MARK("eig");
+    // ---- keep the eigenpairs beyond the cutoff, largest |log lambda| first
     for (int j = g.tid; j < r; j += g.size()) {
         const double* wj = W + (size_t)j * ld;
         double l2 = 0.0;
@@ -509,7 +634,15 @@ NB_HD bool lr_update(const G& g, LrState& L, int D, int Dp, double gamma, double
         const double inv = 1.0 / sqrt(l2);
         const double* wb = W + (size_t)best * ld;
         double* vk = L.vecs + (size_t)k * Dp;
-        for (int i = g.tid; i < D; i += g.size()) vk[i] = wb[i] * inv;
+        if (Q) {  // back to the full space: v = Q w
+            for (int i = g.tid; i < D; i += g.size()) {
+                double a = 0.0;
+                for (int c = 0; c < r; ++c) a += Q[(size_t)c * Dp + i] * wb[c];
+                vk[i] = a * inv;
+            }
+        } else {
+            for (int i = g.tid; i < D; i += g.size()) vk[i] = wb[i] * inv;
+        }
         g.sync();  // everyone has read key[] before it changes
         if (g.tid == 0) {
             L.vals[k] = l2;
