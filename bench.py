@@ -283,8 +283,10 @@ def run_gpu(args):
 
     # ---- device-resident arm: samplers (model data, init state) created up front
     total = args.warmup + args.steps
+    # (trace_buffers=False: nothing is streamed to the host while this arm's kernels run)
     samplers = [_lib.PySamplerDeferred(make_settings(100 + i), model, n_chains=n_chains,
-                                       chain_id_offset=offset, device=device) for i in range(total)]
+                                       chain_id_offset=offset, device=device, trace_buffers=False)
+                for i in range(total)]
     for i in range(args.warmup):
         samplers[i].start()
         samplers[i].wait()

@@ -611,7 +611,9 @@ class PySampler:
                 _check(L.nb200_sampler_set_z_tape(self._h, _ptr(z_tape)))
             if draws_per_launch:
                 _check(L.nb200_sampler_set_draws_per_launch(self._h, int(draws_per_launch)))
-            if trace_buffers is None:
+            if trace_buffers is False:  # no streaming: one copy when the trace is taken
+                trace_buffers = None
+            elif trace_buffers is None:
                 # the default call: plain (pageable) result arrays, registered as the streaming
                 # target all the same — finished rows land in them while the kernel runs (through
                 # the engine's pinned staging ring, nb200_api.cu d2h_block), so that the trace is
