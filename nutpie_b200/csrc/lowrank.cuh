@@ -130,24 +130,40 @@ NB_HD void lr_switch(LrState& L) {
 // share one reduction), which is what hides the L2 / HBM latency of a single warp walking a
 // matrix that lives in global memory.  Sweeps until a whole sweep rotates nothing.
 constexpr int kJacobiPairs = 4;
+NB_HD double nb_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 // Jacobi rotation that makes two columns with squared norms alpha, beta and inner product gam
-// orthogonal: (c, s).  Returns false when they already are (|cos| <= 1e-13); cos2 receives the
-// squared cosine.  t = tan(theta) is the smaller root of t^2 + 2 zeta t - 1 = 0 with
-// zeta = (beta - alpha) / (2 gam), written with one square root and one division.
-NB_HD bool lr_rotation(double alpha, double beta, double gam, double& c, double& s, double& cos2) {
+// orthogonal: (c, s).  Returns false when they already are (|cos| <= 1e-13); `coarse` is set when
+// the cosine was above 1e-7 (another sweep is needed after this one).  t = tan(theta) is the
+// smaller root of t^2 + 2 zeta t - 1 = 0, zeta = (beta - alpha) / (2 gam), written on reciprocal
+// square roots only: an IEEE division or square root is ~30 dependent instructions in fp64, and
+// the four rotations of a step are most of its scalar work.
+NB_HD bool lr_rotation(double alpha, double beta, double gam, double& c, double& s, bool& coarse) {
     const double ab = alpha * beta, g2 = gam * gam;
-    cos2 = ab > 0.0 ? g2 / ab : 0.0;
     if (!(g2 > 1e-26 * ab)) return false;
+    coarse = coarse || g2 > 1e-14 * ab;
     const double a = beta - alpha, b = 2.0 * gam;
-    const double h = sqrt(a * a + b * b);
-    const double t = (a >= 0.0 ? b : -b) / (fabs(a) + h);
-    c = 1.0 / sqrt(1.0 + t * t);
+    const double d = a * a + b * b;
+    const double h = d * nb_rsqrt(d);           // sqrt(a^2 + b^2) > 0
+    const double rd = nb_rsqrt(fabs(a) + h);
+    const double t = (a >= 0.0 ? b : -b) * (rd * rd);
+    c = nb_rsqrt(1.0 + t * t);
     s = c * t;
     return true;
 }
+// pair k of round t in a tournament of m players (circle method; t < m - 1, k < m / 2)
 NB_HD void lr_round_robin_pair(int t, int k, int m, int& a, int& b) {
-    a = k == 0 ? m - 1 : (t + k) % (m - 1);
-    b = k == 0 ? t : (t + (m - 1) - k) % (m - 1);
+    const int w = m - 1;  // t + k and t - k + w are below 2 w: one conditional subtraction each
+    int x = t + k, y = t + w - k;
+    x = x >= w ? x - w : x;
+    y = y >= w ? y - w : y;
+    a = k == 0 ? w : x;
+    b = k == 0 ? t : y;
 }
 #ifdef __CUDACC__
 // A warp per chain and r <= 32 NR: the columns of the kJacobiPairs pairs of a step live in
@@ -161,7 +177,7 @@ __device__ __noinline__ void lr_jacobi_warp(double* A, int r, int nc, int ld) {
     const int m = (nc + 1) & ~1;
     for (int sweep = 0; sweep < 40; ++sweep) {
         int rotated = 0;
-        double worst = 0.0;  // largest squared cosine rotated away in this sweep
+        bool coarse = false;  // a cosine above 1e-7 was rotated away in this sweep
         for (int t = 0; t < m - 1; ++t) {
             for (int k0 = 0; k0 < m / 2; k0 += NP) {
                 double* ap[NP];
@@ -201,9 +217,8 @@ __device__ __noinline__ void lr_jacobi_warp(double* A, int r, int nc, int ld) {
                 bool any = false;
 #pragma unroll
                 for (int u = 0; u < NP; ++u) {
-                    double c, sn, cos2;
-                    if (on[u] && lr_rotation(acc[3 * u], acc[3 * u + 1], acc[3 * u + 2], c, sn, cos2)) {
-                        worst = cos2 > worst ? cos2 : worst;
+                    double c, sn;
+                    if (on[u] && lr_rotation(acc[3 * u], acc[3 * u + 1], acc[3 * u + 2], c, sn, coarse)) {
 #pragma unroll
                         for (int it = 0; it < NR; ++it) {
                             const int i = lane + 32 * it;
@@ -223,9 +238,9 @@ __device__ __noinline__ void lr_jacobi_warp(double* A, int r, int nc, int ld) {
         }
         // quadratic convergence: a sweep whose worst cosine was below 1e-7 leaves them below ~1e-13
 #ifdef NB200_LR_PROFILE
-        if (blockIdx.x == 0 && threadIdx.x == 0) printf("  jacobi sweep %d: worst cos^2 %.3e\n", sweep, worst);
+        if (blockIdx.x == 0 && threadIdx.x == 0) printf("  jacobi sweep %d: coarse %d\n", sweep, (int)coarse);
 #endif
-        if (!rotated || worst < 1e-14) break;
+        if (!rotated || !coarse) break;
     }
 }
 #endif
@@ -249,7 +264,7 @@ NB_HD void lr_jacobi_columns(const G& g, double* A, int r, int nc, int ld) {
     const int m = (nc + 1) & ~1;  // players of the tournament (an odd count gets a bye: index nc)
     for (int sweep = 0; sweep < 40; ++sweep) {
         int rotated = 0;
-        double worst = 0.0;  // largest squared cosine rotated away in this sweep
+        bool coarse = false;  // a cosine above 1e-7 was rotated away in this sweep
         for (int t = 0; t < m - 1; ++t) {
             for (int k0 = 0; k0 < m / 2; k0 += NP) {
                 double* ap[NP];
@@ -282,10 +297,8 @@ NB_HD void lr_jacobi_columns(const G& g, double* A, int r, int nc, int ld) {
                 bool any = false;
 #pragma unroll
                 for (int u = 0; u < NP; ++u) {
-                    double cos2;
                     // (uniform over the group: the reduced sums are bit-identical on every thread)
-                    if (on[u] && lr_rotation(acc[3 * u], acc[3 * u + 1], acc[3 * u + 2], c[u], s[u], cos2)) {
-                        worst = cos2 > worst ? cos2 : worst;
+                    if (on[u] && lr_rotation(acc[3 * u], acc[3 * u + 1], acc[3 * u + 2], c[u], s[u], coarse)) {
                         any = true;
                     } else {
                         on[u] = false;
@@ -309,7 +322,7 @@ NB_HD void lr_jacobi_columns(const G& g, double* A, int r, int nc, int ld) {
             }
         }
         // quadratic convergence: a sweep whose worst cosine was below 1e-7 leaves them below ~1e-13
-        if (!rotated || worst < 1e-14) break;
+        if (!rotated || !coarse) break;
     }
 }
 
