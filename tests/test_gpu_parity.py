@@ -682,3 +682,19 @@ def test_store_divergences_rows_match_oracle(radon_data):
                              store_divergences=True, progress_bar=False)
     for name in _lib.DIVERGENCE_COLUMNS:
         assert res.sample_stats[name].shape == (4, 40, 37)
+
+
+def test_trace_lands_identically_through_every_host_path(radon_data):
+    """The trace of one job through the three device -> host paths of nb200_api.cu: rows streamed
+    into pageable arrays (the default: pinned staging ring + parallel host copies, several chunks
+    per block), rows streamed into caller-provided pinned buffers (direct DMA), and one copy
+    when the trace is taken (trace_buffers=False; an 80 MB block = two staging chunks)."""
+    gm, _ = models(radon_data)["radon"]
+    mk = lambda: settings_pair(seed=41, num_tune=150, num_draws=150, init_radius=1.0)[0]
+    default = run_gpu(mk(), gm, 192)
+    single = run_gpu(mk(), gm, 192, trace_buffers=False)
+    pd_, ps_ = _lib.PinnedArray((300, 192, 175)), _lib.PinnedArray((300, 192, _lib.NSTAT))
+    pinned = run_gpu(mk(), gm, 192, trace_buffers={"draws": pd_.array, "stats": ps_.array})
+    assert default.draws.shape == (192, 300, 175) and np.isfinite(default.draws).all()
+    for other in (single, pinned):
+        assert np.array_equal(other.draws, default.draws) and np.array_equal(other.stats, default.stats)
