@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sys/mman.h>
 #include <thread>
 #include <vector>
 
@@ -27,10 +28,19 @@ int main(int argc, char** argv) {
         CK(cudaSetDevice(d));
         CK(cudaMalloc(&dsrc[d], chunk));
         CK(cudaMemset(dsrc[d], 1, chunk));
-        CK(cudaHostAlloc(&hdst[d], chunk * ring, cudaHostAllocDefault));
+        if (argc > 2 && !strcmp(argv[2], "huge")) {
+            // destination in transparent huge pages, pinned by registration: does the page size
+            // of the host buffer change what the box's DMA path sustains?
+            if (posix_memalign(&hdst[d], 2u << 20, chunk * ring)) { printf("posix_memalign failed\n"); return 1; }
+            madvise(hdst[d], chunk * ring, MADV_HUGEPAGE);
+            memset(hdst[d], 0, chunk * ring);
+            CK(cudaHostRegister(hdst[d], chunk * ring, cudaHostRegisterPortable));
+        } else {
+            CK(cudaHostAlloc(&hdst[d], chunk * ring, cudaHostAllocDefault));
+        }
         CK(cudaStreamCreateWithFlags(&st[d], cudaStreamNonBlocking));
     }
-    printf("{\"how\": \"n devices copy 256 MB chunks device->pinned host concurrently for 2 s each\", \"points\": [");
+    printf("{\"buffers\": \"%s\", \"how\": \"n devices copy 256 MB chunks device->pinned host concurrently for 2 s each\", \"points\": [", argc > 2 ? argv[2] : "cudaHostAlloc");
     for (int n = 1; n <= ndev; n = n < 4 ? n * 2 : n + 2) {
         std::atomic<bool> go{false}, stop{false};
         std::vector<double> bytes(n, 0.0);
