@@ -203,6 +203,19 @@ static __device__ __noinline__ double2 nb_flush_parked(double de, unsigned n, do
 }
 #endif
 
+#ifdef __CUDACC__
+// The uniforms of a transition's merges (Philox keyed by the merge's sequence number) do not
+// depend on anything the transition computes: lane k draws the one for merge base + k, so a warp
+// runs the generator once per 32 merges instead of once per merge (ChainCtx::merge_uniform).
+// Out of line: it runs rarely and its 80 instructions stay out of the hot loop.
+static __device__ __noinline__ double nb_refill_merge_uniforms(uint64_t seed, uint32_t chain, uint32_t draw,
+                                                               uint32_t base) {
+    uint64_t a, b;
+    rng_u64x2(seed, chain, draw, RNG_MERGE, base + (threadIdx.x & 31u), a, b);
+    return rng_u01(a);
+}
+#endif
+
 // NIT > 0: every per-dimension loop runs exactly NIT predicated iterations
 // (NIT * group size >= D), fully unrolled so independent loads overlap;
 // NIT == 0: run-time trip count (any D).
@@ -246,6 +259,8 @@ struct ChainCtx {
     double de_parked;
     unsigned n_parked;
     bool defer_acc;
+    double u_parked;   // merge uniforms drawn ahead, one per lane (warp-per-chain geometry)
+    uint32_t u_base;   // u_parked of lane k belongs to merge u_base + k
     bool l0_turn;          // U-turn verdict between src and the new leaf, fused into the leapfrog
     unsigned fused_bits;   // verdicts of the other pairs planned for this leapfrog (bit c = plist[c])
     // tree bookkeeping (slot ids; -1 = none)
@@ -1389,11 +1404,28 @@ struct ChainCtx {
     }
 #endif
 
+    // uniform for merge number n_merge of draw t (same value as drawing it on the spot)
+    NB_HD double merge_uniform(uint32_t t) {
+#ifdef __CUDA_ARCH__
+        if constexpr (G::kThreads == 32) {
+            if (n_merge - u_base >= 32u) {
+                u_base = n_merge;
+                u_parked = nb_refill_merge_uniforms(st().seed, chain_gid, t, u_base);
+            }
+            return __shfl_sync(0xffffffffu, u_parked, (int)(n_merge - u_base));
+        }
+#endif
+        uint64_t ra, rb;
+        rng_u64x2(st().seed, chain_gid, t, RNG_MERGE, n_merge, ra, rb);
+        return rng_u01(ra);
+    }
+
     // ------------------------------------------------------------- transition
     template <bool PIPED = false>
     NB_HD int transition(int cur, uint32_t t, SampleInfo& info) {
         draw = t;
         n_merge = 0;
+        u_base = 0x80000000u;  // nothing drawn ahead yet
         acc_sum = acc_sym = 0.0;
         acc_count = 0;
         n_parked = 0;
@@ -1541,9 +1573,8 @@ struct ChainCtx {
                         }
                     }
                     const double new_ls = nb_logaddexp(s_ls, t_ls);
-                    rng_u64x2(st().seed, chain_gid, t, RNG_MERGE, n_merge, ra, rb);
+                    const double u = merge_uniform(t);
                     n_merge += 1;
-                    const double u = rng_u01(ra);
                     // multinomial pick inside a sub-tree, biased progressive for the main tree
                     const double ref_ls = with_main ? s_ls : new_ls;
                     const bool take_new = t_ls >= ref_ls || u < exp(t_ls - ref_ls);
