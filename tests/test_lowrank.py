@@ -437,3 +437,30 @@ def test_gpu_low_rank_through_the_reference_plugin_abi(radon_data):
     for name in ("intercept", "sigma"):
         xa, xb = a.posterior[name], b.posterior[name]
         assert abs(xa.mean() - xb.mean()) < 0.5 * xb.std(), name
+
+
+@pytest.mark.gpu
+def test_gpu_deprecated_keywords_and_extra_stats_like_the_reference_tests(radon_data):
+    """/root/reference/tests/test_pymc.py:150-173 (deprecated `low_rank_modified_mass_matrix` /
+    `use_grad_based_mass_matrix` still work and warn) and :305-327 (all four store_* flags at once)."""
+    import nutpie_b200
+
+    m = nutpie_b200.normal_model(1)
+    with pytest.warns(FutureWarning, match="low_rank_modified_mass_matrix"):
+        tr = nutpie_b200.sample(m, chains=1, low_rank_modified_mass_matrix=True, progress_bar=False, seed=3)
+    assert tr.posterior["x"].shape[:2] == (1, 1000)
+    with pytest.warns(FutureWarning, match="use_grad_based_mass_matrix"):
+        tr = nutpie_b200.sample(m, chains=1, use_grad_based_mass_matrix=False, progress_bar=False, seed=3)
+    assert tr.posterior["x"].shape[:2] == (1, 1000)
+    d = radon_data
+    rm = nutpie_b200.radon_model(d["y"], d["county"], d["floor"], d["n_county"])
+    for adaptation in ("diag", "low_rank"):
+        tr = nutpie_b200.sample(rm, chains=2, tune=60, draws=40, seed=4, adaptation=adaptation, progress_bar=False,
+                                store_mass_matrix=True, store_divergences=True, store_unconstrained=True,
+                                store_gradient=True)
+        ss = tr.sample_stats
+        for name in ("gradient", "unconstrained_draw", "divergence_start", "divergence_momentum"):
+            assert ss[name].shape[:2] == (2, 40) and ss[name].shape[-1] == rm.n_dim, name
+        mm = "mass_matrix_stds" if adaptation == "low_rank" else "mass_matrix_inv"
+        assert ss[mm].shape == (2, 40, rm.n_dim) and np.isfinite(ss[mm]).all()
+        assert ("mass_matrix_eigvals" in ss) == (adaptation == "low_rank")
