@@ -12,8 +12,9 @@ namespace nb200 {
 // shared-memory front (q, p, grad, p_sum of the newest leaf) for densities that gather
 // across dimensions; elementwise densities stream straight from the pool
 template <class M>
-__host__ __device__ inline size_t stage_bytes(int Dp) {
-    return M::kElementwise ? 0 : ((4 * sizeof(double) * (size_t)Dp + 15) & ~size_t(15));
+__host__ __device__ inline size_t stage_bytes(int Dp, bool low_rank = false) {
+    // (the low-rank engine builds every leaf on the front, whatever the density)
+    return (M::kElementwise && !low_rank) ? 0 : ((4 * sizeof(double) * (size_t)Dp + 15) & ~size_t(15));
 }
 
 template <class M, int W, int NIT, class G = GroupCuda<W>, bool LR = false>
@@ -48,7 +49,7 @@ __device__ __forceinline__ void setup_ctx(ChainCtx<M, G, NIT, LR>& ctx, const KP
     }
     ctx.front = reinterpret_cast<double*>(smem_chain + off);
     ctx.front_slot = -1;
-    off += stage_bytes<M>(P.Dp);
+    off += stage_bytes<M>(P.Dp, LR);
     double* svar = reinterpret_cast<double*>(smem_chain + off);
     if (P.var_in_smem) off += (sizeof(double) * P.Dp + 15) & ~size_t(15);
     ctx.spool = reinterpret_cast<double*>(smem_chain + off);

@@ -515,7 +515,10 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
         hd.rcbox = s->host->d_rcbox; hd.req = s->host->d_req; hd.resp = s->host->d_resp;
         hd.stop = s->host->d_stop; hd.chain = 0; hd.Dp = s->Dp;
     }
-    const size_t fixed = smem_for<M>(s->W, P.mdata, s->Dp);
+    // (low rank: every leaf is built on a shared-memory front of four vectors, also for the
+    // elementwise densities that stream straight from the pool under the diagonal metric)
+    const size_t fixed = smem_for<M>(s->W, P.mdata, s->Dp) +
+                         ((s->lr && M::kElementwise) ? align16(4 * sizeof(double) * (size_t)s->Dp) : 0);
     size_t bdata = 0;
     if (s->W == 1) {
         int c = g_chains_per_block.load();

@@ -916,9 +916,11 @@ struct ChainCtx {
     // ------------------------------------------------ low-rank metric (lowrank.cuh)
     // One leapfrog under M^-1 = S (I + V (L - I) V^T) S.  The velocity needs a contraction over
     // ALL dimensions between the momentum half step and the position step, so the pass cannot be
-    // fused like the diagonal one: five short passes over the slot's vectors in global memory /
-    // L2 (the state pool has no shared-memory tier here) and two k x D contractions with V.  The
-    // velocity of every state is kept in the slot (VV): the U-turn criterion projects on it.
+    // fused like the diagonal one.  The leaf under construction lives in the shared-memory front
+    // (q, p, grad, velocity): the source state is read from its pool slot once, the short passes
+    // and the two k x D contractions with V (streamed from L2) work on shared memory, and the new
+    // state is only STORED to its slot — nothing waits on a global round trip between the passes.
+    // The velocity of every state is kept in the slot (VV): the U-turn criterion projects on it.
     NB_HD int leapfrog_lr(int src, int dst, int dir) {
         const double eps = (double)dir * step_size;
         const double heps = 0.5 * eps;
@@ -931,23 +933,57 @@ struct ChainCtx {
         double* gd = gvec(dst, VG);
         double* sd = gvec(dst, VS);
         double* vd = gvec(dst, VV);
+        double* fq = front;
+        double* fp = front + (size_t)Dp;
+        double* fg = front + 2 * (size_t)Dp;
+        double* fv = front + 3 * (size_t)Dp;
+        front_slot = -1;  // the front is this function's scratch, not a mirror of a slot
         const int new_idx = sh->idx[src] + dir;
         const bool restart_sum = new_idx == -1;
-        for (int i = g.tid; i < D; i += g.size()) pd[i] = ps[i] + heps * gs[i];
+        for (int i = g.tid; i < D; i += g.size()) {
+            fp[i] = ps[i] + heps * gs[i];
+            fq[i] = qs[i];
+        }
         g.sync();
-        lr_velocity(g, lr, D, Dp, pd, vd);
-        for (int i = g.tid; i < D; i += g.size()) qd[i] = qs[i] + eps * vd[i];
+        lr_velocity(g, lr, D, Dp, fp, fv);
+        for (int i = g.tid; i < D; i += g.size()) {
+            const double qn = fq[i] + eps * fv[i];
+            fq[i] = qn;
+            qd[i] = qn;
+        }
         g.sync();
-        bool bad;
-        const double lp = eval_logp(dst, bad);
+        double lp;
+        double flag[2] = {0.0, 0.0};
+        if constexpr (M::kElementwise) {
+            for (int i = g.tid; i < D; i += g.size()) {
+                double gn;
+                flag[1] += M::term(md, i, fq[i], gn);
+                fg[i] = gn;
+                if (!nb_isfinite(gn)) flag[0] += 1.0;
+            }
+            g.reduce(flag);
+            lp = M::finish(md, flag[1], D);
+        } else {
+            lp = M::logp_grad(g, md, D, fq, fg, msm);
+            g.sync();
+            for (int i = g.tid; i < D; i += g.size())
+                if (!nb_isfinite(fg[i])) flag[0] += 1.0;
+            g.reduce(flag);
+        }
+        const bool bad = flag[0] > 0.0;
+        for (int i = g.tid; i < D; i += g.size()) {
+            const double gn = fg[i];
+            fp[i] = fp[i] + heps * gn;
+            gd[i] = gn;
+        }
         g.sync();
-        for (int i = g.tid; i < D; i += g.size()) pd[i] = pd[i] + heps * gd[i];
-        g.sync();
-        lr_velocity(g, lr, D, Dp, pd, vd);
+        lr_velocity(g, lr, D, Dp, fp, fv);
         double acc[1] = {0.0};
         for (int i = g.tid; i < D; i += g.size()) {
-            const double pn = pd[i];
-            acc[0] += pn * vd[i];
+            const double pn = fp[i], vn = fv[i];
+            acc[0] += pn * vn;
+            pd[i] = pn;
+            vd[i] = vn;
             sd[i] = restart_sum ? pn : ss[i] + pn;
         }
         g.reduce(acc);
