@@ -451,3 +451,8 @@ extern "C" int emul_lowrank_component(uint64_t dim, uint64_t n, const double* dr
     if (rank_out) *rank_out = (uint64_t)L.k;
     return ok ? 0 : 1;
 }
+
+// the tournament schedule of the one-sided Jacobi (lowrank.cuh): pairs of round t, for tests
+extern "C" void emul_round_robin_pairs(int m, int t, int* a_out, int* b_out) {
+    for (int k = 0; k < m / 2; ++k) lr_round_robin_pair(t, k, m, a_out[k], b_out[k]);
+}

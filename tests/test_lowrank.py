@@ -135,6 +135,20 @@ def test_oracle_window_without_spread_keeps_the_previous_scale():
     assert stds[2] == 3.5 and np.all(np.isfinite(stds)) and np.all(np.isfinite(vals))
 
 
+def test_jacobi_tournament_pairs_every_two_columns_exactly_once():
+    """lr_round_robin_pair: m - 1 rounds of m / 2 disjoint pairs cover all m (m - 1) / 2 pairs."""
+    L = E.lib()
+    for m in (2, 4, 6, 12, 38, 176):
+        seen = set()
+        for t in range(m - 1):
+            a, b = (C.c_int * (m // 2))(), (C.c_int * (m // 2))()
+            L.emul_round_robin_pairs(C.c_int(m), C.c_int(t), a, b)
+            cols = list(a) + list(b)
+            assert sorted(cols) == list(range(m)), (m, t)  # a round touches every column once
+            seen |= {frozenset(p) for p in zip(a, b)}
+        assert len(seen) == m * (m - 1) // 2
+
+
 # ------------------------------------------------- the engine's route on the host (tests/emul)
 # (the last three take the engine's SUBSPACE route: fewer than 0.3 dim draws)
 @pytest.mark.parametrize("dim,n,gamma", [(13, 11, 1e-5), (13, 40, 1e-5), (30, 20, 1e-5), (30, 20, 1e-3),
@@ -252,7 +266,8 @@ def test_oracle_low_rank_shortens_trajectories_on_a_correlated_posterior():
 
 # ----------------------------------------------------------------------------- GPU (-m gpu)
 @pytest.mark.gpu
-@pytest.mark.parametrize("dim,n", [(13, 11), (30, 20), (64, 200), (175, 90), (64, 12), (175, 20), (175, 50)])
+# (300: more than 256 rows — the two-pass Jacobi loop instead of the register-resident one)
+@pytest.mark.parametrize("dim,n", [(13, 11), (30, 20), (64, 200), (175, 90), (64, 12), (175, 20), (175, 50), (300, 100)])
 def test_gpu_refresh_matches_its_host_emulation_and_the_oracle(dim, n):
     from nutpie_b200 import _lib
 
