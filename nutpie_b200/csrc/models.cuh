@@ -315,17 +315,12 @@ struct RadonModel {
                 double m[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) rec[u] = nb_ldg_obs(ob + (size_t)(j0 + u) * T, d.in_smem);
-#ifdef NB200_OLD_OBS_WALK  // A/B baseline: predictor loads interleaved with the stores
-                step(rec[0], ss0); step(rec[1], ss1); step(rec[2], ss2); step(rec[3], ss3);
-                (void)m;
-#else
 #pragma unroll
                 for (int u = 0; u < 4; ++u) m[u] = *reinterpret_cast<const double*>(mub + (rec[u].meta & ~7));
                 step_m(rec[0], m[0], ss0);
                 step_m(rec[1], m[1], ss1);
                 step_m(rec[2], m[2], ss2);
                 step_m(rec[3], m[3], ss3);
-#endif
             }
 #pragma unroll 1  // at most three steps: not worth 100 instructions of unrolled remainder
             for (; j0 < d.n_steps; ++j0) step(nb_ldg_obs(ob + (size_t)j0 * T, d.in_smem), ss0);

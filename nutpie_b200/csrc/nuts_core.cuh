@@ -728,7 +728,6 @@ struct ChainCtx {
                 // density evaluation
                 double ph[NIT], vr[NIT];
                 NB_PROF_MARK_INIT();
-#ifndef NB200_OLD_LEAPFROG_LOADS
                 // every load of the pass before its first store: the front, the mass matrix and the
                 // pool slot are reached through pointers the compiler cannot tell apart, so a load
                 // placed after a store waits for it (six serialised shared-memory round trips)
@@ -753,19 +752,6 @@ struct ChainCtx {
                         }
                     }
                 }
-#else
-#pragma unroll
-                for (int it = 0; it < NIT; ++it) {
-                    const int i = g.tid + it * G::kThreads;
-                    if (it + 1 < NIT || i < D) {
-                        vr[it] = var[i];
-                        ph[it] = fp[i] + heps * fg[i];
-                        const double qn = fq[i] + eps * (vr[it] * ph[it]);
-                        fq[i] = qn;
-                        qd[i] = qn;
-                    }
-                }
-#endif
                 g.sync();
                 NB_PROF_MARK(0);
                 lp = M::logp_grad(g, md, D, fq, fg, msm);
@@ -774,7 +760,6 @@ struct ChainCtx {
                 double tacc[2 + 2 * kMaxFused];
 #pragma unroll
                 for (int c = 0; c < 2 + 2 * kMaxFused; ++c) tacc[c] = 0.0;
-#ifndef NB200_OLD_LEAPFROG_LOADS
                 double gnv[NIT], pov[NIT], sov[NIT];
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
@@ -785,24 +770,15 @@ struct ChainCtx {
                         sov[it] = fs[i];
                     }
                 }
-#endif
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
                     const int i = g.tid + it * G::kThreads;
                     if (it + 1 < NIT || i < D) {
-#ifndef NB200_OLD_LEAPFROG_LOADS
                         const double gn = gnv[it];
-#else
-                        const double gn = fg[i];
-#endif
                         const double pn = ph[it] + heps * gn;
                         const double vpn = vr[it] * pn;
                         acc[0] += pn * vpn;
-#ifndef NB200_OLD_LEAPFROG_LOADS
                         const double p_old = pov[it], s_old = sov[it];
-#else
-                        const double p_old = fp[i], s_old = fs[i];
-#endif
                         const double sn = restart_sum ? pn : s_old + pn;
                         if (want_l0) turn_terms(m_src, p_old, s_old, pn, sn, vr[it], vpn, tacc[0], tacc[1]);
 #pragma unroll
