@@ -251,6 +251,7 @@ struct nb200_sampler {
     double *d_draws = nullptr, *d_stats = nullptr, *d_grads = nullptr, *d_mm = nullptr;
     double* d_div = nullptr;  // store_divergences: [n_rows][n_chains][4][grad_dim]
     // adaptation = low_rank (lowrank.cuh): per-chain metric, window, scratch; eigenvalue trace
+    bool l2_persist = false;  // mass matrices held in a persisting L2 window (streaming regime)
     bool lr = false;
     int lr_cap = 0, lr_max_rank = 0;
     double *d_lr_stds = nullptr, *d_lr_vals = nullptr, *d_lr_vecs = nullptr, *d_lr_coef = nullptr;
@@ -674,6 +675,35 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
     // meets a fatal return code can raise it without a CUDA call
     P.stop_flag = s->host ? s->host->d_stop : s->d_stop;
     s->rows_filled.assign(n_chains, 0);
+    // Streaming regime (a CTA per chain, state pool >> L2): the mass matrix is the one vector that
+    // EVERY pass of a chain reads again (leapfrog and U-turn passes alike: 1 of 7 and 1 of 5
+    // vectors moved).  All chains' copies together are a few tens of MB — they fit the L2 if the
+    // terabytes streaming past do not evict them: an access-policy window marks them persisting in
+    // a set-aside part of the L2 (NB200_L2_PERSIST=0 turns it off for A/B runs).
+    if (M::kElementwise && s->W >= 4 && s->smem_slots == 0) {
+        const char* env = std::getenv("NB200_L2_PERSIST");
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        const size_t bytes = n_chains * sizeof(double) * (size_t)s->Dp;
+        if (!(env && env[0] == '0') && max_persist > 0 && max_window > 0) {
+            const size_t carve = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+            const size_t window = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                cudaStreamAttrValue attr;
+                std::memset(&attr, 0, sizeof(attr));
+                attr.accessPolicyWindow.base_ptr = s->d_var;
+                attr.accessPolicyWindow.num_bytes = window;
+                attr.accessPolicyWindow.hitRatio = window > 0 ? (float)((double)carve / (double)window) : 0.f;
+                if (attr.accessPolicyWindow.hitRatio > 1.f) attr.accessPolicyWindow.hitRatio = 1.f;
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess)
+                    s->l2_persist = true;
+            }
+            cudaGetLastError();  // the window is an optimisation: never an error
+        }
+    }
     return s;
 }
 
@@ -1360,6 +1390,7 @@ int nb200_sampler_destroy(nb200_sampler* s) {
         if (p) cudaFreeHost(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->l2_persist) cudaCtxResetPersistingL2Cache();
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->side) cudaStreamDestroy(s->side);
     delete s;

@@ -5,6 +5,8 @@ import json
 import nutpie_b200
 from nutpie_b200 import _lib
 D, C = 10000, 512
+if __import__("os").environ.get("STAGE_MODE"):  # nb200_set_stage_loads bit mask (4 = L2 eviction hints on the bulk copies)
+    _lib.set_stage_loads(int(__import__("os").environ["STAGE_MODE"]))
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if __import__("os").path.exists("MEASURED_PEAKS.json") else 6555.2
 for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     s = _lib.PyNutsSettings.Diag(7)
