@@ -97,6 +97,7 @@ static void pool_keep_memory(int device) {
 extern "C" {
 static bool is_pinned_host(const void* p);
 }
+static std::atomic<int> g_persist_users[16];  // samplers holding a persisting L2 window, per device
 static int usable_cores() {
     cpu_set_t set;
     CPU_ZERO(&set);
@@ -698,8 +699,10 @@ static nb200_sampler* create_impl(const nb200_settings* st, const nb200_model_de
                 if (attr.accessPolicyWindow.hitRatio > 1.f) attr.accessPolicyWindow.hitRatio = 1.f;
                 attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
                 attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess)
+                if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) {
                     s->l2_persist = true;
+                    g_persist_users[device & 15].fetch_add(1);
+                }
             }
             cudaGetLastError();  // the window is an optimisation: never an error
         }
@@ -1390,7 +1393,12 @@ int nb200_sampler_destroy(nb200_sampler* s) {
         if (p) cudaFreeHost(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
-    if (s->l2_persist) cudaCtxResetPersistingL2Cache();
+    if (s->l2_persist) {
+        // the set-aside is device-wide: hand the L2 back when the last sampler that uses it goes
+        cudaCtxResetPersistingL2Cache();
+        if (g_persist_users[s->device & 15].fetch_sub(1) == 1) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        cudaGetLastError();
+    }
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->side) cudaStreamDestroy(s->side);
     delete s;
