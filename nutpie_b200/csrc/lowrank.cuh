@@ -128,7 +128,8 @@ NB_HD void lr_switch(LrState& L) {
 // pairs every column with exactly one other, so its pairs are independent — kJacobiPairs of them
 // are rotated together (their column loads are in flight at the same time and their dot products
 // share one reduction), which is what hides the L2 / HBM latency of a single warp walking a
-// matrix that lives in global memory.  Sweeps until a whole sweep rotates nothing.
+// matrix that lives in global memory.  Sweeps until a sweep met no cosine above 1e-7 (the method
+// converges quadratically: what that sweep left is below 1e-13, no verification sweep is run).
 constexpr int kJacobiPairs = 4;
 NB_HD double nb_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
@@ -169,7 +170,7 @@ NB_HD void lr_round_robin_pair(int t, int k, int m, int& a, int& b) {
 // A warp per chain and r <= 32 NR: the columns of the kJacobiPairs pairs of a step live in
 // REGISTERS (NR rows per lane) between the dot products and the rotation — one round trip to
 // L2 / HBM per step with all its loads in flight together, instead of one per 32 rows and pass.
-// Same arithmetic in the same order as the generic loop below (bit-identical results).
+// Same arithmetic in the same order as the generic two-pass loop below.
 template <int NR>
 __device__ __noinline__ void lr_jacobi_warp(double* A, int r, int nc, int ld) {
     constexpr int NP = kJacobiPairs;
