@@ -253,18 +253,20 @@ struct GroupLanes {
     }
 };
 
-template <class M, int T, int NIT>
+template <class M, int T, int NIT, bool LR = false>
 struct LaneLaunch {
     const KParams<M>* P;
     ChainShared* sh;
     double *msm, *front, *pool, *var, *wf, *spool, *svar;
     uint64_t chain, chain_id_offset;
     LaneSched* sched;
+    LrState lr0;  // low-rank adaptation: the chain's buffers (every lane keeps its own counters)
     static void body(int lane, void* arg) {
         LaneLaunch& L = *static_cast<LaneLaunch*>(arg);
         const KParams<M>& P = *L.P;
-        ChainCtx<M, GroupLanes<T>, NIT> ctx;
+        ChainCtx<M, GroupLanes<T>, NIT, LR> ctx;
         std::memset((void*)&ctx, 0, sizeof(ctx));
+        ctx.lr = L.lr0;
         ctx.g.tid = lane;
         ctx.g.s = L.sched;
         ctx.P = &P; ctx.md = P.mdata; ctx.sh = L.sh; ctx.msm = L.msm;
@@ -280,7 +282,7 @@ struct LaneLaunch {
     }
 };
 
-template <class M, int T, int NIT>
+template <class M, int T, int NIT, bool LR = false>
 static int run_lanes_nit(const nb200_settings* st, const typename M::Data& md, uint64_t dim,
                          uint64_t n_chains, uint64_t chain_id_offset, double* draws, double* stats,
                          uint64_t* total_steps, int max_per_launch, int smem_slots, int lane_order,
@@ -303,11 +305,23 @@ static int run_lanes_nit(const nb200_settings* st, const typename M::Data& md, u
     P.max_draws_per_launch = max_per_launch;
     P.smem_slots = smem_slots < P.NS ? smem_slots : P.NS;
     P.var_in_smem = smem_slots > 0;
-    std::vector<double> pool((size_t)P.NS * 4 * P.Dp), var(P.Dp), wf(8 * (size_t)P.Dp);
+    std::vector<double> pool((size_t)P.NS * (LR ? 5 : 4) * P.Dp), var(P.Dp), wf(8 * (size_t)P.Dp);
     std::vector<ChainScalars> sc(n_chains);
     std::memset(sc.data(), 0, sizeof(ChainScalars) * n_chains);
     P.sc = sc.data();
     P.draws = draws; P.stats = stats;
+    const uint64_t lr_f = st->mass_matrix_switch_freq > st->early_mass_matrix_switch_freq
+                              ? st->mass_matrix_switch_freq : st->early_mass_matrix_switch_freq;
+    const int lr_cap = LR ? (int)(3 * lr_f + 2) : 1;
+    const int lr_rank = LR ? (int)(st->mass_matrix_max_rank < dim ? st->mass_matrix_max_rank : dim) : 1;
+    std::vector<double> lr_stds(P.Dp), lr_vals(lr_rank), lr_vecs((size_t)lr_rank * P.Dp), lr_coef(lr_rank);
+    std::vector<double> lr_win(LR ? (size_t)lr_cap * 2 * P.Dp : 1), lr_mat(LR ? 2 * (size_t)P.D * P.Dp : 1);
+    std::vector<double> lr_cols(6 * (size_t)P.Dp);
+    LrState lr0;
+    std::memset(&lr0, 0, sizeof(lr0));
+    lr0.stds = lr_stds.data(); lr0.vals = lr_vals.data(); lr0.vecs = lr_vecs.data(); lr0.coef = lr_coef.data();
+    lr0.win = lr_win.data(); lr0.matL = lr_mat.data(); lr0.matW = lr_mat.data() + (LR ? (size_t)P.D * P.Dp : 0);
+    lr0.cols = lr_cols.data(); lr0.cap = lr_cap; lr0.max_rank = lr_rank;
     std::vector<double> msm(M::smem_doubles(md, T) + 1), front(4 * (size_t)P.Dp + 1);
     std::vector<double> spool((size_t)P.smem_slots * 4 * P.Dp + 1), svar(P.Dp);
     ChainShared sh;
@@ -321,9 +335,9 @@ static int run_lanes_nit(const nb200_settings* st, const typename M::Data& md, u
             std::fill(front.begin(), front.end(), -555.0);
             LaneSched sched;
             sched.order = lane_order;
-            LaneLaunch<M, T, NIT> L{&P, &sh, msm.data(), front.data(), pool.data(), var.data(), wf.data(),
-                                    spool.data(), svar.data(), c, chain_id_offset, &sched};
-            run_lanes(sched, T, &LaneLaunch<M, T, NIT>::body, &L);
+            LaneLaunch<M, T, NIT, LR> L{&P, &sh, msm.data(), front.data(), pool.data(), var.data(), wf.data(),
+                                        spool.data(), svar.data(), c, chain_id_offset, &sched, lr0};
+            run_lanes(sched, T, &LaneLaunch<M, T, NIT, LR>::body, &L);
             if (sc[c].status == 2 || sc[c].status < 0) break;
         }
         if (sc[c].status < 0) err = sc[c].status;
@@ -344,6 +358,30 @@ extern "C" int emul_sample_lanes(const nb200_settings* st, const nb200_model_des
     if (T == TT && nit == NN)                                                                    \
         return run_lanes_nit<MODEL, TT, NN>(st, DATA, dim, n_chains, chain_id_offset, draws, stats, \
                                             total_steps, max_per_launch, smem_slots, lane_order, expand);
+    if (st->adaptation == 1) {  // low-rank engine: a warp of lanes, run-time loops
+        if (T != 32) return NB200_EINVAL;
+        switch (model->kind) {
+        case NB200_MODEL_NORMAL: {
+            NormalModel::Data d{model->mu, 1.0 / (model->sigma * model->sigma)};
+            return run_lanes_nit<NormalModel, 32, 0, true>(st, d, dim, n_chains, chain_id_offset, draws, stats,
+                                                           total_steps, max_per_launch, 0, lane_order, expand);
+        }
+        case NB200_MODEL_FUNNEL: {
+            FunnelModel::Data d{0};
+            return run_lanes_nit<FunnelModel, 32, 0, true>(st, d, dim, n_chains, chain_id_offset, draws, stats,
+                                                           total_steps, max_per_launch, 0, lane_order, expand);
+        }
+        case NB200_MODEL_RADON: {
+            RadonLayout L = build_radon_layout(model->n_obs, model->n_county, model->y, model->county,
+                                               model->floor, 32);
+            RadonModel::Data d{L.J, L.N, L.n_steps, L.G, L.kmax, 32, 0, L.obs.data(), L.group_base.data(),
+                               L.group_list.data()};
+            return run_lanes_nit<RadonModel, 32, 0, true>(st, d, dim, n_chains, chain_id_offset, draws, stats,
+                                                          total_steps, max_per_launch, 0, lane_order, expand);
+        }
+        }
+        return NB200_EINVAL;
+    }
     switch (model->kind) {
     case NB200_MODEL_NORMAL: {
         NormalModel::Data d{model->mu, 1.0 / (model->sigma * model->sigma)};

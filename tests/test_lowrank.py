@@ -238,6 +238,23 @@ def test_emulated_engine_resumes_bit_identically_in_low_rank_mode():
     assert np.array_equal(a["draws"], b["draws"]) and np.array_equal(a["stats"], b["stats"])
 
 
+@pytest.mark.parametrize("kind,dim,tune", [("radon", 13, 100), ("normal", 40, 50)])
+def test_lane_emulation_of_the_low_rank_engine_is_schedule_independent(kind, dim, tune):
+    """The low-rank engine run by 32 cooperative lanes (tests/emul GroupLanes: the lanes run one
+    after another between two barriers — in ascending, descending or freshly shuffled order, all
+    of them schedules independent thread scheduling allows): identical traces under every order,
+    i.e. no barrier is missing in lowrank.cuh / leapfrog_lr; and the same trees as the one-thread
+    emulation over the first draws.  normal-40: the early windows take the subspace route."""
+    kw = small_radon() if kind == "radon" else dict(mu=1.0, sigma=2.0)
+    s = lr_settings(num_tune=tune, num_draws=10)
+    runs = [E.sample_lanes(kind, dim, s, 1, threads_per_chain=32, lane_order=o, **kw) for o in (0, 1, 5)]
+    for other in runs[1:]:
+        assert np.array_equal(other["draws"], runs[0]["draws"]) and np.array_equal(other["stats"], runs[0]["stats"])
+    serial = E.sample(kind, dim, s, 1, **kw)
+    assert np.array_equal(serial["stats"][:, :11, STAT_N_STEPS], runs[0]["stats"][:, :11, STAT_N_STEPS])
+    np.testing.assert_allclose(runs[0]["draws"][:, :11], serial["draws"][:, :11], rtol=0, atol=1e-8)
+
+
 # ------------------------------------------------------------------- oracle sampler (CPU)
 def test_oracle_low_rank_shortens_trajectories_on_a_correlated_posterior():
     rng = np.random.default_rng(3)
