@@ -12,8 +12,11 @@ def mcse_z(a, b):
     se = np.sqrt(ma.var(0, ddof=1) / len(ma) + mb.var(0, ddof=1) / len(mb))
     return np.abs(ma.mean(0) - mb.mean(0)) / se
 
-def report(name, gm, om, n_gpu, n_cpu, tune, draws, **kw):
-    s = _lib.PyNutsSettings.Diag(11); so = O.default_settings(seed=11)
+def report(name, gm, om, n_gpu, n_cpu, tune, draws, low_rank=False, **kw):
+    s = _lib.PyNutsSettings.LowRank(11) if low_rank else _lib.PyNutsSettings.Diag(11)
+    so = O.default_settings(seed=11)
+    if low_rank:
+        kw = dict(adaptation=1, mass_matrix_update_freq=10, **kw)
     for k, v in dict(num_tune=tune, num_draws=draws, **kw).items():
         setattr(s._c, k, v); setattr(so, k, v)
     smp = _lib.PySampler(s, gm, n_chains=n_gpu); smp.wait(); tr = smp.take_results(); ms = smp.kernel_ms(); smp.close()
@@ -39,3 +42,17 @@ report("2: radon D=175, 1024 chains", nutpie_b200.radon_model(d["y"], d["county"
        O.Model("radon", 2*J+5, y=d["y"], county=d["county"], floor=d["floor"], n_county=J), 1024, 256, 1000, 1000, init_radius=1.0)
 report("4: iid normal D=10000, 512 chains (first 16 coords stored)", nutpie_b200.normal_model(10000), O.Model("normal", 10000), 512, 32, 200, 200, store_dims=16)
 report("5: funnel D=9, 4096 chains, maxdepth 12", nutpie_b200.funnel_model(9), O.Model("funnel", 9), 4096, 1024, 1000, 1000, maxdepth=12)
+# adaptation="low_rank" (SURVEY §8 f4): correlated logistic regression as run-time compiled CUDA source, and radon
+from tests import custom_densities as CD
+rng = np.random.default_rng(3)
+n_obs, dim = 500, 24
+zz = rng.normal(size=(n_obs, dim))
+for a in range(0, dim - 1, 2):
+    zz[:, a + 1] = zz[:, a] * 0.95 + 0.1 * zz[:, a + 1]
+yy = (rng.uniform(size=n_obs) < 1 / (1 + np.exp(-zz @ rng.normal(size=dim)))).astype(float)
+flat = np.concatenate([[n_obs, dim], zz.ravel(), yy])
+report("low_rank: logistic regression D=24 (NVRTC density), 1024 chains", nutpie_b200.from_cuda_source(dim, CD.LOGREG, data=flat, scratch=n_obs),
+       O.Model("logreg", dim, data=flat), 1024, 64, 800, 400, low_rank=True)
+report("low_rank: radon D=175, 256 chains, cutoff 4", nutpie_b200.radon_model(d["y"], d["county"], d["floor"], J),
+       O.Model("radon", 2*J+5, y=d["y"], county=d["county"], floor=d["floor"], n_county=J), 256, 16, 400, 200, low_rank=True,
+       init_radius=1.0, mass_matrix_eigval_cutoff=4.0)
