@@ -336,7 +336,7 @@ static int validate(const nb200_settings* st, const nb200_model_desc* m) {
     if (st->adaptation == 1) {
         // the refresh factorises two dim x dim matrices per chain (lowrank.cuh)
         if (m->dim > 1024)
-            return fail(NB200_EINVAL, "adaptation='low_rank' supports models of up to 1024 dimensions");
+            return fail(NB200_EINVAL, "adaptation='low_rank': the model dimension must be <= 1024 dimensions");
         if (!(st->mass_matrix_eigval_cutoff > 1.0))
             return fail(NB200_EINVAL, "mass_matrix_eigval_cutoff must be > 1");
         if (!(st->mass_matrix_gamma > 0.0)) return fail(NB200_EINVAL, "mass_matrix_gamma must be > 0");

@@ -496,3 +496,30 @@ def test_gpu_deprecated_keywords_and_extra_stats_like_the_reference_tests(radon_
         mm = "mass_matrix_stds" if adaptation == "low_rank" else "mass_matrix_inv"
         assert ss[mm].shape == (2, 40, rm.n_dim) and np.isfinite(ss[mm]).all()
         assert ("mass_matrix_eigvals" in ss) == (adaptation == "low_rank")
+
+
+def test_low_rank_settings_are_validated_by_the_c_abi_before_any_device_work():
+    """nb200_sampler_create refuses what the low-rank engine cannot run (no GPU needed: the checks
+    come before the first CUDA call), with the option names of src/wrapper.rs:307-346."""
+    import nutpie_b200
+    from nutpie_b200 import _lib
+
+    def make(dim=3, **kw):
+        s = _lib.PyNutsSettings.LowRank(1)
+        for k, v in kw.items():
+            setattr(s._c, k, v)
+        return _lib.PySampler(s, nutpie_b200.normal_model(dim), n_chains=2, autostart=False)
+
+    with pytest.raises(ValueError, match="1024 dimensions"):
+        make(dim=2000)
+    with pytest.raises(ValueError, match="mass_matrix_eigval_cutoff"):
+        make(mass_matrix_eigval_cutoff=1.0)
+    with pytest.raises(ValueError, match="mass_matrix_gamma"):
+        make(mass_matrix_gamma=0.0)
+    with pytest.raises(ValueError, match="mass_matrix_max_rank"):
+        make(mass_matrix_max_rank=0)
+    s = _lib.PyNutsSettings.LowRank(1)
+    assert (s._c.adaptation, s._c.mass_matrix_update_freq, s.num_tune) == (1, 10, 800)
+    assert s.as_dict()["adaptation"] == "low_rank"
+    with pytest.raises(ValueError):  # wrapper.rs:138-145: a diag-only option on the low-rank settings
+        s.use_grad_based_mass_matrix = False
