@@ -59,7 +59,8 @@ WORKLOAD = "radon_hierarchical_D175_1024chains_per_gpu_1000tune_1000draws"
 #   profiles/r2_config4_full_length_ncu.txt    : 6294.5 GB / 7 043 325 evaluations (the full-length
 #       launch; the 50-draw warm-up capture of round 1 gave 763 KB per evaluation — early trees
 #       are short and do fewer separate U-turn passes per leaf)
-NCU_DRAM_BYTES_PER_EVAL = {"radon": 729.67e6 / 1323933, "config4": 6294.4818e9 / 7043325}
+#       with the L2 persisting window over the mass matrices (the default): 5591.2 GB
+NCU_DRAM_BYTES_PER_EVAL = {"radon": 729.67e6 / 1323933, "config4": 5591.2271e9 / 7043325}
 
 
 def _peaks():
