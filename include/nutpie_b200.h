@@ -292,6 +292,12 @@ int nb200_sampler_trace_into(nb200_sampler *s, double *draws, double *stats,
  * nb200_sampler_trace_into with the same pointers afterwards copies nothing twice. */
 int nb200_sampler_set_trace_target(nb200_sampler *s, double *draws, size_t draws_bytes,
                                    double *stats, size_t stats_bytes);
+/* The same with ROW-STRIDED targets: row r of the draws lands at draws + r * draws_row_stride
+ * (doubles; >= n_chains * width), likewise the stats.  The shards of one multi-GPU job — the
+ * role of `cores` in src/wrapper.rs:977-1085 — write their chains into their own columns of the
+ * job's single [row][chain][width] array, so the result needs no concatenation. */
+int nb200_sampler_set_trace_target_strided(nb200_sampler *s, double *draws, size_t draws_row_stride,
+                                           double *stats, size_t stats_row_stride);
 /* exact sizes in bytes the two buffers above must have */
 int nb200_sampler_trace_bytes(nb200_sampler *s, size_t *draws_bytes, size_t *stats_bytes);
 int nb200_sampler_destroy(nb200_sampler *s);

@@ -175,6 +175,9 @@ def load_library() -> C.CDLL:
                                                 C.POINTER(C.c_size_t)]
         L.nb200_sampler_divergence_trace_into.restype = C.c_int
         L.nb200_sampler_divergence_trace_into.argtypes = [C.c_void_p, C.c_void_p]
+        L.nb200_sampler_set_trace_target_strided.restype = C.c_int
+        L.nb200_sampler_set_trace_target_strided.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                             C.c_size_t]
         L.nb200_sampler_eigvals_trace_into.restype = C.c_int
         L.nb200_sampler_eigvals_trace_into.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.nb200_lowrank_component.restype = C.c_int
@@ -620,19 +623,9 @@ class PySampler:
                 # on the host when sampling ends instead of one serial copy afterwards
                 sh = self.trace_shapes()
                 trace_buffers = {"draws": np.empty(sh["draws"]), "stats": np.empty(sh["stats"])}
-            self._trace_buffers = trace_buffers
-            if trace_buffers is not None:  # rows are streamed into these while sampling runs
-                sh = self.trace_shapes()
-                for k in ("draws", "stats"):
-                    a = trace_buffers[k]
-                    if not a.flags["C_CONTIGUOUS"] or a.dtype != np.float64:
-                        raise ValueError("trace buffers must be C-contiguous float64 arrays")
-                    if tuple(a.shape) != sh[k]:  # checked BEFORE the engine may write into them
-                        raise ValueError(f"trace buffer '{k}' must be a row-major array of shape "
-                                         f"{sh[k]}, got {tuple(a.shape)}")
-                _check(L.nb200_sampler_set_trace_target(
-                    self._h, _ptr(trace_buffers["draws"]), trace_buffers["draws"].nbytes,
-                    _ptr(trace_buffers["stats"]), trace_buffers["stats"].nbytes))
+            self._trace_buffers = None
+            if trace_buffers is not None:
+                self._register_trace_buffers(trace_buffers)
         except Exception:
             L.nb200_sampler_destroy(self._h)
             self._h = None
@@ -645,6 +638,36 @@ class PySampler:
         self._started = False
         if autostart:
             self.start()
+
+    def _register_trace_buffers(self, trace_buffers):
+        """Rows are streamed into these host arrays while sampling runs (before start only)."""
+        L = self._L
+        sh = self.trace_shapes()
+        strided = False
+        for k in ("draws", "stats"):
+            a = trace_buffers[k]
+            if tuple(a.shape) != sh[k]:  # checked BEFORE the engine may write into them
+                raise ValueError(f"trace buffer '{k}' must be a row-major array of shape "
+                                 f"{sh[k]}, got {tuple(a.shape)}")
+            # dense, or the column block [:, a:b, :] of a wider row-major array (the
+            # shards of a multi-GPU job share ONE result array): rows may be strided
+            w = a.shape[2]
+            ok = (a.dtype == np.float64 and a.strides[2] == 8 and a.strides[1] == 8 * w
+                  and a.strides[0] >= 8 * w * a.shape[1] and a.strides[0] % 8 == 0)
+            if not ok:
+                raise ValueError("trace buffers must be float64 arrays, C-contiguous or a "
+                                 "block of chains of a C-contiguous [row][chain][width] array")
+            strided |= not a.flags["C_CONTIGUOUS"]
+        if strided:
+            _check(L.nb200_sampler_set_trace_target_strided(
+                self._h, C.c_void_p(trace_buffers["draws"].ctypes.data),
+                trace_buffers["draws"].strides[0] // 8,
+                C.c_void_p(trace_buffers["stats"].ctypes.data), trace_buffers["stats"].strides[0] // 8))
+        else:
+            _check(L.nb200_sampler_set_trace_target(
+                self._h, _ptr(trace_buffers["draws"]), trace_buffers["draws"].nbytes,
+                _ptr(trace_buffers["stats"]), trace_buffers["stats"].nbytes))
+        self._trace_buffers = trace_buffers
 
     def start(self):
         """Launch the sampling kernel (non-blocking), like nuts_rs::Sampler::new returning
@@ -866,13 +889,15 @@ class MultiTrace:
     order (device 0's block first); `draws` / `stats` concatenate the per-device blocks on first
     access (each block is a view of that device's own — pinned, if supplied — host buffer)."""
 
-    def __init__(self, parts):
+    def __init__(self, parts, whole=None):
         self.parts = parts
         self.expanded = parts[0].expanded
         self.expand_fn = parts[0].expand_fn
         self.variables = parts[0].variables
         self._expand = parts[0]._expand
         self._cache = {}
+        if whole is not None:  # the shards wrote into one [row][chain][width] array: chain-major views
+            self._cache = {k: a.transpose(1, 0, 2) for k, a in whole.items()}
         self._taken = False
 
     def _cat(self, name):
@@ -938,6 +963,8 @@ class PyMultiSampler:
         self.devices = devices
         self.n_chains = n_chains
         self.parts = []
+        self._offsets = []
+        self._big = None
         self._progress_type = progress_type or ProgressType.none()
         self._model = model
         self._stop_progress = threading.Event()
@@ -948,14 +975,23 @@ class PyMultiSampler:
                 if n_local == 0:
                     continue
                 sl = slice(off, off + n_local)
-                bufs = None
+                bufs = False  # registered below: every shard writes into the job's ONE result array
                 if trace_buffers is not None:  # per-device list of dict(draws=, stats=)
                     bufs = trace_buffers[i]
+                self._offsets.append((off, n_local))
                 self.parts.append(PySampler(
                     settings, model, n_chains=n_local, chain_id_offset=int(chain_id_offset) + off,
                     device=dev, trace_buffers=bufs, autostart=False,
                     q0=None if q0 is None else np.asarray(q0)[sl],
                     z_tape=None if z_tape is None else np.asarray(z_tape)[sl], **kw))
+            if trace_buffers is None and self.parts:
+                # one [row][chain][width] array for the whole job: device i streams its chains into
+                # its own block of columns (row-strided targets), nothing is concatenated afterwards
+                sh = self.parts[0].trace_shapes()
+                self._big = {"draws": np.empty((sh["draws"][0], n_chains, sh["draws"][2])),
+                             "stats": np.empty((sh["stats"][0], n_chains, sh["stats"][2]))}
+                for p, (off, n_local) in zip(self.parts, self._offsets):
+                    p._register_trace_buffers({k: a[:, off:off + n_local, :] for k, a in self._big.items()})
             for p in self.parts:  # all devices start before anyone waits
                 p.start()
         except Exception:
@@ -1022,7 +1058,7 @@ class PyMultiSampler:
         return None
 
     def inspect(self, out=None):
-        return MultiTrace([p.inspect() for p in self.parts])
+        return MultiTrace([p.inspect() for p in self.parts], whole=self._big)
 
     def take_results(self, out=None):
         if not self.is_finished():
@@ -1039,7 +1075,7 @@ class PyMultiSampler:
             t.join()
         if any(r is None for r in res):
             raise ValueError("Sampler is empty")
-        return MultiTrace(res)
+        return MultiTrace(res, whole=self._big)
 
     def kernel_ms(self):
         """device time of the slowest device (the job's time)"""

@@ -272,6 +272,7 @@ struct nb200_sampler {
     int sampler_error = 0;
     // streaming of finished trace rows to host buffers while the kernel runs
     double *tgt_draws = nullptr, *tgt_stats = nullptr;
+    size_t tgt_draws_pitch = 0, tgt_stats_pitch = 0;  // row stride of the targets in doubles (0 = dense)
     uint64_t streamed_rows = 0;
     std::chrono::steady_clock::time_point last_stream{};
 };
@@ -863,6 +864,22 @@ int nb200_sampler_set_trace_target(nb200_sampler* s, double* draws, size_t draws
     return 0;
 }
 
+int nb200_sampler_set_trace_target_strided(nb200_sampler* s, double* draws, size_t draws_row_stride,
+                                           double* stats, size_t stats_row_stride) {
+    if (!s) return fail(NB200_EINVAL, "null sampler");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state != RunState::Created) return fail(NB200_ESTATE, "trace target must be set before start");
+    if (draws && draws_row_stride < s->n_chains * s->sdim)
+        return fail(NB200_EINVAL, "trace target: draws row stride must be >= n_chains * width doubles");
+    if (stats && stats_row_stride < s->n_chains * NB200_NSTAT)
+        return fail(NB200_EINVAL, "trace target: stats row stride must be >= n_chains * 16 doubles");
+    s->tgt_draws = draws;
+    s->tgt_stats = stats;
+    s->tgt_draws_pitch = draws ? draws_row_stride : 0;
+    s->tgt_stats_pitch = stats ? stats_row_stride : 0;
+    return 0;
+}
+
 int nb200_sampler_set_draws_per_launch(nb200_sampler* s, uint64_t n) {
     if (!s) return fail(NB200_EINVAL, "null sampler");
     std::lock_guard<std::mutex> lk(s->mu);
@@ -1004,6 +1021,60 @@ static int d2h_block(void* dst, const void* src, size_t bytes, cudaStream_t stre
     return 0;
 }
 
+// `n_rows` rows of `row` doubles, dense on the device, to a host buffer whose rows are `pitch`
+// doubles apart (a shard of a multi-GPU job writes its chains into ITS columns of the job's one
+// [row][chain][width] array): dense -> d2h_block; pinned -> one 2-D DMA; pageable -> whole rows
+// through the staging ring, moved on row by row by the copy threads.
+static int d2h_rows(double* dst, size_t pitch, const double* src, size_t row, size_t n_rows,
+                    cudaStream_t stream, int device) {
+    if (n_rows == 0 || row == 0) return 0;
+    if (pitch == 0 || pitch == row) return d2h_block(dst, src, n_rows * row * sizeof(double), stream, device);
+    if (is_pinned_host(dst)) {
+        CU(cudaMemcpy2DAsync(dst, pitch * sizeof(double), src, row * sizeof(double), row * sizeof(double),
+                             n_rows, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    StageRing& g_stage = g_stage_of_device[device & 15];
+    std::lock_guard<std::mutex> lk(g_stage.mu);
+    const size_t rb = row * sizeof(double);
+    if (g_stage.init() != 0 || rb > StageRing::kChunk) {  // no staging: the driver's own 2-D path
+        cudaGetLastError();
+        CU(cudaMemcpy2DAsync(dst, pitch * sizeof(double), src, rb, rb, n_rows, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    int T = usable_cores() / 2;
+    T = T < 1 ? 1 : (T > 8 ? 8 : T);
+    const size_t per = StageRing::kChunk / rb;  // rows per chunk
+    const size_t n = (n_rows + per - 1) / per;
+    auto rows_of = [&](size_t c) { return c + 1 < n ? per : n_rows - c * per; };
+    CU(cudaMemcpyAsync(g_stage.buf[0], src, rows_of(0) * rb, cudaMemcpyDeviceToHost, stream));
+    CU(cudaEventRecord(g_stage.ev[0], stream));
+    for (size_t c = 0; c < n; ++c) {
+        const int b = (int)(c & 1);
+        if (c + 1 < n) {
+            CU(cudaMemcpyAsync(g_stage.buf[b ^ 1], src + (c + 1) * per * row, rows_of(c + 1) * rb,
+                               cudaMemcpyDeviceToHost, stream));
+            CU(cudaEventRecord(g_stage.ev[b ^ 1], stream));
+        }
+        CU(cudaEventSynchronize(g_stage.ev[b]));
+        const size_t nr = rows_of(c);
+        double* d0 = dst + c * per * pitch;
+        const char* s0 = g_stage.buf[b];
+        std::vector<std::thread> th;
+        const int TT = (size_t)T < nr ? T : (int)nr;
+        for (int t = 0; t < TT; ++t) {
+            const size_t lo = nr * t / TT, hi = nr * (t + 1) / TT;
+            th.emplace_back([=] {
+                for (size_t r = lo; r < hi; ++r) std::memcpy(d0 + r * pitch, s0 + r * rb, rb);
+            });
+        }
+        for (auto& t : th) t.join();
+    }
+    return 0;
+}
+
 // refresh h_sc from the device on the side stream (safe while the kernel runs)
 static int fetch_scalars(nb200_sampler* s);
 static int stream_rows(nb200_sampler* s, uint64_t from, uint64_t to);
@@ -1022,12 +1093,11 @@ static int stream_rows(nb200_sampler* s, uint64_t from, uint64_t to) {
     CU(cudaSetDevice(s->device));
     const size_t drow = s->n_chains * s->sdim, srow = s->n_chains * NB200_NSTAT;  // doubles per row
     int rc = 0;
+    const size_t dp = s->tgt_draws_pitch ? s->tgt_draws_pitch : drow, sp = s->tgt_stats_pitch ? s->tgt_stats_pitch : srow;
     if (s->tgt_draws)
-        rc = d2h_block(s->tgt_draws + from * drow, s->d_draws + from * drow,
-                       (to - from) * drow * sizeof(double), s->side, s->device);
+        rc = d2h_rows(s->tgt_draws + from * dp, dp, s->d_draws + from * drow, drow, to - from, s->side, s->device);
     if (rc == 0 && s->tgt_stats)
-        rc = d2h_block(s->tgt_stats + from * srow, s->d_stats + from * srow,
-                       (to - from) * srow * sizeof(double), s->side, s->device);
+        rc = d2h_rows(s->tgt_stats + from * sp, sp, s->d_stats + from * srow, srow, to - from, s->side, s->device);
     if (rc != 0) return rc;
     s->streamed_rows = to;
     return 0;
@@ -1233,8 +1303,15 @@ static int copy_trace(nb200_sampler* s, double* draws, double* stats, double* gr
     const size_t nd = s->n_chains * s->n_rows * s->sdim * sizeof(double);
     const size_t ns = s->n_chains * s->n_rows * NB200_NSTAT * sizeof(double);
     const bool streamed = s->streamed_rows >= s->n_rows;  // already landed in the target buffers
-    if (draws && !(streamed && draws == s->tgt_draws) && (rc = d2h_block(draws, s->d_draws, nd, s->side, s->device))) return rc;
-    if (stats && !(streamed && stats == s->tgt_stats) && (rc = d2h_block(stats, s->d_stats, ns, s->side, s->device))) return rc;
+    // (the registered targets may be row-strided: a caller that passes them back gets their pitch)
+    const size_t drow = s->n_chains * s->sdim, srow = s->n_chains * NB200_NSTAT;
+    if (draws && !(streamed && draws == s->tgt_draws) &&
+        (rc = d2h_rows(draws, draws == s->tgt_draws ? s->tgt_draws_pitch : 0, s->d_draws, drow, s->n_rows, s->side, s->device)))
+        return rc;
+    if (stats && !(streamed && stats == s->tgt_stats) &&
+        (rc = d2h_rows(stats, stats == s->tgt_stats ? s->tgt_stats_pitch : 0, s->d_stats, srow, s->n_rows, s->side, s->device)))
+        return rc;
+    (void)nd; (void)ns;
     const size_t ng = s->n_chains * s->n_rows * s->grad_dim * sizeof(double);
     if (grads && s->d_grads && (rc = d2h_block(grads, s->d_grads, ng, s->side, s->device))) return rc;
     if (mm && s->d_mm && (rc = d2h_block(mm, s->d_mm, ng, s->side, s->device))) return rc;

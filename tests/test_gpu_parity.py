@@ -698,3 +698,34 @@ def test_trace_lands_identically_through_every_host_path(radon_data):
     assert default.draws.shape == (192, 300, 175) and np.isfinite(default.draws).all()
     for other in (single, pinned):
         assert np.array_equal(other.draws, default.draws) and np.array_equal(other.stats, default.stats)
+
+
+def test_shards_of_one_job_stream_into_one_result_array(radon_data):
+    """sample(devices=...) / PyMultiSampler: every shard writes its chains into its own block of
+    columns of the job's single [row][chain][width] array (row-strided trace targets,
+    nb200_sampler_set_trace_target_strided) — pageable (staging ring, row-wise host copies) and
+    pinned (one 2-D DMA per block).  Two shards on ONE device here; chain for chain the
+    single-sampler run, and the result is a view of one array, not a concatenation."""
+    gm, _ = models(radon_data)["radon"]
+    mk = lambda: settings_pair(seed=43, num_tune=100, num_draws=60, init_radius=1.0)[0]
+    single = run_gpu(mk(), gm, 40)
+    ms = _lib.PyMultiSampler(mk(), gm, n_chains=40, devices=[0, 0])
+    try:
+        ms.wait()
+        tr = ms.take_results()
+        big = ms._big["draws"]
+    finally:
+        ms.close()
+    assert np.shares_memory(tr.draws, big) and tr.draws.shape == (40, 160, 175)
+    assert np.array_equal(tr.draws, single.draws) and np.array_equal(tr.stats, single.stats)
+    pd_, ps_ = _lib.PinnedArray((160, 40, 175)), _lib.PinnedArray((160, 40, _lib.NSTAT))
+    bufs = [{"draws": pd_.array[:, :20], "stats": ps_.array[:, :20]},
+            {"draws": pd_.array[:, 20:], "stats": ps_.array[:, 20:]}]
+    ms = _lib.PyMultiSampler(mk(), gm, n_chains=40, devices=[0, 0], trace_buffers=bufs)
+    try:
+        ms.wait()
+        ms.take_results()
+    finally:
+        ms.close()
+    assert np.array_equal(pd_.array.transpose(1, 0, 2), single.draws)
+    assert np.array_equal(ps_.array.transpose(1, 0, 2), single.stats)
